@@ -1,0 +1,124 @@
+"""Synthetic finite-volume assembly of the monolithic conjugate-heat-transfer T system.
+
+Produces the matrices that ``coupledFvMatrix<scalar>::solve`` hands to the coupled Krylov
+solver for the flowOverHeatedPlate topology:
+
+  fluid  (transportTemperature, /root/reference/src/regions/transportTemperature/transportTemperature.C:129-150)
+         rho*cp*(ddt(T) + div(phi,T)) = laplacian(k,T),  U = (1,0,0) prescribed, upwind  -> asymmetric
+  solid  (conductTemperature, /root/reference/src/regions/conductTemperature/conductTemperature.C:135-152)
+         rho*cv*ddt(T) = laplacian(k,T)                                                  -> symmetric
+  fluid 'interface' <-> solid 'top': regionCouple patch pair; series (harmonic) conductance on both
+         sides (monolithicThermalDiffusivityFvPatchScalarField.C:257-276 without radiation), conformal
+         => identity GGI addressing, weights 1.
+
+Constants: constant/{fluid,solid}/transportProperties (rho=1, cp=250, k=5 | rho=1, cv=100, k=100),
+system/controlDict deltaT 1e-2, 0/*/orig/monolithic/T (inlet 300 K, solid bottom 310 K).
+The matrices are representative of, not identical to, the reference's (identical ones need the
+foam-extend dump path).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+
+from .case import Case, Interface, RankSystem, Region, REGION_COUPLE
+from .mesh import StructuredRegion, flow_over_heated_plate
+
+
+def _laplacian_ddt(reg: StructuredRegion, rho_c: float, k: float, dt: float, T_old: float):
+    D = k * reg.faceArea / reg.faceDelta
+    l, u = reg.lowerAddr, reg.upperAddr
+    diag = rho_c * reg.volume / dt
+    source = diag * T_old
+    diag = diag + np.bincount(l, weights=D, minlength=reg.nCells) + np.bincount(u, weights=D, minlength=reg.nCells)
+    return D, diag, source
+
+
+def assemble_cht(fluid: StructuredRegion, solid: StructuredRegion, *, dt: float = 1e-2,
+                 Ux: float = 1.0, name: str = "cht") -> Case:
+    rho_f, cp_f, k_f = 1.0, 250.0, 5.0
+    rho_s, cv_s, k_s = 1.0, 100.0, 100.0
+    T_f0, T_s0, T_in, T_bot = 300.0, 310.0, 300.0, 310.0
+
+    # ------------------------------------------------------------------ fluid
+    D, diag_f, src_f = _laplacian_ddt(fluid, rho_f * cp_f, k_f, dt, T_f0)
+    l, u = fluid.lowerAddr, fluid.upperAddr
+    # convective flux rho*cp*U.S_f through +x faces (owner -> neighbour), upwind
+    F = np.where(fluid.faceDir == 0, rho_f * cp_f * Ux * fluid.faceArea, 0.0)
+    upper_f = -D + np.minimum(F, 0.0)
+    lower_f = -D - np.maximum(F, 0.0)
+    diag_f = diag_f + np.bincount(l, weights=np.maximum(F, 0.0), minlength=fluid.nCells) \
+                    - np.bincount(u, weights=np.minimum(F, 0.0), minlength=fluid.nCells)
+    # inlet: fixedValue T_in (diffusion + convective inflow)
+    c, a, d = fluid.side_xmin()
+    Db = k_f * a / d
+    Fb = -rho_f * cp_f * Ux * a            # outward normal is -x
+    np.add.at(diag_f, c, Db + np.maximum(Fb, 0.0))
+    np.add.at(src_f, c, (Db - np.minimum(Fb, 0.0)) * T_in)
+    # outlet: zeroGradient, convective outflow
+    c, a, d = fluid.side_xmax()
+    np.add.at(diag_f, c, np.maximum(rho_f * cp_f * Ux * a, 0.0))
+
+    # ------------------------------------------------------------------ solid
+    Ds, diag_s, src_s = _laplacian_ddt(solid, rho_s * cv_s, k_s, dt, T_s0)
+    upper_s = -Ds
+    c, a, d = solid.side_y(0, top=False)   # bottom: fixedValue 310
+    Db = k_s * a / d
+    np.add.at(diag_s, c, Db)
+    np.add.at(src_s, c, Db * T_bot)
+
+    # ------------------------------------------------------------------ interface
+    fc_f, a_f, d_f = fluid.side_y(1, top=False)  # fluid block 2 bottom ('interface')
+    fc_s, a_s, d_s = solid.side_y(0, top=True)   # solid top
+    assert fc_f.size == fc_s.size
+    kOwn = k_f / d_f
+    kNei = k_s / d_s
+    cond = a_f * kOwn * kNei / (kOwn + kNei)
+    np.add.at(diag_f, fc_f, cond)                # addBoundaryDiag(internalCoeffs)
+    np.add.at(diag_s, fc_s, cond)
+
+    reg_f = Region("fluid", fluid.nCells, l, u, diag_f, upper_f, lower_f, src_f,
+                   np.full(fluid.nCells, T_f0))
+    reg_s = Region("solid", solid.nCells, solid.lowerAddr, solid.upperAddr, diag_s, upper_s, None,
+                   src_s, np.full(solid.nCells, T_s0))
+    reg_f.interfaces.append(Interface(REGION_COUPLE, fc_f, cond.copy(), cond.copy(), 0, 1, 0, name="interface"))
+    reg_s.interfaces.append(Interface(REGION_COUPLE, fc_s, cond.copy(), cond.copy(), 0, 0, 0, name="top"))
+    return Case(name, [RankSystem(0, 1, [reg_f, reg_s])])
+
+
+def cht_case(r: int = 1, layers: int = 1, **kw) -> Tuple[Case, StructuredRegion, StructuredRegion]:
+    fluid, solid = flow_over_heated_plate(r, layers)
+    return assemble_cht(fluid, solid, name=f"cht_r{r}_L{layers}", **kw), fluid, solid
+
+
+WORKLOADS = {
+    # BASELINE.json configs; (r, layers)
+    "C1": (1, 1),        # as-shipped flowOverHeatedPlate mesh, 21 812 cells
+    "C2": (3, 22),       # 3-D, 4 318 776 cells   (metric config)
+    "C2-2D": (14, 1),    # 2-D-faithful, 4 275 152 cells
+    "C3": (4, 183),      # 3-D, 63 865 536 cells
+    "C3-2D": (54, 1),
+}
+
+
+def synthetic_coeffs(nCells: int, l: np.ndarray, u: np.ndarray, *, symmetric: bool, seed: int = 12345,
+                     name: str = "addr") -> Region:
+    """Addressing-only fixture: seeded diagonally dominant coefficients on a
+    given LDU addressing; b = A x*, x0 = 300."""
+    rng = np.random.default_rng(seed)
+    F = l.size
+    upper = -(0.5 + rng.random(F))
+    lower = None if symmetric else upper * (1.0 + 0.2 * (2.0 * rng.random(F) - 1.0))
+    lo = upper if lower is None else lower
+    diag = 0.01 - np.bincount(l, weights=upper, minlength=nCells) - np.bincount(u, weights=lo, minlength=nCells)
+    xstar = 300.0 + 10.0 * rng.random(nCells)
+    b = diag * xstar
+    b += np.bincount(l, weights=upper * xstar[u], minlength=nCells)
+    b += np.bincount(u, weights=lo * xstar[l], minlength=nCells)
+    return Region(name, nCells, l.astype(np.int32), u.astype(np.int32), diag, upper, lower, b,
+                  np.full(nCells, 300.0))
+
+
+def single_region_case(reg: Region, name: str = "single") -> Case:
+    return Case(name, [RankSystem(0, 1, [reg])])

@@ -1,0 +1,846 @@
+/*
+ * ldu_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE ONLY).  See ldu_oracle.h for
+ * scope, the reference files restated and the "parity unpinned" statement.
+ *
+ * Compile: gcc -O3 -ffp-contract=off -fPIC -shared (see Makefile).
+ */
+#include "ldu_oracle.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_GREAT 1.0e+20  /* lduMatrix::great_ */
+#define ORC_SMALL 1.0e-20  /* lduMatrix::small_ */
+#define ORC_VSMALL 1.0e-300 /* VSMALL (checkSingularity) */
+#define ORC_SMALL_ 1.0e-15 /* SMALL (relTol > SMALL test in checkConvergence) */
+
+typedef struct orc_iface
+{
+    int kind;
+    int nFaces;
+    int* faceCells;
+    double* bouCoeffs;
+    double* intCoeffs;
+    int peerRow, peerIface;
+    int* ggiOffsets; /* NULL => identity */
+    int* ggiAddr;
+    double* ggiWeights;
+    double* buf; /* matrixUpdateBuffer_ written by init of THIS patch; size = peer nFaces */
+    int bufSize;
+} orc_iface;
+
+typedef struct orc_row
+{
+    int rank, region;
+    int nCells, nFaces;
+    int offset; /* into concatenated vectors */
+    int *l, *u;
+    int* losort; /* faces sorted by u (stable): lduAddressing::losortAddr */
+    double *diag, *upper, *lower; /* lower == upper when symmetric */
+    int symmetric;
+    int nIfaces, capIfaces;
+    orc_iface* ifaces;
+    double* rD;
+    int precond; /* effective per-row type after Cholesky resolution */
+} orc_row;
+
+struct orc_sys
+{
+    int nRows, nRanks;
+    orc_row* rows;
+    int total;
+    int precond;
+    double* rankPartial;
+};
+
+const char* orc_version(void) { return "ldu_oracle 1.0 (foam-extend-4.1 restatement, parity unpinned)"; }
+
+/* ------------------------------------------------------------------ build */
+
+orc_sys* orc_create(int nRows, int nRanks)
+{
+    orc_sys* s = (orc_sys*)calloc(1, sizeof(orc_sys));
+    s->nRows = nRows;
+    s->nRanks = nRanks > 0 ? nRanks : 1;
+    s->rows = (orc_row*)calloc((size_t)nRows, sizeof(orc_row));
+    s->rankPartial = (double*)calloc((size_t)s->nRanks, sizeof(double));
+    s->precond = -1;
+    return s;
+}
+
+void orc_destroy(orc_sys* s)
+{
+    if (!s) return;
+    for (int r = 0; r < s->nRows; r++)
+    {
+        orc_row* R = &s->rows[r];
+        free(R->l);
+        free(R->u);
+        free(R->losort);
+        free(R->diag);
+        if (R->lower != R->upper) free(R->lower);
+        free(R->upper);
+        free(R->rD);
+        for (int i = 0; i < R->nIfaces; i++)
+        {
+            orc_iface* I = &R->ifaces[i];
+            free(I->faceCells);
+            free(I->bouCoeffs);
+            free(I->intCoeffs);
+            free(I->ggiOffsets);
+            free(I->ggiAddr);
+            free(I->ggiWeights);
+            free(I->buf);
+        }
+        free(R->ifaces);
+    }
+    free(s->rows);
+    free(s->rankPartial);
+    free(s);
+}
+
+static void* dupmem(const void* p, size_t n)
+{
+    void* q = malloc(n ? n : 1);
+    if (p && n) memcpy(q, p, n);
+    return q;
+}
+
+static void recompute_offsets(orc_sys* s)
+{
+    int off = 0;
+    for (int r = 0; r < s->nRows; r++)
+    {
+        s->rows[r].offset = off;
+        off += s->rows[r].nCells;
+    }
+    s->total = off;
+}
+
+int orc_set_row(orc_sys* s, int row, int rank, int region, int nCells, int nFaces,
+                const int* lowerAddr, const int* upperAddr)
+{
+    if (row < 0 || row >= s->nRows || rank < 0 || rank >= s->nRanks) return -1;
+    orc_row* R = &s->rows[row];
+    R->rank = rank;
+    R->region = region;
+    R->nCells = nCells;
+    R->nFaces = nFaces;
+    R->l = (int*)dupmem(lowerAddr, sizeof(int) * (size_t)nFaces);
+    R->u = (int*)dupmem(upperAddr, sizeof(int) * (size_t)nFaces);
+    for (int f = 0; f < nFaces; f++)
+        if (R->l[f] < 0 || R->u[f] >= nCells || R->l[f] >= R->u[f]) return -2;
+    /* losort: stable counting sort of faces by upper address (lduAddressing::calcLosort) */
+    R->losort = (int*)malloc(sizeof(int) * (size_t)(nFaces ? nFaces : 1));
+    int* cnt = (int*)calloc((size_t)nCells + 1, sizeof(int));
+    for (int f = 0; f < nFaces; f++) cnt[R->u[f] + 1]++;
+    for (int c = 0; c < nCells; c++) cnt[c + 1] += cnt[c];
+    for (int f = 0; f < nFaces; f++) R->losort[cnt[R->u[f]]++] = f;
+    free(cnt);
+    recompute_offsets(s);
+    return 0;
+}
+
+int orc_set_coeffs(orc_sys* s, int row, const double* diag, const double* upper, const double* lower)
+{
+    if (row < 0 || row >= s->nRows) return -1;
+    orc_row* R = &s->rows[row];
+    free(R->diag);
+    if (R->lower != R->upper) free(R->lower);
+    free(R->upper);
+    R->diag = (double*)dupmem(diag, sizeof(double) * (size_t)R->nCells);
+    R->upper = (double*)dupmem(upper, sizeof(double) * (size_t)R->nFaces);
+    if (lower)
+    {
+        R->lower = (double*)dupmem(lower, sizeof(double) * (size_t)R->nFaces);
+        R->symmetric = 0;
+    }
+    else
+    {
+        R->lower = R->upper;
+        R->symmetric = 1;
+    }
+    s->precond = -1;
+    return 0;
+}
+
+int orc_add_iface(orc_sys* s, int row, int kind, int nFaces, const int* faceCells,
+                  const double* bouCoeffs, const double* intCoeffs, int peerRow, int peerIface,
+                  const int* ggiOffsets, const int* ggiAddr, const double* ggiWeights)
+{
+    if (row < 0 || row >= s->nRows) return -1;
+    orc_row* R = &s->rows[row];
+    if (R->nIfaces == R->capIfaces)
+    {
+        R->capIfaces = R->capIfaces ? 2 * R->capIfaces : 4;
+        R->ifaces = (orc_iface*)realloc(R->ifaces, sizeof(orc_iface) * (size_t)R->capIfaces);
+    }
+    orc_iface* I = &R->ifaces[R->nIfaces];
+    memset(I, 0, sizeof(*I));
+    I->kind = kind;
+    I->nFaces = nFaces;
+    I->faceCells = (int*)dupmem(faceCells, sizeof(int) * (size_t)nFaces);
+    I->bouCoeffs = (double*)dupmem(bouCoeffs, sizeof(double) * (size_t)nFaces);
+    if (intCoeffs)
+        I->intCoeffs = (double*)dupmem(intCoeffs, sizeof(double) * (size_t)nFaces);
+    else
+        I->intCoeffs = (double*)calloc((size_t)(nFaces ? nFaces : 1), sizeof(double));
+    I->peerRow = peerRow;
+    I->peerIface = peerIface;
+    if (ggiOffsets)
+    {
+        int nnz = ggiOffsets[nFaces];
+        I->ggiOffsets = (int*)dupmem(ggiOffsets, sizeof(int) * ((size_t)nFaces + 1));
+        I->ggiAddr = (int*)dupmem(ggiAddr, sizeof(int) * (size_t)nnz);
+        I->ggiWeights = (double*)dupmem(ggiWeights, sizeof(double) * (size_t)nnz);
+    }
+    for (int i = 0; i < nFaces; i++)
+        if (faceCells[i] < 0 || faceCells[i] >= R->nCells) return -2;
+    return R->nIfaces++;
+}
+
+int orc_total_cells(const orc_sys* s) { return s->total; }
+
+/* ------------------------------------------------------------ reductions */
+/* gSumProd / gSumMag / gSum over a FieldField: per rank, rows in list order,
+ * cells sequentially (FieldFunctions.C sumProd / FieldFieldFunctions.C), then
+ * reduce(sum) over ranks (taken in ascending rank order). */
+
+double orc_gsumprod(const orc_sys* s, const double* a, const double* b)
+{
+    for (int k = 0; k < s->nRanks; k++) s->rankPartial[k] = 0.0;
+    for (int r = 0; r < s->nRows; r++)
+    {
+        const orc_row* R = &s->rows[r];
+        const double* pa = a + R->offset;
+        const double* pb = b + R->offset;
+        double sum = 0.0;
+        for (int c = 0; c < R->nCells; c++) sum += pa[c] * pb[c];
+        s->rankPartial[R->rank] += sum;
+    }
+    double tot = s->rankPartial[0];
+    for (int k = 1; k < s->nRanks; k++) tot += s->rankPartial[k];
+    return tot;
+}
+
+double orc_gsummag(const orc_sys* s, const double* a)
+{
+    for (int k = 0; k < s->nRanks; k++) s->rankPartial[k] = 0.0;
+    for (int r = 0; r < s->nRows; r++)
+    {
+        const orc_row* R = &s->rows[r];
+        const double* pa = a + R->offset;
+        double sum = 0.0;
+        for (int c = 0; c < R->nCells; c++) sum += fabs(pa[c]);
+        s->rankPartial[R->rank] += sum;
+    }
+    double tot = s->rankPartial[0];
+    for (int k = 1; k < s->nRanks; k++) tot += s->rankPartial[k];
+    return tot;
+}
+
+static double gsum(const orc_sys* s, const double* a)
+{
+    for (int k = 0; k < s->nRanks; k++) s->rankPartial[k] = 0.0;
+    for (int r = 0; r < s->nRows; r++)
+    {
+        const orc_row* R = &s->rows[r];
+        const double* pa = a + R->offset;
+        double sum = 0.0;
+        for (int c = 0; c < R->nCells; c++) sum += pa[c];
+        s->rankPartial[R->rank] += sum;
+    }
+    double tot = s->rankPartial[0];
+    for (int k = 1; k < s->nRanks; k++) tot += s->rankPartial[k];
+    return tot;
+}
+
+/* gSum(mag(Ax - tmp) + mag(b - tmp)) */
+static double gsum_normterms(const orc_sys* s, const double* Ax, const double* b, const double* tmp)
+{
+    for (int k = 0; k < s->nRanks; k++) s->rankPartial[k] = 0.0;
+    for (int r = 0; r < s->nRows; r++)
+    {
+        const orc_row* R = &s->rows[r];
+        int o = R->offset;
+        double sum = 0.0;
+        for (int c = 0; c < R->nCells; c++)
+            sum += fabs(Ax[o + c] - tmp[o + c]) + fabs(b[o + c] - tmp[o + c]);
+        s->rankPartial[R->rank] += sum;
+    }
+    double tot = s->rankPartial[0];
+    for (int k = 1; k < s->nRanks; k++) tot += s->rankPartial[k];
+    return tot;
+}
+
+/* ------------------------------------------------------------ interfaces */
+
+void orc_ggi_interpolate(int nTo, const int* offsets, const int* addr, const double* weights,
+                         const double* ff, int nComp, double* result)
+{
+    /* GGIInterpolate.C: result zero-initialised; result[faceI] += ff[curAddr[i]]*curWeights[i] */
+    for (int i = 0; i < nTo; i++)
+        for (int d = 0; d < nComp; d++)
+        {
+            double acc = 0.0;
+            for (int k = offsets[i]; k < offsets[i + 1]; k++) acc += ff[addr[k] * nComp + d] * weights[k];
+            result[i * nComp + d] = acc;
+        }
+}
+
+/* init phase of one interface: fill buf of THIS patch with this side's
+ * patchInternalField mapped onto the PEER's faces
+ * (monolithicCouplingFvPatchField.C:392-405; processorFvPatchField send). */
+static int iface_init(orc_sys* s, orc_row* R, orc_iface* I, const double* x)
+{
+    if (I->peerRow < 0 || I->peerRow >= s->nRows) return -3;
+    orc_row* PR = &s->rows[I->peerRow];
+    if (I->peerIface < 0 || I->peerIface >= PR->nIfaces) return -3;
+    orc_iface* Q = &PR->ifaces[I->peerIface];
+    const double* xr = x + R->offset;
+    int nOut = Q->nFaces;
+    if (I->bufSize < nOut)
+    {
+        free(I->buf);
+        I->buf = (double*)malloc(sizeof(double) * (size_t)(nOut ? nOut : 1));
+        I->bufSize = nOut;
+    }
+    if (Q->ggiOffsets)
+    {
+        for (int i = 0; i < nOut; i++)
+        {
+            double acc = 0.0;
+            for (int k = Q->ggiOffsets[i]; k < Q->ggiOffsets[i + 1]; k++)
+                acc += xr[I->faceCells[Q->ggiAddr[k]]] * Q->ggiWeights[k];
+            I->buf[i] = acc;
+        }
+    }
+    else
+    {
+        if (nOut != I->nFaces) return -4;
+        for (int i = 0; i < nOut; i++) I->buf[i] = xr[I->faceCells[i]];
+    }
+    return 0;
+}
+
+/* update phase: pnf = shadow().matrixUpdateBuffer(); result[fc[i]] -= coeffs[i]*pnf[i]
+ * (+= when switchToLhs)  -- monolithicCouplingFvPatchField.C:430-455 */
+static void iface_update(orc_sys* s, orc_row* R, orc_iface* I, const double* coeffs, double* y,
+                         int switchToLhs)
+{
+    orc_iface* P = &s->rows[I->peerRow].ifaces[I->peerIface];
+    const double* pnf = P->buf;
+    double* yr = y + R->offset;
+    if (switchToLhs)
+        for (int i = 0; i < I->nFaces; i++) yr[I->faceCells[i]] += coeffs[i] * pnf[i];
+    else
+        for (int i = 0; i < I->nFaces; i++) yr[I->faceCells[i]] -= coeffs[i] * pnf[i];
+}
+
+/* coupledLduMatrix::initMatrixInterfaces: all non-processor interfaces of all
+ * rows first, then all processor interfaces. */
+static int init_interfaces(orc_sys* s, const double* x)
+{
+    for (int phase = 0; phase < 2; phase++)
+        for (int r = 0; r < s->nRows; r++)
+        {
+            orc_row* R = &s->rows[r];
+            for (int i = 0; i < R->nIfaces; i++)
+            {
+                orc_iface* I = &R->ifaces[i];
+                if ((I->kind == ORC_IFACE_PROCESSOR) != (phase == 1)) continue;
+                int rc = iface_init(s, R, I, x);
+                if (rc) return rc;
+            }
+        }
+    return 0;
+}
+
+static void update_interfaces(orc_sys* s, double* y, int useInt, int switchToLhs)
+{
+    for (int phase = 0; phase < 2; phase++)
+        for (int r = 0; r < s->nRows; r++)
+        {
+            orc_row* R = &s->rows[r];
+            for (int i = 0; i < R->nIfaces; i++)
+            {
+                orc_iface* I = &R->ifaces[i];
+                if ((I->kind == ORC_IFACE_PROCESSOR) != (phase == 1)) continue;
+                iface_update(s, R, I, useInt ? I->intCoeffs : I->bouCoeffs, y, switchToLhs);
+            }
+        }
+}
+
+/* --------------------------------------------------------------- products */
+
+int orc_amul(orc_sys* s, const double* x, double* y)
+{
+    for (int i = 0; i < s->total; i++) y[i] = 0.0; /* coupledLduMatrix::Amul: result = 0 */
+    int rc = init_interfaces(s, x);
+    if (rc) return rc;
+    for (int r = 0; r < s->nRows; r++)
+    {
+        /* lduMatrix::AmulCore (lduMatrixATmul.C) */
+        const orc_row* R = &s->rows[r];
+        const double* psi = x + R->offset;
+        double* Apsi = y + R->offset;
+        for (int c = 0; c < R->nCells; c++) Apsi[c] = R->diag[c] * psi[c];
+        for (int f = 0; f < R->nFaces; f++)
+        {
+            Apsi[R->u[f]] += R->lower[f] * psi[R->l[f]];
+            Apsi[R->l[f]] += R->upper[f] * psi[R->u[f]];
+        }
+    }
+    update_interfaces(s, y, 0, 0);
+    return 0;
+}
+
+int orc_tmul(orc_sys* s, const double* x, double* y)
+{
+    for (int i = 0; i < s->total; i++) y[i] = 0.0;
+    int rc = init_interfaces(s, x);
+    if (rc) return rc;
+    for (int r = 0; r < s->nRows; r++)
+    {
+        /* lduMatrix::TmulCore */
+        const orc_row* R = &s->rows[r];
+        const double* psi = x + R->offset;
+        double* Tpsi = y + R->offset;
+        for (int c = 0; c < R->nCells; c++) Tpsi[c] = R->diag[c] * psi[c];
+        for (int f = 0; f < R->nFaces; f++)
+        {
+            Tpsi[R->u[f]] += R->upper[f] * psi[R->l[f]];
+            Tpsi[R->l[f]] += R->lower[f] * psi[R->u[f]];
+        }
+    }
+    update_interfaces(s, y, 1, 0);
+    return 0;
+}
+
+int orc_sumA(orc_sys* s, double* sumA)
+{
+    for (int r = 0; r < s->nRows; r++)
+    {
+        const orc_row* R = &s->rows[r];
+        double* sa = sumA + R->offset;
+        for (int c = 0; c < R->nCells; c++) sa[c] = R->diag[c];
+        for (int f = 0; f < R->nFaces; f++)
+        {
+            sa[R->u[f]] += R->lower[f];
+            sa[R->l[f]] += R->upper[f];
+        }
+        for (int i = 0; i < R->nIfaces; i++)
+        {
+            const orc_iface* I = &R->ifaces[i];
+            for (int k = 0; k < I->nFaces; k++) sa[I->faceCells[k]] -= I->bouCoeffs[k];
+        }
+    }
+    return 0;
+}
+
+int orc_residual(orc_sys* s, const double* x, const double* b, double* res)
+{
+    int rc = init_interfaces(s, x);
+    if (rc) return rc;
+    for (int r = 0; r < s->nRows; r++)
+    {
+        const orc_row* R = &s->rows[r];
+        const double* psi = x + R->offset;
+        const double* src = b + R->offset;
+        double* rA = res + R->offset;
+        for (int c = 0; c < R->nCells; c++) rA[c] = src[c] - R->diag[c] * psi[c];
+        for (int f = 0; f < R->nFaces; f++)
+        {
+            rA[R->u[f]] -= R->lower[f] * psi[R->l[f]];
+            rA[R->l[f]] -= R->upper[f] * psi[R->u[f]];
+        }
+    }
+    update_interfaces(s, res, 0, 1);
+    return 0;
+}
+
+/* --------------------------------------------------------- preconditioners */
+
+int orc_precond_setup(orc_sys* s, int precond)
+{
+    if (precond < ORC_PRECOND_NONE || precond > ORC_PRECOND_CHOLESKY) return -1;
+    for (int r = 0; r < s->nRows; r++)
+    {
+        orc_row* R = &s->rows[r];
+        if (!R->diag) return -2;
+        free(R->rD);
+        R->rD = (double*)malloc(sizeof(double) * (size_t)(R->nCells ? R->nCells : 1));
+        int eff = precond;
+        if (precond == ORC_PRECOND_CHOLESKY) eff = R->symmetric ? ORC_PRECOND_DIC : ORC_PRECOND_DILU;
+        R->precond = eff;
+        double* rD = R->rD;
+        for (int c = 0; c < R->nCells; c++) rD[c] = R->diag[c];
+        if (eff == ORC_PRECOND_DIC)
+        {
+            /* DICPreconditioner::calcReciprocalD / CholeskyPrecon::calcPreconDiag (symmetric) */
+            for (int f = 0; f < R->nFaces; f++)
+                rD[R->u[f]] -= R->upper[f] * R->upper[f] / rD[R->l[f]];
+        }
+        else if (eff == ORC_PRECOND_DILU)
+        {
+            /* DILUPreconditioner::calcReciprocalD / CholeskyPrecon (asymmetric) */
+            for (int f = 0; f < R->nFaces; f++)
+                rD[R->u[f]] -= R->upper[f] * R->lower[f] / rD[R->l[f]];
+        }
+        if (eff != ORC_PRECOND_NONE)
+            for (int c = 0; c < R->nCells; c++) rD[c] = 1.0 / rD[c];
+    }
+    s->precond = precond;
+    return 0;
+}
+
+int orc_get_rD(orc_sys* s, double* out)
+{
+    if (s->precond < 0) return -1;
+    for (int r = 0; r < s->nRows; r++)
+    {
+        const orc_row* R = &s->rows[r];
+        memcpy(out + R->offset, R->rD, sizeof(double) * (size_t)R->nCells);
+    }
+    return 0;
+}
+
+static int precondition_impl(orc_sys* s, const double* rIn, double* wOut, int transpose)
+{
+    if (s->precond < 0) return -1;
+    for (int r = 0; r < s->nRows; r++)
+    {
+        const orc_row* R = &s->rows[r];
+        const double* rA = rIn + R->offset;
+        double* wA = wOut + R->offset;
+        const double* rD = R->rD;
+        const int nF = R->nFaces;
+        if (R->precond == ORC_PRECOND_NONE)
+        {
+            for (int c = 0; c < R->nCells; c++) wA[c] = rA[c];
+            continue;
+        }
+        for (int c = 0; c < R->nCells; c++) wA[c] = rD[c] * rA[c];
+        if (R->precond == ORC_PRECOND_DIC)
+        {
+            for (int f = 0; f < nF; f++) wA[R->u[f]] -= rD[R->u[f]] * R->upper[f] * wA[R->l[f]];
+            for (int f = nF - 1; f >= 0; f--) wA[R->l[f]] -= rD[R->l[f]] * R->upper[f] * wA[R->u[f]];
+        }
+        else if (R->precond == ORC_PRECOND_DILU)
+        {
+            if (!transpose)
+            {
+                for (int k = 0; k < nF; k++)
+                {
+                    int sf = R->losort[k];
+                    wA[R->u[sf]] -= rD[R->u[sf]] * R->lower[sf] * wA[R->l[sf]];
+                }
+                for (int f = nF - 1; f >= 0; f--) wA[R->l[f]] -= rD[R->l[f]] * R->upper[f] * wA[R->u[f]];
+            }
+            else
+            {
+                /* DILUPreconditioner::preconditionT: roles of upper/lower swapped */
+                for (int f = 0; f < nF; f++) wA[R->u[f]] -= rD[R->u[f]] * R->upper[f] * wA[R->l[f]];
+                for (int k = nF - 1; k >= 0; k--)
+                {
+                    int sf = R->losort[k];
+                    wA[R->l[sf]] -= rD[R->l[sf]] * R->lower[sf] * wA[R->u[sf]];
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+int orc_precondition(orc_sys* s, const double* r, double* w) { return precondition_impl(s, r, w, 0); }
+int orc_preconditionT(orc_sys* s, const double* r, double* w) { return precondition_impl(s, r, w, 1); }
+
+/* ------------------------------------------------------------------ solve */
+
+static int orc_stop(const orc_opts* o, orc_perf* p)
+{
+    /* lduMatrix::solver::stop + lduSolverPerformance::checkConvergence */
+    if (p->nIterations < o->minIter) return 0;
+    if (p->finalResidual < o->tolerance ||
+        (o->relTol > ORC_SMALL_ && p->finalResidual <= o->relTol * p->initialResidual))
+        p->converged = 1;
+    else
+        p->converged = 0;
+    if (p->nIterations >= o->maxIter || p->converged) return 1;
+    return 0;
+}
+
+static int check_singularity(orc_perf* p, double residual)
+{
+    p->singular = !(residual > ORC_VSMALL);
+    return p->singular;
+}
+
+/* coupledIterativeSolver::normFactor / lduMatrix::solver::normFactor (foam-extend:
+ * full Amul with the mean value, HJ 5/Nov/2007) */
+static double norm_factor(orc_sys* s, const double* x, const double* b, const double* Ax, double* tmp,
+                          double* xRefField)
+{
+    double xRef = gsum(s, x) / (double)s->total; /* gAverage */
+    for (int i = 0; i < s->total; i++) xRefField[i] = xRef;
+    orc_amul(s, xRefField, tmp);
+    return gsum_normterms(s, Ax, b, tmp) + ORC_SMALL;
+}
+
+#define HIST(k, v)                                   \
+    do                                               \
+    {                                                \
+        if (history && (k) < historyCap) history[(k)] = (v); \
+    } while (0)
+
+static int solve_pcg(orc_sys* s, const orc_opts* o, double* x, const double* b, orc_perf* perf,
+                     double* history, int historyCap)
+{
+    const int n = s->total;
+    double* pA = (double*)malloc(sizeof(double) * (size_t)n);
+    double* wA = (double*)malloc(sizeof(double) * (size_t)n);
+    double* rA = (double*)malloc(sizeof(double) * (size_t)n);
+    double* xRefF = (double*)malloc(sizeof(double) * (size_t)n);
+    orc_amul(s, x, wA);
+    for (int i = 0; i < n; i++) rA[i] = b[i] - wA[i];
+    double nf = norm_factor(s, x, b, wA, pA, xRefF);
+    perf->normFactor = nf;
+    perf->initialResidual = orc_gsummag(s, rA) / nf;
+    perf->finalResidual = perf->initialResidual;
+    HIST(0, perf->initialResidual);
+    if (!orc_stop(o, perf))
+    {
+        double wArA = ORC_GREAT, wArAold = wArA;
+        orc_precond_setup(s, o->precond);
+        do
+        {
+            wArAold = wArA;
+            orc_precondition(s, rA, wA);
+            wArA = orc_gsumprod(s, wA, rA);
+            if (perf->nIterations == 0)
+                for (int i = 0; i < n; i++) pA[i] = wA[i];
+            else
+            {
+                double beta = wArA / wArAold;
+                for (int i = 0; i < n; i++) pA[i] = wA[i] + beta * pA[i];
+            }
+            orc_amul(s, pA, wA);
+            double wApA = orc_gsumprod(s, wA, pA);
+            if (check_singularity(perf, fabs(wApA) / nf)) break;
+            double alpha = wArA / wApA;
+            for (int i = 0; i < n; i++)
+            {
+                x[i] += alpha * pA[i];
+                rA[i] -= alpha * wA[i];
+            }
+            perf->finalResidual = orc_gsummag(s, rA) / nf;
+            perf->nIterations++;
+            HIST(perf->nIterations, perf->finalResidual);
+        } while (!orc_stop(o, perf));
+    }
+    free(pA);
+    free(wA);
+    free(rA);
+    free(xRefF);
+    return 0;
+}
+
+static int solve_bicgstab(orc_sys* s, const orc_opts* o, double* x, const double* b, orc_perf* perf,
+                          double* history, int historyCap)
+{
+    /* bicgStabSolver::solve / coupledBicgStabSolver::solve */
+    const int n = s->total;
+    size_t nb = sizeof(double) * (size_t)(n ? n : 1);
+    double* p = (double*)malloc(nb);
+    double* r = (double*)malloc(nb);
+    double* tmp = (double*)malloc(nb);
+    double* xRefF = (double*)malloc(nb);
+    /* normFactor(x, b): own Amul of x */
+    orc_amul(s, x, p);
+    double nf = norm_factor(s, x, b, p, tmp, xRefF);
+    perf->normFactor = nf;
+    orc_amul(s, x, p);
+    for (int i = 0; i < n; i++) r[i] = b[i] - p[i];
+    perf->initialResidual = orc_gsummag(s, r) / nf;
+    perf->finalResidual = perf->initialResidual;
+    HIST(0, perf->initialResidual);
+    if (!orc_stop(o, perf))
+    {
+        double rho = ORC_GREAT, rhoOld = rho, alpha = 0, omega = ORC_GREAT, beta;
+        double* ph = (double*)calloc((size_t)(n ? n : 1), sizeof(double));
+        double* v = (double*)calloc((size_t)(n ? n : 1), sizeof(double));
+        double* sv = (double*)calloc((size_t)(n ? n : 1), sizeof(double));
+        double* sh = (double*)calloc((size_t)(n ? n : 1), sizeof(double));
+        double* t = (double*)calloc((size_t)(n ? n : 1), sizeof(double));
+        double* rw = (double*)malloc(nb);
+        for (int i = 0; i < n; i++) p[i] = 0.0;
+        for (int i = 0; i < n; i++) rw[i] = r[i];
+        orc_precond_setup(s, o->precond);
+        do
+        {
+            rhoOld = rho;
+            rho = orc_gsumprod(s, rw, r);
+            beta = rho / rhoOld * (alpha / omega);
+            if (rho == 0)
+            {
+                /* restart if breakdown occurs */
+                for (int i = 0; i < n; i++) rw[i] = r[i];
+                rho = orc_gsumprod(s, rw, r);
+                alpha = 0;
+                omega = 0;
+                beta = 0;
+            }
+            for (int i = 0; i < n; i++) p[i] = r[i] + beta * p[i] - beta * omega * v[i];
+            orc_precondition(s, p, ph);
+            orc_amul(s, ph, v);
+            alpha = rho / orc_gsumprod(s, rw, v);
+            for (int i = 0; i < n; i++) sv[i] = r[i] - alpha * v[i];
+            orc_precondition(s, sv, sh);
+            orc_amul(s, sh, t);
+            omega = orc_gsumprod(s, t, sv) / orc_gsumprod(s, t, t);
+            for (int i = 0; i < n; i++) x[i] = x[i] + alpha * ph[i] + omega * sh[i];
+            for (int i = 0; i < n; i++) r[i] = sv[i] - omega * t[i];
+            perf->finalResidual = orc_gsummag(s, r) / nf;
+            perf->nIterations++;
+            HIST(perf->nIterations, perf->finalResidual);
+        } while (!orc_stop(o, perf));
+        free(ph);
+        free(v);
+        free(sv);
+        free(sh);
+        free(t);
+        free(rw);
+    }
+    free(p);
+    free(r);
+    free(tmp);
+    free(xRefF);
+    return 0;
+}
+
+static int solve_pbicg(orc_sys* s, const orc_opts* o, double* x, const double* b, orc_perf* perf,
+                       double* history, int historyCap)
+{
+    /* PBiCG::solve (foam/matrices/lduMatrix/solvers/PBiCG/PBiCG.C) */
+    const int n = s->total;
+    size_t nb = sizeof(double) * (size_t)(n ? n : 1);
+    double* pA = (double*)malloc(nb);
+    double* pT = (double*)calloc((size_t)(n ? n : 1), sizeof(double));
+    double* wA = (double*)malloc(nb);
+    double* wT = (double*)malloc(nb);
+    double* rA = (double*)malloc(nb);
+    double* rT = (double*)malloc(nb);
+    double* xRefF = (double*)malloc(nb);
+    orc_amul(s, x, wA);
+    orc_tmul(s, x, wT);
+    for (int i = 0; i < n; i++) rA[i] = b[i] - wA[i];
+    for (int i = 0; i < n; i++) rT[i] = b[i] - wT[i];
+    double nf = norm_factor(s, x, b, wA, pA, xRefF);
+    perf->normFactor = nf;
+    perf->initialResidual = orc_gsummag(s, rA) / nf;
+    perf->finalResidual = perf->initialResidual;
+    HIST(0, perf->initialResidual);
+    if (!orc_stop(o, perf))
+    {
+        double wArT = ORC_GREAT, wArTold = wArT;
+        orc_precond_setup(s, o->precond);
+        do
+        {
+            wArTold = wArT;
+            orc_precondition(s, rA, wA);
+            orc_preconditionT(s, rT, wT);
+            wArT = orc_gsumprod(s, wA, rT);
+            if (perf->nIterations == 0)
+            {
+                for (int i = 0; i < n; i++)
+                {
+                    pA[i] = wA[i];
+                    pT[i] = wT[i];
+                }
+            }
+            else
+            {
+                double beta = wArT / wArTold;
+                for (int i = 0; i < n; i++)
+                {
+                    pA[i] = wA[i] + beta * pA[i];
+                    pT[i] = wT[i] + beta * pT[i];
+                }
+            }
+            orc_amul(s, pA, wA);
+            orc_tmul(s, pT, wT);
+            double wApT = orc_gsumprod(s, wA, pT);
+            if (check_singularity(perf, fabs(wApT) / nf)) break;
+            double alpha = wArT / wApT;
+            for (int i = 0; i < n; i++)
+            {
+                x[i] += alpha * pA[i];
+                rA[i] -= alpha * wA[i];
+                rT[i] -= alpha * wT[i];
+            }
+            perf->finalResidual = orc_gsummag(s, rA) / nf;
+            perf->nIterations++;
+            HIST(perf->nIterations, perf->finalResidual);
+        } while (!orc_stop(o, perf));
+    }
+    free(pA);
+    free(pT);
+    free(wA);
+    free(wT);
+    free(rA);
+    free(rT);
+    free(xRefF);
+    return 0;
+}
+
+int orc_solve(orc_sys* s, const orc_opts* o, double* x, const double* b, orc_perf* perf,
+              double* history, int historyCap)
+{
+    memset(perf, 0, sizeof(*perf));
+    for (int r = 0; r < s->nRows; r++)
+        if (!s->rows[r].diag) return -2;
+    switch (o->solver)
+    {
+        case ORC_SOLVER_PCG: return solve_pcg(s, o, x, b, perf, history, historyCap);
+        case ORC_SOLVER_BICGSTAB: return solve_bicgstab(s, o, x, b, perf, history, historyCap);
+        case ORC_SOLVER_PBICG: return solve_pbicg(s, o, x, b, perf, history, historyCap);
+        default: return -1;
+    }
+}
+
+/* ------------------------------------------- partitioned face transfer */
+
+void orc_patch_face_to_global(int nRanks, const int* pieceOffsets, const int* faceToGlobalAddr,
+                              const double* pField, int nComp, int nZoneFaces, double* gField)
+{
+    /* globalPolyPatchTemplates.C:162-179: every rank zero-fills a zone-sized
+     * field, scatters its own patch values, then reduce(sum) over ranks. */
+    double* piece = (double*)malloc(sizeof(double) * (size_t)(nZoneFaces * nComp + 1));
+    for (int i = 0; i < nZoneFaces * nComp; i++) gField[i] = 0.0;
+    for (int k = 0; k < nRanks; k++)
+    {
+        for (int i = 0; i < nZoneFaces * nComp; i++) piece[i] = 0.0;
+        for (int i = pieceOffsets[k]; i < pieceOffsets[k + 1]; i++)
+            for (int d = 0; d < nComp; d++) piece[faceToGlobalAddr[i] * nComp + d] = pField[i * nComp + d];
+        if (k == 0)
+            for (int i = 0; i < nZoneFaces * nComp; i++) gField[i] = piece[i];
+        else
+            for (int i = 0; i < nZoneFaces * nComp; i++) gField[i] += piece[i];
+    }
+    free(piece);
+}
+
+void orc_global_face_to_patch(int nLocal, const int* faceToGlobalAddr, const double* gField,
+                              int nComp, double* pField)
+{
+    for (int i = 0; i < nLocal; i++)
+        for (int d = 0; d < nComp; d++) pField[i * nComp + d] = gField[faceToGlobalAddr[i] * nComp + d];
+}
+
+void orc_direct_map(int nTo, const int* map, const double* from, int nComp, double* to)
+{
+    for (int i = 0; i < nTo; i++)
+        for (int d = 0; d < nComp; d++) to[i * nComp + d] = from[map[i] * nComp + d];
+}
