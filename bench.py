@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- coupled-solve throughput of the B200 LDU solver on BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload C2] [--iters 50]
+
+A *step* is one monolithic coupled solve (BiCGStab + DILU, fixed ``--iters`` Krylov iterations:
+minIter = maxIter, tolerance 0) of the synthetic two-region CHT system, from the same initial
+guess every step.  metric = cell-iterations/s = cells x iterations executed / time.
+
+* ``value``: device-resident (matrix, x0, b already in HBM), timed with CUDA events inside the library
+  on its stream (b200_perf.deviceMs summed over the K steps; max over ranks).
+* ``e2e``: the reference-facing call ``b200_sys_set_coeffs`` + ``b200_solve`` with HOST buffers
+  (page-locked): coefficients, x and b go host->device and x comes back inside the timed region.
+* ``roofline``: the dominant kernel class (by device time, measured live with per-launch CUDA events
+  in a separate profiled pass over the same steps) against MEASURED_PEAKS.json.
+* ``cpu_baseline`` / ``--impl reference``: the CPU oracle port (oracle/ldu_oracle.c, serial, same
+  algorithm) on a bounded sample of the same workload; the reference's own solver lives in
+  foam-extend 4.1, which is not in the reference tree.
+
+N > 1 (torchrun): every rank owns one z-slab of the same size (weak scaling, foam-extend processor
+decomposition ``simple (1 1 N)``), halo exchange + all-reduce over NCCL inside the library.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "coupled_solve_cell_iterations_per_s"
+UNIT = "cell-iterations/s"
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.proc, self.path = None, f"/tmp/b200_clocks_{os.getpid()}.csv"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_rank_system(workload: str, rank: int, nranks: int):
+    from multiregionfoam_b200.assembly import WORKLOADS, cht_rank_slab
+    r, L = WORKLOADS[workload]
+    return cht_rank_slab(r, L, rank, nranks), (r, L)
+
+
+def oracle_sample(workload: str, iters: int):
+    """The CPU port on the N=1 workload for `iters` BiCGStab+DILU iterations (serial)."""
+    from multiregionfoam_b200.case import Case
+    from oracle import pyoracle
+    rs, _ = build_rank_system(workload, 0, 1)
+    case = Case(workload, [rs])
+    O = pyoracle.OracleSystem(case)
+    x0, b = case.concat("psi"), case.concat("source")
+    t = time.perf_counter()
+    _, info = O.solve(x0, b, "BiCGStab", "DILU", tolerance=0.0, minIter=iters, maxIter=iters)
+    dt = time.perf_counter() - t
+    return case.nCells * info["nIterations"] / dt, dt, case.nCells, case.nFaces, info["nIterations"]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, times = [], []
+    it = max(1, min(args.iters, args.ref_iters))
+    nCells = nFaces = 0
+    for s in range(args.warmup + args.steps):
+        v, dt, nCells, nFaces, _ = oracle_sample(args.workload, it)
+        if s >= args.warmup:
+            vals.append(v)
+            times.append(dt)
+    total = nCells * it * len(times) / sum(times)
+    sample = f"{it} BiCGStab+DILU iterations per step on the full {args.workload} system ({nCells} cells), serial oracle port"
+    out = {
+        "impl": "reference", "metric": METRIC, "value": total, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "cells": nCells, "faces": nFaces, "solver": "BiCGStab", "preconditioner": "DILU",
+                   "iterations_per_step": it},
+        "cpu_baseline": {"value": total, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": total, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference = CPU oracle port of foam-extend's coupled BiCGStab/DILU (foam-extend 4.1 is not in the reference tree; oracle/_ref unbuildable)",
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--iters", type=int, default=50, help="Krylov iterations per step (minIter = maxIter)")
+    ap.add_argument("--ref-iters", type=int, default=8, help="iterations per step of the CPU arm (bounded sample)")
+    ap.add_argument("--cpu-baseline-iters", type=int, default=30)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    from multiregionfoam_b200 import ldu
+    from multiregionfoam_b200.case import algorithmic_bytes_per_iteration
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            # relaunch under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000)] + sys.argv
+            os.execv(sys.executable, cmd)
+        raise SystemExit(f"WORLD_SIZE={world} but --gpus {args.gpus}")
+    torch.cuda.set_device(local)
+    uid = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            t = torch.frombuffer(bytearray(ldu.nccl_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(t, 0)
+        uid = bytes(t.cpu().numpy().tobytes())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ctx = ldu.Context(device=local, rank=rank, nranks=world, unique_id=uid)
+    rs, (r, L) = build_rank_system(args.workload, rank, world)
+    t0 = time.perf_counter()
+    S = ldu.LduSystem(ctx, rs)
+    finalize_s = time.perf_counter() - t0
+    nLocal, fLocal = S.nCells, S.nFaces
+    nGlobal, fGlobal = nLocal * world, fLocal * world
+    x0 = np.concatenate([reg.psi for reg in rs.regions])
+    b = np.concatenate([reg.source for reg in rs.regions])
+    S.upload(x0, b)
+    S.x_save()
+    kw = dict(solver=ldu.SOLVER_BICGSTAB, precond=ldu.PRECOND_DILU, tolerance=0.0, relTol=0.0, minIter=args.iters, maxIter=args.iters)
+
+    def resident_step():
+        S.x_restore()
+        return S.solve_resident(**kw)
+
+    # ---- device-resident timing
+    for _ in range(args.warmup):
+        resident_step()
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    launches0 = ctx.launches
+    dev_ms, its = 0.0, 0
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        info = resident_step()
+        dev_ms += info["deviceMs"]
+        its += info["nIterations"]
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - wall0)
+    launches = ctx.launches - launches0
+    clk = clocks.stop() if clocks else None
+    dev_ms = max_over_ranks(dev_ms)
+    wall_ms = max_over_ranks(wall_ms)
+    value = nGlobal * its / (dev_ms * 1e-3)
+    final_res = info["finalResidual"]
+
+    # ---- profiled pass: per-launch CUDA events per kernel class (separate from the timed run)
+    S.set_profiling(True)
+    S.kernel_times(reset=True)
+    prof_steps = min(args.steps, 2)
+    for _ in range(prof_steps):
+        resident_step()
+    kt = S.kernel_times(reset=True)
+    S.set_profiling(False)
+    peak, peak_src = measured_peak_gbs()
+    N, F = nLocal, fLocal
+    alg_bytes = {  # per launch, SURVEY 8(d) / DESIGN.md section 5
+        "amul": 24 * N + 24 * F, "sweep_fwd": 24 * N + 16 * F, "sweep_bwd": 24 * N + 16 * F,
+    }
+    kernels = {}
+    for k, (ms, n) in kt.items():
+        if n == 0:
+            continue
+        kernels[k] = {"ms_total": ms, "launches": n, "ms_per_launch": ms / n}
+        if k in alg_bytes and ms > 0:
+            kernels[k]["gbs"] = alg_bytes[k] * n / (ms * 1e-3) / 1e9
+            kernels[k]["frac"] = kernels[k]["gbs"] / peak
+    tot_ms = sum(v["ms_total"] for v in kernels.values())
+    for v in kernels.values():
+        v["share"] = v["ms_total"] / tot_ms if tot_ms else 0.0
+    dom = max((k for k in kernels if k in alg_bytes), key=lambda k: kernels[k]["ms_total"])
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(args.workload, {}).get(dom)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes[dom]}
+    bytes_it = algorithmic_bytes_per_iteration(N, F, "BiCGStab")
+    solve_gbs = bytes_it * its / (dev_ms * 1e-3) / 1e9  # per GPU (N, F local; dev_ms = max over ranks)
+
+    # ---- end to end through the reference-facing call with host buffers
+    e2e = None
+    if not args.no_e2e:
+        hostx = [np.ascontiguousarray(reg.psi.copy()) for reg in rs.regions]
+        keep = []
+        for reg in rs.regions:
+            for a in (reg.diag, reg.upper, reg.lower, reg.source):
+                if a is not None:
+                    keep.append(a)
+            for itf in reg.interfaces:
+                keep += [itf.bouCoeffs, itf.intCoeffs]
+        keep += hostx
+        for a in keep:
+            ctx.host_register(a)
+        h2d = sum(reg.diag.nbytes + reg.upper.nbytes * 2 + reg.source.nbytes + reg.psi.nbytes +
+                  sum(2 * i.bouCoeffs.nbytes for i in reg.interfaces) for reg in rs.regions)
+        d2h = sum(reg.psi.nbytes for reg in rs.regions)
+        import ctypes as C
+        Lib = ldu.load()
+        opts, perf = ldu.SolverOpts(kw["solver"], kw["precond"], 0.0, 0.0, args.iters, args.iters), ldu.Perf()
+        bs = ldu._dpp([reg.source for reg in rs.regions])
+
+        def e2e_step():
+            for ri, reg in enumerate(rs.regions):
+                hostx[ri][...] = reg.psi
+            S.set_all_coeffs()                       # this solve's matrix: host -> device
+            xs = ldu._dpp(hostx)
+            ctx.check(Lib.b200_solve(S.h, C.byref(opts), xs, bs, C.byref(perf), None, 0))  # x, b H2D; solve; x D2H
+            return perf.nIterations
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t1 = time.perf_counter()
+        its_e = 0
+        n_e = max(2, min(args.steps, 5))
+        for _ in range(n_e):
+            its_e += e2e_step()
+        barrier()
+        e_s = max_over_ranks(time.perf_counter() - t1)
+        e2e = {"value": nGlobal * its_e / e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": 1e3 * e_s / n_e, "steps": n_e}
+        for a in keep:
+            ctx.host_unregister(a)
+
+    # ---- CPU baseline (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        it = max(1, min(args.iters, args.cpu_baseline_iters))
+        v, dt, nc, nf, _ = oracle_sample(args.workload, it)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{it} BiCGStab+DILU iterations on the full {args.workload} system ({nc} cells) with the serial CPU oracle port, {dt:.1f} s",
+               "host_cores_available": os.cpu_count()}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "case": f"two-region CHT (flowOverHeatedPlate topology) r={r}, {L} z-layers per GPU",
+                       "cells": nGlobal, "faces": fGlobal, "cells_per_gpu": nLocal, "solver": "BiCGStab", "preconditioner": "DILU",
+                       "iterations_per_step": args.iters, "l2": "inputs larger than L2 (matrix + vectors >> 126 MB)",
+                       "decomposition": f"simple (1 1 {world})"},
+            "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
+            "solve_hbm_gbs_per_gpu": solve_gbs, "solve_roofline_frac": solve_gbs / peak,
+            "algorithmic_bytes_per_iteration_per_gpu": bytes_it,
+            "kernels": kernels, "wall_ms_per_step": wall_ms / args.steps, "finalize_s": finalize_s,
+            "final_residual": final_res,
+        }
+        print(json.dumps(out))
+    S.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,189 @@
+/*
+ * b200_ldu.h -- C ABI of libb200ldu.so: B200 (sm_100a) Krylov solve of (coupled) LDU systems.
+ *
+ * This is the drop-in boundary for the one hot path of multiRegionFoam this repository
+ * accelerates.  Every entry point names the reference / foam-extend-4.1 interface it replaces;
+ * INTEGRATION.md shows the foam-extend side binding (lduMatrix::solver / coupledLduSolver
+ * adapters registered through addToRunTimeSelectionTable-style constructor tables).
+ *
+ *   caller in the reference                                    ->  entry points used
+ *   coupledFvMatrix<scalar>::solve(dict)                           b200_sys_* + b200_solve
+ *     (src/multiRegionSystem/multiRegionSystem.C:150-153)
+ *   fvMatrix<Type>::solve()  (multiRegionSystem.C:293,             same, nRegions = 1, once per component
+ *     src/regions/icoFluid/icoFluid.C:360,411-414, ...)
+ *   monolithicCouplingFvPatchField::{init,update}InterfaceMatrix   b200_sys_add_interface (kind REGION_COUPLE):
+ *     (src/fvPatchFields/.../monolithicCouplingFvPatchField.C:380-464)   static tables extracted once, applied on device
+ *   processorFvPatchField::{init,update}InterfaceMatrix [FE]       b200_sys_add_interface (kind PROCESSOR): NCCL halo
+ *   gSumProd / gSumMag / gAverage [FE Pstream]                     device reductions + ncclAllReduce inside b200_solve
+ *   globalPolyPatch::patchFaceToGlobal/globalFaceToPatch +          b200_ggi_* (partitioned face transfer)
+ *     ggiInterfaceToInterfaceMapping::transferFacesZoneToZone
+ *     (src/numerics/globalPolyPatch/globalPolyPatchTemplates.C:140-235,
+ *      src/numerics/interfaceToInterfaceMappings/.../ggiInterfaceToInterfaceMappingTemplates.C:37-77)
+ *
+ * Conventions: plain pointers and sizes, no C++ or torch types; every function returns 0 on
+ * success or a negative B200_E* code, with text in b200_last_error().  Host arrays are owned by
+ * the caller and copied; no pointer is retained past the call.  One b200_ctx per process / MPI
+ * rank bound to one GPU; not thread-safe; with nranks > 1 all ranks call b200_sys_finalize,
+ * b200_solve*, b200_amul, b200_precondition collectively.  There is no CPU fallback: without a
+ * usable CUDA device b200_ctx_create fails.
+ *
+ * scalar = IEEE double, label = int32 (reference build: -DWM_DP -DWM_LABEL_SIZE=32).
+ */
+#ifndef B200_LDU_H
+#define B200_LDU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_ctx b200_ctx;
+typedef struct b200_sys b200_sys;
+
+/* error codes */
+#define B200_OK 0
+#define B200_EINVAL -1   /* bad argument / call order            */
+#define B200_ECUDA -2    /* CUDA runtime failure                 */
+#define B200_ENCCL -3    /* NCCL failure / NCCL not loadable     */
+#define B200_ENOMEM -4
+#define B200_ESTATE -5   /* e.g. solve before finalize/coeffs    */
+#define B200_EUNSUPPORTED -6
+#define B200_EDEVICE -7  /* device-side failure (sweep timeout)  */
+
+/* interface kinds (lduInterfaceField flavours the adapter recognises) */
+#define B200_IFACE_REGION_COUPLE 0 /* regionCouple / ggi (monolithicCouplingFvPatchField) */
+#define B200_IFACE_PROCESSOR 1     /* processorFvPatchField                                */
+
+/* solver / preconditioner selection (fvSolution words in comments) */
+#define B200_SOLVER_PCG 0      /* cudaPCG      : PCG, CG (symmetric)            */
+#define B200_SOLVER_BICGSTAB 1 /* cudaPBiCGStab: BiCGStab (lduSolvers, coupled) */
+#define B200_SOLVER_PBICG 2    /* cudaPBiCG    : PBiCG, BiCG                    */
+
+#define B200_PRECOND_NONE 0
+#define B200_PRECOND_DIAGONAL 1
+#define B200_PRECOND_DIC 2      /* cudaDIC  : DIC, FDIC                          */
+#define B200_PRECOND_DILU 3     /* cudaDILU : DILU                               */
+#define B200_PRECOND_CHOLESKY 4 /* Cholesky (per region: DIC if symmetric else DILU) */
+
+typedef struct b200_solver_opts
+{
+    int solver;
+    int precond;
+    double tolerance; /* fvSolution default 1e-6 */
+    double relTol;    /* 0                       */
+    int minIter;      /* 0                       */
+    int maxIter;      /* 1000                    */
+} b200_solver_opts;
+
+typedef struct b200_perf
+{
+    double initialResidual;
+    double finalResidual;
+    int nIterations;
+    int converged;
+    int singular;
+    double normFactor;
+    double deviceMs; /* CUDA-event time of the Krylov solve on the compute stream (no H2D/D2H) */
+} b200_perf;
+
+/* kernel classes for b200_get_kernel_times */
+#define B200_K_AMUL 0
+#define B200_K_IFACE 1
+#define B200_K_SWEEP_FWD 2
+#define B200_K_SWEEP_BWD 3
+#define B200_K_VECTOR 4
+#define B200_K_REDUCE 5
+#define B200_K_PACK 6
+#define B200_K_HALO 7
+#define B200_K_NCLASSES 8
+
+/* ---- context: one per process / rank ----------------------------------------------------- */
+/* Fill 128 bytes with an NCCL unique id (rank 0 calls it and broadcasts the bytes). */
+int b200_nccl_unique_id(void* out128);
+/* ncclUniqueId may be NULL when nranks == 1. */
+int b200_ctx_create(int device, int rank, int nranks, const void* ncclUniqueId, b200_ctx** out);
+int b200_ctx_destroy(b200_ctx* ctx);
+/* Text of the last error on this context (ctx may be NULL: last error of ctx_create). */
+const char* b200_last_error(const b200_ctx* ctx);
+int b200_version(void);
+
+/* ---- system: the coupledLduMatrix of this rank (nRegions rows) ---------------------------- */
+int b200_sys_create(b200_ctx* ctx, int nRegions, b200_sys** out);
+int b200_sys_destroy(b200_sys* sys);
+/* lduAddressing of region r: lowerAddr/upperAddr in OpenFOAM upper-triangular order. */
+int b200_sys_set_region(b200_sys* sys, int r, int32_t nCells, int32_t nFaces,
+                        const int32_t* lowerAddr, const int32_t* upperAddr);
+/* One coupled patch of region r (call in patch-list order; processor patches last).
+ * (peerRank, peerRegion, peerIface) name the shadow patch.  ggiOffsets == NULL: identity pairing
+ * (conformal interface, processor patch); otherwise the CSR maps the shadow's nPeerFaces patch
+ * values onto this patch: val[i] = sum_k peerVal[ggiAddr[k]] * ggiWeights[k].
+ * Returns the interface index within region r (>= 0) or an error code. */
+int b200_sys_add_interface(b200_sys* sys, int r, int kind, int32_t nFaces, const int32_t* faceCells,
+                           int peerRank, int peerRegion, int peerIface, int32_t nPeerFaces,
+                           const int32_t* ggiOffsets, const int32_t* ggiAddr, const double* ggiWeights);
+/* Build device tables: row-packed Amul layout, interface/halo plans, sweep schedules.  Cached
+ * until the addressing changes (topology change -> destroy and re-create). */
+int b200_sys_finalize(b200_sys* sys);
+/* lduMatrix coefficients of region r (host -> device).  lower == NULL: symmetric matrix. */
+int b200_sys_set_coeffs(b200_sys* sys, int r, const double* diag, const double* upper, const double* lower);
+/* boundaryCoeffs / internalCoeffs of interface iface of region r (intCoeffs may be NULL). */
+int b200_sys_set_interface_coeffs(b200_sys* sys, int r, int iface, const double* bouCoeffs, const double* intCoeffs);
+int64_t b200_sys_num_cells(const b200_sys* sys);
+int64_t b200_sys_num_faces(const b200_sys* sys);
+
+/* ---- solve -------------------------------------------------------------------------------- */
+/* coupledLduSolver::solve / lduMatrix::solver::solve: x[r] (in: initial guess, out: solution) and
+ * b[r] are host arrays of region r.  history (may be NULL) receives the normalised residual after
+ * k iterations at history[k], k < historyCap. */
+int b200_solve(b200_sys* sys, const b200_solver_opts* opts, double* const* x, const double* const* b,
+               b200_perf* perf, double* history, int historyCap);
+/* Device-resident variant: x and b already uploaded with b200_upload; result stays on device. */
+int b200_upload(b200_sys* sys, const double* const* x, const double* const* b);
+int b200_solve_resident(b200_sys* sys, const b200_solver_opts* opts, b200_perf* perf, double* history,
+                        int historyCap);
+int b200_download(b200_sys* sys, double* const* x);
+/* Device-side copy of the resident field: save x -> x0 / restore x0 -> x, for repeated solves from one
+ * initial guess (PICARD / DNA sub-iterations of assembleAndSolveEqns, multiRegionSystem.C:280-306). */
+int b200_x_save(b200_sys* sys);
+int b200_x_restore(b200_sys* sys);
+/* Page-lock / unlock a caller-owned host array (an OpenFOAM Field's storage) so that the copies inside
+ * b200_solve / b200_sys_set_coeffs run at full PCIe rate.  Optional. */
+int b200_host_register(b200_ctx* ctx, void* p, uint64_t bytes);
+int b200_host_unregister(b200_ctx* ctx, void* p);
+
+/* ---- test hooks (single operations through the same kernels) -------------------------------- */
+/* y = A x (transpose != 0: y = A^T x with internalCoeffs on interfaces) */
+int b200_amul(b200_sys* sys, const double* const* x, double* const* y, int transpose);
+/* w = M^-1 r with the given preconditioner (transpose != 0: preconditionT) */
+int b200_precondition(b200_sys* sys, int precond, const double* const* r, double* const* w, int transpose);
+/* reciprocal preconditioned diagonal of the last preconditioner setup */
+int b200_get_rD(b200_sys* sys, int precond, double* const* rD);
+/* global reductions as used by the solver: out[0] = sum a*b, out[1] = sum |a| */
+int b200_reduce(b200_sys* sys, const double* const* a, const double* const* b, double* out2);
+
+/* ---- profiling ------------------------------------------------------------------------------ */
+/* enable != 0: bracket every kernel launch with CUDA events (adds launch overhead; use a separate run) */
+int b200_set_profiling(b200_sys* sys, int enable);
+/* accumulated device ms and launch counts per kernel class since the last reset */
+int b200_get_kernel_times(b200_sys* sys, double* msPerClass, int64_t* launchesPerClass, int reset);
+/* number of kernels launched by this library on this context since creation */
+int64_t b200_launch_count(const b200_ctx* ctx);
+
+/* ---- partitioned-coupling face transfer -------------------------------- */
+/* result[i*nComp+d] = sum_k ff[addr[k]*nComp+d]*weights[k] on the device; host in/out. */
+int b200_ggi_interpolate(b200_ctx* ctx, int32_t nTo, int32_t nFrom, const int32_t* offsets,
+                         const int32_t* addr, const double* weights, const double* ff, int nComp,
+                         double* result);
+/* globalPolyPatch::patchFaceToGlobal: zone field = all-reduce(sum) of the zero-padded scatter of the
+ * local patch values through faceToGlobalAddr (collective over the context's ranks). */
+int b200_patch_face_to_global(b200_ctx* ctx, int32_t nLocal, const int32_t* faceToGlobalAddr,
+                              const double* pField, int nComp, int32_t nZoneFaces, double* gField);
+/* globalPolyPatch::globalFaceToPatch: pField[i] = gField[faceToGlobalAddr[i]] */
+int b200_global_face_to_patch(b200_ctx* ctx, int32_t nLocal, const int32_t* faceToGlobalAddr,
+                              const double* gField, int nComp, double* pField);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_LDU_H */

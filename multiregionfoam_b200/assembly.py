@@ -22,7 +22,7 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-from .case import Case, Interface, RankSystem, Region, REGION_COUPLE
+from .case import Case, Interface, PROCESSOR, RankSystem, Region, REGION_COUPLE
 from .mesh import StructuredRegion, flow_over_heated_plate
 
 
@@ -87,9 +87,36 @@ def assemble_cht(fluid: StructuredRegion, solid: StructuredRegion, *, dt: float 
     return Case(name, [RankSystem(0, 1, [reg_f, reg_s])])
 
 
-def cht_case(r: int = 1, layers: int = 1, **kw) -> Tuple[Case, StructuredRegion, StructuredRegion]:
-    fluid, solid = flow_over_heated_plate(r, layers)
+def cht_case(r: int = 1, layers: int = 1, z1: float = 0.4, **kw) -> Tuple[Case, StructuredRegion, StructuredRegion]:
+    fluid, solid = flow_over_heated_plate(r, layers, z1)
     return assemble_cht(fluid, solid, name=f"cht_r{r}_L{layers}", **kw), fluid, solid
+
+
+def cht_rank_slab(r: int, layers_per_rank: int, rank: int, nranks: int) -> RankSystem:
+    """Rank ``rank`` of the CHT case with ``layers_per_rank * nranks`` z-layers decomposed into z-slabs
+    (``simple; n (1 1 nranks)``), assembled directly from the local slab: identical to
+    ``decompose_cht_zslabs(cht_case(r, L*nranks, z1=0.4*nranks), ...).ranks[rank]`` (tests/test_decompose.py)
+    without ever building the global mesh.  Every rank holds the same number of cells (weak scaling);
+    processor patches (rank-1, rank+1) follow the regionCouple patch, ordered by neighbour rank."""
+    fluid, solid = flow_over_heated_plate(r, layers_per_rank)
+    rs = assemble_cht(fluid, solid, name=f"cht_r{r}_L{layers_per_rank}x{nranks}").ranks[0]
+    rs.rank, rs.nRanks = rank, nranks
+    k_of = {0: 5.0, 1: 100.0}
+    for ri, (reg, mesh) in enumerate(zip(rs.regions, (fluid, solid))):
+        for itf in reg.interfaces:
+            itf.peerRank = rank
+        nbrs = [nb for nb in (rank - 1, rank + 1) if 0 <= nb < nranks]
+        base = len(reg.interfaces)
+        for k, nb in enumerate(nbrs):
+            c, a, d = mesh.side_z(top=(nb > rank))
+            D = k_of[ri] * a / (2.0 * d)
+            np.add.at(reg.diag, c, D)
+            # the peer's patch list: [regionCouple, (its lower neighbour), (its upper neighbour)]
+            peerNbrs = [q for q in (nb - 1, nb + 1) if 0 <= q < nranks]
+            peerIface = base + peerNbrs.index(rank)
+            reg.interfaces.append(Interface(PROCESSOR, c, D.copy(), D.copy(), nb, ri, peerIface,
+                                            name=f"procBoundary{rank}to{nb}"))
+    return rs
 
 
 WORKLOADS = {

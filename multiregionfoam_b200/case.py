@@ -32,6 +32,7 @@ class Interface:
     ggiAddr: Optional[np.ndarray] = None
     ggiWeights: Optional[np.ndarray] = None
     name: str = ""
+    nPeerFaces: Optional[int] = None  # faces of the shadow patch (None: same as this patch)
 
     @property
     def nFaces(self) -> int:

@@ -1,0 +1,1418 @@
+// b200_ldu.cu -- C ABI (include/b200_ldu.h) and host orchestration of the B200 LDU solver.
+// Streams and launches only; all arithmetic is in kernels.cuh, all table construction in
+// schedule.hpp.  There is no CPU fallback: every entry point needs a CUDA device.
+#include "../../include/b200_ldu.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "schedule.hpp"
+
+using namespace b200;
+
+#define B200_VERSION 100
+
+// ------------------------------------------------------------------------------------------ NCCL (dlopen)
+struct NcclApi
+{
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi g_nccl;
+static std::string g_lastError;
+
+static bool load_nccl(std::string& err)
+{
+    if (g_nccl.handle) return true;
+    const char* cands[] = {getenv("B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so",
+                           "/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/nccl/lib/libnccl.so.2"};
+    void* h = nullptr;
+    for (const char* c : cands)
+    {
+        if (!c || !*c) continue;
+        h = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h)
+    {
+        err = std::string("cannot dlopen libnccl.so.2: ") + (dlerror() ? dlerror() : "?");
+        return false;
+    }
+#define LOADSYM(field, name)                                        \
+    *(void**)(&g_nccl.field) = dlsym(h, name);                      \
+    if (!g_nccl.field)                                              \
+    {                                                               \
+        err = std::string("libnccl lacks symbol ") + name;          \
+        return false;                                               \
+    }
+    LOADSYM(GetUniqueId, "ncclGetUniqueId");
+    LOADSYM(CommInitRank, "ncclCommInitRank");
+    LOADSYM(CommDestroy, "ncclCommDestroy");
+    LOADSYM(AllReduce, "ncclAllReduce");
+    LOADSYM(Send, "ncclSend");
+    LOADSYM(Recv, "ncclRecv");
+    LOADSYM(GroupStart, "ncclGroupStart");
+    LOADSYM(GroupEnd, "ncclGroupEnd");
+    LOADSYM(GetErrorString, "ncclGetErrorString");
+#undef LOADSYM
+    g_nccl.handle = h;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------ context
+struct b200_ctx
+{
+    int device = 0, rank = 0, nranks = 1;
+    cudaStream_t stream = nullptr;
+    ncclComm_t comm = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int smCount = 148;
+};
+
+static int set_err(b200_ctx* ctx, int code, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx)
+        ctx->err = buf;
+    else
+        g_lastError = buf;
+    return code;
+}
+
+#define CK(ctx, call)                                                                                        \
+    do                                                                                                       \
+    {                                                                                                        \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess)                                                                               \
+            return set_err(ctx, B200_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define NK(ctx, call)                                                                                           \
+    do                                                                                                          \
+    {                                                                                                           \
+        ncclResult_t r_ = (call);                                                                               \
+        if (r_ != ncclSuccess)                                                                                  \
+            return set_err(ctx, B200_ENCCL, "%s:%d %s: %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+template <class T>
+struct DevBuf
+{
+    T* p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { release(); }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    cudaError_t alloc(size_t count)
+    {
+        release();
+        n = count;
+        if (count == 0) count = 1;
+        return cudaMalloc((void**)&p, count * sizeof(T));
+    }
+    cudaError_t upload(const std::vector<T>& h, cudaStream_t st)
+    {
+        cudaError_t e = alloc(h.size());
+        if (e != cudaSuccess) return e;
+        if (h.empty()) return cudaSuccess;
+        return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+    }
+};
+
+struct SweepDevMem
+{
+    DevBuf<int> nLanes, nSteps, W, laneBase, laneStart, laneLen, chainFace, offFace, offCol;
+    DevBuf<long long> chainBase, offBase;
+    DevBuf<double> chainC, offC;
+    SweepDev dev{};
+    int64_t nWarps = 0;
+    int warpsPerBlock = 1;
+    int nBlocks = 0;
+};
+
+// ------------------------------------------------------------------------------------------ system
+enum VecId
+{
+    V_X = 0,
+    V_B,
+    V_R,
+    V_RW,
+    V_P,
+    V_PH,
+    V_V,
+    V_S,
+    V_SH,
+    V_T,
+    V_TMP,
+    V_TMP2,
+    V_COUNT
+};
+
+struct b200_sys
+{
+    b200_ctx* ctx = nullptr;
+    std::vector<RegionHost> regs;
+    bool finalized = false;
+    int64_t N = 0, F = 0;
+    double nGlobalCells = 0;
+
+    // matrix
+    DevBuf<double> diag, coef /* [upper(F) | lower(F)] */, ifCoefBou, ifCoefInt;
+    std::vector<uint8_t> regionHasCoeffs;
+    bool sellDirty = true, sellTDirty = true;
+    // SELL
+    int64_t nSlices = 0, nSlots = 0;
+    DevBuf<int> sliceOff, sellCol, sellSrc;
+    DevBuf<double> sellVal, sellValT;
+    DevBuf<unsigned> ifaceMask;
+    // interfaces
+    int nTouched = 0;
+    DevBuf<int> ifRows, ifRowStart, ifEntCoef, ifEntSrc, ifEntCnt, ifGSrc, sendCells;
+    DevBuf<double> ifGW, sendBuf, recvBuf;
+    std::vector<int> peers;
+    std::vector<int32_t> sendOff, recvOff;
+    int64_t nIfCoefs = 0;
+    // sweeps
+    SweepDevMem fwd, bwd;
+    DevBuf<double> rD, rDraw;
+    int precondValid = -1; // preconditioner id the packed sweep coefficients belong to (-1: none)
+    bool precondTransposedValid = false;
+    DevBuf<double> chainCT_f, offCT_f, chainCT_b, offCT_b; // transposed sweep coefficients (PBiCG)
+    DevBuf<unsigned> ticket;
+    unsigned ticketBase = 0;
+    DevBuf<int> devErr;
+    // vectors
+    DevBuf<double> vec[V_COUNT];
+    DevBuf<double> x0; // b200_x_save / b200_x_restore
+    bool x0Valid = false;
+    // scalars / reductions
+    DevBuf<DevScalars> sc;
+    DevBuf<double> partials;
+    int pstride = 0;
+    DevBuf<double> history;
+    int* hostFlags = nullptr;  // mapped pinned: [0] done, [1] nIter
+    int* devHostFlags = nullptr;
+    // launch geometry
+    int vecBlocks = 1, amulBlocks = 1, ifaceBlocks = 0;
+    // profiling
+    bool profiling = false;
+    struct EvRec
+    {
+        int cls;
+        cudaEvent_t a, b;
+    };
+    std::vector<EvRec> evRecs;
+    std::vector<cudaEvent_t> evPool;
+    double clsMs[B200_K_NCLASSES] = {0};
+    int64_t clsLaunches[B200_K_NCLASSES] = {0};
+    cudaEvent_t evSolveA = nullptr, evSolveB = nullptr;
+    std::vector<cudaEvent_t> throttle;
+};
+
+struct KScope
+{
+    b200_sys* s;
+    int cls;
+    cudaEvent_t a = nullptr, b = nullptr;
+    KScope(b200_sys* s_, int cls_) : s(s_), cls(cls_)
+    {
+        s->ctx->launches++;
+        s->clsLaunches[cls]++;
+        if (s->profiling)
+        {
+            auto get = [&]() {
+                cudaEvent_t e;
+                if (!s->evPool.empty())
+                {
+                    e = s->evPool.back();
+                    s->evPool.pop_back();
+                }
+                else
+                    cudaEventCreate(&e);
+                return e;
+            };
+            a = get();
+            b = get();
+            cudaEventRecord(a, s->ctx->stream);
+        }
+    }
+    ~KScope()
+    {
+        if (s->profiling)
+        {
+            cudaEventRecord(b, s->ctx->stream);
+            s->evRecs.push_back({cls, a, b});
+        }
+    }
+};
+
+static void harvest_events(b200_sys* s)
+{
+    for (auto& r : s->evRecs)
+    {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) s->clsMs[r.cls] += ms;
+        s->evPool.push_back(r.a);
+        s->evPool.push_back(r.b);
+    }
+    s->evRecs.clear();
+}
+
+// ------------------------------------------------------------------------------------------ C ABI: context
+extern "C" int b200_version(void) { return B200_VERSION; }
+
+extern "C" const char* b200_last_error(const b200_ctx* ctx) { return ctx ? ctx->err.c_str() : g_lastError.c_str(); }
+
+extern "C" int b200_nccl_unique_id(void* out128)
+{
+    std::string err;
+    if (!out128) return set_err(nullptr, B200_EINVAL, "b200_nccl_unique_id: null output");
+    if (!load_nccl(err)) return set_err(nullptr, B200_ENCCL, "%s", err.c_str());
+    ncclUniqueId id;
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) return set_err(nullptr, B200_ENCCL, "ncclGetUniqueId: %s", g_nccl.GetErrorString(r));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(out128, &id, 128);
+    return B200_OK;
+}
+
+extern "C" int b200_ctx_create(int device, int rank, int nranks, const void* ncclUniqueIdBytes, b200_ctx** out)
+{
+    if (!out || nranks < 1 || rank < 0 || rank >= nranks) return set_err(nullptr, B200_EINVAL, "b200_ctx_create: bad arguments");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return set_err(nullptr, B200_ECUDA, "no usable CUDA device (%s); this library has no CPU fallback",
+                       e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return set_err(nullptr, B200_EINVAL, "device %d out of range (0..%d)", device, ndev - 1);
+    std::unique_ptr<b200_ctx> c(new b200_ctx);
+    c->device = device;
+    c->rank = rank;
+    c->nranks = nranks;
+    CK(nullptr, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(nullptr, cudaGetDeviceProperties(&prop, device));
+    c->smCount = prop.multiProcessorCount;
+    CK(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    if (nranks > 1)
+    {
+        std::string err;
+        if (!ncclUniqueIdBytes) return set_err(nullptr, B200_EINVAL, "nranks > 1 needs an NCCL unique id");
+        if (!load_nccl(err)) return set_err(nullptr, B200_ENCCL, "%s", err.c_str());
+        ncclUniqueId id;
+        memcpy(&id, ncclUniqueIdBytes, 128);
+        ncclResult_t r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+        if (r != ncclSuccess) return set_err(nullptr, B200_ENCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+    }
+    *out = c.release();
+    return B200_OK;
+}
+
+extern "C" int b200_ctx_destroy(b200_ctx* ctx)
+{
+    if (!ctx) return B200_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->comm) g_nccl.CommDestroy(ctx->comm);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return B200_OK;
+}
+
+extern "C" int64_t b200_launch_count(const b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------ C ABI: system build
+extern "C" int b200_sys_create(b200_ctx* ctx, int nRegions, b200_sys** out)
+{
+    if (!ctx || !out || nRegions < 1) return set_err(ctx, B200_EINVAL, "b200_sys_create: bad arguments");
+    b200_sys* s = new b200_sys;
+    s->ctx = ctx;
+    s->regs.resize(nRegions);
+    s->regionHasCoeffs.assign(nRegions, 0);
+    *out = s;
+    return B200_OK;
+}
+
+extern "C" int b200_sys_destroy(b200_sys* s)
+{
+    if (!s) return B200_OK;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    harvest_events(s);
+    for (auto e : s->evPool) cudaEventDestroy(e);
+    for (auto e : s->throttle) cudaEventDestroy(e);
+    if (s->evSolveA) cudaEventDestroy(s->evSolveA);
+    if (s->evSolveB) cudaEventDestroy(s->evSolveB);
+    if (s->hostFlags) cudaFreeHost(s->hostFlags);
+    delete s;
+    return B200_OK;
+}
+
+extern "C" int b200_sys_set_region(b200_sys* s, int r, int32_t nCells, int32_t nFaces, const int32_t* lowerAddr,
+                                   const int32_t* upperAddr)
+{
+    if (!s) return B200_EINVAL;
+    if (s->finalized) return set_err(s->ctx, B200_ESTATE, "system already finalized");
+    if (r < 0 || r >= (int)s->regs.size() || nCells < 0 || nFaces < 0 || (nFaces > 0 && (!lowerAddr || !upperAddr)))
+        return set_err(s->ctx, B200_EINVAL, "b200_sys_set_region: bad arguments");
+    RegionHost& R = s->regs[r];
+    R.nCells = nCells;
+    R.nFaces = nFaces;
+    R.l.assign(lowerAddr, lowerAddr + nFaces);
+    R.u.assign(upperAddr, upperAddr + nFaces);
+    for (int32_t f = 0; f < nFaces; f++)
+        if (R.l[f] < 0 || R.u[f] >= nCells || R.l[f] >= R.u[f])
+            return set_err(s->ctx, B200_EINVAL, "region %d face %d: need 0 <= lower < upper < nCells", r, f);
+    R.ifaces.clear();
+    R.set = true;
+    return B200_OK;
+}
+
+extern "C" int b200_sys_add_interface(b200_sys* s, int r, int kind, int32_t nFaces, const int32_t* faceCells, int peerRank,
+                                      int peerRegion, int peerIface, int32_t nPeerFaces, const int32_t* ggiOffsets,
+                                      const int32_t* ggiAddr, const double* ggiWeights)
+{
+    if (!s) return B200_EINVAL;
+    if (s->finalized) return set_err(s->ctx, B200_ESTATE, "system already finalized");
+    if (r < 0 || r >= (int)s->regs.size() || !s->regs[r].set) return set_err(s->ctx, B200_EINVAL, "add_interface: region %d not set", r);
+    if (kind != B200_IFACE_REGION_COUPLE && kind != B200_IFACE_PROCESSOR)
+        return set_err(s->ctx, B200_EUNSUPPORTED, "unknown interface kind %d (no CPU fallback for foreign lduInterfaceFields)", kind);
+    if (nFaces < 0 || (nFaces > 0 && !faceCells) || peerRank < 0 || peerRank >= s->ctx->nranks || nPeerFaces < 0)
+        return set_err(s->ctx, B200_EINVAL, "add_interface: bad arguments");
+    RegionHost& R = s->regs[r];
+    IfaceHost I;
+    I.kind = kind;
+    I.nFaces = nFaces;
+    I.faceCells.assign(faceCells, faceCells + nFaces);
+    for (int i = 0; i < nFaces; i++)
+        if (faceCells[i] < 0 || faceCells[i] >= R.nCells) return set_err(s->ctx, B200_EINVAL, "add_interface: faceCells[%d] out of range", i);
+    I.peerRank = peerRank;
+    I.peerRegion = peerRegion;
+    I.peerIface = peerIface;
+    I.nPeerFaces = nPeerFaces;
+    I.identity = (ggiOffsets == nullptr);
+    if (I.identity)
+    {
+        if (nPeerFaces != nFaces) return set_err(s->ctx, B200_EINVAL, "identity interface needs nPeerFaces == nFaces");
+    }
+    else
+    {
+        if (!ggiAddr || !ggiWeights) return set_err(s->ctx, B200_EINVAL, "GGI interface needs addr and weights");
+        I.ggiOffsets.assign(ggiOffsets, ggiOffsets + nFaces + 1);
+        int nnz = ggiOffsets[nFaces];
+        I.ggiAddr.assign(ggiAddr, ggiAddr + nnz);
+        I.ggiWeights.assign(ggiWeights, ggiWeights + nnz);
+    }
+    R.ifaces.push_back(std::move(I));
+    return (int)R.ifaces.size() - 1;
+}
+
+static int upload_sweep(b200_sys* s, SweepSchedule& S, SweepDevMem& M)
+{
+    b200_ctx* ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    CK(ctx, M.nLanes.upload(S.warpNLanes, st));
+    CK(ctx, M.nSteps.upload(S.warpNSteps, st));
+    CK(ctx, M.W.upload(S.warpW, st));
+    CK(ctx, M.laneBase.upload(S.warpLaneBase, st));
+    std::vector<long long> cb(S.warpChainBase.begin(), S.warpChainBase.end()), ob(S.warpOffBase.begin(), S.warpOffBase.end());
+    CK(ctx, M.chainBase.upload(cb, st));
+    CK(ctx, M.offBase.upload(ob, st));
+    CK(ctx, M.laneStart.upload(S.laneStart, st));
+    CK(ctx, M.laneLen.upload(S.laneLen, st));
+    CK(ctx, M.chainFace.upload(S.chainFace, st));
+    CK(ctx, M.offFace.upload(S.offFace, st));
+    CK(ctx, M.offCol.upload(S.offCol, st));
+    CK(ctx, M.chainC.alloc(S.nChainSlots));
+    CK(ctx, M.offC.alloc(S.nOffSlots));
+    CK(ctx, cudaStreamSynchronize(st)); // host vectors go out of scope after return
+    M.nWarps = S.nWarps;
+    // one warp per CTA while that still fills the machine, else 4
+    M.warpsPerBlock = (S.nWarps <= (int64_t)ctx->smCount * 24) ? 1 : 4;
+    M.nBlocks = (int)((S.nWarps + M.warpsPerBlock - 1) / M.warpsPerBlock);
+    M.dev.nWarps = (int)S.nWarps;
+    M.dev.dir = S.dir;
+    M.dev.nLanes = M.nLanes.p;
+    M.dev.nSteps = M.nSteps.p;
+    M.dev.W = M.W.p;
+    M.dev.laneBase = M.laneBase.p;
+    M.dev.chainBase = M.chainBase.p;
+    M.dev.offBase = M.offBase.p;
+    M.dev.laneStart = M.laneStart.p;
+    M.dev.laneLen = M.laneLen.p;
+    M.dev.chainFace = M.chainFace.p;
+    M.dev.offFace = M.offFace.p;
+    M.dev.offCol = M.offCol.p;
+    M.dev.chainC = M.chainC.p;
+    M.dev.offC = M.offC.p;
+    return B200_OK;
+}
+
+extern "C" int b200_sys_finalize(b200_sys* s)
+{
+    if (!s) return B200_EINVAL;
+    b200_ctx* ctx = s->ctx;
+    if (s->finalized) return B200_OK;
+    for (size_t r = 0; r < s->regs.size(); r++)
+        if (!s->regs[r].set) return set_err(ctx, B200_ESTATE, "region %zu not set", r);
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    try
+    {
+        int64_t co = 0, fo = 0;
+        for (auto& R : s->regs)
+        {
+            R.cellOffset = co;
+            R.faceOffset = fo;
+            co += R.nCells;
+            fo += R.nFaces;
+        }
+        GlobalLdu g;
+        g.build(s->regs);
+        s->N = g.N;
+        s->F = g.F;
+        {
+            SellLayout sell;
+            sell.build(g);
+            s->nSlices = sell.nSlices;
+            s->nSlots = sell.nSlots;
+            CK(ctx, s->sliceOff.upload(sell.sliceOff, st));
+            CK(ctx, s->sellCol.upload(sell.col, st));
+            CK(ctx, s->sellSrc.upload(sell.src, st));
+            CK(ctx, s->sellVal.alloc(sell.nSlots));
+            CK(ctx, cudaStreamSynchronize(st));
+        }
+        {
+            IfacePlan P;
+            P.build(s->regs, ctx->rank, s->N);
+            s->nTouched = (int)P.rows.size();
+            s->nIfCoefs = P.nCoefs;
+            s->peers = P.peers;
+            s->sendOff = P.sendOff;
+            s->recvOff = P.recvOff;
+            CK(ctx, s->ifRows.upload(P.rows, st));
+            CK(ctx, s->ifRowStart.upload(P.rowStart, st));
+            CK(ctx, s->ifEntCoef.upload(P.entCoef, st));
+            CK(ctx, s->ifEntSrc.upload(P.entSrc, st));
+            CK(ctx, s->ifEntCnt.upload(P.entCnt, st));
+            CK(ctx, s->ifGSrc.upload(P.gSrc, st));
+            CK(ctx, s->ifGW.upload(P.gW, st));
+            CK(ctx, s->ifaceMask.upload(P.sliceMask, st));
+            CK(ctx, s->sendCells.upload(P.sendCells, st));
+            CK(ctx, s->sendBuf.alloc(P.sendOff.back()));
+            CK(ctx, s->recvBuf.alloc(P.recvOff.back()));
+            CK(ctx, s->ifCoefBou.alloc(P.nCoefs));
+            CK(ctx, s->ifCoefInt.alloc(P.nCoefs));
+            CK(ctx, cudaMemsetAsync(s->ifCoefBou.p, 0, (P.nCoefs ? P.nCoefs : 1) * sizeof(double), st));
+            CK(ctx, cudaMemsetAsync(s->ifCoefInt.p, 0, (P.nCoefs ? P.nCoefs : 1) * sizeof(double), st));
+            CK(ctx, cudaStreamSynchronize(st));
+        }
+        {
+            SweepSchedule S;
+            S.build(g, +1);
+            int rc = upload_sweep(s, S, s->fwd);
+            if (rc) return rc;
+        }
+        {
+            SweepSchedule S;
+            S.build(g, -1);
+            int rc = upload_sweep(s, S, s->bwd);
+            if (rc) return rc;
+        }
+    }
+    catch (const std::exception& e)
+    {
+        return set_err(ctx, B200_EINVAL, "b200_sys_finalize: %s", e.what());
+    }
+    // matrix + vectors + scalars
+    CK(ctx, s->diag.alloc(s->N));
+    CK(ctx, s->coef.alloc(2 * s->F));
+    CK(ctx, s->rD.alloc(s->N));
+    CK(ctx, s->rDraw.alloc(s->N));
+    for (int v = 0; v < V_COUNT; v++) CK(ctx, s->vec[v].alloc(s->N));
+    CK(ctx, s->sc.alloc(1));
+    CK(ctx, cudaMemsetAsync(s->sc.p, 0, sizeof(DevScalars), st));
+    CK(ctx, s->ticket.alloc(1));
+    CK(ctx, cudaMemsetAsync(s->ticket.p, 0, sizeof(unsigned), st));
+    s->ticketBase = 0;
+    CK(ctx, s->devErr.alloc(1));
+    CK(ctx, cudaMemsetAsync(s->devErr.p, 0, sizeof(int), st));
+    CK(ctx, s->history.alloc(kHistOnDevice));
+    // launch geometry: persistent-style grids sized in multiples of the SM count
+    const int sm = ctx->smCount;
+    auto cdiv = [](int64_t a, int64_t b) { return (a + b - 1) / b; };
+    s->vecBlocks = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(s->N, 256 * 2), (int64_t)sm * 8));
+    s->amulBlocks = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(s->nSlices, 8), (int64_t)sm * 16));
+    s->ifaceBlocks = (int)cdiv(s->nTouched, 128);
+    s->pstride = std::max(s->vecBlocks, s->amulBlocks + s->ifaceBlocks) + 32;
+    CK(ctx, s->partials.alloc((size_t)s->pstride * kMaxDots));
+    CK(ctx, cudaMemsetAsync(s->partials.p, 0, (size_t)s->pstride * kMaxDots * sizeof(double), st));
+    CK(ctx, cudaHostAlloc((void**)&s->hostFlags, 4 * sizeof(int), cudaHostAllocMapped));
+    memset(s->hostFlags, 0, 4 * sizeof(int));
+    CK(ctx, cudaHostGetDevicePointer((void**)&s->devHostFlags, s->hostFlags, 0));
+    CK(ctx, cudaEventCreate(&s->evSolveA));
+    CK(ctx, cudaEventCreate(&s->evSolveB));
+    // global cell count (gAverage denominator)
+    s->nGlobalCells = (double)s->N;
+    if (ctx->nranks > 1)
+    {
+        double* d = s->vec[V_TMP].p;
+        double hN = (double)s->N;
+        CK(ctx, cudaMemcpyAsync(d, &hN, sizeof(double), cudaMemcpyHostToDevice, st));
+        NK(ctx, g_nccl.AllReduce(d, d, 1, ncclDouble, ncclSum, ctx->comm, st));
+        CK(ctx, cudaMemcpyAsync(&hN, d, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(ctx, cudaStreamSynchronize(st));
+        s->nGlobalCells = hN;
+    }
+    CK(ctx, cudaStreamSynchronize(st));
+    s->finalized = true;
+    return B200_OK;
+}
+
+extern "C" int64_t b200_sys_num_cells(const b200_sys* s) { return s ? s->N : 0; }
+extern "C" int64_t b200_sys_num_faces(const b200_sys* s) { return s ? s->F : 0; }
+
+extern "C" int b200_sys_set_coeffs(b200_sys* s, int r, const double* diag, const double* upper, const double* lower)
+{
+    if (!s) return B200_EINVAL;
+    b200_ctx* ctx = s->ctx;
+    if (!s->finalized) return set_err(ctx, B200_ESTATE, "set_coeffs before finalize");
+    if (r < 0 || r >= (int)s->regs.size() || !diag || (!upper && s->regs[r].nFaces > 0))
+        return set_err(ctx, B200_EINVAL, "b200_sys_set_coeffs: bad arguments");
+    CK(ctx, cudaSetDevice(ctx->device));
+    const RegionHost& R = s->regs[r];
+    cudaStream_t st = ctx->stream;
+    if (R.nCells) CK(ctx, cudaMemcpyAsync(s->diag.p + R.cellOffset, diag, sizeof(double) * R.nCells, cudaMemcpyHostToDevice, st));
+    if (R.nFaces)
+    {
+        CK(ctx, cudaMemcpyAsync(s->coef.p + R.faceOffset, upper, sizeof(double) * R.nFaces, cudaMemcpyHostToDevice, st));
+        // symmetric matrix: lower aliases upper
+        CK(ctx, cudaMemcpyAsync(s->coef.p + s->F + R.faceOffset, lower ? lower : upper, sizeof(double) * R.nFaces,
+                                cudaMemcpyHostToDevice, st));
+    }
+    s->regionHasCoeffs[r] = 1;
+    s->sellDirty = s->sellTDirty = true;
+    s->precondValid = -1;
+    s->precondTransposedValid = false;
+    return B200_OK;
+}
+
+extern "C" int b200_sys_set_interface_coeffs(b200_sys* s, int r, int iface, const double* bouCoeffs, const double* intCoeffs)
+{
+    if (!s) return B200_EINVAL;
+    b200_ctx* ctx = s->ctx;
+    if (!s->finalized) return set_err(ctx, B200_ESTATE, "set_interface_coeffs before finalize");
+    if (r < 0 || r >= (int)s->regs.size() || iface < 0 || iface >= (int)s->regs[r].ifaces.size() || !bouCoeffs)
+        return set_err(ctx, B200_EINVAL, "b200_sys_set_interface_coeffs: bad arguments");
+    CK(ctx, cudaSetDevice(ctx->device));
+    const IfaceHost& I = s->regs[r].ifaces[iface];
+    if (I.nFaces)
+    {
+        CK(ctx, cudaMemcpyAsync(s->ifCoefBou.p + I.coefOffset, bouCoeffs, sizeof(double) * I.nFaces, cudaMemcpyHostToDevice, ctx->stream));
+        CK(ctx, cudaMemcpyAsync(s->ifCoefInt.p + I.coefOffset, intCoeffs ? intCoeffs : bouCoeffs, sizeof(double) * I.nFaces,
+                                cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ launch helpers
+static int ensure_sell(b200_sys* s, bool transpose)
+{
+    b200_ctx* ctx = s->ctx;
+    for (size_t r = 0; r < s->regs.size(); r++)
+        if (!s->regionHasCoeffs[r]) return set_err(ctx, B200_ESTATE, "region %zu has no coefficients", r);
+    if (s->nSlots == 0) return B200_OK;
+    const int blocks = (int)std::min<int64_t>((s->nSlots + 255) / 256, (int64_t)ctx->smCount * 16);
+    if (!transpose && s->sellDirty)
+    {
+        KScope k(s, B200_K_PACK);
+        k_pack_sell<<<blocks, 256, 0, ctx->stream>>>((size_t)s->nSlots, s->sellSrc.p, s->coef.p, s->sellVal.p, 0);
+        s->sellDirty = false;
+    }
+    if (transpose && s->sellTDirty)
+    {
+        if (s->sellValT.n != (size_t)s->nSlots) CK(ctx, s->sellValT.alloc(s->nSlots));
+        KScope k(s, B200_K_PACK);
+        k_pack_sell<<<blocks, 256, 0, ctx->stream>>>((size_t)s->nSlots, s->sellSrc.p, s->coef.p, s->sellValT.p, (int)s->F);
+        s->sellTDirty = false;
+    }
+    CK(ctx, cudaGetLastError());
+    return B200_OK;
+}
+
+// all-reduce red[0..nd) over ranks, then apply the scalar op
+static int reduce_finish(b200_sys* s, const PartCounts& cnt, int nd, int op, int force)
+{
+    b200_ctx* ctx = s->ctx;
+    const bool multi = ctx->nranks > 1;
+    {
+        KScope k(s, B200_K_REDUCE);
+        k_finalize<<<1, 1024, 0, ctx->stream>>>(s->partials.p, s->pstride, cnt, nd, s->sc.p, op, multi ? 0 : 1, force,
+                                                 s->history.p, s->devHostFlags);
+    }
+    if (multi)
+    {
+        {
+            KScope k(s, B200_K_HALO);
+            double* red = reinterpret_cast<double*>(s->sc.p); // DevScalars::red is the first member
+            NK(ctx, g_nccl.AllReduce(red, red, nd, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+        }
+        KScope k(s, B200_K_REDUCE);
+        k_scalar_op<<<1, 1, 0, ctx->stream>>>(s->sc.p, op, force, s->history.p, s->devHostFlags);
+    }
+    CK(ctx, cudaGetLastError());
+    return B200_OK;
+}
+
+// y = A x (or A^T x) with nd fused dots of y: nd=1: (y,d0); nd=2: (y,d0),(y,y).  Leaves the
+// partials of the dots in quantities 0..nd-1 with counts amulBlocks + ifaceBlocks.
+static int launch_amul(b200_sys* s, const double* x, double* y, int nd, const double* d0, bool transpose, int force,
+                       PartCounts* cntOut)
+{
+    b200_ctx* ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    int rc = ensure_sell(s, transpose);
+    if (rc) return rc;
+    const double* val = transpose ? s->sellValT.p : s->sellVal.p;
+    const double* ifc = transpose ? s->ifCoefInt.p : s->ifCoefBou.p;
+    // halo exchange of the shadow-side patchInternalField (processorFvPatchField init/update)
+    if (!s->peers.empty())
+    {
+        const int nSend = s->sendOff.back();
+        if (nSend)
+        {
+            KScope k(s, B200_K_PACK);
+            k_halo_pack<<<(nSend + 255) / 256, 256, 0, st>>>(nSend, s->sendCells.p, x, s->sendBuf.p, s->sc.p, 1);
+        }
+        KScope k(s, B200_K_HALO);
+        NK(ctx, g_nccl.GroupStart());
+        for (size_t p = 0; p < s->peers.size(); p++)
+        {
+            const int ns = s->sendOff[p + 1] - s->sendOff[p], nr = s->recvOff[p + 1] - s->recvOff[p];
+            if (ns) NK(ctx, g_nccl.Send(s->sendBuf.p + s->sendOff[p], ns, ncclDouble, s->peers[p], ctx->comm, st));
+            if (nr) NK(ctx, g_nccl.Recv(s->recvBuf.p + s->recvOff[p], nr, ncclDouble, s->peers[p], ctx->comm, st));
+        }
+        NK(ctx, g_nccl.GroupEnd());
+    }
+    if (s->N > 0)
+    {
+        KScope k(s, B200_K_AMUL);
+        const unsigned* mask = s->nTouched ? s->ifaceMask.p : nullptr;
+        if (nd == 0)
+            k_amul<0><<<s->amulBlocks, 256, 0, st>>>((int)s->N, (int)s->nSlices, s->diag.p, s->sliceOff.p, s->sellCol.p, val, x, y,
+                                                     nullptr, mask, s->partials.p, s->pstride, s->sc.p, force);
+        else if (nd == 1)
+            k_amul<1><<<s->amulBlocks, 256, 0, st>>>((int)s->N, (int)s->nSlices, s->diag.p, s->sliceOff.p, s->sellCol.p, val, x, y,
+                                                     d0, mask, s->partials.p, s->pstride, s->sc.p, force);
+        else
+            k_amul<2><<<s->amulBlocks, 256, 0, st>>>((int)s->N, (int)s->nSlices, s->diag.p, s->sliceOff.p, s->sellCol.p, val, x, y,
+                                                     d0, mask, s->partials.p, s->pstride, s->sc.p, force);
+    }
+    if (s->nTouched > 0)
+    {
+        KScope k(s, B200_K_IFACE);
+#define IFACE_ARGS                                                                                                           \
+    s->nTouched, s->ifRows.p, s->ifRowStart.p, s->ifEntCoef.p, s->ifEntSrc.p, s->ifEntCnt.p, s->ifGSrc.p, s->ifGW.p, ifc, x, \
+        s->recvBuf.p, y, d0, s->partials.p, s->pstride, s->amulBlocks, s->sc.p, force
+        if (nd == 0)
+            k_iface<0><<<s->ifaceBlocks, 128, 0, st>>>(IFACE_ARGS);
+        else if (nd == 1)
+            k_iface<1><<<s->ifaceBlocks, 128, 0, st>>>(IFACE_ARGS);
+        else
+            k_iface<2><<<s->ifaceBlocks, 128, 0, st>>>(IFACE_ARGS);
+#undef IFACE_ARGS
+    }
+    CK(ctx, cudaGetLastError());
+    if (cntOut)
+        for (int k = 0; k < kMaxDots; k++) cntOut->n[k] = (s->N > 0 ? s->amulBlocks : 0) + s->ifaceBlocks;
+    return B200_OK;
+}
+
+template <int MODE>
+static int launch_sweep(b200_sys* s, SweepDevMem& M, const double* a, const double* b, double* out, int force)
+{
+    b200_ctx* ctx = s->ctx;
+    if (M.nWarps == 0) return B200_OK;
+    KScope k(s, M.dev.dir > 0 ? B200_K_SWEEP_FWD : B200_K_SWEEP_BWD);
+    k_sweep<MODE><<<M.nBlocks, 32 * M.warpsPerBlock, 0, ctx->stream>>>(M.dev, a, b, out, s->ticket.p, s->ticketBase, s->devErr.p,
+                                                                      s->sc.p, force);
+    s->ticketBase += (unsigned)M.nBlocks;
+    CK(ctx, cudaGetLastError());
+    return B200_OK;
+}
+
+static int fill_sentinel(b200_sys* s, double* a, double* b, int force)
+{
+    if (s->N == 0) return B200_OK;
+    KScope k(s, B200_K_VECTOR);
+    k_fill2_sentinel<<<s->vecBlocks, 256, 0, s->ctx->stream>>>((size_t)s->N, a, b, s->sc.p, force);
+    CK(s->ctx, cudaGetLastError());
+    return B200_OK;
+}
+
+// Preconditioner construction: calcReciprocalD as a forward sweep in division mode, then the
+// pre-multiplied sweep coefficients rD[row]*lower[f] / rD[row]*upper[f].
+static int ensure_precond(b200_sys* s, int precond, bool transposed)
+{
+    b200_ctx* ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    if (precond == B200_PRECOND_NONE) return B200_OK;
+    if (s->precondValid == precond && (!transposed || s->precondTransposedValid)) return B200_OK;
+    if (s->N == 0)
+    {
+        s->precondValid = precond;
+        return B200_OK;
+    }
+    const double* cU = s->coef.p;
+    const double* cL = (precond == B200_PRECOND_DIC) ? s->coef.p : s->coef.p + s->F; // DIC uses upper both ways
+    if (s->precondValid != precond)
+    {
+        if (precond == B200_PRECOND_DIAGONAL)
+        {
+            KScope k(s, B200_K_VECTOR);
+            k_invert<<<s->vecBlocks, 256, 0, st>>>((size_t)s->N, s->diag.p, s->rD.p);
+        }
+        else
+        {
+            {
+                KScope k(s, B200_K_PACK);
+                k_pack_sweep<<<(unsigned)s->fwd.nWarps, 256, 0, st>>>(s->fwd.dev, cU, cL, nullptr, 1);
+            }
+            int rc = fill_sentinel(s, s->rDraw.p, nullptr, 1);
+            if (rc) return rc;
+            rc = launch_sweep<2>(s, s->fwd, s->diag.p, nullptr, s->rDraw.p, 1);
+            if (rc) return rc;
+            {
+                KScope k(s, B200_K_VECTOR);
+                k_invert<<<s->vecBlocks, 256, 0, st>>>((size_t)s->N, s->rDraw.p, s->rD.p);
+            }
+            {
+                KScope k(s, B200_K_PACK);
+                k_pack_sweep<<<(unsigned)s->fwd.nWarps, 256, 0, st>>>(s->fwd.dev, cL, nullptr, s->rD.p, 0);
+            }
+            {
+                KScope k(s, B200_K_PACK);
+                k_pack_sweep<<<(unsigned)s->bwd.nWarps, 256, 0, st>>>(s->bwd.dev, cU, nullptr, s->rD.p, 0);
+            }
+        }
+        s->precondValid = precond;
+        s->precondTransposedValid = false;
+    }
+    if (transposed && !s->precondTransposedValid && precond != B200_PRECOND_DIAGONAL)
+    {
+        // preconditionT: roles of upper and lower swapped (DILUPreconditioner::preconditionT)
+        if (s->chainCT_f.n != s->fwd.chainC.n) CK(ctx, s->chainCT_f.alloc(s->fwd.chainC.n));
+        if (s->offCT_f.n != s->fwd.offC.n) CK(ctx, s->offCT_f.alloc(s->fwd.offC.n));
+        if (s->chainCT_b.n != s->bwd.chainC.n) CK(ctx, s->chainCT_b.alloc(s->bwd.chainC.n));
+        if (s->offCT_b.n != s->bwd.offC.n) CK(ctx, s->offCT_b.alloc(s->bwd.offC.n));
+        SweepDev f = s->fwd.dev, b = s->bwd.dev;
+        f.chainC = s->chainCT_f.p;
+        f.offC = s->offCT_f.p;
+        b.chainC = s->chainCT_b.p;
+        b.offC = s->offCT_b.p;
+        {
+            KScope k(s, B200_K_PACK);
+            k_pack_sweep<<<(unsigned)s->fwd.nWarps, 256, 0, st>>>(f, cU, nullptr, s->rD.p, 0);
+        }
+        {
+            KScope k(s, B200_K_PACK);
+            k_pack_sweep<<<(unsigned)s->bwd.nWarps, 256, 0, st>>>(b, cL, nullptr, s->rD.p, 0);
+        }
+        s->precondTransposedValid = true;
+    }
+    CK(ctx, cudaGetLastError());
+    return B200_OK;
+}
+
+// w = M^-1 r.  tmp: scratch for the forward result.  If prefilled, the caller already wrote the
+// sentinel into tmp and w (fused into the preceding vector kernel).
+static int launch_precondition(b200_sys* s, int precond, const double* r, double* w, double* tmp, bool prefilled,
+                               bool transposed, int force)
+{
+    b200_ctx* ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    if (s->N == 0) return B200_OK;
+    if (precond == B200_PRECOND_NONE)
+    {
+        KScope k(s, B200_K_VECTOR);
+        k_copy<<<s->vecBlocks, 256, 0, st>>>((size_t)s->N, r, w, s->sc.p, force);
+        CK(ctx, cudaGetLastError());
+        return B200_OK;
+    }
+    if (precond == B200_PRECOND_DIAGONAL)
+    {
+        KScope k(s, B200_K_VECTOR);
+        k_mul<<<s->vecBlocks, 256, 0, st>>>((size_t)s->N, s->rD.p, r, w, s->sc.p, force);
+        CK(ctx, cudaGetLastError());
+        return B200_OK;
+    }
+    if (!prefilled)
+    {
+        int rc = fill_sentinel(s, tmp, w, force);
+        if (rc) return rc;
+    }
+    SweepDev fdev = s->fwd.dev, bdev = s->bwd.dev;
+    if (transposed)
+    {
+        fdev.chainC = s->chainCT_f.p;
+        fdev.offC = s->offCT_f.p;
+        bdev.chainC = s->chainCT_b.p;
+        bdev.offC = s->offCT_b.p;
+    }
+    {
+        KScope k(s, B200_K_SWEEP_FWD);
+        k_sweep<0><<<s->fwd.nBlocks, 32 * s->fwd.warpsPerBlock, 0, st>>>(fdev, s->rD.p, r, tmp, s->ticket.p, s->ticketBase,
+                                                                        s->devErr.p, s->sc.p, force);
+        s->ticketBase += (unsigned)s->fwd.nBlocks;
+    }
+    {
+        KScope k(s, B200_K_SWEEP_BWD);
+        k_sweep<1><<<s->bwd.nBlocks, 32 * s->bwd.warpsPerBlock, 0, st>>>(bdev, tmp, nullptr, w, s->ticket.p, s->ticketBase,
+                                                                        s->devErr.p, s->sc.p, force);
+        s->ticketBase += (unsigned)s->bwd.nBlocks;
+    }
+    CK(ctx, cudaGetLastError());
+    return B200_OK;
+}
+
+static PartCounts vec_counts(const b200_sys* s)
+{
+    PartCounts c;
+    for (int k = 0; k < kMaxDots; k++) c.n[k] = s->N > 0 ? s->vecBlocks : 0;
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------ vectors in / out
+static int upload_vec(b200_sys* s, int v, const double* const* h)
+{
+    b200_ctx* ctx = s->ctx;
+    for (size_t r = 0; r < s->regs.size(); r++)
+    {
+        const RegionHost& R = s->regs[r];
+        if (!h[r] && R.nCells) return set_err(ctx, B200_EINVAL, "null host vector for region %zu", r);
+        if (R.nCells)
+            CK(ctx, cudaMemcpyAsync(s->vec[v].p + R.cellOffset, h[r], sizeof(double) * R.nCells, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return B200_OK;
+}
+
+static int download_vec(b200_sys* s, const double* dev, double* const* h)
+{
+    b200_ctx* ctx = s->ctx;
+    for (size_t r = 0; r < s->regs.size(); r++)
+    {
+        const RegionHost& R = s->regs[r];
+        if (!h[r] && R.nCells) return set_err(ctx, B200_EINVAL, "null host vector for region %zu", r);
+        if (R.nCells)
+            CK(ctx, cudaMemcpyAsync(h[r], dev + R.cellOffset, sizeof(double) * R.nCells, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return B200_OK;
+}
+
+static int check_device_error(b200_sys* s)
+{
+    int e = 0;
+    CK(s->ctx, cudaMemcpyAsync(&e, s->devErr.p, sizeof(int), cudaMemcpyDeviceToHost, s->ctx->stream));
+    CK(s->ctx, cudaStreamSynchronize(s->ctx->stream));
+    if (e)
+    {
+        cudaMemsetAsync(s->devErr.p, 0, sizeof(int), s->ctx->stream);
+        return set_err(s->ctx, B200_EDEVICE, "sweep kernel timed out waiting for a dependency (device error %d)", e);
+    }
+    return B200_OK;
+}
+
+extern "C" int b200_upload(b200_sys* s, const double* const* x, const double* const* b)
+{
+    if (!s || !s->finalized) return s ? set_err(s->ctx, B200_ESTATE, "upload before finalize") : B200_EINVAL;
+    CK(s->ctx, cudaSetDevice(s->ctx->device));
+    int rc = B200_OK;
+    if (x) rc = upload_vec(s, V_X, x);
+    if (!rc && b) rc = upload_vec(s, V_B, b);
+    if (rc) return rc;
+    CK(s->ctx, cudaStreamSynchronize(s->ctx->stream));
+    return B200_OK;
+}
+
+extern "C" int b200_download(b200_sys* s, double* const* x)
+{
+    if (!s || !s->finalized || !x) return s ? set_err(s->ctx, B200_ESTATE, "download before finalize") : B200_EINVAL;
+    CK(s->ctx, cudaSetDevice(s->ctx->device));
+    int rc = download_vec(s, s->vec[V_X].p, x);
+    if (rc) return rc;
+    CK(s->ctx, cudaStreamSynchronize(s->ctx->stream));
+    return B200_OK;
+}
+
+extern "C" int b200_x_save(b200_sys* s)
+{
+    if (!s || !s->finalized) return s ? set_err(s->ctx, B200_ESTATE, "x_save before finalize") : B200_EINVAL;
+    CK(s->ctx, cudaSetDevice(s->ctx->device));
+    if (s->x0.n != (size_t)s->N) CK(s->ctx, s->x0.alloc(s->N));
+    if (s->N) CK(s->ctx, cudaMemcpyAsync(s->x0.p, s->vec[V_X].p, sizeof(double) * s->N, cudaMemcpyDeviceToDevice, s->ctx->stream));
+    s->x0Valid = true;
+    return B200_OK;
+}
+
+extern "C" int b200_x_restore(b200_sys* s)
+{
+    if (!s || !s->finalized) return s ? set_err(s->ctx, B200_ESTATE, "x_restore before finalize") : B200_EINVAL;
+    if (!s->x0Valid) return set_err(s->ctx, B200_ESTATE, "x_restore without x_save");
+    CK(s->ctx, cudaSetDevice(s->ctx->device));
+    if (s->N) CK(s->ctx, cudaMemcpyAsync(s->vec[V_X].p, s->x0.p, sizeof(double) * s->N, cudaMemcpyDeviceToDevice, s->ctx->stream));
+    return B200_OK;
+}
+
+extern "C" int b200_host_register(b200_ctx* ctx, void* p, uint64_t bytes)
+{
+    if (!ctx || !p) return set_err(ctx, B200_EINVAL, "b200_host_register: null argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (bytes) CK(ctx, cudaHostRegister(p, (size_t)bytes, cudaHostRegisterDefault));
+    return B200_OK;
+}
+
+extern "C" int b200_host_unregister(b200_ctx* ctx, void* p)
+{
+    if (!ctx || !p) return set_err(ctx, B200_EINVAL, "b200_host_unregister: null argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaHostUnregister(p));
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ Krylov drivers
+static int upload_scalars(b200_sys* s, const b200_solver_opts* o, int histCap)
+{
+    DevScalars h;
+    memset(&h, 0, sizeof(h));
+    h.tolerance = o->tolerance;
+    h.relTol = o->relTol;
+    h.minIter = o->minIter;
+    h.maxIter = o->maxIter;
+    h.nGlobalCells = s->nGlobalCells;
+    h.histCap = std::min(histCap, (int)kHistOnDevice);
+    s->hostFlags[0] = 0;
+    s->hostFlags[1] = 0;
+    CK(s->ctx, cudaMemcpyAsync(s->sc.p, &h, sizeof(h), cudaMemcpyHostToDevice, s->ctx->stream));
+    CK(s->ctx, cudaStreamSynchronize(s->ctx->stream)); // h is on the stack
+    return B200_OK;
+}
+
+// Common head of every solver: wA = A x, normFactor, r = b - wA, initial residual, stop check.
+static int solve_head(b200_sys* s, int op, double* Ax, double* r, double* rw, double* zero1, double* zero2)
+{
+    b200_ctx* ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    int rc;
+    const size_t n = (size_t)s->N;
+    if ((rc = launch_amul(s, s->vec[V_X].p, Ax, 0, nullptr, false, 1, nullptr))) return rc;
+    // xRef = gAverage(x); tmp = A * xRef (coupledIterativeSolver::normFactor)
+    if (n)
+    {
+        KScope k(s, B200_K_VECTOR);
+        k_sum<<<s->vecBlocks, 256, 0, st>>>(n, s->vec[V_X].p, s->partials.p, s->pstride);
+    }
+    if ((rc = reduce_finish(s, vec_counts(s), 1, OP_XREF, 1))) return rc;
+    if (n)
+    {
+        KScope k(s, B200_K_VECTOR);
+        k_fill_xref<<<s->vecBlocks, 256, 0, st>>>(n, s->vec[V_TMP2].p, s->sc.p);
+    }
+    if ((rc = launch_amul(s, s->vec[V_TMP2].p, s->vec[V_TMP].p, 0, nullptr, false, 1, nullptr))) return rc;
+    if (n)
+    {
+        KScope k(s, B200_K_VECTOR);
+        k_init_residual<<<s->vecBlocks, 256, 0, st>>>(n, s->vec[V_B].p, Ax, s->vec[V_TMP].p, r, rw, zero1, zero2, s->partials.p,
+                                                      s->pstride);
+    }
+    if ((rc = reduce_finish(s, vec_counts(s), 3, op, 1))) return rc;
+    CK(ctx, cudaGetLastError());
+    return B200_OK;
+}
+
+// keep the host at most kAhead iterations ahead of the device so that the done flag is seen soon
+static int throttle_wait(b200_sys* s, int it)
+{
+    const int kAhead = 8;
+    if ((int)s->throttle.size() < kAhead)
+    {
+        s->throttle.resize(kAhead, nullptr);
+        for (auto& e : s->throttle)
+            if (!e) CK(s->ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    cudaEvent_t e = s->throttle[it % kAhead];
+    if (it >= kAhead) CK(s->ctx, cudaEventSynchronize(e));
+    return B200_OK;
+}
+static int throttle_mark(b200_sys* s, int it)
+{
+    CK(s->ctx, cudaEventRecord(s->throttle[it % 8], s->ctx->stream));
+    return B200_OK;
+}
+
+static int solve_bicgstab(b200_sys* s, const b200_solver_opts* o)
+{
+    b200_ctx* ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    const size_t n = (size_t)s->N;
+    double *x = s->vec[V_X].p, *r = s->vec[V_R].p, *rw = s->vec[V_RW].p, *p = s->vec[V_P].p, *ph = s->vec[V_PH].p;
+    double *v = s->vec[V_V].p, *sv = s->vec[V_S].p, *sh = s->vec[V_SH].p, *t = s->vec[V_T].p, *tmp = s->vec[V_TMP2].p;
+    int rc;
+    // p doubles as the Amul helper of the head (bicgStabSolver: "Multiplication helper p")
+    if ((rc = solve_head(s, OP_NORM_INIT_BICGSTAB, p, r, rw, nullptr, v))) return rc;
+    if (n)
+    {
+        KScope k(s, B200_K_VECTOR);
+        k_fill<<<s->vecBlocks, 256, 0, st>>>(n, p, 0.0); // p = 0
+    }
+    if ((rc = ensure_precond(s, o->precond, false))) return rc;
+    const bool sweeps = o->precond >= B200_PRECOND_DIC;
+    PartCounts cnt;
+    for (int it = 0; it < o->maxIter; it++)
+    {
+        if (*(volatile int*)&s->hostFlags[0]) break;
+        if ((rc = throttle_wait(s, it))) return rc;
+        if (n)
+        {
+            KScope k(s, B200_K_VECTOR);
+            k_bicg_p<<<s->vecBlocks, 256, 0, st>>>(n, r, p, v, rw, sweeps ? tmp : nullptr, sweeps ? ph : nullptr, s->partials.p,
+                                                   s->pstride, s->sc.p);
+        }
+        if ((rc = launch_precondition(s, o->precond, p, ph, tmp, true, false, 0))) return rc;
+        if ((rc = launch_amul(s, ph, v, 1, rw, false, 0, &cnt))) return rc;
+        cnt.n[1] = n ? s->vecBlocks : 0; // quantity 1 = (r, r) from k_bicg_p
+        if ((rc = reduce_finish(s, cnt, 2, OP_BICG_ALPHA, 0))) return rc;
+        if (n)
+        {
+            KScope k(s, B200_K_VECTOR);
+            k_bicg_s<<<s->vecBlocks, 256, 0, st>>>(n, r, v, sv, sweeps ? tmp : nullptr, sweeps ? sh : nullptr, s->sc.p);
+        }
+        if ((rc = launch_precondition(s, o->precond, sv, sh, tmp, true, false, 0))) return rc;
+        if ((rc = launch_amul(s, sh, t, 2, sv, false, 0, &cnt))) return rc;
+        if ((rc = reduce_finish(s, cnt, 2, OP_BICG_OMEGA, 0))) return rc;
+        if (n)
+        {
+            KScope k(s, B200_K_VECTOR);
+            k_bicg_xr<<<s->vecBlocks, 256, 0, st>>>(n, x, ph, sh, sv, t, r, rw, s->partials.p, s->pstride, s->sc.p);
+        }
+        if ((rc = reduce_finish(s, vec_counts(s), 2, OP_BICG_RESIDUAL, 0))) return rc;
+        if ((rc = throttle_mark(s, it))) return rc;
+    }
+    CK(ctx, cudaGetLastError());
+    return B200_OK;
+}
+
+static int solve_pcg(b200_sys* s, const b200_solver_opts* o)
+{
+    b200_ctx* ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    const size_t n = (size_t)s->N;
+    double *x = s->vec[V_X].p, *rA = s->vec[V_R].p, *pA = s->vec[V_P].p, *wA = s->vec[V_V].p, *z = s->vec[V_PH].p;
+    double* tmp = s->vec[V_TMP2].p;
+    int rc;
+    if ((rc = solve_head(s, OP_NORM_INIT_PCG, wA, rA, nullptr, pA, nullptr))) return rc;
+    if ((rc = ensure_precond(s, o->precond, false))) return rc;
+    const bool sweeps = o->precond >= B200_PRECOND_DIC;
+    if (sweeps && (rc = fill_sentinel(s, tmp, z, 1))) return rc;
+    PartCounts cnt;
+    for (int it = 0; it < o->maxIter; it++)
+    {
+        if (*(volatile int*)&s->hostFlags[0]) break;
+        if ((rc = throttle_wait(s, it))) return rc;
+        if ((rc = launch_precondition(s, o->precond, rA, z, tmp, true, false, 0))) return rc; // wA = M^-1 rA
+        if (n)
+        {
+            KScope k(s, B200_K_VECTOR);
+            k_dot<<<s->vecBlocks, 256, 0, st>>>(n, z, rA, s->partials.p, s->pstride, s->sc.p); // wArA
+        }
+        if ((rc = reduce_finish(s, vec_counts(s), 1, OP_PCG_RHO, 0))) return rc;
+        if (n)
+        {
+            KScope k(s, B200_K_VECTOR);
+            k_pcg_p<<<s->vecBlocks, 256, 0, st>>>(n, z, pA, s->sc.p);
+        }
+        if ((rc = launch_amul(s, pA, wA, 1, pA, false, 0, &cnt))) return rc; // wA = A pA, wApA
+        if ((rc = reduce_finish(s, cnt, 1, OP_PCG_ALPHA, 0))) return rc;
+        if (n)
+        {
+            KScope k(s, B200_K_VECTOR);
+            k_pcg_xr<<<s->vecBlocks, 256, 0, st>>>(n, x, pA, rA, wA, sweeps ? tmp : nullptr, sweeps ? z : nullptr, s->partials.p,
+                                                   s->pstride, s->sc.p);
+        }
+        if ((rc = reduce_finish(s, vec_counts(s), 1, OP_PCG_RESIDUAL, 0))) return rc;
+        if ((rc = throttle_mark(s, it))) return rc;
+    }
+    CK(ctx, cudaGetLastError());
+    return B200_OK;
+}
+
+extern "C" int b200_solve_resident(b200_sys* s, const b200_solver_opts* o, b200_perf* perf, double* history, int historyCap)
+{
+    if (!s || !o || !perf) return s ? set_err(s->ctx, B200_EINVAL, "b200_solve: null argument") : B200_EINVAL;
+    b200_ctx* ctx = s->ctx;
+    if (!s->finalized) return set_err(ctx, B200_ESTATE, "solve before finalize");
+    if (o->solver == B200_SOLVER_PBICG) return set_err(ctx, B200_EUNSUPPORTED, "PBiCG is not built in this round; use BiCGStab");
+    if (o->solver != B200_SOLVER_PCG && o->solver != B200_SOLVER_BICGSTAB) return set_err(ctx, B200_EINVAL, "unknown solver %d", o->solver);
+    if (o->precond < B200_PRECOND_NONE || o->precond > B200_PRECOND_CHOLESKY)
+        return set_err(ctx, B200_EINVAL, "unknown preconditioner %d", o->precond);
+    if (o->maxIter < 0 || o->minIter < 0) return set_err(ctx, B200_EINVAL, "negative iteration bounds");
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc = ensure_sell(s, false);
+    if (rc) return rc;
+    // like the reference, every solve constructs its preconditioner from the current coefficients
+    s->precondValid = -1;
+    s->precondTransposedValid = false;
+    if ((rc = upload_scalars(s, o, history ? historyCap : 0))) return rc;
+    CK(ctx, cudaEventRecord(s->evSolveA, ctx->stream));
+    rc = (o->solver == B200_SOLVER_PCG) ? solve_pcg(s, o) : solve_bicgstab(s, o);
+    if (rc) return rc;
+    CK(ctx, cudaEventRecord(s->evSolveB, ctx->stream));
+    DevScalars h;
+    CK(ctx, cudaMemcpyAsync(&h, s->sc.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    CK(ctx, cudaEventElapsedTime(&ms, s->evSolveA, s->evSolveB));
+    perf->initialResidual = h.initialResidual;
+    perf->finalResidual = h.finalResidual;
+    perf->nIterations = h.nIter;
+    perf->converged = h.converged;
+    perf->singular = h.singular;
+    perf->normFactor = h.normFactor;
+    perf->deviceMs = ms;
+    if (history && historyCap > 0)
+    {
+        int nh = std::min({historyCap, h.nIter + 1, (int)kHistOnDevice});
+        CK(ctx, cudaMemcpy(history, s->history.p, sizeof(double) * nh, cudaMemcpyDeviceToHost));
+    }
+    if (s->profiling) harvest_events(s);
+    return check_device_error(s);
+}
+
+extern "C" int b200_solve(b200_sys* s, const b200_solver_opts* o, double* const* x, const double* const* b, b200_perf* perf,
+                          double* history, int historyCap)
+{
+    if (!s || !x || !b) return s ? set_err(s->ctx, B200_EINVAL, "b200_solve: null argument") : B200_EINVAL;
+    if (!s->finalized) return set_err(s->ctx, B200_ESTATE, "solve before finalize");
+    CK(s->ctx, cudaSetDevice(s->ctx->device));
+    int rc;
+    if ((rc = upload_vec(s, V_X, x))) return rc;
+    if ((rc = upload_vec(s, V_B, b))) return rc;
+    if ((rc = b200_solve_resident(s, o, perf, history, historyCap))) return rc;
+    if ((rc = download_vec(s, s->vec[V_X].p, x))) return rc;
+    CK(s->ctx, cudaStreamSynchronize(s->ctx->stream));
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ test hooks
+extern "C" int b200_amul(b200_sys* s, const double* const* x, double* const* y, int transpose)
+{
+    if (!s || !x || !y) return B200_EINVAL;
+    if (!s->finalized) return set_err(s->ctx, B200_ESTATE, "amul before finalize");
+    CK(s->ctx, cudaSetDevice(s->ctx->device));
+    int rc;
+    if ((rc = upload_vec(s, V_P, x))) return rc;
+    if ((rc = launch_amul(s, s->vec[V_P].p, s->vec[V_V].p, 0, nullptr, transpose != 0, 1, nullptr))) return rc;
+    if ((rc = download_vec(s, s->vec[V_V].p, y))) return rc;
+    CK(s->ctx, cudaStreamSynchronize(s->ctx->stream));
+    if (s->profiling) harvest_events(s);
+    return B200_OK;
+}
+
+extern "C" int b200_precondition(b200_sys* s, int precond, const double* const* r, double* const* w, int transpose)
+{
+    if (!s || !r || !w) return B200_EINVAL;
+    if (!s->finalized) return set_err(s->ctx, B200_ESTATE, "precondition before finalize");
+    if (precond < B200_PRECOND_NONE || precond > B200_PRECOND_CHOLESKY) return set_err(s->ctx, B200_EINVAL, "unknown preconditioner");
+    CK(s->ctx, cudaSetDevice(s->ctx->device));
+    int rc;
+    for (size_t q = 0; q < s->regs.size(); q++)
+        if (!s->regionHasCoeffs[q]) return set_err(s->ctx, B200_ESTATE, "region %zu has no coefficients", q);
+    if ((rc = upload_vec(s, V_S, r))) return rc;
+    if ((rc = ensure_precond(s, precond, transpose != 0))) return rc;
+    if ((rc = launch_precondition(s, precond, s->vec[V_S].p, s->vec[V_SH].p, s->vec[V_TMP2].p, false, transpose != 0, 1))) return rc;
+    if ((rc = download_vec(s, s->vec[V_SH].p, w))) return rc;
+    CK(s->ctx, cudaStreamSynchronize(s->ctx->stream));
+    if (s->profiling) harvest_events(s);
+    return check_device_error(s);
+}
+
+extern "C" int b200_get_rD(b200_sys* s, int precond, double* const* rD)
+{
+    if (!s || !rD) return B200_EINVAL;
+    if (!s->finalized) return set_err(s->ctx, B200_ESTATE, "get_rD before finalize");
+    if (precond < B200_PRECOND_DIAGONAL || precond > B200_PRECOND_CHOLESKY) return set_err(s->ctx, B200_EINVAL, "preconditioner has no rD");
+    CK(s->ctx, cudaSetDevice(s->ctx->device));
+    int rc;
+    if ((rc = ensure_precond(s, precond, false))) return rc;
+    if ((rc = download_vec(s, s->rD.p, rD))) return rc;
+    CK(s->ctx, cudaStreamSynchronize(s->ctx->stream));
+    return check_device_error(s);
+}
+
+extern "C" int b200_reduce(b200_sys* s, const double* const* a, const double* const* b, double* out2)
+{
+    if (!s || !a || !b || !out2) return B200_EINVAL;
+    if (!s->finalized) return set_err(s->ctx, B200_ESTATE, "reduce before finalize");
+    b200_ctx* ctx = s->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = upload_vec(s, V_S, a))) return rc;
+    if ((rc = upload_vec(s, V_SH, b))) return rc;
+    if (s->N)
+    {
+        KScope k(s, B200_K_VECTOR);
+        k_dot_mag<<<s->vecBlocks, 256, 0, ctx->stream>>>((size_t)s->N, s->vec[V_S].p, s->vec[V_SH].p, s->partials.p, s->pstride);
+    }
+    if ((rc = reduce_finish(s, vec_counts(s), 2, OP_STORE_RED, 1))) return rc;
+    DevScalars h;
+    CK(ctx, cudaMemcpyAsync(&h, s->sc.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    out2[0] = h.red[0];
+    out2[1] = h.red[1];
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ profiling
+extern "C" int b200_set_profiling(b200_sys* s, int enable)
+{
+    if (!s) return B200_EINVAL;
+    cudaStreamSynchronize(s->ctx->stream);
+    harvest_events(s);
+    s->profiling = enable != 0;
+    return B200_OK;
+}
+
+extern "C" int b200_get_kernel_times(b200_sys* s, double* msPerClass, int64_t* launchesPerClass, int reset)
+{
+    if (!s) return B200_EINVAL;
+    cudaStreamSynchronize(s->ctx->stream);
+    harvest_events(s);
+    for (int k = 0; k < B200_K_NCLASSES; k++)
+    {
+        if (msPerClass) msPerClass[k] = s->clsMs[k];
+        if (launchesPerClass) launchesPerClass[k] = s->clsLaunches[k];
+        if (reset)
+        {
+            s->clsMs[k] = 0;
+            s->clsLaunches[k] = 0;
+        }
+    }
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ partitioned face transfer
+extern "C" int b200_ggi_interpolate(b200_ctx* ctx, int32_t nTo, int32_t nFrom, const int32_t* offsets, const int32_t* addr,
+                                    const double* weights, const double* ff, int nComp, double* result)
+{
+    if (!ctx || nTo < 0 || nFrom < 0 || nComp < 1 || !offsets || !result) return set_err(ctx, B200_EINVAL, "b200_ggi_interpolate: bad arguments");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (nTo == 0) return B200_OK;
+    const int nnz = offsets[nTo];
+    for (int k = 0; k < nnz; k++)
+        if (addr[k] < 0 || addr[k] >= nFrom) return set_err(ctx, B200_EINVAL, "GGI address %d out of range", addr[k]);
+    DevBuf<int> dOff, dAddr;
+    DevBuf<double> dW, dF, dR;
+    cudaStream_t st = ctx->stream;
+    CK(ctx, dOff.alloc(nTo + 1));
+    CK(ctx, dAddr.alloc(nnz));
+    CK(ctx, dW.alloc(nnz));
+    CK(ctx, dF.alloc((size_t)nFrom * nComp));
+    CK(ctx, dR.alloc((size_t)nTo * nComp));
+    CK(ctx, cudaMemcpyAsync(dOff.p, offsets, sizeof(int) * (nTo + 1), cudaMemcpyHostToDevice, st));
+    if (nnz)
+    {
+        CK(ctx, cudaMemcpyAsync(dAddr.p, addr, sizeof(int) * nnz, cudaMemcpyHostToDevice, st));
+        CK(ctx, cudaMemcpyAsync(dW.p, weights, sizeof(double) * nnz, cudaMemcpyHostToDevice, st));
+    }
+    if (nFrom) CK(ctx, cudaMemcpyAsync(dF.p, ff, sizeof(double) * nFrom * nComp, cudaMemcpyHostToDevice, st));
+    ctx->launches++;
+    k_ggi_interpolate<<<(nTo * nComp + 127) / 128, 128, 0, st>>>(nTo, dOff.p, dAddr.p, dW.p, dF.p, nComp, dR.p);
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaMemcpyAsync(result, dR.p, sizeof(double) * nTo * nComp, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+extern "C" int b200_patch_face_to_global(b200_ctx* ctx, int32_t nLocal, const int32_t* faceToGlobalAddr, const double* pField,
+                                         int nComp, int32_t nZoneFaces, double* gField)
+{
+    if (!ctx || nLocal < 0 || nZoneFaces < 0 || nComp < 1 || !gField) return set_err(ctx, B200_EINVAL, "b200_patch_face_to_global: bad arguments");
+    CK(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < nLocal; i++)
+        if (faceToGlobalAddr[i] < 0 || faceToGlobalAddr[i] >= nZoneFaces) return set_err(ctx, B200_EINVAL, "faceToGlobalAddr out of range");
+    DevBuf<int> dAddr;
+    DevBuf<double> dP, dG;
+    cudaStream_t st = ctx->stream;
+    CK(ctx, dAddr.alloc(nLocal));
+    CK(ctx, dP.alloc((size_t)nLocal * nComp));
+    CK(ctx, dG.alloc((size_t)nZoneFaces * nComp));
+    CK(ctx, cudaMemsetAsync(dG.p, 0, sizeof(double) * std::max<size_t>(1, (size_t)nZoneFaces * nComp), st));
+    if (nLocal)
+    {
+        CK(ctx, cudaMemcpyAsync(dAddr.p, faceToGlobalAddr, sizeof(int) * nLocal, cudaMemcpyHostToDevice, st));
+        CK(ctx, cudaMemcpyAsync(dP.p, pField, sizeof(double) * nLocal * nComp, cudaMemcpyHostToDevice, st));
+        ctx->launches++;
+        k_scatter_zone<<<(nLocal * nComp + 127) / 128, 128, 0, st>>>(nLocal, dAddr.p, dP.p, nComp, dG.p);
+        CK(ctx, cudaGetLastError());
+    }
+    if (ctx->nranks > 1 && nZoneFaces > 0)
+        NK(ctx, g_nccl.AllReduce(dG.p, dG.p, (size_t)nZoneFaces * nComp, ncclDouble, ncclSum, ctx->comm, st)); // reduce(gField, sumOp)
+    if (nZoneFaces) CK(ctx, cudaMemcpyAsync(gField, dG.p, sizeof(double) * nZoneFaces * nComp, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+extern "C" int b200_global_face_to_patch(b200_ctx* ctx, int32_t nLocal, const int32_t* faceToGlobalAddr, const double* gField,
+                                         int nComp, double* pField)
+{
+    if (!ctx || nLocal < 0 || nComp < 1) return set_err(ctx, B200_EINVAL, "b200_global_face_to_patch: bad arguments");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (nLocal == 0) return B200_OK;
+    int nZone = 0;
+    for (int i = 0; i < nLocal; i++)
+    {
+        if (faceToGlobalAddr[i] < 0) return set_err(ctx, B200_EINVAL, "faceToGlobalAddr out of range");
+        nZone = std::max(nZone, faceToGlobalAddr[i] + 1);
+    }
+    DevBuf<int> dAddr;
+    DevBuf<double> dP, dG;
+    cudaStream_t st = ctx->stream;
+    CK(ctx, dAddr.alloc(nLocal));
+    CK(ctx, dP.alloc((size_t)nLocal * nComp));
+    CK(ctx, dG.alloc((size_t)nZone * nComp));
+    CK(ctx, cudaMemcpyAsync(dAddr.p, faceToGlobalAddr, sizeof(int) * nLocal, cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(dG.p, gField, sizeof(double) * nZone * nComp, cudaMemcpyHostToDevice, st));
+    ctx->launches++;
+    k_gather_zone<<<(nLocal * nComp + 127) / 128, 128, 0, st>>>(nLocal, dAddr.p, dG.p, nComp, dP.p);
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaMemcpyAsync(pField, dP.p, sizeof(double) * nLocal * nComp, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    return B200_OK;
+}

@@ -178,6 +178,17 @@ class StructuredRegion:
         a = self._dx[b][None, :] * self._dz[:, None]
         return c.reshape(-1).astype(np.int32), a.reshape(-1), np.full(c.size, 0.5 * self._dy[j])
 
+    def side_z(self, top: bool):
+        """Cells adjacent to z-min (top=False) or z-max in ascending cell order (block by block, (j, i)
+        i-fastest): the order of the faces of a z-cut processor patch on both sides of the cut."""
+        k = self.nz - 1 if top else 0
+        cs, as_ = [], []
+        for b in range(len(self.blocks)):
+            cs.append(self._cells(b)[k, :, :].reshape(-1))
+            as_.append((self._dx[b][None, :] * self._dy[:, None]).reshape(-1))
+        c = np.concatenate(cs)
+        return c.astype(np.int32), np.concatenate(as_), np.full(c.size, 0.5 * self._dz[k])
+
     def cell_centres_x(self) -> np.ndarray:
         xs = []
         for b, blk in enumerate(self.blocks):
@@ -202,7 +213,7 @@ class StructuredRegion:
         return np.concatenate(js)
 
 
-def flow_over_heated_plate(r: int = 1, layers: int = 1) -> Tuple[StructuredRegion, StructuredRegion]:
+def flow_over_heated_plate(r: int = 1, layers: int = 1, z1: float = 0.4) -> Tuple[StructuredRegion, StructuredRegion]:
     """The two regions of tutorials/conjugateHeatTransfer/flowOverHeatedPlate refined by the
     integer factor r in x and y and extruded to ``layers`` cells in z
     (blockMeshDictMonolithic: fluid blocks (81 41 1)(200 41 1)(51 41 1) simpleGrading
@@ -210,10 +221,10 @@ def flow_over_heated_plate(r: int = 1, layers: int = 1) -> Tuple[StructuredRegio
     fluid = StructuredRegion(
         "fluid",
         [Block(81 * r, -0.5, 0.0, 0.2), Block(200 * r, 0.0, 1.0, 5.0), Block(51 * r, 1.0, 3.0, 1.0)],
-        ny=41 * r, nz=layers, y0=0.0, y1=0.5, grady=16.0).build()
+        ny=41 * r, nz=layers, y0=0.0, y1=0.5, grady=16.0, z1=z1).build()
     solid = StructuredRegion(
         "solid", [Block(200 * r, 0.0, 1.0, 5.0)],
-        ny=41 * r, nz=layers, y0=-0.25, y1=0.0, grady=0.0625).build()
+        ny=41 * r, nz=layers, y0=-0.25, y1=0.0, grady=0.0625, z1=z1).build()
     return fluid, solid
 
 
