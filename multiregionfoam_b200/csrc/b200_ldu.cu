@@ -148,15 +148,14 @@ struct DevBuf
     }
 };
 
-struct SweepDevMem
+struct PipeDirMem
 {
-    DevBuf<int> nLanes, nSteps, W, laneBase, laneStart, laneLen, chainFace, offFace, offCol;
-    DevBuf<long long> chainBase, offBase;
-    DevBuf<double> chainC, offC;
-    SweepDev dev{};
-    int64_t nWarps = 0;
-    int warpsPerBlock = 1;
-    int nBlocks = 0;
+    DevBuf<int> gW, gCH, gShflMask, face, order;
+    DevBuf<long long> gTermOff;
+    DevBuf<unsigned char> stream;
+    PipeDev dev{};
+    int smemBytes = 0;
+    int packedFor = -1; // 0: plain coefficients packed, 1: transposed, -1: none
 };
 
 // ------------------------------------------------------------------------------------------ system
@@ -188,9 +187,15 @@ struct b200_sys
     // matrix
     DevBuf<double> diag, coef /* [upper(F) | lower(F)] */, ifCoefBou, ifCoefInt;
     std::vector<uint8_t> regionHasCoeffs;
-    bool sellDirty = true, sellTDirty = true;
+    bool sellDirty = true, sellTDirty = true, diagDirty = false;
+    DevBuf<double> diagCell; // cell-ordered diag as set by the caller (regions arrive one by one)
+    // slot order (sweep schedule order) of all device vectors
+    int64_t nSlots = 0;
+    DevBuf<int> slotOfCell, cellOfSlot, gBase, gNT;
+    DevBuf<double> stageCell; // cell-ordered staging for host <-> device copies
+    int nGroups = 0;
     // SELL
-    int64_t nSlices = 0, nSlots = 0;
+    int64_t nSlices = 0, nEntries = 0;
     DevBuf<int> sliceOff, sellCol, sellSrc;
     DevBuf<double> sellVal, sellValT;
     DevBuf<unsigned> ifaceMask;
@@ -202,11 +207,9 @@ struct b200_sys
     std::vector<int32_t> sendOff, recvOff;
     int64_t nIfCoefs = 0;
     // sweeps
-    SweepDevMem fwd, bwd;
+    PipeDirMem fwd, bwd;
     DevBuf<double> rD, rDraw;
-    int precondValid = -1; // preconditioner id the packed sweep coefficients belong to (-1: none)
-    bool precondTransposedValid = false;
-    DevBuf<double> chainCT_f, offCT_f, chainCT_b, offCT_b; // transposed sweep coefficients (PBiCG)
+    int precondValid = -1; // preconditioner id rD belongs to (-1: none)
     DevBuf<unsigned> ticket;
     unsigned ticketBase = 0;
     DevBuf<int> devErr;
@@ -435,44 +438,50 @@ extern "C" int b200_sys_add_interface(b200_sys* s, int r, int kind, int32_t nFac
     return (int)R.ifaces.size() - 1;
 }
 
-static int upload_sweep(b200_sys* s, SweepSchedule& S, SweepDevMem& M)
+static int upload_pipe_dir(b200_sys* s, const PipeSchedule& S, const PipeSchedule::Dir& D, int dir, PipeDirMem& M)
 {
     b200_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
-    CK(ctx, M.nLanes.upload(S.warpNLanes, st));
-    CK(ctx, M.nSteps.upload(S.warpNSteps, st));
-    CK(ctx, M.W.upload(S.warpW, st));
-    CK(ctx, M.laneBase.upload(S.warpLaneBase, st));
-    std::vector<long long> cb(S.warpChainBase.begin(), S.warpChainBase.end()), ob(S.warpOffBase.begin(), S.warpOffBase.end());
-    CK(ctx, M.chainBase.upload(cb, st));
-    CK(ctx, M.offBase.upload(ob, st));
-    CK(ctx, M.laneStart.upload(S.laneStart, st));
-    CK(ctx, M.laneLen.upload(S.laneLen, st));
-    CK(ctx, M.chainFace.upload(S.chainFace, st));
-    CK(ctx, M.offFace.upload(S.offFace, st));
-    CK(ctx, M.offCol.upload(S.offCol, st));
-    CK(ctx, M.chainC.alloc(S.nChainSlots));
-    CK(ctx, M.offC.alloc(S.nOffSlots));
+    CK(ctx, M.gW.upload(D.gW, st));
+    CK(ctx, M.gCH.upload(D.gCH, st));
+    CK(ctx, M.gShflMask.upload(D.gShflMask, st));
+    std::vector<long long> to(D.gTermOff.begin(), D.gTermOff.end());
+    CK(ctx, M.gTermOff.upload(to, st));
+    CK(ctx, M.face.upload(D.face, st));
+    // stream: code parts are static, coefficient parts are packed once per solve
+    std::vector<unsigned char> stream((size_t)D.nTerms * 12, 0);
+    for (int g = 0; g < S.nGroups; g++)
+    {
+        const int W = D.gW[g], nT = S.gNT[g];
+        unsigned char* gs = stream.data() + (size_t)D.gTermOff[g] * 12;
+        for (int step = 0; step < nT; step++)
+            memcpy(gs + (size_t)step * W * 384 + (size_t)W * 256, &D.code[D.gTermOff[g] + (int64_t)step * W * 32], (size_t)W * 128);
+    }
+    CK(ctx, M.stream.upload(stream, st));
+    if (dir < 0) CK(ctx, M.order.upload(S.orderB, st));
     CK(ctx, cudaStreamSynchronize(st)); // host vectors go out of scope after return
-    M.nWarps = S.nWarps;
-    // one warp per CTA while that still fills the machine, else 4
-    M.warpsPerBlock = (S.nWarps <= (int64_t)ctx->smCount * 24) ? 1 : 4;
-    M.nBlocks = (int)((S.nWarps + M.warpsPerBlock - 1) / M.warpsPerBlock);
-    M.dev.nWarps = (int)S.nWarps;
-    M.dev.dir = S.dir;
-    M.dev.nLanes = M.nLanes.p;
-    M.dev.nSteps = M.nSteps.p;
-    M.dev.W = M.W.p;
-    M.dev.laneBase = M.laneBase.p;
-    M.dev.chainBase = M.chainBase.p;
-    M.dev.offBase = M.offBase.p;
-    M.dev.laneStart = M.laneStart.p;
-    M.dev.laneLen = M.laneLen.p;
-    M.dev.chainFace = M.chainFace.p;
-    M.dev.offFace = M.offFace.p;
-    M.dev.offCol = M.offCol.p;
-    M.dev.chainC = M.chainC.p;
-    M.dev.offC = M.offC.p;
+    const int stageBytes = (D.maxStageBytes + 127) / 128 * 128;
+    // raw ring: 4 stages (the producer warps run up to ~20 steps ahead of the consumer); prepared-record
+    // ring: kRB blocks of kNH steps of (512 + 768 W) bytes for the fast path (W <= 6).  About 90 KB per CTA
+    // for W = 3, so that two groups are co-resident per SM.
+    const int nStages = 4;
+    const int wFast = std::min(D.maxW, 6);
+    const int crecBytes = kRB * kNH * (512 + 768 * wFast);
+    M.smemBytes = 256 + nStages * stageBytes + crecBytes;
+    M.dev.nGroups = S.nGroups;
+    M.dev.dir = dir;
+    M.dev.nStages = nStages;
+    M.dev.stageBytes = stageBytes;
+    M.dev.gBase = s->gBase.p;
+    M.dev.gNT = s->gNT.p;
+    M.dev.gW = M.gW.p;
+    M.dev.gCH = M.gCH.p;
+    M.dev.gShflMask = M.gShflMask.p;
+    M.dev.gTermOff = M.gTermOff.p;
+    M.dev.order = dir < 0 ? M.order.p : nullptr;
+    M.dev.stream = M.stream.p;
+    M.dev.face = M.face.p;
+    M.packedFor = -1;
     return B200_OK;
 }
 
@@ -499,20 +508,28 @@ extern "C" int b200_sys_finalize(b200_sys* s)
         g.build(s->regs);
         s->N = g.N;
         s->F = g.F;
+        PipeSchedule S;
+        S.build(g, s->regs);
+        s->nSlots = S.nSlots;
+        s->nGroups = S.nGroups;
+        CK(ctx, s->slotOfCell.upload(S.slotOfCell, st));
+        CK(ctx, s->cellOfSlot.upload(S.cellOfSlot, st));
+        CK(ctx, s->gBase.upload(S.gBase, st));
+        CK(ctx, s->gNT.upload(S.gNT, st));
         {
             SellLayout sell;
-            sell.build(g);
+            sell.build(g, S);
             s->nSlices = sell.nSlices;
-            s->nSlots = sell.nSlots;
+            s->nEntries = sell.nEntries;
             CK(ctx, s->sliceOff.upload(sell.sliceOff, st));
             CK(ctx, s->sellCol.upload(sell.col, st));
             CK(ctx, s->sellSrc.upload(sell.src, st));
-            CK(ctx, s->sellVal.alloc(sell.nSlots));
+            CK(ctx, s->sellVal.alloc(sell.nEntries));
             CK(ctx, cudaStreamSynchronize(st));
         }
         {
             IfacePlan P;
-            P.build(s->regs, ctx->rank, s->N);
+            P.build(s->regs, ctx->rank, S);
             s->nTouched = (int)P.rows.size();
             s->nIfCoefs = P.nCoefs;
             s->peers = P.peers;
@@ -535,29 +552,35 @@ extern "C" int b200_sys_finalize(b200_sys* s)
             CK(ctx, cudaMemsetAsync(s->ifCoefInt.p, 0, (P.nCoefs ? P.nCoefs : 1) * sizeof(double), st));
             CK(ctx, cudaStreamSynchronize(st));
         }
-        {
-            SweepSchedule S;
-            S.build(g, +1);
-            int rc = upload_sweep(s, S, s->fwd);
-            if (rc) return rc;
-        }
-        {
-            SweepSchedule S;
-            S.build(g, -1);
-            int rc = upload_sweep(s, S, s->bwd);
-            if (rc) return rc;
-        }
+        int rc = upload_pipe_dir(s, S, S.fwd, +1, s->fwd);
+        if (rc) return rc;
+        rc = upload_pipe_dir(s, S, S.bwd, -1, s->bwd);
+        if (rc) return rc;
     }
     catch (const std::exception& e)
     {
         return set_err(ctx, B200_EINVAL, "b200_sys_finalize: %s", e.what());
     }
     // matrix + vectors + scalars
-    CK(ctx, s->diag.alloc(s->N));
+    CK(ctx, s->diag.alloc(s->nSlots));
+    CK(ctx, cudaMemsetAsync(s->diag.p, 0, std::max<size_t>(1, s->nSlots) * sizeof(double), st));
     CK(ctx, s->coef.alloc(2 * s->F));
-    CK(ctx, s->rD.alloc(s->N));
-    CK(ctx, s->rDraw.alloc(s->N));
-    for (int v = 0; v < V_COUNT; v++) CK(ctx, s->vec[v].alloc(s->N));
+    CK(ctx, s->rD.alloc(s->nSlots));
+    CK(ctx, s->rDraw.alloc(s->nSlots));
+    CK(ctx, s->stageCell.alloc(s->N));
+    CK(ctx, s->diagCell.alloc(s->N));
+    for (int v = 0; v < V_COUNT; v++)
+    {
+        CK(ctx, s->vec[v].alloc(s->nSlots));
+        CK(ctx, cudaMemsetAsync(s->vec[v].p, 0, std::max<size_t>(1, s->nSlots) * sizeof(double), st));
+    }
+    {
+        const int maxSmem = std::max(s->fwd.smemBytes, s->bwd.smemBytes);
+        if (maxSmem > 227 * 1024) return set_err(ctx, B200_EUNSUPPORTED, "sweep stage needs %d bytes of shared memory", maxSmem);
+        CK(ctx, cudaFuncSetAttribute(k_sweep<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        CK(ctx, cudaFuncSetAttribute(k_sweep<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        CK(ctx, cudaFuncSetAttribute(k_sweep<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+    }
     CK(ctx, s->sc.alloc(1));
     CK(ctx, cudaMemsetAsync(s->sc.p, 0, sizeof(DevScalars), st));
     CK(ctx, s->ticket.alloc(1));
@@ -569,7 +592,7 @@ extern "C" int b200_sys_finalize(b200_sys* s)
     // launch geometry: persistent-style grids sized in multiples of the SM count
     const int sm = ctx->smCount;
     auto cdiv = [](int64_t a, int64_t b) { return (a + b - 1) / b; };
-    s->vecBlocks = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(s->N, 256 * 2), (int64_t)sm * 8));
+    s->vecBlocks = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(s->nSlots, 256 * 2), (int64_t)sm * 8));
     s->amulBlocks = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(s->nSlices, 8), (int64_t)sm * 16));
     s->ifaceBlocks = (int)cdiv(s->nTouched, 128);
     s->pstride = std::max(s->vecBlocks, s->amulBlocks + s->ifaceBlocks) + 32;
@@ -610,7 +633,8 @@ extern "C" int b200_sys_set_coeffs(b200_sys* s, int r, const double* diag, const
     CK(ctx, cudaSetDevice(ctx->device));
     const RegionHost& R = s->regs[r];
     cudaStream_t st = ctx->stream;
-    if (R.nCells) CK(ctx, cudaMemcpyAsync(s->diag.p + R.cellOffset, diag, sizeof(double) * R.nCells, cudaMemcpyHostToDevice, st));
+    if (R.nCells) CK(ctx, cudaMemcpyAsync(s->diagCell.p + R.cellOffset, diag, sizeof(double) * R.nCells, cudaMemcpyHostToDevice, st));
+    s->diagDirty = true; // permuted to slot order once all regions are in (ensure_sell)
     if (R.nFaces)
     {
         CK(ctx, cudaMemcpyAsync(s->coef.p + R.faceOffset, upper, sizeof(double) * R.nFaces, cudaMemcpyHostToDevice, st));
@@ -621,7 +645,7 @@ extern "C" int b200_sys_set_coeffs(b200_sys* s, int r, const double* diag, const
     s->regionHasCoeffs[r] = 1;
     s->sellDirty = s->sellTDirty = true;
     s->precondValid = -1;
-    s->precondTransposedValid = false;
+    s->fwd.packedFor = s->bwd.packedFor = -1;
     return B200_OK;
 }
 
@@ -650,18 +674,24 @@ static int ensure_sell(b200_sys* s, bool transpose)
     for (size_t r = 0; r < s->regs.size(); r++)
         if (!s->regionHasCoeffs[r]) return set_err(ctx, B200_ESTATE, "region %zu has no coefficients", r);
     if (s->nSlots == 0) return B200_OK;
-    const int blocks = (int)std::min<int64_t>((s->nSlots + 255) / 256, (int64_t)ctx->smCount * 16);
+    if (s->diagDirty)
+    {
+        KScope k(s, B200_K_PACK);
+        k_to_slots<<<s->vecBlocks, 256, 0, ctx->stream>>>((size_t)s->nSlots, s->cellOfSlot.p, s->diagCell.p, s->diag.p);
+        s->diagDirty = false;
+    }
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((s->nEntries + 255) / 256, (int64_t)ctx->smCount * 16));
     if (!transpose && s->sellDirty)
     {
         KScope k(s, B200_K_PACK);
-        k_pack_sell<<<blocks, 256, 0, ctx->stream>>>((size_t)s->nSlots, s->sellSrc.p, s->coef.p, s->sellVal.p, 0);
+        k_pack_sell<<<blocks, 256, 0, ctx->stream>>>((size_t)s->nEntries, s->sellSrc.p, s->coef.p, s->sellVal.p, 0);
         s->sellDirty = false;
     }
     if (transpose && s->sellTDirty)
     {
-        if (s->sellValT.n != (size_t)s->nSlots) CK(ctx, s->sellValT.alloc(s->nSlots));
+        if (s->sellValT.n != (size_t)s->nEntries) CK(ctx, s->sellValT.alloc(s->nEntries));
         KScope k(s, B200_K_PACK);
-        k_pack_sell<<<blocks, 256, 0, ctx->stream>>>((size_t)s->nSlots, s->sellSrc.p, s->coef.p, s->sellValT.p, (int)s->F);
+        k_pack_sell<<<blocks, 256, 0, ctx->stream>>>((size_t)s->nEntries, s->sellSrc.p, s->coef.p, s->sellValT.p, (int)s->F);
         s->sellTDirty = false;
     }
     CK(ctx, cudaGetLastError());
@@ -722,18 +752,18 @@ static int launch_amul(b200_sys* s, const double* x, double* y, int nd, const do
         }
         NK(ctx, g_nccl.GroupEnd());
     }
-    if (s->N > 0)
+    if (s->nSlots > 0)
     {
         KScope k(s, B200_K_AMUL);
         const unsigned* mask = s->nTouched ? s->ifaceMask.p : nullptr;
         if (nd == 0)
-            k_amul<0><<<s->amulBlocks, 256, 0, st>>>((int)s->N, (int)s->nSlices, s->diag.p, s->sliceOff.p, s->sellCol.p, val, x, y,
+            k_amul<0><<<s->amulBlocks, 256, 0, st>>>((int)s->nSlots, (int)s->nSlices, s->diag.p, s->sliceOff.p, s->sellCol.p, val, x, y,
                                                      nullptr, mask, s->partials.p, s->pstride, s->sc.p, force);
         else if (nd == 1)
-            k_amul<1><<<s->amulBlocks, 256, 0, st>>>((int)s->N, (int)s->nSlices, s->diag.p, s->sliceOff.p, s->sellCol.p, val, x, y,
+            k_amul<1><<<s->amulBlocks, 256, 0, st>>>((int)s->nSlots, (int)s->nSlices, s->diag.p, s->sliceOff.p, s->sellCol.p, val, x, y,
                                                      d0, mask, s->partials.p, s->pstride, s->sc.p, force);
         else
-            k_amul<2><<<s->amulBlocks, 256, 0, st>>>((int)s->N, (int)s->nSlices, s->diag.p, s->sliceOff.p, s->sellCol.p, val, x, y,
+            k_amul<2><<<s->amulBlocks, 256, 0, st>>>((int)s->nSlots, (int)s->nSlices, s->diag.p, s->sliceOff.p, s->sellCol.p, val, x, y,
                                                      d0, mask, s->partials.p, s->pstride, s->sc.p, force);
     }
     if (s->nTouched > 0)
@@ -752,45 +782,58 @@ static int launch_amul(b200_sys* s, const double* x, double* y, int nd, const do
     }
     CK(ctx, cudaGetLastError());
     if (cntOut)
-        for (int k = 0; k < kMaxDots; k++) cntOut->n[k] = (s->N > 0 ? s->amulBlocks : 0) + s->ifaceBlocks;
+        for (int k = 0; k < kMaxDots; k++) cntOut->n[k] = (s->nSlots > 0 ? s->amulBlocks : 0) + s->ifaceBlocks;
     return B200_OK;
 }
 
 template <int MODE>
-static int launch_sweep(b200_sys* s, SweepDevMem& M, const double* a, const double* b, double* out, int force)
+static int launch_sweep(b200_sys* s, PipeDirMem& M, const double* a, const double* b, double* out, int force)
 {
     b200_ctx* ctx = s->ctx;
-    if (M.nWarps == 0) return B200_OK;
+    if (s->nGroups == 0) return B200_OK;
     KScope k(s, M.dev.dir > 0 ? B200_K_SWEEP_FWD : B200_K_SWEEP_BWD);
-    k_sweep<MODE><<<M.nBlocks, 32 * M.warpsPerBlock, 0, ctx->stream>>>(M.dev, a, b, out, s->ticket.p, s->ticketBase, s->devErr.p,
-                                                                      s->sc.p, force);
-    s->ticketBase += (unsigned)M.nBlocks;
+    k_sweep<MODE><<<s->nGroups, kSweepThreads, M.smemBytes, ctx->stream>>>(M.dev, a, b, out, s->ticket.p, s->ticketBase, s->devErr.p, s->sc.p,
+                                                                          force);
+    s->ticketBase += (unsigned)s->nGroups;
     CK(ctx, cudaGetLastError());
     return B200_OK;
 }
 
 static int fill_sentinel(b200_sys* s, double* a, double* b, int force)
 {
-    if (s->N == 0) return B200_OK;
+    if (s->nSlots == 0) return B200_OK;
     KScope k(s, B200_K_VECTOR);
-    k_fill2_sentinel<<<s->vecBlocks, 256, 0, s->ctx->stream>>>((size_t)s->N, a, b, s->sc.p, force);
+    k_fill2_sentinel<<<s->vecBlocks, 256, 0, s->ctx->stream>>>((size_t)s->nSlots, a, b, s->sc.p, force);
+    CK(s->ctx, cudaGetLastError());
+    return B200_OK;
+}
+
+static int pack_stream(b200_sys* s, PipeDirMem& M, const double* c1, const double* c2, const double* rD, int prodMode)
+{
+    if (s->nGroups == 0) return B200_OK;
+    KScope k(s, B200_K_PACK);
+    k_pack_stream<<<s->nGroups, 256, 0, s->ctx->stream>>>(M.dev, c1, c2, rD, prodMode);
     CK(s->ctx, cudaGetLastError());
     return B200_OK;
 }
 
 // Preconditioner construction: calcReciprocalD as a forward sweep in division mode, then the
-// pre-multiplied sweep coefficients rD[row]*lower[f] / rD[row]*upper[f].
+// pre-multiplied sweep coefficients rD[row]*lower[f] / rD[row]*upper[f] packed into the streams.
 static int ensure_precond(b200_sys* s, int precond, bool transposed)
 {
     b200_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
     if (precond == B200_PRECOND_NONE) return B200_OK;
-    if (s->precondValid == precond && (!transposed || s->precondTransposedValid)) return B200_OK;
-    if (s->N == 0)
+    const int want = transposed ? 1 : 0;
+    const bool sweeps = precond >= B200_PRECOND_DIC;
+    if (s->precondValid == precond && (!sweeps || (s->fwd.packedFor == want && s->bwd.packedFor == want))) return B200_OK;
+    if (s->nSlots == 0)
     {
         s->precondValid = precond;
         return B200_OK;
     }
+    int rc;
+    if ((rc = ensure_sell(s, false))) return rc; // diag in slot order
     const double* cU = s->coef.p;
     const double* cL = (precond == B200_PRECOND_DIC) ? s->coef.p : s->coef.p + s->F; // DIC uses upper both ways
     if (s->precondValid != precond)
@@ -798,55 +841,27 @@ static int ensure_precond(b200_sys* s, int precond, bool transposed)
         if (precond == B200_PRECOND_DIAGONAL)
         {
             KScope k(s, B200_K_VECTOR);
-            k_invert<<<s->vecBlocks, 256, 0, st>>>((size_t)s->N, s->diag.p, s->rD.p);
+            k_invert<<<s->vecBlocks, 256, 0, st>>>((size_t)s->nSlots, s->diag.p, s->rD.p, s->cellOfSlot.p);
         }
         else
         {
-            {
-                KScope k(s, B200_K_PACK);
-                k_pack_sweep<<<(unsigned)s->fwd.nWarps, 256, 0, st>>>(s->fwd.dev, cU, cL, nullptr, 1);
-            }
-            int rc = fill_sentinel(s, s->rDraw.p, nullptr, 1);
-            if (rc) return rc;
-            rc = launch_sweep<2>(s, s->fwd, s->diag.p, nullptr, s->rDraw.p, 1);
-            if (rc) return rc;
+            if ((rc = pack_stream(s, s->fwd, cU, cL, nullptr, 1))) return rc;
+            s->fwd.packedFor = -1;
+            if ((rc = fill_sentinel(s, s->rDraw.p, nullptr, 1))) return rc;
+            if ((rc = launch_sweep<2>(s, s->fwd, s->diag.p, nullptr, s->rDraw.p, 1))) return rc;
             {
                 KScope k(s, B200_K_VECTOR);
-                k_invert<<<s->vecBlocks, 256, 0, st>>>((size_t)s->N, s->rDraw.p, s->rD.p);
-            }
-            {
-                KScope k(s, B200_K_PACK);
-                k_pack_sweep<<<(unsigned)s->fwd.nWarps, 256, 0, st>>>(s->fwd.dev, cL, nullptr, s->rD.p, 0);
-            }
-            {
-                KScope k(s, B200_K_PACK);
-                k_pack_sweep<<<(unsigned)s->bwd.nWarps, 256, 0, st>>>(s->bwd.dev, cU, nullptr, s->rD.p, 0);
+                k_invert<<<s->vecBlocks, 256, 0, st>>>((size_t)s->nSlots, s->rDraw.p, s->rD.p, s->cellOfSlot.p);
             }
         }
         s->precondValid = precond;
-        s->precondTransposedValid = false;
     }
-    if (transposed && !s->precondTransposedValid && precond != B200_PRECOND_DIAGONAL)
+    if (sweeps && (s->fwd.packedFor != want || s->bwd.packedFor != want))
     {
-        // preconditionT: roles of upper and lower swapped (DILUPreconditioner::preconditionT)
-        if (s->chainCT_f.n != s->fwd.chainC.n) CK(ctx, s->chainCT_f.alloc(s->fwd.chainC.n));
-        if (s->offCT_f.n != s->fwd.offC.n) CK(ctx, s->offCT_f.alloc(s->fwd.offC.n));
-        if (s->chainCT_b.n != s->bwd.chainC.n) CK(ctx, s->chainCT_b.alloc(s->bwd.chainC.n));
-        if (s->offCT_b.n != s->bwd.offC.n) CK(ctx, s->offCT_b.alloc(s->bwd.offC.n));
-        SweepDev f = s->fwd.dev, b = s->bwd.dev;
-        f.chainC = s->chainCT_f.p;
-        f.offC = s->offCT_f.p;
-        b.chainC = s->chainCT_b.p;
-        b.offC = s->offCT_b.p;
-        {
-            KScope k(s, B200_K_PACK);
-            k_pack_sweep<<<(unsigned)s->fwd.nWarps, 256, 0, st>>>(f, cU, nullptr, s->rD.p, 0);
-        }
-        {
-            KScope k(s, B200_K_PACK);
-            k_pack_sweep<<<(unsigned)s->bwd.nWarps, 256, 0, st>>>(b, cL, nullptr, s->rD.p, 0);
-        }
-        s->precondTransposedValid = true;
+        // preconditionT swaps the roles of upper and lower (DILUPreconditioner::preconditionT)
+        if ((rc = pack_stream(s, s->fwd, transposed ? cU : cL, nullptr, s->rD.p, 0))) return rc;
+        if ((rc = pack_stream(s, s->bwd, transposed ? cL : cU, nullptr, s->rD.p, 0))) return rc;
+        s->fwd.packedFor = s->bwd.packedFor = want;
     }
     CK(ctx, cudaGetLastError());
     return B200_OK;
@@ -854,59 +869,36 @@ static int ensure_precond(b200_sys* s, int precond, bool transposed)
 
 // w = M^-1 r.  tmp: scratch for the forward result.  If prefilled, the caller already wrote the
 // sentinel into tmp and w (fused into the preceding vector kernel).
-static int launch_precondition(b200_sys* s, int precond, const double* r, double* w, double* tmp, bool prefilled,
-                               bool transposed, int force)
+static int launch_precondition(b200_sys* s, int precond, const double* r, double* w, double* tmp, bool prefilled, int force)
 {
     b200_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
-    if (s->N == 0) return B200_OK;
+    if (s->nSlots == 0) return B200_OK;
     if (precond == B200_PRECOND_NONE)
     {
         KScope k(s, B200_K_VECTOR);
-        k_copy<<<s->vecBlocks, 256, 0, st>>>((size_t)s->N, r, w, s->sc.p, force);
+        k_copy<<<s->vecBlocks, 256, 0, st>>>((size_t)s->nSlots, r, w, s->sc.p, force);
         CK(ctx, cudaGetLastError());
         return B200_OK;
     }
     if (precond == B200_PRECOND_DIAGONAL)
     {
         KScope k(s, B200_K_VECTOR);
-        k_mul<<<s->vecBlocks, 256, 0, st>>>((size_t)s->N, s->rD.p, r, w, s->sc.p, force);
+        k_mul<<<s->vecBlocks, 256, 0, st>>>((size_t)s->nSlots, s->rD.p, r, w, s->sc.p, force);
         CK(ctx, cudaGetLastError());
         return B200_OK;
     }
-    if (!prefilled)
-    {
-        int rc = fill_sentinel(s, tmp, w, force);
-        if (rc) return rc;
-    }
-    SweepDev fdev = s->fwd.dev, bdev = s->bwd.dev;
-    if (transposed)
-    {
-        fdev.chainC = s->chainCT_f.p;
-        fdev.offC = s->offCT_f.p;
-        bdev.chainC = s->chainCT_b.p;
-        bdev.offC = s->offCT_b.p;
-    }
-    {
-        KScope k(s, B200_K_SWEEP_FWD);
-        k_sweep<0><<<s->fwd.nBlocks, 32 * s->fwd.warpsPerBlock, 0, st>>>(fdev, s->rD.p, r, tmp, s->ticket.p, s->ticketBase,
-                                                                        s->devErr.p, s->sc.p, force);
-        s->ticketBase += (unsigned)s->fwd.nBlocks;
-    }
-    {
-        KScope k(s, B200_K_SWEEP_BWD);
-        k_sweep<1><<<s->bwd.nBlocks, 32 * s->bwd.warpsPerBlock, 0, st>>>(bdev, tmp, nullptr, w, s->ticket.p, s->ticketBase,
-                                                                        s->devErr.p, s->sc.p, force);
-        s->ticketBase += (unsigned)s->bwd.nBlocks;
-    }
-    CK(ctx, cudaGetLastError());
+    int rc;
+    if (!prefilled && (rc = fill_sentinel(s, tmp, w, force))) return rc;
+    if ((rc = launch_sweep<0>(s, s->fwd, s->rD.p, r, tmp, force))) return rc;
+    if ((rc = launch_sweep<1>(s, s->bwd, tmp, nullptr, w, force))) return rc;
     return B200_OK;
 }
 
 static PartCounts vec_counts(const b200_sys* s)
 {
     PartCounts c;
-    for (int k = 0; k < kMaxDots; k++) c.n[k] = s->N > 0 ? s->vecBlocks : 0;
+    for (int k = 0; k < kMaxDots; k++) c.n[k] = s->nSlots > 0 ? s->vecBlocks : 0;
     return c;
 }
 
@@ -919,7 +911,13 @@ static int upload_vec(b200_sys* s, int v, const double* const* h)
         const RegionHost& R = s->regs[r];
         if (!h[r] && R.nCells) return set_err(ctx, B200_EINVAL, "null host vector for region %zu", r);
         if (R.nCells)
-            CK(ctx, cudaMemcpyAsync(s->vec[v].p + R.cellOffset, h[r], sizeof(double) * R.nCells, cudaMemcpyHostToDevice, ctx->stream));
+            CK(ctx, cudaMemcpyAsync(s->stageCell.p + R.cellOffset, h[r], sizeof(double) * R.nCells, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (s->nSlots)
+    {
+        KScope k(s, B200_K_PACK);
+        k_to_slots<<<s->vecBlocks, 256, 0, ctx->stream>>>((size_t)s->nSlots, s->cellOfSlot.p, s->stageCell.p, s->vec[v].p);
+        CK(ctx, cudaGetLastError());
     }
     return B200_OK;
 }
@@ -927,12 +925,18 @@ static int upload_vec(b200_sys* s, int v, const double* const* h)
 static int download_vec(b200_sys* s, const double* dev, double* const* h)
 {
     b200_ctx* ctx = s->ctx;
+    if (s->N)
+    {
+        KScope k(s, B200_K_PACK);
+        k_from_slots<<<s->vecBlocks, 256, 0, ctx->stream>>>((size_t)s->N, s->slotOfCell.p, dev, s->stageCell.p);
+        CK(ctx, cudaGetLastError());
+    }
     for (size_t r = 0; r < s->regs.size(); r++)
     {
         const RegionHost& R = s->regs[r];
         if (!h[r] && R.nCells) return set_err(ctx, B200_EINVAL, "null host vector for region %zu", r);
         if (R.nCells)
-            CK(ctx, cudaMemcpyAsync(h[r], dev + R.cellOffset, sizeof(double) * R.nCells, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(ctx, cudaMemcpyAsync(h[r], s->stageCell.p + R.cellOffset, sizeof(double) * R.nCells, cudaMemcpyDeviceToHost, ctx->stream));
     }
     return B200_OK;
 }
@@ -976,8 +980,8 @@ extern "C" int b200_x_save(b200_sys* s)
 {
     if (!s || !s->finalized) return s ? set_err(s->ctx, B200_ESTATE, "x_save before finalize") : B200_EINVAL;
     CK(s->ctx, cudaSetDevice(s->ctx->device));
-    if (s->x0.n != (size_t)s->N) CK(s->ctx, s->x0.alloc(s->N));
-    if (s->N) CK(s->ctx, cudaMemcpyAsync(s->x0.p, s->vec[V_X].p, sizeof(double) * s->N, cudaMemcpyDeviceToDevice, s->ctx->stream));
+    if (s->x0.n != (size_t)s->nSlots) CK(s->ctx, s->x0.alloc(s->nSlots));
+    if (s->nSlots) CK(s->ctx, cudaMemcpyAsync(s->x0.p, s->vec[V_X].p, sizeof(double) * s->nSlots, cudaMemcpyDeviceToDevice, s->ctx->stream));
     s->x0Valid = true;
     return B200_OK;
 }
@@ -987,7 +991,7 @@ extern "C" int b200_x_restore(b200_sys* s)
     if (!s || !s->finalized) return s ? set_err(s->ctx, B200_ESTATE, "x_restore before finalize") : B200_EINVAL;
     if (!s->x0Valid) return set_err(s->ctx, B200_ESTATE, "x_restore without x_save");
     CK(s->ctx, cudaSetDevice(s->ctx->device));
-    if (s->N) CK(s->ctx, cudaMemcpyAsync(s->vec[V_X].p, s->x0.p, sizeof(double) * s->N, cudaMemcpyDeviceToDevice, s->ctx->stream));
+    if (s->nSlots) CK(s->ctx, cudaMemcpyAsync(s->vec[V_X].p, s->x0.p, sizeof(double) * s->nSlots, cudaMemcpyDeviceToDevice, s->ctx->stream));
     return B200_OK;
 }
 
@@ -1031,7 +1035,7 @@ static int solve_head(b200_sys* s, int op, double* Ax, double* r, double* rw, do
     b200_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
     int rc;
-    const size_t n = (size_t)s->N;
+    const size_t n = (size_t)s->nSlots;
     if ((rc = launch_amul(s, s->vec[V_X].p, Ax, 0, nullptr, false, 1, nullptr))) return rc;
     // xRef = gAverage(x); tmp = A * xRef (coupledIterativeSolver::normFactor)
     if (n)
@@ -1081,7 +1085,7 @@ static int solve_bicgstab(b200_sys* s, const b200_solver_opts* o)
 {
     b200_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
-    const size_t n = (size_t)s->N;
+    const size_t n = (size_t)s->nSlots;
     double *x = s->vec[V_X].p, *r = s->vec[V_R].p, *rw = s->vec[V_RW].p, *p = s->vec[V_P].p, *ph = s->vec[V_PH].p;
     double *v = s->vec[V_V].p, *sv = s->vec[V_S].p, *sh = s->vec[V_SH].p, *t = s->vec[V_T].p, *tmp = s->vec[V_TMP2].p;
     int rc;
@@ -1105,7 +1109,7 @@ static int solve_bicgstab(b200_sys* s, const b200_solver_opts* o)
             k_bicg_p<<<s->vecBlocks, 256, 0, st>>>(n, r, p, v, rw, sweeps ? tmp : nullptr, sweeps ? ph : nullptr, s->partials.p,
                                                    s->pstride, s->sc.p);
         }
-        if ((rc = launch_precondition(s, o->precond, p, ph, tmp, true, false, 0))) return rc;
+        if ((rc = launch_precondition(s, o->precond, p, ph, tmp, true, 0))) return rc;
         if ((rc = launch_amul(s, ph, v, 1, rw, false, 0, &cnt))) return rc;
         cnt.n[1] = n ? s->vecBlocks : 0; // quantity 1 = (r, r) from k_bicg_p
         if ((rc = reduce_finish(s, cnt, 2, OP_BICG_ALPHA, 0))) return rc;
@@ -1114,7 +1118,7 @@ static int solve_bicgstab(b200_sys* s, const b200_solver_opts* o)
             KScope k(s, B200_K_VECTOR);
             k_bicg_s<<<s->vecBlocks, 256, 0, st>>>(n, r, v, sv, sweeps ? tmp : nullptr, sweeps ? sh : nullptr, s->sc.p);
         }
-        if ((rc = launch_precondition(s, o->precond, sv, sh, tmp, true, false, 0))) return rc;
+        if ((rc = launch_precondition(s, o->precond, sv, sh, tmp, true, 0))) return rc;
         if ((rc = launch_amul(s, sh, t, 2, sv, false, 0, &cnt))) return rc;
         if ((rc = reduce_finish(s, cnt, 2, OP_BICG_OMEGA, 0))) return rc;
         if (n)
@@ -1133,7 +1137,7 @@ static int solve_pcg(b200_sys* s, const b200_solver_opts* o)
 {
     b200_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
-    const size_t n = (size_t)s->N;
+    const size_t n = (size_t)s->nSlots;
     double *x = s->vec[V_X].p, *rA = s->vec[V_R].p, *pA = s->vec[V_P].p, *wA = s->vec[V_V].p, *z = s->vec[V_PH].p;
     double* tmp = s->vec[V_TMP2].p;
     int rc;
@@ -1146,7 +1150,7 @@ static int solve_pcg(b200_sys* s, const b200_solver_opts* o)
     {
         if (*(volatile int*)&s->hostFlags[0]) break;
         if ((rc = throttle_wait(s, it))) return rc;
-        if ((rc = launch_precondition(s, o->precond, rA, z, tmp, true, false, 0))) return rc; // wA = M^-1 rA
+        if ((rc = launch_precondition(s, o->precond, rA, z, tmp, true, 0))) return rc; // wA = M^-1 rA
         if (n)
         {
             KScope k(s, B200_K_VECTOR);
@@ -1188,7 +1192,6 @@ extern "C" int b200_solve_resident(b200_sys* s, const b200_solver_opts* o, b200_
     if (rc) return rc;
     // like the reference, every solve constructs its preconditioner from the current coefficients
     s->precondValid = -1;
-    s->precondTransposedValid = false;
     if ((rc = upload_scalars(s, o, history ? historyCap : 0))) return rc;
     CK(ctx, cudaEventRecord(s->evSolveA, ctx->stream));
     rc = (o->solver == B200_SOLVER_PCG) ? solve_pcg(s, o) : solve_bicgstab(s, o);
@@ -1256,7 +1259,7 @@ extern "C" int b200_precondition(b200_sys* s, int precond, const double* const* 
         if (!s->regionHasCoeffs[q]) return set_err(s->ctx, B200_ESTATE, "region %zu has no coefficients", q);
     if ((rc = upload_vec(s, V_S, r))) return rc;
     if ((rc = ensure_precond(s, precond, transpose != 0))) return rc;
-    if ((rc = launch_precondition(s, precond, s->vec[V_S].p, s->vec[V_SH].p, s->vec[V_TMP2].p, false, transpose != 0, 1))) return rc;
+    if ((rc = launch_precondition(s, precond, s->vec[V_S].p, s->vec[V_SH].p, s->vec[V_TMP2].p, false, 1))) return rc;
     if ((rc = download_vec(s, s->vec[V_SH].p, w))) return rc;
     CK(s->ctx, cudaStreamSynchronize(s->ctx->stream));
     if (s->profiling) harvest_events(s);
@@ -1285,10 +1288,10 @@ extern "C" int b200_reduce(b200_sys* s, const double* const* a, const double* co
     int rc;
     if ((rc = upload_vec(s, V_S, a))) return rc;
     if ((rc = upload_vec(s, V_SH, b))) return rc;
-    if (s->N)
+    if (s->nSlots)
     {
         KScope k(s, B200_K_VECTOR);
-        k_dot_mag<<<s->vecBlocks, 256, 0, ctx->stream>>>((size_t)s->N, s->vec[V_S].p, s->vec[V_SH].p, s->partials.p, s->pstride);
+        k_dot_mag<<<s->vecBlocks, 256, 0, ctx->stream>>>((size_t)s->nSlots, s->vec[V_S].p, s->vec[V_SH].p, s->partials.p, s->pstride);
     }
     if ((rc = reduce_finish(s, vec_counts(s), 2, OP_STORE_RED, 1))) return rc;
     DevScalars h;

@@ -6,6 +6,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "schedule.hpp" // term codes (kCodeNone / kCodeOwn / kCodeShfl)
+
 namespace b200
 {
 
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(256) k_amul(int nRows, int nSlices, const doub
     for (int k = 0; k < (ND > 0 ? ND : 1); k++) dots[k] = 0.0;
     for (int s = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); s < nSlices; s += gridDim.x * warpsPerBlock)
     {
-        const int row = s * 32 + lane;
+        const int row = s * 32 + lane; // slot; padding slots have diag 0 and no entries
         const int o0 = sliceOff[s], o1 = sliceOff[s + 1];
         const size_t base = (size_t)o0 * 32 + lane;
         const int width = o1 - o0;
@@ -387,207 +389,556 @@ __global__ void k_pack_sell(size_t nSlots, const int* __restrict__ src, const do
 }
 
 // ------------------------------------------------------------------------------ sweeps
-struct SweepDev
+// Pipelined DIC/DILU sweeps over the slot-ordered system (see schedule.hpp).  One warp per group.
+// The per-step records (pre-multiplied coefficients + term codes) and the input vectors are
+// streamed into a shared-memory ring by bulk asynchronous copies (TMA, cp.async.bulk + mbarrier);
+// in-warp dependencies travel through one warp shuffle per time step, the own-lane dependency
+// stays in a register, dependencies on other warps are read from the output vector, which
+// doubles as its own ready flag (sentinel until written), and are prefetched kPF steps ahead.
+struct PipeDev
 {
-    int nWarps;
-    int dir;
-    const int* nLanes;
-    const int* nSteps;
-    const int* W;
-    const int* laneBase;
-    const long long* chainBase;
-    const long long* offBase;
-    const int* laneStart;
-    const int* laneLen;
-    const int* chainFace;
-    const int* offFace;
-    const int* offCol;
-    double* chainC; // packed coefficients (mode specific)
-    double* offC;
+    int nGroups;
+    int dir;      // +1 forward, -1 backward (time reversed)
+    int nStages;  // shared-memory ring stages
+    int stageBytes;
+    const int* gBase;
+    const int* gNT;
+    const int* gW;
+    const int* gCH;
+    const int* gShflMask; // bit 31: group must take the generic single-warp path
+    const long long* gTermOff;
+    const int* order; // ticket -> group (nullptr: identity)
+    unsigned char* stream; // group g: 12*gTermOff[g]; step record = coef[W][32] f64 | code[W][32] i32
+    const int* face;       // [nTerms] face of each term (pack time)
 };
 
-// MODE 0: forward  : acc = a[row]*b[row];  acc -= c * w[nbr]      (a = rD, b = rA,  c = rD[row]*lower[f])
-// MODE 1: backward : acc = a[row];         acc -= c * w[nbr]      (a = forward result, c = rD[row]*upper[f])
-// MODE 2: calcReciprocalD: acc = a[row];   acc -= c / w[nbr]      (a = diag,        c = upper[f]*lower[f])
+constexpr int kPF = 4; // prefetch distance (time steps) of cross-warp values
+
+// MODE 0: forward  : acc = a[slot]*b[slot]; acc -= c * w[nbr]   (a = rD, b = rA, c = rD[row]*lower[f])
+// MODE 1: backward : acc = a[slot];         acc -= c * w[nbr]   (a = forward result, c = rD[row]*upper[f])
+// MODE 2: calcReciprocalD: acc = a[slot];   acc -= c / w[nbr]   (a = diag, c = upper[f]*lower[f])
 template <int MODE>
 __device__ __forceinline__ double sweep_apply(double acc, double c, double v)
 {
     return MODE == 2 ? acc - c / v : acc - c * v;
 }
 
+__device__ __forceinline__ double ld_relaxed(const double* p)
+{
+    double v;
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(double* p, double v)
+{
+    asm volatile("st.global.cg.f64 [%0], %1;" ::"l"(p), "d"(v));
+}
+
 __device__ __noinline__ double sweep_spin(const double* p, int* err)
 {
-    unsigned ns = 20;
-    for (long long tries = 0; tries < (1ll << 22); tries++)
+    for (long long tries = 0; tries < (1ll << 24); tries++)
     {
-        const double v = ld_volatile(p);
+        const double v = ld_relaxed(p);
         if (!is_sentinel(v)) return v;
-        __nanosleep(ns);
-        if (ns < 200) ns += ns;
-        if ((tries & 1023) == 1023 && *(volatile int*)err) break;
+        if (tries > 64) __nanosleep(tries > 4096 ? 400 : 40);
+        if ((tries & 4095) == 4095 && *(volatile int*)err) break;
     }
     atomicExch(err, 1);
-    return ld_volatile(p);
+    return ld_relaxed(p);
 }
 
-template <int MODE, int WMAX, int D>
-__device__ __forceinline__ void sweep_warp_fast(const SweepDev& S, int w, int lane, const double* __restrict__ a,
-                                                const double* __restrict__ b, double* out, int* err)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
 {
-    const int nl = S.nLanes[w], nSteps = S.nSteps[w], W = S.W[w];
-    const bool act = lane < nl;
-    const int start = act ? S.laneStart[S.laneBase[w] + lane] : 0;
-    const int len = act ? S.laneLen[S.laneBase[w] + lane] : 0;
-    const long long cb = S.chainBase[w] + lane, ob = S.offBase[w] + lane;
-    const int dir = S.dir;
-    const double* __restrict__ chainC = S.chainC;
-    const double* __restrict__ offC = S.offC;
-    const int* __restrict__ offCol = S.offCol;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    unsigned ok = 0;
+    while (!ok)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+}
 
-    double rc[D], ra[D], rb[D], roc[D][WMAX], rv[D][WMAX];
-    int rcol[D][WMAX];
+// Shared set-up of one group's shared-memory ring.
+struct SweepRing
+{
+    int W, CHg, nT, base, nChunks, recBytes, schedBytes, NS, dir, stageBytes;
+    unsigned shflMask, vecBytes, chunkBytes;
+    unsigned long long* bars;
+    unsigned char* stages;
+    const unsigned char* gstream;
+};
 
-#define B200_LOAD_STEP(d, sArg)                                                        \
-    {                                                                                  \
-        const int s_ = (sArg);                                                         \
-        if (s_ < len)                                                                  \
-        {                                                                              \
-            const int row_ = start + dir * s_;                                         \
-            rc[d] = chainC[cb + (long long)s_ * nl];                                   \
-            ra[d] = a[row_];                                                           \
-            if (MODE == 0) rb[d] = b[row_];                                            \
-            _Pragma("unroll") for (int j = 0; j < WMAX; j++)                           \
-            {                                                                          \
-                rcol[d][j] = -1;                                                       \
-                if (j < W)                                                             \
-                {                                                                      \
-                    const long long idx_ = ob + ((long long)s_ * W + j) * nl;          \
-                    rcol[d][j] = offCol[idx_];                                         \
-                    roc[d][j] = offC[idx_];                                            \
-                }                                                                      \
-            }                                                                          \
-            _Pragma("unroll") for (int j = 0; j < WMAX; j++)                           \
-            {                                                                          \
-                if (rcol[d][j] >= 0) rv[d][j] = ld_volatile(out + rcol[d][j]);         \
-            }                                                                          \
-        }                                                                              \
-    }
+template <int MODE>
+__device__ __forceinline__ void ring_issue(const SweepRing& R, const double* a, const double* b, int c, int st)
+{
+    unsigned char* dst = R.stages + (size_t)st * R.stageBytes;
+    mbar_expect_tx(&R.bars[st], R.chunkBytes);
+    bulk_g2s(dst, R.gstream + (size_t)c * R.schedBytes, (unsigned)R.schedBytes, &R.bars[st]);
+    const long long s0 =
+        R.dir > 0 ? ((long long)R.base + (long long)c * R.CHg) * 32 : ((long long)R.base + R.nT - (long long)(c + 1) * R.CHg) * 32;
+    bulk_g2s(dst + R.schedBytes, a + s0, R.vecBytes, &R.bars[st]);
+    if (MODE == 0) bulk_g2s(dst + R.schedBytes + R.vecBytes, b + s0, R.vecBytes, &R.bars[st]);
+}
 
-#pragma unroll
-    for (int d = 0; d < D; d++) B200_LOAD_STEP(d, d);
-
-    double prev = 0.0;
-    for (int s0 = 0; s0 < nSteps; s0 += D)
+template <int MODE>
+__device__ __forceinline__ SweepRing ring_setup(const PipeDev& S, int g, int lane, const double* a, const double* b, unsigned char* smem)
+{
+    SweepRing R;
+    R.W = S.gW[g];
+    R.CHg = S.gCH[g];
+    R.nT = S.gNT[g];
+    R.base = S.gBase[g];
+    R.shflMask = (unsigned)S.gShflMask[g] & 0x7fffffffu;
+    R.nChunks = R.nT / R.CHg;
+    R.recBytes = R.W * 384;
+    R.schedBytes = R.CHg * R.recBytes;
+    R.NS = S.nStages;
+    R.dir = S.dir;
+    R.stageBytes = S.stageBytes;
+    R.bars = reinterpret_cast<unsigned long long*>(smem);
+    R.stages = smem + 128;
+    R.gstream = S.stream + 12ll * S.gTermOff[g];
+    R.vecBytes = (unsigned)(R.CHg * 256);
+    R.chunkBytes = (unsigned)R.schedBytes + R.vecBytes * (MODE == 0 ? 2u : 1u);
+    if (lane == 0)
     {
-#pragma unroll
-        for (int d = 0; d < D; d++)
+        for (int st = 0; st < R.NS; st++) mbar_init(&R.bars[st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int c = 0; c < R.NS && c < R.nChunks; c++) ring_issue<MODE>(R, a, b, c, c);
+    }
+    __syncwarp();
+    mbar_wait(&R.bars[0], 0u);
+    return R;
+}
+
+// Fast path (W = 1..6 terms per row): warp-specialised CTA.  A lone warp issues one instruction
+// every ~5 cycles, so the serial recurrence must execute as few instructions per time step as
+// possible.  kNH producer warps therefore PREPARE the steps (producer h takes step 4b+h of block b):
+// they read the streamed record, fetch and verify the cross-warp values (prefetched one block
+// ahead), apply -- in reference order -- the leading terms that do not depend on this group's previous
+// step, and write a compact record {acc0, (coef, source lane) per remaining term} into a second
+// shared-memory ring.  The consumer warp (warp 0) runs only the recurrence:
+//     per remaining term:  v = shfl(prev, source lane);  acc -= coef * v      then one store.
+// Terms a lane has already applied appear as padding (coef 0, source = own lane): exact no-ops.
+// Steps in which a remaining term needs a cross-warp value (block seams) take a slower select path.
+constexpr int kNH = 4; // producer warps = steps per block
+constexpr int kRB = 3; // blocks in the prepared-record ring
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int MODE, int W>
+__device__ __forceinline__ void sweep_group_fast(const PipeDev& S, const int g, const int warp, const int lane,
+                                                 const double* __restrict__ a, const double* __restrict__ b, double* out, int* err,
+                                                 unsigned char* smem)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    // ---- shared memory: [0,128) raw-stage barriers | [128,256) crec full/empty barriers | raw ring | crec ring
+    unsigned long long* rawBar = reinterpret_cast<unsigned long long*>(smem);
+    unsigned long long* crecFull = reinterpret_cast<unsigned long long*>(smem + 128);
+    unsigned long long* crecEmpty = crecFull + kRB;
+    SweepRing R;
+    R.W = W;
+    R.CHg = S.gCH[g];
+    R.nT = S.gNT[g];
+    R.base = S.gBase[g];
+    R.shflMask = 0;
+    R.nChunks = R.nT / R.CHg;
+    R.recBytes = W * 384;
+    R.schedBytes = R.CHg * R.recBytes;
+    R.NS = S.nStages;
+    R.dir = S.dir;
+    R.stageBytes = S.stageBytes;
+    R.bars = rawBar;
+    R.stages = smem + 256;
+    R.gstream = S.stream + 12ll * S.gTermOff[g];
+    R.vecBytes = (unsigned)(R.CHg * 256);
+    R.chunkBytes = (unsigned)R.schedBytes + R.vecBytes * (MODE == 0 ? 2u : 1u);
+    unsigned char* crecRing = R.stages + (size_t)R.NS * R.stageBytes;
+    constexpr int stepBytes = 512 + W * 768; // 512 (hdr) + W*512 (terms) + W*256 (const values)
+    constexpr int termOff = 512, cvalOff = 512 + W * 512;
+    const int CHg = R.CHg, nT = R.nT, NS = R.NS, dir = R.dir;
+    const int nBlocks = nT / kNH;
+
+    if (warp == 0 && lane == 0)
+    {
+        for (int st = 0; st < NS; st++) mbar_init(&rawBar[st], 1);
+        for (int i = 0; i < kRB; i++)
         {
-            const int s = s0 + d;
-            if (s < len)
+            mbar_init(&crecFull[i], kNH);
+            mbar_init(&crecEmpty[i], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int c = 0; c < NS && c < R.nChunks; c++) ring_issue<MODE>(R, a, b, c, c);
+    }
+    __syncthreads();
+
+    if (warp == 0)
+    {
+        // ================================================================= consumer: the recurrence
+        double* outPtr = out + ((long long)R.base + (dir > 0 ? 0 : nT - 1)) * 32 + lane;
+        const long long outStride = dir > 0 ? 32 : -32;
+        double prev = 0.0;
+        int slot = 0;
+        unsigned par = 0u;
+        int stepsInChunk = 0, chunk = 0, stRefill = 0;
+        for (int blk = 0; blk < nBlocks; blk++)
+        {
+            mbar_wait(&crecFull[slot], par);
+            const unsigned char* rec = crecRing + (size_t)slot * (kNH * stepBytes) + lane * 16;
+            // all operands of the block's 4 steps are read up front; terms below a step's common leading
+            // count are padding for every lane, so all W terms are always executed: no branch in the chain
+            double2 hdr[kNH], tm[kNH][W];
+#pragma unroll
+            for (int q = 0; q < kNH; q++)
             {
-                const int row = start + dir * s;
-                double acc = MODE == 0 ? ra[d] * rb[d] : ra[d];
+                hdr[q] = *reinterpret_cast<const double2*>(rec + q * stepBytes); // {acc0, info}
 #pragma unroll
-                for (int j = 0; j < WMAX; j++)
-                {
-                    if (rcol[d][j] >= 0)
-                    {
-                        double v = rv[d][j];
-                        if (is_sentinel(v)) v = sweep_spin(out + rcol[d][j], err);
-                        acc = sweep_apply<MODE>(acc, roc[d][j], v);
-                    }
-                }
-                if (s > 0) acc = sweep_apply<MODE>(acc, rc[d], prev);
-                st_volatile(out + row, acc);
-                prev = acc;
+                for (int j = 0; j < W; j++) tm[q][j] = *reinterpret_cast<const double2*>(rec + q * stepBytes + termOff + j * 512); // {coef, src}
             }
-            B200_LOAD_STEP(d, s + D);
+            int fastAll = 0x100;
+#pragma unroll
+            for (int q = 0; q < kNH; q++) fastAll &= __double2loint(hdr[q].y);
+            if (MODE != 2 && fastAll)
+            {
+#pragma unroll
+                for (int q = 0; q < kNH; q++)
+                {
+                    double sh[W];
+#pragma unroll
+                    for (int j = 0; j < W; j++) sh[j] = __shfl_sync(FULL, prev, __double2loint(tm[q][j].y));
+                    double acc = hdr[q].x;
+#pragma unroll
+                    for (int j = 0; j < W; j++) acc -= tm[q][j].x * sh[j];
+                    st_relaxed(outPtr, acc);
+                    prev = acc;
+                    outPtr += outStride;
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (int q = 0; q < kNH; q++)
+                {
+                    double acc = hdr[q].x;
+#pragma unroll
+                    for (int j = 0; j < W; j++)
+                    {
+                        const int src = __double2loint(tm[q][j].y);
+                        const double cv = *reinterpret_cast<const double*>(rec - lane * 16 + q * stepBytes + cvalOff + j * 256 + lane * 8);
+                        const double sh = __shfl_sync(FULL, prev, src < 0 ? lane : src);
+                        acc = sweep_apply<MODE>(acc, tm[q][j].x, src < 0 ? cv : sh);
+                    }
+                    st_relaxed(outPtr, acc);
+                    prev = acc;
+                    outPtr += outStride;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&crecEmpty[slot]);
+            if (++slot == kRB)
+            {
+                slot = 0;
+                par ^= 1u;
+            }
+            // raw chunk fully consumed (the producers are ahead of this warp) -> refill its stage
+            stepsInChunk += kNH;
+            if (stepsInChunk == CHg)
+            {
+                stepsInChunk = 0;
+                if (lane == 0 && chunk + NS < R.nChunks) ring_issue<MODE>(R, a, b, chunk + NS, stRefill);
+                chunk++;
+                if (++stRefill == NS) stRefill = 0;
+            }
         }
     }
-#undef B200_LOAD_STEP
-}
-
-template <int MODE>
-__device__ __noinline__ void sweep_warp_generic(const SweepDev& S, int w, int lane, const double* __restrict__ a,
-                                                const double* __restrict__ b, double* out, int* err)
-{
-    const int nl = S.nLanes[w], W = S.W[w];
-    if (lane >= nl) return;
-    const int start = S.laneStart[S.laneBase[w] + lane];
-    const int len = S.laneLen[S.laneBase[w] + lane];
-    const long long cb = S.chainBase[w] + lane, ob = S.offBase[w] + lane;
-    double prev = 0.0;
-    for (int s = 0; s < len; s++)
+    else
     {
-        const int row = start + S.dir * s;
-        double acc = MODE == 0 ? a[row] * b[row] : a[row];
-        for (int j = 0; j < W; j++)
+        // ================================================================= producers
+        const int h = warp - 1; // step within a block
+        const int codeOff = W * 256 + lane * 4;
+        const int coefOff = lane * 8;
+        const int vecStart = dir > 0 ? lane : (CHg - 1) * 32 + lane;
+        const int vecStride = dir > 0 ? 32 : -32;
+        const double neutral = MODE == 2 ? 1.0 : 0.0;
+        int codes[W], codesN[W];
+        double mv[W], mvN[W];
+        int q = h;            // step index inside the current raw chunk
+        int st = 0;           // raw stage of the current chunk
+        unsigned parRaw = 0u; // parity of that stage's barrier
+        int chunk = 0, chunksWaited = 0;
+        auto wait_chunk = [&](int cidx, int stg, unsigned parity) {
+            if (cidx >= chunksWaited)
+            {
+                mbar_wait(&rawBar[stg], parity);
+                chunksWaited = cidx + 1;
+            }
+        };
+        auto fetch = [&](const unsigned char* rec, int* cd, double* vals) {
+#pragma unroll
+            for (int j = 0; j < W; j++)
+            {
+                cd[j] = *reinterpret_cast<const int*>(rec + codeOff + j * 128);
+                vals[j] = 0.0;
+                if (cd[j] >= 0) vals[j] = ld_relaxed(out + cd[j]);
+            }
+        };
+        wait_chunk(0, 0, 0u);
+        fetch(R.stages + (size_t)q * R.recBytes, codes, mv);
+        int slot = 0;
+        unsigned parC = 0u;
+        for (int blk = 0; blk < nBlocks; blk++)
         {
-            const long long idx = ob + ((long long)s * W + j) * nl;
-            const int col = S.offCol[idx];
-            if (col < 0) break; // entries are packed first
-            double v = ld_volatile(out + col);
-            if (is_sentinel(v)) v = sweep_spin(out + col, err);
-            acc = sweep_apply<MODE>(acc, S.offC[idx], v);
+            const unsigned char* sb = R.stages + (size_t)st * R.stageBytes;
+            const unsigned char* rec = sb + (size_t)q * R.recBytes;
+            const double* aP = reinterpret_cast<const double*>(sb + R.schedBytes) + vecStart + q * vecStride;
+            // ---- prefetch the codes / cross-warp values of this producer's next step (next block)
+            int qN = q + kNH, stN = st, chunkN = chunk;
+            unsigned parN = parRaw;
+            if (qN >= CHg)
+            {
+                qN -= CHg;
+                chunkN++;
+                if (++stN == NS)
+                {
+                    stN = 0;
+                    parN ^= 1u;
+                }
+            }
+            if (blk + 1 < nBlocks)
+            {
+                wait_chunk(chunkN, stN, parN);
+                fetch(R.stages + (size_t)stN * R.stageBytes + (size_t)qN * R.recBytes, codesN, mvN);
+            }
+            // ---- prepare the current step
+            bool bad = false;
+#pragma unroll
+            for (int j = 0; j < W; j++) bad |= codes[j] >= 0 && is_sentinel(mv[j]);
+            if (__any_sync(FULL, bad))
+            { // a cross-warp value had not arrived when it was prefetched: poll for it
+#pragma unroll
+                for (int j = 0; j < W; j++)
+                    if (codes[j] >= 0 && is_sentinel(mv[j])) mv[j] = sweep_spin(out + codes[j], err);
+            }
+            double acc = *aP;
+            if (MODE == 0) acc *= aP[CHg * 32];
+            double cf[W];
+            int ld = 0;
+            bool still = true;
+#pragma unroll
+            for (int j = 0; j < W; j++)
+            {
+                cf[j] = *reinterpret_cast<const double*>(rec + coefOff + j * 256);
+                still = still && (codes[j] >= 0 || codes[j] == kCodeNone);
+                if (still)
+                {
+                    ld = j + 1;
+                    acc = sweep_apply<MODE>(acc, cf[j], codes[j] >= 0 ? mv[j] : neutral);
+                }
+            }
+            const int leadMin = __reduce_min_sync(FULL, ld);
+            bool fastOk = true;
+#pragma unroll
+            for (int j = 0; j < W; j++) fastOk = fastOk && !(j >= ld && codes[j] >= 0);
+            const int allFast = __all_sync(FULL, fastOk) ? 0x100 : 0;
+            // ---- write the prepared record once the consumer has released the ring slot
+            if (blk >= kRB) mbar_wait(&crecEmpty[slot], parC ^ 1u);
+            unsigned char* cr = crecRing + (size_t)slot * (kNH * stepBytes) + (size_t)h * stepBytes;
+            *reinterpret_cast<double2*>(cr + lane * 16) = make_double2(acc, __hiloint2double(0, leadMin | allFast));
+#pragma unroll
+            for (int j = 0; j < W; j++)
+            {
+                double coef = cf[j], cval = neutral;
+                int src = lane;
+                if (j < ld || codes[j] == kCodeNone)
+                { // already applied by this lane / padding term: exact no-op
+                    coef = 0.0;
+                    if (MODE == 2) src = -1;
+                }
+                else if (codes[j] >= 0)
+                {
+                    src = -1;
+                    cval = mv[j];
+                }
+                else if (codes[j] <= kCodeShfl)
+                    src = kCodeShfl - codes[j];
+                *reinterpret_cast<double2*>(cr + termOff + j * 512 + lane * 16) = make_double2(coef, __hiloint2double(0, src));
+                *reinterpret_cast<double*>(cr + cvalOff + j * 256 + lane * 8) = cval;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&crecFull[slot]);
+            if (++slot == kRB)
+            {
+                slot = 0;
+                parC ^= 1u;
+            }
+            // ---- advance
+            q = qN;
+            st = stN;
+            parRaw = parN;
+            chunk = chunkN;
+#pragma unroll
+            for (int j = 0; j < W; j++)
+            {
+                codes[j] = codesN[j];
+                mv[j] = mvN[j];
+            }
         }
-        if (s > 0) acc = sweep_apply<MODE>(acc, S.chainC[cb + (long long)s * nl], prev);
-        st_volatile(out + row, acc);
-        prev = acc;
     }
 }
 
-// One warp per 32 independent chains; CTAs take tickets so that warps start in chain-level order.
+// Generic path (any W): plain loops, cross-warp values read when consumed.
 template <int MODE>
-__global__ void __launch_bounds__(128) k_sweep(SweepDev S, const double* __restrict__ a, const double* __restrict__ b,
-                                                double* out, unsigned* ticket, unsigned ticketBase, int* err,
-                                                const DevScalars* sc, int force)
+__device__ __noinline__ void sweep_group_generic(const PipeDev& S, const int g, const int lane, const double* __restrict__ a,
+                                                 const double* __restrict__ b, double* out, int* err, unsigned char* smem)
 {
+    constexpr unsigned FULL = 0xffffffffu;
+    const SweepRing R = ring_setup<MODE>(S, g, lane, a, b, smem);
+    const int W = R.W, CHg = R.CHg, recBytes = R.recBytes, NS = R.NS, dir = R.dir;
+    const unsigned shflMask = R.shflMask;
+    const int codeOff = W * 256 + lane * 4;
+    const int coefOff = lane * 8;
+    const long long outStride = dir > 0 ? 32 : -32;
+    double* outPtr = out + ((long long)R.base + (dir > 0 ? 0 : R.nT - 1)) * 32 + lane;
+    const int vecStart = dir > 0 ? lane : (CHg - 1) * 32 + lane;
+    const int vecStride = dir > 0 ? 32 : -32;
+    double prev = 0.0;
+    int stCur = 0;
+    unsigned par = 0u;
+    for (int c = 0; c < R.nChunks; c++)
+    {
+        const unsigned char* sb = R.stages + (size_t)stCur * R.stageBytes;
+        const unsigned char* recPtr = sb;
+        const double* aP = reinterpret_cast<const double*>(sb + R.schedBytes) + vecStart;
+        const double* bP = aP + CHg * 32;
+        const int stNext = (stCur + 1 == NS) ? 0 : stCur + 1;
+        const unsigned parNext = (stNext == 0) ? (par ^ 1u) : par;
+        for (int q = 0; q < CHg; q++)
+        {
+            double acc = *aP;
+            if (MODE == 0) acc *= *bP;
+            for (int j = 0; j < W; j++)
+            {
+                const int code = *reinterpret_cast<const int*>(recPtr + codeOff + j * 128);
+                const double cfj = *reinterpret_cast<const double*>(recPtr + coefOff + j * 256);
+                double v = prev;
+                if ((shflMask >> j) & 1u) v = __shfl_sync(FULL, prev, code <= kCodeShfl ? kCodeShfl - code : lane);
+                if (code >= 0)
+                {
+                    v = ld_relaxed(out + code);
+                    if (is_sentinel(v)) v = sweep_spin(out + code, err);
+                }
+                if (code != kCodeNone) acc = sweep_apply<MODE>(acc, cfj, v);
+            }
+            st_relaxed(outPtr, acc);
+            prev = acc;
+            recPtr += recBytes;
+            aP += vecStride;
+            bP += vecStride;
+            outPtr += outStride;
+        }
+        if (c + 1 < R.nChunks) mbar_wait(&R.bars[stNext], parNext);
+        __syncwarp();
+        if (lane == 0 && c + NS < R.nChunks) ring_issue<MODE>(R, a, b, c + NS, stCur);
+        stCur = stNext;
+        par = parNext;
+    }
+}
+
+// One CTA (1 consumer + kNH producer warps) per group; CTAs take tickets so that groups start in a
+// topological order of the group graph: a group only ever waits for groups that are already running.
+constexpr int kSweepThreads = 32 * (1 + kNH);
+template <int MODE>
+__global__ void __launch_bounds__(kSweepThreads) k_sweep(PipeDev S, const double* __restrict__ a, const double* __restrict__ b,
+                                                          double* out, unsigned* ticket, unsigned ticketBase, int* err,
+                                                          const DevScalars* sc, int force)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
     __shared__ unsigned sTicket;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) sTicket = atomicAdd(ticket, 1u) - ticketBase;
     __syncthreads();
+    const unsigned t = sTicket;
     if (sc->done && !force) return;
-    const int w = (int)sTicket * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= S.nWarps) return;
-    const int lane = threadIdx.x & 31;
-    const int W = S.W[w];
-    if (W <= 2)
-        sweep_warp_fast<MODE, 2, 8>(S, w, lane, a, b, out, err);
-    else if (W <= 4)
-        sweep_warp_fast<MODE, 4, 4>(S, w, lane, a, b, out, err);
-    else
-        sweep_warp_generic<MODE>(S, w, lane, a, b, out, err);
+    if ((int)t >= S.nGroups) return;
+    const int g = S.order ? S.order[t] : (int)t;
+    const int W = (S.gShflMask[g] < 0) ? 0 : S.gW[g];
+    switch (W)
+    {
+        case 1: sweep_group_fast<MODE, 1>(S, g, warp, lane, a, b, out, err, smem); break;
+        case 2: sweep_group_fast<MODE, 2>(S, g, warp, lane, a, b, out, err, smem); break;
+        case 3: sweep_group_fast<MODE, 3>(S, g, warp, lane, a, b, out, err, smem); break;
+        case 4: sweep_group_fast<MODE, 4>(S, g, warp, lane, a, b, out, err, smem); break;
+        case 5: sweep_group_fast<MODE, 5>(S, g, warp, lane, a, b, out, err, smem); break;
+        case 6: sweep_group_fast<MODE, 6>(S, g, warp, lane, a, b, out, err, smem); break;
+        default:
+            if (warp == 0) sweep_group_generic<MODE>(S, g, lane, a, b, out, err, smem);
+            break;
+    }
 }
 
-// Fill the packed sweep coefficients from the face coefficients.
-// prodMode 1: c = c1[f]*c2[f]  (calcReciprocalD);  prodMode 0: c = rD[row]*c1[f]
-__global__ void __launch_bounds__(256) k_pack_sweep(SweepDev S, const double* __restrict__ c1,
-                                                     const double* __restrict__ c2, const double* __restrict__ rD,
-                                                     int prodMode)
+// Fill the coefficient part of a sweep stream from the face coefficients (once per solve).
+// prodMode 1: c = c1[f]*c2[f]  (calcReciprocalD);  prodMode 0: c = rD[slot]*c1[f]
+__global__ void __launch_bounds__(256) k_pack_stream(PipeDev S, const double* __restrict__ c1, const double* __restrict__ c2,
+                                                      const double* __restrict__ rD, int prodMode)
 {
-    const int w = blockIdx.x;
-    if (w >= S.nWarps) return;
-    const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5, ny = blockDim.x >> 5;
-    const int nl = S.nLanes[w], nSteps = S.nSteps[w], W = S.W[w];
-    if (lane >= nl) return;
-    const int start = S.laneStart[S.laneBase[w] + lane];
-    const int len = S.laneLen[S.laneBase[w] + lane];
-    const long long cb = S.chainBase[w] + lane, ob = S.offBase[w] + lane;
-    for (int s = ty; s < nSteps; s += ny)
+    const int g = blockIdx.x;
+    if (g >= S.nGroups) return;
+    const int W = S.gW[g], nT = S.gNT[g], base = S.gBase[g];
+    const long long off = S.gTermOff[g];
+    const int perStep = W * 32;
+    const long long n = (long long)nT * perStep;
+    unsigned char* gs = S.stream + 12ll * off;
+    for (long long e = threadIdx.x; e < n; e += blockDim.x)
     {
-        if (s >= len) continue;
-        const double scale = prodMode ? 1.0 : rD[start + S.dir * s];
+        const int step = (int)(e / perStep);
+        const int rem = (int)(e - (long long)step * perStep);
+        const int f = S.face[off + e];
+        double v = 0.0;
+        if (f >= 0)
         {
-            const long long idx = cb + (long long)s * nl;
-            const int f = S.chainFace[idx];
-            S.chainC[idx] = f >= 0 ? (prodMode ? c1[f] * c2[f] : scale * c1[f]) : 0.0;
+            if (prodMode)
+                v = c1[f] * c2[f];
+            else
+            {
+                const long long slot = ((long long)base + (S.dir > 0 ? step : nT - 1 - step)) * 32 + (rem & 31);
+                v = rD[slot] * c1[f];
+            }
         }
-        for (int j = 0; j < W; j++)
-        {
-            const long long idx = ob + ((long long)s * W + j) * nl;
-            const int f = S.offFace[idx];
-            S.offC[idx] = f >= 0 ? (prodMode ? c1[f] * c2[f] : scale * c1[f]) : 0.0;
-        }
+        reinterpret_cast<double*>(gs + (size_t)step * perStep * 12)[rem] = v;
     }
+}
+
+// slot <-> cell permutation of vectors
+__global__ void k_to_slots(size_t nSlots, const int* __restrict__ cellOfSlot, const double* __restrict__ in, double* __restrict__ out)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nSlots; i += (size_t)gridDim.x * blockDim.x)
+    {
+        const int c = cellOfSlot[i];
+        out[i] = c >= 0 ? in[c] : 0.0;
+    }
+}
+__global__ void k_from_slots(size_t nCells, const int* __restrict__ slotOfCell, const double* __restrict__ in, double* __restrict__ out)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nCells; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = in[slotOfCell[i]];
 }
 
 // ------------------------------------------------------------------------------ vector kernels
@@ -613,9 +964,9 @@ __global__ void k_fill_xref(size_t n, double* __restrict__ a, const DevScalars* 
     const double v = sc->xRef;
     B200_GRID_STRIDE(i, n) a[i] = v;
 }
-__global__ void k_invert(size_t n, const double* __restrict__ in, double* __restrict__ out)
+__global__ void k_invert(size_t n, const double* __restrict__ in, double* __restrict__ out, const int* __restrict__ cellOfSlot)
 {
-    B200_GRID_STRIDE(i, n) out[i] = 1.0 / in[i];
+    B200_GRID_STRIDE(i, n) out[i] = cellOfSlot[i] >= 0 ? 1.0 / in[i] : 0.0; // padding slots stay zero
 }
 __global__ void k_mul(size_t n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out,
                       const DevScalars* sc, int force)

@@ -1,9 +1,24 @@
 // schedule.hpp -- host-side (pure C++) construction of the device tables of one rank's coupled
-// LDU system: the row-packed (sliced-ELL) Amul layout, the interface / halo plan and the
-// chain-pipelined DIC/DILU sweep schedules.  No CUDA in this file: it is also compiled into the
-// CPU schedule-emulation test (tests/cpp/schedule_emulate.cpp).
+// LDU system.  No CUDA in this file: it is also compiled into the CPU schedule-emulation test
+// (tests/cpp/schedule_emulate.cpp), which walks the tables exactly as the kernels do.
 //
-// Reference semantics restated (file list: DESIGN.md section 1):
+// Central idea: every vector of the solver lives in SLOT ORDER, the order in which the DIC/DILU
+// sweeps visit the rows.  Rows are packed into *groups* (one warp each) of 32 lanes x nT time
+// steps; slot = (groupBase + t) * 32 + lane.  At time step t a warp finalises the (up to) 32 rows
+// of that step; the forward sweep walks t upwards, the backward sweep walks the same groups with
+// time reversed.  Two ways of forming groups, chosen per region:
+//   LINE  mode (structured / blockMesh-like numbering): a lane walks a *path* of rows in which each
+//         row has the previous one as a neighbour (x-lines, continued across block seams); lanes
+//         of a warp are paths linked row-by-row (line j depends on line j-1) and are skewed by one
+//         time step per lane, so that every in-warp dependency is exactly one time step old and
+//         travels through a warp shuffle.  Only dependencies on other warps go through memory.
+//   BLOCK mode (unstructured numbering, no long lines): rows sorted by wavefront level are cut
+//         into blocks of 32 independent rows; a group is 16 consecutive blocks.
+// Cross-warp dependencies are resolved through the output vector itself: it is pre-filled with a
+// sentinel, and a consumer re-reads until the value is there.  Warps start in a topological order
+// of the group graph (ticket counter), so a warp only ever waits on warps that already run.
+//
+// Reference semantics preserved (file list: DESIGN.md section 1):
 //  * lduMatrix::Amul face loop: row c accumulates diag, then lower neighbours by ascending
 //    column, then upper neighbours by ascending column (faces are in upper-triangular order).
 //  * DIC/DILU precondition: forward sweep row c consumes its lower neighbours in ascending
@@ -51,9 +66,9 @@ struct RegionHost
 struct GlobalLdu
 {
     int64_t N = 0, F = 0;
-    std::vector<int32_t> L, U;       // [F] global lower / upper cell of each face
-    std::vector<int32_t> ownerStart; // [N+1] faces of row c as lower cell: [ownerStart[c], ownerStart[c+1])
-    std::vector<int32_t> losort;     // [F] faces sorted by upper cell (stable)
+    std::vector<int32_t> L, U;        // [F] global lower / upper cell of each face
+    std::vector<int32_t> ownerStart;  // [N+1] faces of row c as lower cell: [ownerStart[c], ownerStart[c+1])
+    std::vector<int32_t> losort;      // [F] faces sorted by upper cell (stable)
     std::vector<int32_t> losortStart; // [N+1]
 
     void build(const std::vector<RegionHost>& regs)
@@ -65,7 +80,7 @@ struct GlobalLdu
             N += r.nCells;
             F += r.nFaces;
         }
-        if (N >= (int64_t(1) << 31) || F >= (int64_t(1) << 30))
+        if (N >= (int64_t(1) << 30) || F >= (int64_t(1) << 30))
             throw std::runtime_error("system too large for int32 labels on one rank");
         L.resize(F);
         U.resize(F);
@@ -94,50 +109,561 @@ struct GlobalLdu
         std::vector<int32_t> pos(losortStart.begin(), losortStart.end() - 1);
         for (int64_t f = 0; f < F; f++) losort[pos[U[f]]++] = int32_t(f);
     }
+    // lower neighbours of row c in ascending column order: faces losort[losortStart[c] .. losortStart[c+1])
+    // upper neighbours of row c in ascending column order: faces [ownerStart[c] .. ownerStart[c+1])
+};
+
+// term codes of the sweep streams
+constexpr int32_t kCodeNone = -1; // padding term
+constexpr int32_t kCodeOwn = -2;  // value this lane produced in the previous time step (register)
+constexpr int32_t kCodeShfl = -3; // -3 - m: value lane m produced in the previous time step (shuffle)
+                                  // >= 0 : slot of a value produced elsewhere (memory, sentinel-guarded)
+
+// ------------------------------------------------------------------------------------------
+struct PipeSchedule
+{
+    static constexpr int CH = 16;              // time steps per group are padded to a multiple of CH
+    static constexpr int kStageBudget = 16384; // shared-memory bytes of one pipeline stage of the sweep kernel
+    static constexpr int kLineModeMinAvgChain = 8;
+
+    int64_t N = 0, nSlots = 0;
+    int nGroups = 0;
+    std::vector<int32_t> slotOfCell, cellOfSlot;
+    std::vector<int32_t> gBase, gNT; // per group, groups numbered in forward ticket order
+    std::vector<int32_t> orderB;     // backward ticket order (group ids)
+
+    struct Dir
+    {
+        std::vector<int32_t> gW, gCH, gShflMask;
+        std::vector<int64_t> gTermOff;   // [nGroups+1] in terms; stream byte offset = 12 * gTermOff
+        std::vector<int32_t> code, face; // [nTerms] index = gTermOff[g] + (step*W + j)*32 + lane, step in PROCESSING order
+        int64_t nTerms = 0;
+        int maxW = 0, maxStageBytes = 0, nLevels = 0;
+    } fwd, bwd;
+
+    // statistics
+    int nLineRegions = 0, nBlockRegions = 0;
+    int64_t nPaths = 0, nLinkedGroups = 0, nMemTermsF = 0, nShflTermsF = 0, nOwnTermsF = 0;
+
+    struct Placement
+    {
+        std::vector<int32_t> grp, tim, lan; // per cell
+    };
+    Placement place_;
+
+    static int stage_steps(int W, int nVec)
+    {
+        int ch = CH;
+        while (ch > 1 && ch * (W * 384 + nVec * 256) > kStageBudget) ch >>= 1;
+        return ch;
+    }
+
+    void build(const GlobalLdu& g, const std::vector<RegionHost>& regs)
+    {
+        N = g.N;
+        Placement P;
+        P.grp.assign(N, -1);
+        P.tim.assign(N, -1);
+        P.lan.assign(N, -1);
+        std::vector<int32_t> grpNT; // provisional groups (unordered)
+        for (auto& R : regs)
+        {
+            if (R.nCells == 0) continue;
+            const int64_t c0 = R.cellOffset, c1 = R.cellOffset + R.nCells;
+            int64_t nChains = 0;
+            for (int64_t c = c0; c < c1; c++)
+                if (!continues_chain(g, c, c0)) nChains++;
+            bool line = (R.nCells / std::max<int64_t>(1, nChains)) >= kLineModeMinAvgChain;
+            bool ok = false;
+            if (line)
+            {
+                const size_t mark = grpNT.size();
+                ok = place_lines(g, c0, c1, P, grpNT);
+                if (!ok)
+                { // undo and fall back
+                    grpNT.resize(mark);
+                    for (int64_t c = c0; c < c1; c++) P.grp[c] = P.tim[c] = P.lan[c] = -1;
+                }
+                else
+                    nLineRegions++;
+            }
+            if (!ok)
+            {
+                place_blocks(g, c0, c1, P, grpNT);
+                nBlockRegions++;
+            }
+        }
+        order_and_number(g, P, grpNT);
+        build_terms(g, +1, fwd);
+        build_terms(g, -1, bwd);
+    }
+
+  private:
+    static bool continues_chain(const GlobalLdu& g, int64_t c, int64_t c0)
+    {
+        if (c == c0) return false;
+        const int32_t e = g.losortStart[c + 1];
+        return e > g.losortStart[c] && g.L[g.losort[e - 1]] == c - 1;
+    }
+
+    // ------------------------------------------------------------------ LINE mode
+    bool place_lines(const GlobalLdu& g, int64_t c0, int64_t c1, Placement& P, std::vector<int32_t>& grpNT)
+    {
+        const int64_t n = c1 - c0;
+        // chains: maximal runs of consecutive rows c-1 -> c joined by a face
+        std::vector<int32_t> cFirst, cLast, chainOf(n);
+        for (int64_t c = c0; c < c1; c++)
+        {
+            if (!continues_chain(g, c, c0))
+            {
+                cFirst.push_back(int32_t(c));
+                cLast.push_back(int32_t(c));
+            }
+            else
+                cLast.back() = int32_t(c);
+            chainOf[c - c0] = int32_t(cFirst.size() - 1);
+        }
+        const int nCh = int(cFirst.size());
+        // merge chains into paths across seams: head(B) has tail(A) as a lower neighbour
+        std::vector<int32_t> nextCh(nCh, -1), prevCh(nCh, -1);
+        for (int b = 0; b < nCh; b++)
+        {
+            const int32_t h = cFirst[b];
+            for (int32_t k = g.losortStart[h + 1] - 1; k >= g.losortStart[h]; k--)
+            {
+                const int32_t nb = g.L[g.losort[k]];
+                const int a = chainOf[nb - c0];
+                if (cLast[a] == nb && nextCh[a] < 0 && a != b)
+                {
+                    nextCh[a] = b;
+                    prevCh[b] = a;
+                    break;
+                }
+            }
+        }
+        for (int attempt = 0; attempt < 2; attempt++)
+        {
+            std::vector<int32_t> pathOf(n, -1), posOf(n, -1);
+            std::vector<std::vector<int32_t>> pathChains;
+            for (int a = 0; a < nCh; a++)
+                if (prevCh[a] < 0)
+                {
+                    pathChains.emplace_back();
+                    int32_t pos = 0;
+                    for (int b = a; b >= 0; b = nextCh[b])
+                    {
+                        pathChains.back().push_back(b);
+                        for (int32_t c = cFirst[b]; c <= cLast[b]; c++)
+                        {
+                            pathOf[c - c0] = int32_t(pathChains.size() - 1);
+                            posOf[c - c0] = pos++;
+                        }
+                    }
+                }
+            const int nP = int(pathChains.size());
+            std::vector<int32_t> pLen(nP, 0), pFirst(nP);
+            for (int p = 0; p < nP; p++)
+            {
+                pFirst[p] = cFirst[pathChains[p][0]];
+                for (int b : pathChains[p]) pLen[p] += cLast[b] - cFirst[b] + 1;
+            }
+            // path dependencies: (pred path, all dependencies aligned = same position in both paths)
+            std::vector<std::vector<std::pair<int32_t, bool>>> preds(nP);
+            {
+                std::vector<int32_t> seen(nP, -1), idx(nP, -1);
+                for (int p = 0; p < nP; p++)
+                    for (int b : pathChains[p])
+                        for (int32_t c = cFirst[b]; c <= cLast[b]; c++)
+                            for (int32_t k = g.losortStart[c]; k < g.losortStart[c + 1]; k++)
+                            {
+                                const int32_t nb = g.L[g.losort[k]];
+                                const int q = pathOf[nb - c0];
+                                if (q == p) continue;
+                                const bool aligned = posOf[nb - c0] == posOf[c - c0];
+                                if (seen[q] != p)
+                                {
+                                    seen[q] = p;
+                                    idx[q] = int32_t(preds[p].size());
+                                    preds[p].push_back({q, aligned});
+                                }
+                                else if (!aligned)
+                                    preds[p][idx[q]].second = false;
+                            }
+            }
+            // path levels, and acyclicity of the path graph
+            std::vector<int32_t> pLevel(nP, 0), indeg(nP, 0);
+            std::vector<std::vector<int32_t>> succs(nP);
+            for (int p = 0; p < nP; p++)
+                for (auto& e : preds[p])
+                {
+                    succs[e.first].push_back(p);
+                    indeg[p]++;
+                }
+            std::vector<int32_t> queue;
+            for (int p = 0; p < nP; p++)
+                if (!indeg[p]) queue.push_back(p);
+            for (size_t qi = 0; qi < queue.size(); qi++)
+            {
+                const int p = queue[qi];
+                for (int s : succs[p])
+                {
+                    pLevel[s] = std::max(pLevel[s], pLevel[p] + 1);
+                    if (--indeg[s] == 0) queue.push_back(s);
+                }
+            }
+            if (int(queue.size()) != nP)
+            {
+                if (attempt == 0)
+                { // seam merging made the path graph cyclic: use plain chains
+                    std::fill(nextCh.begin(), nextCh.end(), -1);
+                    std::fill(prevCh.begin(), prevCh.end(), -1);
+                    continue;
+                }
+                return false;
+            }
+            // link predecessor: the nearest aligned predecessor path; each path links at most one successor
+            std::vector<int32_t> linkPred(nP, -1), linkSucc(nP, -1);
+            for (int p = 0; p < nP; p++)
+            {
+                int best = -1;
+                for (auto& e : preds[p])
+                    if (e.second && linkSucc[e.first] < 0 && pFirst[e.first] < pFirst[p] && (best < 0 || pFirst[e.first] > pFirst[best]))
+                        best = e.first;
+                if (best >= 0)
+                {
+                    linkPred[p] = best;
+                    linkSucc[best] = p;
+                }
+            }
+            // sequences of linked paths, cut into warps of <= 32 lanes (skew = lane)
+            std::vector<std::vector<int32_t>> groups; // lanes -> path
+            std::vector<int32_t> singles;
+            for (int p = 0; p < nP; p++)
+            {
+                if (linkPred[p] >= 0) continue;
+                std::vector<int32_t> seq;
+                for (int q = p; q >= 0; q = linkSucc[q]) seq.push_back(q);
+                size_t i = 0;
+                while (i < seq.size())
+                {
+                    std::vector<int32_t> lanes{seq[i]};
+                    size_t j = i + 1;
+                    for (; j < seq.size() && lanes.size() < 32; j++)
+                    {
+                        // admit seq[j] as the next lane only if all its dependencies on lanes already in
+                        // this warp are exactly one time step old: the aligned link to the previous lane
+                        const int q = seq[j];
+                        bool okLane = true;
+                        for (auto& e : preds[q])
+                        {
+                            auto it = std::find(lanes.begin(), lanes.end(), e.first);
+                            if (it == lanes.end()) continue;
+                            if (!(e.second && size_t(it - lanes.begin()) == lanes.size() - 1)) okLane = false;
+                        }
+                        if (!okLane) break;
+                        lanes.push_back(q);
+                    }
+                    if (lanes.size() == 1)
+                        singles.push_back(lanes[0]);
+                    else
+                        groups.push_back(lanes);
+                    i = j;
+                }
+            }
+            nLinkedGroups += int64_t(groups.size());
+            nPaths += nP;
+            // singles: pack by (level, length descending); no skew
+            std::stable_sort(singles.begin(), singles.end(), [&](int a, int b) {
+                if (pLevel[a] != pLevel[b]) return pLevel[a] < pLevel[b];
+                return pLen[a] > pLen[b];
+            });
+            std::vector<uint8_t> skewed(groups.size(), 1);
+            for (size_t i = 0; i < singles.size();)
+            {
+                size_t j = i;
+                std::vector<int32_t> lanes;
+                while (j < singles.size() && lanes.size() < 32 && pLevel[singles[j]] == pLevel[singles[i]]) lanes.push_back(singles[j++]);
+                groups.push_back(lanes);
+                skewed.push_back(0);
+                i = j;
+            }
+            for (size_t gi = 0; gi < groups.size(); gi++)
+            {
+                const int gid = int(grpNT.size());
+                int nT = 0;
+                for (size_t ln = 0; ln < groups[gi].size(); ln++)
+                {
+                    const int p = groups[gi][ln];
+                    const int skew = skewed[gi] ? int(ln) : 0;
+                    nT = std::max(nT, skew + pLen[p]);
+                    int32_t pos = 0;
+                    for (int b : pathChains[p])
+                        for (int32_t c = cFirst[b]; c <= cLast[b]; c++, pos++)
+                        {
+                            P.grp[c] = gid;
+                            P.tim[c] = skew + pos;
+                            P.lan[c] = int32_t(ln);
+                        }
+                }
+                grpNT.push_back(nT);
+            }
+            return true;
+        }
+        return false;
+    }
+
+    // ------------------------------------------------------------------ BLOCK mode
+    void place_blocks(const GlobalLdu& g, int64_t c0, int64_t c1, Placement& P, std::vector<int32_t>& grpNT)
+    {
+        const int64_t n = c1 - c0;
+        std::vector<int32_t> lev(n, 0);
+        int32_t nLev = 0;
+        for (int64_t c = c0; c < c1; c++)
+        {
+            int32_t lv = 0;
+            for (int32_t k = g.losortStart[c]; k < g.losortStart[c + 1]; k++) lv = std::max(lv, lev[g.L[g.losort[k]] - c0] + 1);
+            lev[c - c0] = lv;
+            nLev = std::max(nLev, lv + 1);
+        }
+        std::vector<int32_t> cnt(nLev + 1, 0);
+        for (int64_t i = 0; i < n; i++) cnt[lev[i] + 1]++;
+        for (int32_t l = 0; l < nLev; l++) cnt[l + 1] += cnt[l];
+        std::vector<int32_t> byLevel(n);
+        {
+            std::vector<int32_t> pos(cnt.begin(), cnt.end() - 1);
+            for (int64_t i = 0; i < n; i++) byLevel[pos[lev[i]]++] = int32_t(c0 + i);
+        }
+        int gid = -1, t = CH;
+        for (int32_t l = 0; l < nLev; l++)
+            for (int32_t i = cnt[l]; i < cnt[l + 1]; i += 32)
+            {
+                if (t == CH)
+                {
+                    gid = int(grpNT.size());
+                    grpNT.push_back(0);
+                    t = 0;
+                }
+                const int32_t e = std::min(i + 32, cnt[l + 1]);
+                for (int32_t k = i; k < e; k++)
+                {
+                    const int32_t c = byLevel[k];
+                    P.grp[c] = gid;
+                    P.tim[c] = t;
+                    P.lan[c] = k - i;
+                }
+                t++;
+                grpNT[gid] = t;
+            }
+    }
+
+    // ------------------------------------------------------------------ ordering, slots
+    void order_and_number(const GlobalLdu& g, Placement& P, std::vector<int32_t>& grpNT)
+    {
+        const int nG = int(grpNT.size());
+        // group graph: edge H -> G if a row of G has a lower neighbour in H
+        std::vector<std::vector<int32_t>> succ(nG);
+        std::vector<int32_t> indeg(nG, 0);
+        {
+            std::vector<int64_t> edges;
+            for (int64_t f = 0; f < g.F; f++)
+            {
+                const int32_t a = P.grp[g.L[f]], b = P.grp[g.U[f]];
+                if (a != b)
+                    edges.push_back((int64_t(a) << 32) | uint32_t(b));
+                else if (P.tim[g.L[f]] >= P.tim[g.U[f]])
+                    throw std::runtime_error("internal: in-warp dependency does not point back in time");
+                if (edges.size() > (size_t(1) << 22))
+                {
+                    std::sort(edges.begin(), edges.end());
+                    edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+                }
+            }
+            std::sort(edges.begin(), edges.end());
+            edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+            for (int64_t e : edges)
+            {
+                const int32_t a = int32_t(e >> 32), b = int32_t(e & 0xffffffff);
+                succ[a].push_back(b);
+                indeg[b]++;
+            }
+        }
+        std::vector<int32_t> levF(nG, 0), levB(nG, 0), topo;
+        {
+            std::vector<int32_t> deg(indeg);
+            for (int a = 0; a < nG; a++)
+                if (!deg[a]) topo.push_back(a);
+            for (size_t qi = 0; qi < topo.size(); qi++)
+            {
+                const int a = topo[qi];
+                for (int b : succ[a])
+                {
+                    levF[b] = std::max(levF[b], levF[a] + 1);
+                    if (--deg[b] == 0) topo.push_back(b);
+                }
+            }
+            if (int(topo.size()) != nG) throw std::runtime_error("internal: group graph is cyclic");
+            for (int i = nG - 1; i >= 0; i--)
+            {
+                const int a = topo[i];
+                for (int b : succ[a]) levB[a] = std::max(levB[a], levB[b] + 1);
+            }
+        }
+        std::vector<int32_t> ordF(nG), newId(nG);
+        std::iota(ordF.begin(), ordF.end(), 0);
+        std::stable_sort(ordF.begin(), ordF.end(), [&](int a, int b) { return levF[a] < levF[b]; });
+        for (int i = 0; i < nG; i++) newId[ordF[i]] = i;
+        nGroups = nG;
+        gNT.resize(nG);
+        gBase.resize(nG);
+        std::vector<int32_t> lb(nG);
+        int64_t base = 0;
+        for (int i = 0; i < nG; i++)
+        {
+            const int old = ordF[i];
+            gNT[i] = (grpNT[old] + CH - 1) / CH * CH;
+            gBase[i] = int32_t(base);
+            base += gNT[i];
+            lb[i] = levB[old];
+        }
+        if (base * 32 >= (int64_t(1) << 31)) throw std::runtime_error("slot space exceeds int32");
+        nSlots = base * 32;
+        fwd.nLevels = nG ? *std::max_element(levF.begin(), levF.end()) + 1 : 0;
+        bwd.nLevels = nG ? *std::max_element(levB.begin(), levB.end()) + 1 : 0;
+        orderB.resize(nG);
+        std::iota(orderB.begin(), orderB.end(), 0);
+        std::stable_sort(orderB.begin(), orderB.end(), [&](int a, int b) { return lb[a] != lb[b] ? lb[a] < lb[b] : a > b; });
+        slotOfCell.resize(N);
+        cellOfSlot.assign(nSlots, -1);
+        for (int64_t c = 0; c < N; c++)
+        {
+            P.grp[c] = newId[P.grp[c]];
+            const int64_t s = (int64_t(gBase[P.grp[c]]) + P.tim[c]) * 32 + P.lan[c];
+            slotOfCell[c] = int32_t(s);
+            cellOfSlot[s] = int32_t(c);
+        }
+        place_ = std::move(P);
+    }
+
+    // ------------------------------------------------------------------ sweep terms
+    void build_terms(const GlobalLdu& g, int dir, Dir& D)
+    {
+        const int nG = nGroups;
+        D.gW.assign(nG, 0);
+        for (int64_t c = 0; c < N; c++)
+        {
+            const int cnt = dir > 0 ? g.losortStart[c + 1] - g.losortStart[c] : g.ownerStart[c + 1] - g.ownerStart[c];
+            int32_t& w = D.gW[place_.grp[c]];
+            w = std::max(w, cnt);
+        }
+        D.gTermOff.assign(nG + 1, 0);
+        D.gCH.assign(nG, CH);
+        D.gShflMask.assign(nG, 0);
+        D.maxW = 0;
+        D.maxStageBytes = 0;
+        const int nVec = dir > 0 ? 2 : 1;
+        for (int i = 0; i < nG; i++)
+        {
+            D.gTermOff[i + 1] = D.gTermOff[i] + int64_t(gNT[i]) * D.gW[i] * 32;
+            D.gCH[i] = stage_steps(D.gW[i], nVec);
+            D.maxW = std::max(D.maxW, D.gW[i]);
+            D.maxStageBytes = std::max(D.maxStageBytes, D.gCH[i] * (D.gW[i] * 384 + nVec * 256));
+        }
+        D.nTerms = D.gTermOff[nG];
+        D.code.assign(D.nTerms, kCodeNone);
+        D.face.assign(D.nTerms, -1);
+        for (int64_t c = 0; c < N; c++)
+        {
+            const int gI = place_.grp[c], t = place_.tim[c], ln = place_.lan[c];
+            const int W = D.gW[gI];
+            const int step = dir > 0 ? t : gNT[gI] - 1 - t;
+            const int64_t base = D.gTermOff[gI] + int64_t(step) * W * 32 + ln;
+            int j = 0;
+            auto put = [&](int32_t f, int32_t nb) {
+                int32_t code;
+                if (place_.grp[nb] == gI && place_.tim[nb] == t - dir)
+                {
+                    if (place_.lan[nb] == ln)
+                    {
+                        code = kCodeOwn;
+                        if (dir > 0) nOwnTermsF++;
+                    }
+                    else
+                    {
+                        code = kCodeShfl - place_.lan[nb];
+                        if (j < 31) D.gShflMask[gI] |= (1 << j);
+                        if (dir > 0) nShflTermsF++;
+                    }
+                }
+                else
+                {
+                    code = slotOfCell[nb];
+                    if (dir > 0) nMemTermsF++;
+                    // a memory dependency on a step of the same group inside the same block of 4 steps would
+                    // dead-lock the producer/consumer CTA (the consumer needs the whole block): such groups
+                    // take the single-warp generic path (bit 31 of gShflMask)
+                    if (place_.grp[nb] == gI)
+                    {
+                        const int stepNb = dir > 0 ? place_.tim[nb] : gNT[gI] - 1 - place_.tim[nb];
+                        if (stepNb / 4 == step / 4) D.gShflMask[gI] |= int32_t(0x80000000u);
+                    }
+                }
+                D.code[base + int64_t(j) * 32] = code;
+                D.face[base + int64_t(j) * 32] = f;
+                j++;
+            };
+            if (dir > 0)
+                for (int32_t k = g.losortStart[c]; k < g.losortStart[c + 1]; k++) put(g.losort[k], g.L[g.losort[k]]); // ascending lower column
+            else
+                for (int32_t f = g.ownerStart[c + 1] - 1; f >= g.ownerStart[c]; f--) put(f, g.U[f]); // DESCENDING upper column
+        }
+    }
 };
 
 // ------------------------------------------------------------------------------------------
-// Row-packed Amul layout: slices of 32 rows, column-major inside a slice (slot = base + j*32 + lane).
+// Row-packed Amul layout over slots: slice s = the 32 slots of one (group, time step);
+// column-major inside a slice (entry = sliceOff[s]*32 + j*32 + lane); columns are slots.
 struct SellLayout
 {
-    int64_t nSlices = 0, nSlots = 0;
-    std::vector<int32_t> sliceOff; // [nSlices+1] in units of 32 slots
-    std::vector<int32_t> col;      // [nSlots] column or -1 (padding)
-    std::vector<int32_t> src;      // [nSlots] index into coef = [upper(F) | lower(F)], -1 for padding
+    int64_t nSlices = 0, nEntries = 0;
+    std::vector<int32_t> sliceOff; // [nSlices+1] in units of 32 entries
+    std::vector<int32_t> col;      // [nEntries] column slot or -1 (padding)
+    std::vector<int32_t> src;      // [nEntries] index into coef = [upper(F) | lower(F)], -1 for padding
 
-    void build(const GlobalLdu& g)
+    void build(const GlobalLdu& g, const PipeSchedule& S)
     {
-        const int64_t N = g.N, F = g.F;
-        nSlices = (N + 31) / 32;
+        const int64_t F = g.F;
+        nSlices = S.nSlots / 32;
         sliceOff.assign(nSlices + 1, 0);
+        std::vector<int32_t> width(nSlices, 0);
+        for (int64_t c = 0; c < g.N; c++)
+        {
+            const int cnt = (g.losortStart[c + 1] - g.losortStart[c]) + (g.ownerStart[c + 1] - g.ownerStart[c]);
+            int32_t& w = width[S.slotOfCell[c] >> 5];
+            w = std::max(w, cnt);
+        }
         for (int64_t s = 0; s < nSlices; s++)
         {
-            int w = 0;
-            for (int64_t c = s * 32; c < std::min<int64_t>(N, s * 32 + 32); c++)
-            {
-                int cnt = (g.losortStart[c + 1] - g.losortStart[c]) + (g.ownerStart[c + 1] - g.ownerStart[c]);
-                w = std::max(w, cnt);
-            }
-            int64_t next = int64_t(sliceOff[s]) + w;
-            if (next >= (int64_t(1) << 31) / 32) throw std::runtime_error("SELL layout exceeds int32 slots");
+            const int64_t next = int64_t(sliceOff[s]) + width[s];
+            if (next >= (int64_t(1) << 31) / 32) throw std::runtime_error("SELL layout exceeds int32 entries");
             sliceOff[s + 1] = int32_t(next);
         }
-        nSlots = int64_t(sliceOff[nSlices]) * 32;
-        col.assign(nSlots, -1);
-        src.assign(nSlots, -1);
-        for (int64_t c = 0; c < N; c++)
+        nEntries = int64_t(sliceOff[nSlices]) * 32;
+        col.assign(nEntries, -1);
+        src.assign(nEntries, -1);
+        for (int64_t c = 0; c < g.N; c++)
         {
-            int64_t base = int64_t(sliceOff[c >> 5]) * 32 + (c & 31);
+            const int32_t sl = S.slotOfCell[c];
+            const int64_t base = int64_t(sliceOff[sl >> 5]) * 32 + (sl & 31);
             int j = 0;
             for (int32_t k = g.losortStart[c]; k < g.losortStart[c + 1]; k++, j++)
             {
-                int32_t f = g.losort[k]; // row c = U[f], column L[f], coefficient lower[f]
-                col[base + int64_t(j) * 32] = g.L[f];
+                const int32_t f = g.losort[k]; // row c = U[f], column L[f], coefficient lower[f]
+                col[base + int64_t(j) * 32] = S.slotOfCell[g.L[f]];
                 src[base + int64_t(j) * 32] = int32_t(F + f);
             }
             for (int32_t f = g.ownerStart[c]; f < g.ownerStart[c + 1]; f++, j++)
             {
-                col[base + int64_t(j) * 32] = g.U[f]; // row c = L[f], column U[f], coefficient upper[f]
+                col[base + int64_t(j) * 32] = S.slotOfCell[g.U[f]]; // row c = L[f], column U[f], coefficient upper[f]
                 src[base + int64_t(j) * 32] = f;
             }
         }
@@ -146,12 +672,13 @@ struct SellLayout
 
 // ------------------------------------------------------------------------------------------
 // Interface plan: rows touched by coupled patches, their ordered entries, and the halo layout.
+// All row / source indices are SLOTS.
 struct IfacePlan
 {
-    std::vector<int32_t> rows;     // unique touched rows, ascending
+    std::vector<int32_t> rows;     // slots of the touched rows (ascending cell order)
     std::vector<int32_t> rowStart; // [rows+1]
     std::vector<int32_t> entCoef;  // index into the concatenated interface coefficient array
-    std::vector<int32_t> entSrc;   // cnt==0: source code (>=0: x index, <0: recv index -1-k); else start into g*
+    std::vector<int32_t> entSrc;   // cnt==0: source code (>=0: x slot, <0: recv index -1-k); else start into g*
     std::vector<int32_t> entCnt;   // 0 = identity
     std::vector<int32_t> gSrc;     // source codes of GGI terms
     std::vector<double> gW;
@@ -159,12 +686,11 @@ struct IfacePlan
     // halo
     std::vector<int> peers;
     std::vector<int32_t> sendOff, recvOff; // [peers+1]
-    std::vector<int32_t> sendCells;        // x indices packed into the send buffer
+    std::vector<int32_t> sendCells;        // x slots packed into the send buffer
     int64_t nCoefs = 0;
 
-    void build(std::vector<RegionHost>& regs, int myRank, int64_t N)
+    void build(std::vector<RegionHost>& regs, int myRank, const PipeSchedule& S)
     {
-        // coefficient offsets
         nCoefs = 0;
         for (auto& r : regs)
             for (auto& I : r.ifaces)
@@ -172,7 +698,6 @@ struct IfacePlan
                 I.coefOffset = nCoefs;
                 nCoefs += I.nFaces;
             }
-        // peers
         for (auto& r : regs)
             for (auto& I : r.ifaces)
                 if (I.peerRank != myRank && std::find(peers.begin(), peers.end(), I.peerRank) == peers.end())
@@ -195,7 +720,7 @@ struct IfacePlan
                 for (auto& I : regs[r].ifaces)
                     if (I.peerRank == peers[p])
                     {
-                        for (int i = 0; i < I.nFaces; i++) sendCells.push_back(int32_t(regs[r].cellOffset + I.faceCells[i]));
+                        for (int i = 0; i < I.nFaces; i++) sendCells.push_back(S.slotOfCell[regs[r].cellOffset + I.faceCells[i]]);
                         so += I.nFaces;
                     }
             sendOff[p + 1] = so;
@@ -237,16 +762,19 @@ struct IfacePlan
         std::stable_sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) {
             return a.row != b.row ? a.row < b.row : a.key < b.key;
         });
-        sliceMask.assign((N + 31) / 32, 0u);
+        sliceMask.assign(S.nSlots / 32, 0u);
         rowStart.push_back(0);
+        int32_t lastRow = -1;
         for (size_t e = 0; e < ents.size(); e++)
         {
             const Ent& E = ents[e];
-            if (rows.empty() || rows.back() != E.row)
+            if (rows.empty() || lastRow != E.row)
             {
                 if (!rows.empty()) rowStart.push_back(int32_t(entCoef.size()));
-                rows.push_back(E.row);
-                sliceMask[E.row >> 5] |= (1u << (E.row & 31));
+                const int32_t sl = S.slotOfCell[E.row];
+                rows.push_back(sl);
+                lastRow = E.row;
+                sliceMask[sl >> 5] |= (1u << (sl & 31));
             }
             const IfaceHost& I = regs[E.region].ifaces[E.iface];
             entCoef.push_back(int32_t(I.coefOffset + E.face));
@@ -258,7 +786,7 @@ struct IfacePlan
                         throw std::runtime_error("interface peer (region, iface) does not exist on this rank");
                     const IfaceHost& Q = regs[I.peerRegion].ifaces[I.peerIface];
                     if (peerFace < 0 || peerFace >= Q.nFaces) throw std::runtime_error("GGI address out of range of the shadow patch");
-                    return int32_t(regs[I.peerRegion].cellOffset + Q.faceCells[peerFace]);
+                    return S.slotOfCell[regs[I.peerRegion].cellOffset + Q.faceCells[peerFace]];
                 }
                 if (peerFace < 0 || peerFace >= I.nPeerFaces) throw std::runtime_error("GGI address out of range of the shadow patch");
                 return -1 - (recvSegOff[E.region][E.iface] + peerFace);
@@ -278,205 +806,10 @@ struct IfacePlan
                     gSrc.push_back(srcCode(I.ggiAddr[k]));
                     gW.push_back(I.ggiWeights[k]);
                 }
-                if (cnt == 0)
-                {
-                    // uncovered face: contributes coeff*0 (bridgeOverlap is off in every shipped case)
-                    entCnt.back() = -1;
-                }
+                if (cnt == 0) entCnt.back() = -1; // uncovered face: contributes coeff*0 (bridgeOverlap off in every shipped case)
             }
         }
         if (!rows.empty()) rowStart.push_back(int32_t(entCoef.size()));
-    }
-};
-
-// ------------------------------------------------------------------------------------------
-// Chain-pipelined sweep schedule (one per direction).
-//
-// A *chain* is a maximal run of consecutive rows c-1 -> c joined by a face; one thread walks a
-// chain keeping the previous row's value in a register (it is always the LAST neighbour in the
-// reference's order: the largest lower / smallest upper index).  All other neighbours are read
-// from global memory, where every row value doubles as its own ready flag (sentinel until
-// written).  Chains of equal *chain level* are independent and are packed 32 to a warp; warps are
-// issued in level order through a ticket counter, so a warp only ever waits on warps that are
-// already running: deadlock-free without co-residency requirements.
-struct SweepSchedule
-{
-    int dir = +1; // +1 forward (lower neighbours), -1 backward (upper neighbours)
-    int64_t nWarps = 0;
-    int nLevels = 0;
-    int maxW = 0;
-    int64_t nChains = 0;
-    std::vector<int32_t> warpNLanes, warpNSteps, warpW; // [nWarps]
-    std::vector<int32_t> warpLaneBase;                  // [nWarps] into laneStart/laneLen
-    std::vector<int64_t> warpChainBase;                 // [nWarps] into chainFace   (index = base + s*nl + lane)
-    std::vector<int64_t> warpOffBase;                   // [nWarps] into offFace/Col (index = base + (s*W+j)*nl + lane)
-    std::vector<int32_t> laneStart, laneLen;            // per lane: first row processed, chain length
-    std::vector<int32_t> chainFace;                     // face of the in-register neighbour, -1 if none
-    std::vector<int32_t> offFace, offCol;               // other neighbours in reference order, -1 padding
-    int64_t nChainSlots = 0, nOffSlots = 0;
-
-    void build(const GlobalLdu& g, int direction)
-    {
-        dir = direction;
-        const int64_t N = g.N;
-        // continuation flags: row c continues the chain of c-1 iff face (c-1, c) exists
-        std::vector<uint8_t> cont(N, 0);
-        for (int64_t c = 1; c < N; c++)
-        {
-            int32_t e = g.losortStart[c + 1];
-            if (e > g.losortStart[c] && g.L[g.losort[e - 1]] == c - 1) cont[c] = 1;
-        }
-        // chains as [first,last] in ascending row order
-        std::vector<int32_t> cFirst, cLast;
-        std::vector<int32_t> chainOf(N);
-        for (int64_t c = 0; c < N; c++)
-        {
-            if (!cont[c])
-            {
-                cFirst.push_back(int32_t(c));
-                cLast.push_back(int32_t(c));
-            }
-            else
-                cLast.back() = int32_t(c);
-            chainOf[c] = int32_t(cFirst.size() - 1);
-        }
-        nChains = int64_t(cFirst.size());
-        // chain levels
-        std::vector<int32_t> lvl(nChains, 0);
-        if (dir > 0)
-        {
-            for (int64_t ch = 0; ch < nChains; ch++)
-            {
-                int32_t lv = 0;
-                for (int32_t c = cFirst[ch]; c <= cLast[ch]; c++)
-                    for (int32_t k = g.losortStart[c]; k < g.losortStart[c + 1]; k++)
-                    {
-                        int32_t nb = g.L[g.losort[k]];
-                        if (chainOf[nb] != ch) lv = std::max(lv, lvl[chainOf[nb]] + 1);
-                    }
-                lvl[ch] = lv;
-            }
-        }
-        else
-        {
-            for (int64_t ch = nChains - 1; ch >= 0; ch--)
-            {
-                int32_t lv = 0;
-                for (int32_t c = cFirst[ch]; c <= cLast[ch]; c++)
-                    for (int32_t f = g.ownerStart[c]; f < g.ownerStart[c + 1]; f++)
-                    {
-                        int32_t nb = g.U[f];
-                        if (chainOf[nb] != ch) lv = std::max(lv, lvl[chainOf[nb]] + 1);
-                    }
-                lvl[ch] = lv;
-            }
-        }
-        nLevels = nChains ? (*std::max_element(lvl.begin(), lvl.end()) + 1) : 0;
-        // order chains by (level, length descending, first row)
-        std::vector<int32_t> order(nChains);
-        std::iota(order.begin(), order.end(), 0);
-        std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
-            if (lvl[a] != lvl[b]) return lvl[a] < lvl[b];
-            int32_t la = cLast[a] - cFirst[a], lb = cLast[b] - cFirst[b];
-            if (la != lb) return la > lb;
-            return dir > 0 ? a < b : a > b;
-        });
-        // pack warps
-        auto nOff = [&](int32_t c, bool isChainHead) -> int {
-            // number of neighbours read from memory for row c
-            if (dir > 0)
-            {
-                int n = g.losortStart[c + 1] - g.losortStart[c];
-                return isChainHead ? n : n - 1;
-            }
-            int n = g.ownerStart[c + 1] - g.ownerStart[c];
-            return isChainHead ? n : n - 1;
-        };
-        nChainSlots = 0;
-        nOffSlots = 0;
-        int64_t i = 0;
-        while (i < nChains)
-        {
-            int64_t j = i;
-            while (j < nChains && j - i < 32 && lvl[order[j]] == lvl[order[i]]) j++;
-            int nl = int(j - i);
-            int steps = 0, W = 0;
-            for (int64_t k = i; k < j; k++)
-            {
-                int32_t ch = order[k];
-                int len = cLast[ch] - cFirst[ch] + 1;
-                steps = std::max(steps, len);
-                for (int s = 0; s < len; s++)
-                {
-                    int32_t c = dir > 0 ? cFirst[ch] + s : cLast[ch] - s;
-                    W = std::max(W, nOff(c, s == 0));
-                }
-            }
-            warpNLanes.push_back(nl);
-            warpNSteps.push_back(steps);
-            warpW.push_back(W);
-            warpLaneBase.push_back(int32_t(laneStart.size()));
-            warpChainBase.push_back(nChainSlots);
-            warpOffBase.push_back(nOffSlots);
-            for (int64_t k = i; k < j; k++)
-            {
-                int32_t ch = order[k];
-                laneStart.push_back(dir > 0 ? cFirst[ch] : cLast[ch]);
-                laneLen.push_back(cLast[ch] - cFirst[ch] + 1);
-            }
-            nChainSlots += int64_t(steps) * nl;
-            nOffSlots += int64_t(steps) * W * nl;
-            maxW = std::max(maxW, W);
-            i = j;
-        }
-        nWarps = int64_t(warpNLanes.size());
-        chainFace.assign(nChainSlots, -1);
-        offFace.assign(nOffSlots, -1);
-        offCol.assign(nOffSlots, -1);
-        for (int64_t w = 0; w < nWarps; w++)
-        {
-            const int nl = warpNLanes[w], W = warpW[w];
-            for (int lane = 0; lane < nl; lane++)
-            {
-                const int32_t start = laneStart[warpLaneBase[w] + lane];
-                const int32_t len = laneLen[warpLaneBase[w] + lane];
-                for (int s = 0; s < len; s++)
-                {
-                    const int32_t c = start + dir * s;
-                    int64_t cb = warpChainBase[w] + int64_t(s) * nl + lane;
-                    int64_t ob = warpOffBase[w] + int64_t(s) * W * nl + lane;
-                    int jj = 0;
-                    if (dir > 0)
-                    {
-                        int32_t b = g.losortStart[c], e = g.losortStart[c + 1];
-                        if (s > 0)
-                        {
-                            chainFace[cb] = g.losort[e - 1];
-                            e--;
-                        }
-                        for (int32_t k = b; k < e; k++, jj++)
-                        {
-                            offFace[ob + int64_t(jj) * nl] = g.losort[k];
-                            offCol[ob + int64_t(jj) * nl] = g.L[g.losort[k]];
-                        }
-                    }
-                    else
-                    {
-                        int32_t b = g.ownerStart[c], e = g.ownerStart[c + 1];
-                        if (s > 0)
-                        {
-                            chainFace[cb] = b; // smallest upper neighbour = c+1, consumed last
-                            b++;
-                        }
-                        for (int32_t f = e - 1; f >= b; f--, jj++) // descending upper index
-                        {
-                            offFace[ob + int64_t(jj) * nl] = f;
-                            offCol[ob + int64_t(jj) * nl] = g.U[f];
-                        }
-                    }
-                }
-            }
-        }
     }
 };
 

@@ -25,7 +25,7 @@ def run_emu(L, reg, dilu, x, r):
     n = reg.nCells
     l, u = np.ascontiguousarray(reg.lowerAddr, np.int32), np.ascontiguousarray(reg.upperAddr, np.int32)
     y, w, rD = np.empty(n), np.empty(n), np.empty(n)
-    stats = np.zeros(8, np.int32)
+    stats = np.zeros(12, np.int32)
     P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
     I = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
     lower = None if reg.lower is None else P(np.ascontiguousarray(reg.lower))
@@ -57,11 +57,24 @@ def test_tables_reproduce_oracle_bitwise(emu, golden_addr):
         assert np.array_equal(w, O.precondition(r)), reg.name
 
 
-def test_chain_structure_on_structured_mesh(emu):
-    # x-lines of a structured block are the chains: ny*nz chains per block, levels = ny+nz-1
+def test_line_structure_on_structured_mesh(emu):
+    # x-lines continued across the two block seams are the paths: ny*nz of them; lines linked along j are
+    # cut into warps of 32 lanes (41 = 32 + 9 per z-layer); every in-warp dependency travels by shuffle
     fluid, _ = flow_over_heated_plate(1, 3)
     reg = synthetic_coeffs(fluid.nCells, fluid.lowerAddr, fluid.upperAddr, symmetric=True)
     _, _, _, stats = run_emu(emu, reg, False, random_vec(reg.nCells, 1), random_vec(reg.nCells, 2))
-    # the three fluid blocks are joined along x, so a chain runs through all of them? no: block seams
-    # connect cell (nx-1,j,k) of block b to (0,j,k) of block b+1, which are not consecutive rows
-    assert stats[3] == 3 * 41 * 3
+    nx, ny, nz = fluid.dims()
+    assert stats[8] == 1                 # LINE mode
+    assert stats[3] == ny * nz           # paths
+    assert stats[4] == 2 * nz and stats[0] == 2 * nz   # warps
+    assert stats[1] == nz + 1            # group levels: k + (second j-group)
+    assert stats[11] == (nx - 1) * ny * nz           # own-lane terms: i-1 neighbours (incl. seams)
+    assert stats[10] == nx * (ny - 2) * nz           # shuffle terms: j-1 neighbours inside a warp
+    assert stats[9] == nx * ny * (nz - 1) + nx * nz  # memory terms: k-1 neighbours + the j-1 of each warp's lane 0
+    assert stats[7] == nz * 32 * (368 + 352)  # 41 lines = 32 + 9 lanes per layer; (332 + skew) steps rounded up to 16
+
+
+def test_block_mode_on_unstructured_mesh(emu, golden_addr):
+    reg = golden_region(golden_addr, "duineveld1", symmetric=True)
+    _, _, _, stats = run_emu(emu, reg, False, random_vec(reg.nCells, 1), random_vec(reg.nCells, 2))
+    assert stats[8] == 0 and stats[2] == 9
