@@ -528,7 +528,7 @@ __device__ __forceinline__ SweepRing ring_setup(const PipeDev& S, int g, int lan
 
 // Fast path (W = 1..6 terms per row): warp-specialised CTA.  A lone warp issues one instruction
 // every ~5 cycles, so the serial recurrence must execute as few instructions per time step as
-// possible.  kNH producer warps therefore PREPARE the steps (producer h takes step 4b+h of block b):
+// possible.  kNH producer warps therefore PREPARE the steps (producer h takes step 8b+h of block b):
 // they read the streamed record, fetch and verify the cross-warp values (prefetched one block
 // ahead), apply -- in reference order -- the leading terms that do not depend on this group's previous
 // step, and write a compact record {acc0, (coef, source lane) per remaining term} into a second
@@ -536,8 +536,8 @@ __device__ __forceinline__ SweepRing ring_setup(const PipeDev& S, int g, int lan
 //     per remaining term:  v = shfl(prev, source lane);  acc -= coef * v      then one store.
 // Terms a lane has already applied appear as padding (coef 0, source = own lane): exact no-ops.
 // Steps in which a remaining term needs a cross-warp value (block seams) take a slower select path.
-constexpr int kNH = 4; // producer warps = steps per block
-constexpr int kRB = 3; // blocks in the prepared-record ring
+constexpr int kNH = kSweepBlock; // producer warps = steps per block (8)
+constexpr int kRB = 2;           // blocks in the prepared-record ring
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
 {
@@ -603,52 +603,57 @@ __device__ __forceinline__ void sweep_group_fast(const PipeDev& S, const int g, 
         {
             mbar_wait(&crecFull[slot], par);
             const unsigned char* rec = crecRing + (size_t)slot * (kNH * stepBytes) + lane * 16;
-            // all operands of the block's 4 steps are read up front; terms below a step's common leading
-            // count are padding for every lane, so all W terms are always executed: no branch in the chain
-            double2 hdr[kNH], tm[kNH][W];
+            // operands are read four steps at a time, up front; terms below a step's common leading count are
+            // padding for every lane, so all W terms are always executed: no branch inside the chain
 #pragma unroll
-            for (int q = 0; q < kNH; q++)
+            for (int hb = 0; hb < kNH; hb += 4)
             {
-                hdr[q] = *reinterpret_cast<const double2*>(rec + q * stepBytes); // {acc0, info}
+                const unsigned char* rb = rec + hb * stepBytes;
+                double2 hdr[4], tm[4][W];
 #pragma unroll
-                for (int j = 0; j < W; j++) tm[q][j] = *reinterpret_cast<const double2*>(rec + q * stepBytes + termOff + j * 512); // {coef, src}
-            }
-            int fastAll = 0x100;
-#pragma unroll
-            for (int q = 0; q < kNH; q++) fastAll &= __double2loint(hdr[q].y);
-            if (MODE != 2 && fastAll)
-            {
-#pragma unroll
-                for (int q = 0; q < kNH; q++)
+                for (int q = 0; q < 4; q++)
                 {
-                    double sh[W];
+                    hdr[q] = *reinterpret_cast<const double2*>(rb + q * stepBytes); // {acc0, info}
 #pragma unroll
-                    for (int j = 0; j < W; j++) sh[j] = __shfl_sync(FULL, prev, __double2loint(tm[q][j].y));
-                    double acc = hdr[q].x;
-#pragma unroll
-                    for (int j = 0; j < W; j++) acc -= tm[q][j].x * sh[j];
-                    st_relaxed(outPtr, acc);
-                    prev = acc;
-                    outPtr += outStride;
+                    for (int j = 0; j < W; j++) tm[q][j] = *reinterpret_cast<const double2*>(rb + q * stepBytes + termOff + j * 512); // {coef, src}
                 }
-            }
-            else
-            {
+                int fastAll = 0x100;
 #pragma unroll
-                for (int q = 0; q < kNH; q++)
+                for (int q = 0; q < 4; q++) fastAll &= __double2loint(hdr[q].y);
+                if (MODE != 2 && fastAll)
                 {
-                    double acc = hdr[q].x;
 #pragma unroll
-                    for (int j = 0; j < W; j++)
+                    for (int q = 0; q < 4; q++)
                     {
-                        const int src = __double2loint(tm[q][j].y);
-                        const double cv = *reinterpret_cast<const double*>(rec - lane * 16 + q * stepBytes + cvalOff + j * 256 + lane * 8);
-                        const double sh = __shfl_sync(FULL, prev, src < 0 ? lane : src);
-                        acc = sweep_apply<MODE>(acc, tm[q][j].x, src < 0 ? cv : sh);
+                        double sh[W];
+#pragma unroll
+                        for (int j = 0; j < W; j++) sh[j] = __shfl_sync(FULL, prev, __double2loint(tm[q][j].y));
+                        double acc = hdr[q].x;
+#pragma unroll
+                        for (int j = 0; j < W; j++) acc -= tm[q][j].x * sh[j];
+                        st_relaxed(outPtr, acc);
+                        prev = acc;
+                        outPtr += outStride;
                     }
-                    st_relaxed(outPtr, acc);
-                    prev = acc;
-                    outPtr += outStride;
+                }
+                else
+                {
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                    {
+                        double acc = hdr[q].x;
+#pragma unroll
+                        for (int j = 0; j < W; j++)
+                        {
+                            const int src = __double2loint(tm[q][j].y);
+                            const double cv = *reinterpret_cast<const double*>(rb - lane * 16 + q * stepBytes + cvalOff + j * 256 + lane * 8);
+                            const double sh = __shfl_sync(FULL, prev, src < 0 ? lane : src);
+                            acc = sweep_apply<MODE>(acc, tm[q][j].x, src < 0 ? cv : sh);
+                        }
+                        st_relaxed(outPtr, acc);
+                        prev = acc;
+                        outPtr += outStride;
+                    }
                 }
             }
             __syncwarp();

@@ -114,6 +114,7 @@ struct GlobalLdu
 };
 
 // term codes of the sweep streams
+constexpr int kSweepBlock = 8;     // steps per producer/consumer block of the sweep kernel (= producer warps)
 constexpr int32_t kCodeNone = -1; // padding term
 constexpr int32_t kCodeOwn = -2;  // value this lane produced in the previous time step (register)
 constexpr int32_t kCodeShfl = -3; // -3 - m: value lane m produced in the previous time step (shuffle)
@@ -123,7 +124,7 @@ constexpr int32_t kCodeShfl = -3; // -3 - m: value lane m produced in the previo
 struct PipeSchedule
 {
     static constexpr int CH = 16;              // time steps per group are padded to a multiple of CH
-    static constexpr int kStageBudget = 16384; // shared-memory bytes of one pipeline stage of the sweep kernel
+    static constexpr int kStageBudget = 24576; // shared-memory bytes of one pipeline stage of the sweep kernel
     static constexpr int kLineModeMinAvgChain = 8;
 
     int64_t N = 0, nSlots = 0;
@@ -155,6 +156,7 @@ struct PipeSchedule
     {
         int ch = CH;
         while (ch > 1 && ch * (W * 384 + nVec * 256) > kStageBudget) ch >>= 1;
+        if (W <= 6 && ch < kSweepBlock) ch = kSweepBlock; // the fast path works on blocks of kSweepBlock steps
         return ch;
     }
 
@@ -598,13 +600,13 @@ struct PipeSchedule
                 {
                     code = slotOfCell[nb];
                     if (dir > 0) nMemTermsF++;
-                    // a memory dependency on a step of the same group inside the same block of 4 steps would
+                    // a memory dependency on a step of the same group inside the same block of kSweepBlock steps would
                     // dead-lock the producer/consumer CTA (the consumer needs the whole block): such groups
                     // take the single-warp generic path (bit 31 of gShflMask)
                     if (place_.grp[nb] == gI)
                     {
                         const int stepNb = dir > 0 ? place_.tim[nb] : gNT[gI] - 1 - place_.tim[nb];
-                        if (stepNb / 4 == step / 4) D.gShflMask[gI] |= int32_t(0x80000000u);
+                        if (stepNb / kSweepBlock == step / kSweepBlock) D.gShflMask[gI] |= int32_t(0x80000000u);
                     }
                 }
                 D.code[base + int64_t(j) * 32] = code;

@@ -53,6 +53,8 @@ struct orc_sys
     int total;
     int precond;
     double* rankPartial;
+    int redMode; /* 0: sequential sums (the reference); 1: pairwise sums -- only to MEASURE how sensitive a
+                    residual history is to the summation order (tests), never the parity target */
 };
 
 const char* orc_version(void) { return "ldu_oracle 1.0 (foam-extend-4.1 restatement, parity unpinned)"; }
@@ -204,12 +206,52 @@ int orc_add_iface(orc_sys* s, int row, int kind, int nFaces, const int* faceCell
 int orc_total_cells(const orc_sys* s) { return s->total; }
 
 /* ------------------------------------------------------------ reductions */
+/* kind: 0 sum a*b, 1 sum |a|, 2 sum a, 3 sum |a-c| + |b-c| */
+static double red_term(int kind, const double* a, const double* b, const double* c, int i)
+{
+    switch (kind)
+    {
+        case 0: return a[i] * b[i];
+        case 1: return fabs(a[i]);
+        case 2: return a[i];
+        default: return fabs(a[i] - c[i]) + fabs(b[i] - c[i]);
+    }
+}
+static double red_pairwise(int kind, const double* a, const double* b, const double* c, int lo, int hi)
+{
+    if (hi - lo <= 64)
+    {
+        double s = 0.0;
+        for (int i = lo; i < hi; i++) s += red_term(kind, a, b, c, i);
+        return s;
+    }
+    int mid = lo + (hi - lo) / 2;
+    return red_pairwise(kind, a, b, c, lo, mid) + red_pairwise(kind, a, b, c, mid, hi);
+}
+static double red_rows(const orc_sys* s, int kind, const double* a, const double* b, const double* c)
+{
+    for (int k = 0; k < s->nRanks; k++) s->rankPartial[k] = 0.0;
+    for (int r = 0; r < s->nRows; r++)
+    {
+        const orc_row* R = &s->rows[r];
+        const double* pa = a + R->offset;
+        const double* pb = b ? b + R->offset : NULL;
+        const double* pc = c ? c + R->offset : NULL;
+        s->rankPartial[R->rank] += red_pairwise(kind, pa, pb, pc, 0, R->nCells);
+    }
+    double tot = s->rankPartial[0];
+    for (int k = 1; k < s->nRanks; k++) tot += s->rankPartial[k];
+    return tot;
+}
+void orc_set_reduction_mode(orc_sys* s, int mode) { s->redMode = mode; }
+
 /* gSumProd / gSumMag / gSum over a FieldField: per rank, rows in list order,
  * cells sequentially (FieldFunctions.C sumProd / FieldFieldFunctions.C), then
  * reduce(sum) over ranks (taken in ascending rank order). */
 
 double orc_gsumprod(const orc_sys* s, const double* a, const double* b)
 {
+    if (s->redMode) return red_rows(s, 0, a, b, NULL);
     for (int k = 0; k < s->nRanks; k++) s->rankPartial[k] = 0.0;
     for (int r = 0; r < s->nRows; r++)
     {
@@ -227,6 +269,7 @@ double orc_gsumprod(const orc_sys* s, const double* a, const double* b)
 
 double orc_gsummag(const orc_sys* s, const double* a)
 {
+    if (s->redMode) return red_rows(s, 1, a, NULL, NULL);
     for (int k = 0; k < s->nRanks; k++) s->rankPartial[k] = 0.0;
     for (int r = 0; r < s->nRows; r++)
     {
@@ -243,6 +286,7 @@ double orc_gsummag(const orc_sys* s, const double* a)
 
 static double gsum(const orc_sys* s, const double* a)
 {
+    if (s->redMode) return red_rows(s, 2, a, NULL, NULL);
     for (int k = 0; k < s->nRanks; k++) s->rankPartial[k] = 0.0;
     for (int r = 0; r < s->nRows; r++)
     {
@@ -260,6 +304,7 @@ static double gsum(const orc_sys* s, const double* a)
 /* gSum(mag(Ax - tmp) + mag(b - tmp)) */
 static double gsum_normterms(const orc_sys* s, const double* Ax, const double* b, const double* tmp)
 {
+    if (s->redMode) return red_rows(s, 3, Ax, b, tmp);
     for (int k = 0; k < s->nRanks; k++) s->rankPartial[k] = 0.0;
     for (int r = 0; r < s->nRows; r++)
     {

@@ -132,6 +132,9 @@ int orc_solve(orc_sys*, const orc_opts*, double* x, const double* b, orc_perf* p
 /* reductions in the reference's order: per rank sequential over rows/cells, then over ranks */
 double orc_gsumprod(const orc_sys*, const double* a, const double* b);
 double orc_gsummag(const orc_sys*, const double* a);
+/* mode 0 (default): the reference's sequential sums.  mode 1: pairwise sums -- used by the tests only to
+ * MEASURE how sensitive a residual history is to the summation order; never the parity target. */
+void orc_set_reduction_mode(orc_sys*, int mode);
 
 /* ---- partitioned-coupling face transfer ---- */
 /* GGIInterpolation::interpolate: result[i] = sum_k ff[addr[k]]*w[k], zero-initialised, list order */

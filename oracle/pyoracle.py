@@ -65,6 +65,7 @@ def lib():
         L.orc_gsumprod.argtypes = [C.c_void_p, dp, dp]
         L.orc_gsummag.restype = C.c_double
         L.orc_gsummag.argtypes = [C.c_void_p, dp]
+        L.orc_set_reduction_mode.argtypes = [C.c_void_p, C.c_int]
         L.orc_ggi_interpolate.argtypes = [C.c_int, ip, ip, dp, dp, C.c_int, dp]
         L.orc_patch_face_to_global.argtypes = [C.c_int, ip, ip, dp, C.c_int, C.c_int, dp]
         L.orc_global_face_to_patch.argtypes = [C.c_int, ip, dp, C.c_int, dp]
@@ -185,6 +186,10 @@ class OracleSystem:
 
     def preconditionT(self, r):
         return self._vv("orc_preconditionT", r)
+
+    def set_reduction_mode(self, mode: int):
+        """0: sequential sums (the reference, default); 1: pairwise sums (sensitivity measurement only)."""
+        lib().orc_set_reduction_mode(self.h, mode)
 
     def gsumprod(self, a, b):
         return lib().orc_gsumprod(self.h, _dp(_f64(a)), _dp(_f64(b)))
