@@ -157,3 +157,184 @@ int emu_run(int nCells, int nFaces, const int* l, const int* u, const double* di
     }
 }
 }
+
+// ------------------------------------------------------------------------------------------------
+// One rank of a decomposed multi-region system on the CPU, driven by the SAME tables the device uses
+// (slot permutation, SELL layout, interface plan, halo send/receive layout).  Used by the
+// world_size-2 gloo test: pack -> exchange over torch.distributed -> Amul + interface update.
+namespace
+{
+struct EmuSys
+{
+    int rank = 0;
+    std::vector<RegionHost> regs;
+    std::vector<std::vector<double>> diag, upper, lower;
+    std::vector<std::vector<std::vector<double>>> bou;
+    GlobalLdu g;
+    PipeSchedule S;
+    SellLayout sell;
+    IfacePlan P;
+    std::vector<double> coef, ifCoef, diagSlots;
+};
+} // namespace
+
+extern "C" {
+
+void* emu_sys_create(int nRegions, int rank)
+{
+    EmuSys* s = new EmuSys;
+    s->rank = rank;
+    s->regs.resize(nRegions);
+    s->diag.resize(nRegions);
+    s->upper.resize(nRegions);
+    s->lower.resize(nRegions);
+    s->bou.resize(nRegions);
+    return s;
+}
+
+void emu_sys_destroy(void* h) { delete static_cast<EmuSys*>(h); }
+
+int emu_sys_set_region(void* h, int r, int nCells, int nFaces, const int* l, const int* u, const double* diag,
+                       const double* upper, const double* lower)
+{
+    EmuSys* s = static_cast<EmuSys*>(h);
+    RegionHost& R = s->regs[r];
+    R.nCells = nCells;
+    R.nFaces = nFaces;
+    R.l.assign(l, l + nFaces);
+    R.u.assign(u, u + nFaces);
+    R.set = true;
+    s->diag[r].assign(diag, diag + nCells);
+    s->upper[r].assign(upper, upper + nFaces);
+    s->lower[r].assign(lower ? lower : upper, (lower ? lower : upper) + nFaces);
+    return 0;
+}
+
+int emu_sys_add_iface(void* h, int r, int kind, int nFaces, const int* fc, int peerRank, int peerRegion, int peerIface,
+                      int nPeerFaces, const int* go, const int* ga, const double* gw, const double* bou)
+{
+    EmuSys* s = static_cast<EmuSys*>(h);
+    IfaceHost I;
+    I.kind = kind;
+    I.nFaces = nFaces;
+    I.faceCells.assign(fc, fc + nFaces);
+    I.peerRank = peerRank;
+    I.peerRegion = peerRegion;
+    I.peerIface = peerIface;
+    I.nPeerFaces = nPeerFaces;
+    I.identity = (go == nullptr);
+    if (go)
+    {
+        I.ggiOffsets.assign(go, go + nFaces + 1);
+        I.ggiAddr.assign(ga, ga + go[nFaces]);
+        I.ggiWeights.assign(gw, gw + go[nFaces]);
+    }
+    s->regs[r].ifaces.push_back(I);
+    s->bou[r].emplace_back(bou, bou + nFaces);
+    return int(s->regs[r].ifaces.size()) - 1;
+}
+
+int emu_sys_finalize(void* h)
+{
+    EmuSys* s = static_cast<EmuSys*>(h);
+    try
+    {
+        int64_t co = 0, fo = 0;
+        for (auto& R : s->regs)
+        {
+            R.cellOffset = co;
+            R.faceOffset = fo;
+            co += R.nCells;
+            fo += R.nFaces;
+        }
+        s->g.build(s->regs);
+        s->S.build(s->g, s->regs);
+        s->sell.build(s->g, s->S);
+        s->P.build(s->regs, s->rank, s->S);
+        s->coef.assign(2 * size_t(s->g.F) + 1, 0.0);
+        s->diagSlots.assign(s->S.nSlots, 0.0);
+        s->ifCoef.assign(size_t(s->P.nCoefs) + 1, 0.0);
+        for (size_t r = 0; r < s->regs.size(); r++)
+        {
+            const RegionHost& R = s->regs[r];
+            for (int f = 0; f < R.nFaces; f++)
+            {
+                s->coef[R.faceOffset + f] = s->upper[r][f];
+                s->coef[s->g.F + R.faceOffset + f] = s->lower[r][f];
+            }
+            for (int c = 0; c < R.nCells; c++) s->diagSlots[s->S.slotOfCell[R.cellOffset + c]] = s->diag[r][c];
+            for (size_t i = 0; i < R.ifaces.size(); i++)
+                for (int f = 0; f < R.ifaces[i].nFaces; f++) s->ifCoef[R.ifaces[i].coefOffset + f] = s->bou[r][i][f];
+        }
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        fprintf(stderr, "emu_sys_finalize: %s\n", e.what());
+        return -1;
+    }
+}
+
+int emu_sys_npeers(void* h) { return int(static_cast<EmuSys*>(h)->P.peers.size()); }
+
+int emu_sys_peer(void* h, int p, int* rank, int* sendOff, int* nSend, int* recvOff, int* nRecv)
+{
+    EmuSys* s = static_cast<EmuSys*>(h);
+    *rank = s->P.peers[p];
+    *sendOff = s->P.sendOff[p];
+    *nSend = s->P.sendOff[p + 1] - s->P.sendOff[p];
+    *recvOff = s->P.recvOff[p];
+    *nRecv = s->P.recvOff[p + 1] - s->P.recvOff[p];
+    return 0;
+}
+
+// k_halo_pack: sendbuf[i] = x[sendCells[i]]   (x given in cell order)
+int emu_sys_pack(void* h, const double* xCells, double* sendbuf)
+{
+    EmuSys* s = static_cast<EmuSys*>(h);
+    for (size_t i = 0; i < s->P.sendCells.size(); i++) sendbuf[i] = xCells[s->S.cellOfSlot[s->P.sendCells[i]]];
+    return 0;
+}
+
+// k_amul + k_iface over slots, result back in cell order
+int emu_sys_amul(void* h, const double* xCells, const double* recv, double* yCells)
+{
+    EmuSys* s = static_cast<EmuSys*>(h);
+    const int64_t nS = s->S.nSlots;
+    std::vector<double> x(nS, 0.0), y(nS, 0.0);
+    for (int64_t c = 0; c < s->g.N; c++) x[s->S.slotOfCell[c]] = xCells[c];
+    for (int64_t sl = 0; sl < nS; sl++)
+    {
+        const int64_t base = int64_t(s->sell.sliceOff[sl >> 5]) * 32 + (sl & 31);
+        const int width = s->sell.sliceOff[(sl >> 5) + 1] - s->sell.sliceOff[sl >> 5];
+        double acc = s->diagSlots[sl] * x[sl];
+        for (int j = 0; j < width; j++)
+        {
+            const int col = s->sell.col[base + int64_t(j) * 32];
+            if (col >= 0) acc += s->coef[s->sell.src[base + int64_t(j) * 32]] * x[col];
+        }
+        y[sl] = acc;
+    }
+    const IfacePlan& P = s->P;
+    for (size_t t = 0; t < P.rows.size(); t++)
+    {
+        double acc = y[P.rows[t]];
+        for (int e = P.rowStart[t]; e < P.rowStart[t + 1]; e++)
+        {
+            double pnf;
+            auto val = [&](int code) { return code >= 0 ? x[code] : recv[-1 - code]; };
+            if (P.entCnt[e] == 0)
+                pnf = val(P.entSrc[e]);
+            else
+            {
+                pnf = 0.0;
+                for (int k = 0; k < P.entCnt[e]; k++) pnf += val(P.gSrc[P.entSrc[e] + k]) * P.gW[P.entSrc[e] + k];
+            }
+            acc -= s->ifCoef[P.entCoef[e]] * pnf;
+        }
+        y[P.rows[t]] = acc;
+    }
+    for (int64_t c = 0; c < s->g.N; c++) yCells[c] = y[s->S.slotOfCell[c]];
+    return 0;
+}
+}
