@@ -150,9 +150,9 @@ struct DevBuf
 
 struct PipeDirMem
 {
-    DevBuf<int> gW, gCH, gShflMask, face, order;
-    DevBuf<long long> gTermOff;
-    DevBuf<unsigned char> stream;
+    DevBuf<int> gW, gCH, gShflMask, face, order, gLg, gRg, gKg, pFace, cFace;
+    DevBuf<long long> gTermOff, gPOff, gCOff, gPFaceOff, gCFaceOff, stats;
+    DevBuf<unsigned char> stream, gFast, pStream, cStream;
     PipeDev dev{};
     int smemBytes = 0;
     int packedFor = -1; // 0: plain coefficients packed, 1: transposed, -1: none
@@ -442,32 +442,49 @@ static int upload_pipe_dir(b200_sys* s, const PipeSchedule& S, const PipeSchedul
 {
     b200_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
+    auto ll = [](const std::vector<int64_t>& v) { return std::vector<long long>(v.begin(), v.end()); };
     CK(ctx, M.gW.upload(D.gW, st));
     CK(ctx, M.gCH.upload(D.gCH, st));
     CK(ctx, M.gShflMask.upload(D.gShflMask, st));
-    std::vector<long long> to(D.gTermOff.begin(), D.gTermOff.end());
-    CK(ctx, M.gTermOff.upload(to, st));
-    CK(ctx, M.face.upload(D.face, st));
-    // stream: code parts are static, coefficient parts are packed once per solve
-    std::vector<unsigned char> stream((size_t)D.nTerms * 12, 0);
+    // unified stream: generic groups only (the fast groups use the split streams)
+    std::vector<long long> genOff = ll(D.gGenOff);
+    CK(ctx, M.gTermOff.upload(genOff, st));
+    std::vector<unsigned char> stream((size_t)D.nGenTerms * 12, 0);
+    std::vector<int> genFace((size_t)D.nGenTerms, -1);
     for (int g = 0; g < S.nGroups; g++)
     {
+        if (D.gFast[g]) continue;
         const int W = D.gW[g], nT = S.gNT[g];
-        unsigned char* gs = stream.data() + (size_t)D.gTermOff[g] * 12;
+        unsigned char* gs = stream.data() + (size_t)D.gGenOff[g] * 12;
         for (int step = 0; step < nT; step++)
             memcpy(gs + (size_t)step * W * 384 + (size_t)W * 256, &D.code[D.gTermOff[g] + (int64_t)step * W * 32], (size_t)W * 128);
+        if (W) memcpy(&genFace[D.gGenOff[g]], &D.face[D.gTermOff[g]], sizeof(int) * (size_t)nT * W * 32);
     }
     CK(ctx, M.stream.upload(stream, st));
+    CK(ctx, M.face.upload(genFace, st));
+    // split streams
+    CK(ctx, M.gFast.upload(D.gFast, st));
+    CK(ctx, M.gLg.upload(D.gLg, st));
+    CK(ctx, M.gRg.upload(D.gRg, st));
+    CK(ctx, M.gKg.upload(D.gKg, st));
+    std::vector<long long> pOff = ll(D.gPOff), cOff = ll(D.gCOff), pfOff = ll(D.gPFaceOff), cfOff = ll(D.gCFaceOff);
+    CK(ctx, M.gPOff.upload(pOff, st));
+    CK(ctx, M.gCOff.upload(cOff, st));
+    CK(ctx, M.gPFaceOff.upload(pfOff, st));
+    CK(ctx, M.gCFaceOff.upload(cfOff, st));
+    CK(ctx, M.pStream.upload(D.pStream, st));
+    CK(ctx, M.cStream.upload(D.cStream, st));
+    CK(ctx, M.pFace.upload(D.pFace, st));
+    CK(ctx, M.cFace.upload(D.cFace, st));
     if (dir < 0) CK(ctx, M.order.upload(S.orderB, st));
     CK(ctx, cudaStreamSynchronize(st)); // host vectors go out of scope after return
-    const int stageBytes = (D.maxStageBytes + 127) / 128 * 128;
-    // raw ring: 4 stages (the producer warps run up to ~20 steps ahead of the consumer); prepared-record
-    // ring: kRB blocks of kNH steps of (512 + 768 W) bytes for the fast path (W <= 6).  About 90 KB per CTA
-    // for W = 3, so that two groups are co-resident per SM.
+    // shared memory: 256 B of barriers | raw ring (nStages stages) | consumer ring (kRB blocks); the generic
+    // single-warp path uses its own layout inside the same allocation.  About 90 KB per CTA for a 3-D
+    // structured mesh, so that two groups are co-resident per SM.
     const int nStages = 4;
-    const int wFast = std::min(D.maxW, 6);
-    const int crecBytes = kRB * kNH * (512 + 768 * wFast);
-    M.smemBytes = 256 + nStages * stageBytes + crecBytes;
+    const int stageBytes = (std::max(D.maxPStage, D.maxGenStage) + 127) / 128 * 128;
+    const int cBlockBytes = (kNH * D.maxCStep + 127) / 128 * 128;
+    M.smemBytes = 256 + nStages * stageBytes + kRB * cBlockBytes;
     M.dev.nGroups = S.nGroups;
     M.dev.dir = dir;
     M.dev.nStages = nStages;
@@ -481,6 +498,21 @@ static int upload_pipe_dir(b200_sys* s, const PipeSchedule& S, const PipeSchedul
     M.dev.order = dir < 0 ? M.order.p : nullptr;
     M.dev.stream = M.stream.p;
     M.dev.face = M.face.p;
+    M.dev.gFast = M.gFast.p;
+    M.dev.gLg = M.gLg.p;
+    M.dev.gRg = M.gRg.p;
+    M.dev.gKg = M.gKg.p;
+    M.dev.gPOff = M.gPOff.p;
+    M.dev.gCOff = M.gCOff.p;
+    M.dev.gPFaceOff = M.gPFaceOff.p;
+    M.dev.gCFaceOff = M.gCFaceOff.p;
+    M.dev.pStream = M.pStream.p;
+    M.dev.cStream = M.cStream.p;
+    M.dev.pFace = M.pFace.p;
+    M.dev.cFace = M.cFace.p;
+    M.dev.cBlockBytes = cBlockBytes;
+    M.dev.stats = nullptr;
+    M.dev.debugFlags = getenv("B200_SWEEP_DEBUG") ? atoi(getenv("B200_SWEEP_DEBUG")) : 0;
     M.packedFor = -1;
     return B200_OK;
 }
@@ -509,6 +541,7 @@ extern "C" int b200_sys_finalize(b200_sys* s)
         s->N = g.N;
         s->F = g.F;
         PipeSchedule S;
+        S.forceGeneric = getenv("B200_FORCE_GENERIC") != nullptr;
         S.build(g, s->regs);
         s->nSlots = S.nSlots;
         s->nGroups = S.nGroups;
@@ -812,7 +845,7 @@ static int pack_stream(b200_sys* s, PipeDirMem& M, const double* c1, const doubl
 {
     if (s->nGroups == 0) return B200_OK;
     KScope k(s, B200_K_PACK);
-    k_pack_stream<<<s->nGroups, 256, 0, s->ctx->stream>>>(M.dev, c1, c2, rD, prodMode);
+    k_pack_stream<<<dim3(s->nGroups, 8), 256, 0, s->ctx->stream>>>(M.dev, c1, c2, rD, prodMode);
     CK(s->ctx, cudaGetLastError());
     return B200_OK;
 }
@@ -1303,6 +1336,27 @@ extern "C" int b200_reduce(b200_sys* s, const double* const* a, const double* co
 }
 
 // ------------------------------------------------------------------------------------------ profiling
+extern "C" int b200_debug_sweep_stats(b200_sys* s, int dir, int enable, long long* out, int cap)
+{
+    if (!s || !s->finalized) return B200_EINVAL;
+    b200_ctx* ctx = s->ctx;
+    PipeDirMem& M = dir > 0 ? s->fwd : s->bwd;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t n = 8 * (size_t)s->nGroups;
+    if (out && M.stats.p)
+        CK(ctx, cudaMemcpy(out, M.stats.p, sizeof(long long) * std::min<size_t>(n, (size_t)cap), cudaMemcpyDeviceToHost));
+    if (enable)
+    {
+        if (M.stats.n != n) CK(ctx, M.stats.alloc(n));
+        CK(ctx, cudaMemset(M.stats.p, 0, sizeof(long long) * std::max<size_t>(n, 1)));
+        M.dev.stats = M.stats.p;
+    }
+    else
+        M.dev.stats = nullptr;
+    return s->nGroups;
+}
+
 extern "C" int b200_set_profiling(b200_sys* s, int enable)
 {
     if (!s) return B200_EINVAL;

@@ -4,6 +4,7 @@
 #pragma once
 
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 #include "schedule.hpp" // term codes (kCodeNone / kCodeOwn / kCodeShfl)
@@ -408,8 +409,24 @@ struct PipeDev
     const int* gShflMask; // bit 31: group must take the generic single-warp path
     const long long* gTermOff;
     const int* order; // ticket -> group (nullptr: identity)
-    unsigned char* stream; // group g: 12*gTermOff[g]; step record = coef[W][32] f64 | code[W][32] i32
-    const int* face;       // [nTerms] face of each term (pack time)
+    unsigned char* stream; // generic groups: 12*gTermOff[g]; step record = coef[W][32] f64 | code[W][32] i32
+    const int* face;       // face of each term of the unified stream (pack time)
+    // split streams of the fast path (schedule.hpp, build_split)
+    const unsigned char* gFast;
+    const int* gLg;
+    const int* gRg;
+    const int* gKg;
+    const long long* gPOff;
+    const long long* gCOff;
+    const long long* gPFaceOff;
+    const long long* gCFaceOff;
+    unsigned char* pStream;
+    unsigned char* cStream;
+    const int* pFace;
+    const int* cFace;
+    int cBlockBytes;  // bytes of one block of the consumer ring (max over the fast groups)
+    int debugFlags;   // bit 0: consumer always takes the select path (debug)
+    long long* stats; // optional [8 * nGroups]: consumer cycles, wait cycles, start ns, end ns, producer polls, nT (debug)
 };
 
 constexpr int kPF = 4; // prefetch distance (time steps) of cross-warp values
@@ -440,7 +457,7 @@ __device__ __noinline__ double sweep_spin(const double* p, int* err)
     {
         const double v = ld_relaxed(p);
         if (!is_sentinel(v)) return v;
-        if (tries > 64) __nanosleep(tries > 4096 ? 400 : 40);
+        __nanosleep(tries > 4096 ? 400 : 64); // a busy-spinning warp would steal issue slots from the consumer warps
         if ((tries & 4095) == 4095 && *(volatile int*)err) break;
     }
     atomicExch(err, 1);
@@ -526,285 +543,382 @@ __device__ __forceinline__ SweepRing ring_setup(const PipeDev& S, int g, int lan
     return R;
 }
 
-// Fast path (W = 1..6 terms per row): warp-specialised CTA.  A lone warp issues one instruction
-// every ~5 cycles, so the serial recurrence must execute as few instructions per time step as
-// possible.  kNH producer warps therefore PREPARE the steps (producer h takes step 8b+h of block b):
-// they read the streamed record, fetch and verify the cross-warp values (prefetched one block
-// ahead), apply -- in reference order -- the leading terms that do not depend on this group's previous
-// step, and write a compact record {acc0, (coef, source lane) per remaining term} into a second
-// shared-memory ring.  The consumer warp (warp 0) runs only the recurrence:
-//     per remaining term:  v = shfl(prev, source lane);  acc -= coef * v      then one store.
-// Terms a lane has already applied appear as padding (coef 0, source = own lane): exact no-ops.
-// Steps in which a remaining term needs a cross-warp value (block seams) take a slower select path.
+// ================================================================================================
+// Fast path: warp-specialised CTA over the SPLIT streams (schedule.hpp, build_split).
+// A lone warp issues one instruction every ~5 cycles and the recurrence is serial, so the consumer
+// warp must execute as little as possible per time step.  Everything static (which terms lead, which
+// lane a term shuffles from, how many terms a step has) was decided on the host:
+//   * kNH = 8 producer warps (producer h prepares step 8b+h of block b): read the P-stream record and
+//     the input vectors from the TMA-fed raw ring, fetch the cross-group values (prefetched one block
+//     ahead, verified against the sentinel), apply the row's LEADING terms in reference order and
+//     hand {acc0, cval[]} to the consumer through the hdr part of the consumer ring;
+//   * the C-stream records {meta, remaining coefficients} go by TMA straight into the consumer ring;
+//   * the consumer warp runs only the recurrence: per remaining term  v = shfl(prev, lane from meta);
+//     acc -= coef * v;  then one store.  Steps whose remaining terms need a cross-group value (block
+//     seams) and calcReciprocalD (division) take a select path.
 constexpr int kNH = kSweepBlock; // producer warps = steps per block (8)
-constexpr int kRB = 2;           // blocks in the prepared-record ring
+constexpr int kRB = 3;           // blocks in the consumer ring
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int MODE, int W>
-__device__ __forceinline__ void sweep_group_fast(const PipeDev& S, const int g, const int warp, const int lane,
-                                                 const double* __restrict__ a, const double* __restrict__ b, double* out, int* err,
-                                                 unsigned char* smem)
+struct SplitCtx
+{
+    int nT, base, dir, nBlocks, NS, stageBytes;
+    int Lg, Rg, Kg, pRec, cRec, hdrStep, cBlockBytes;
+    unsigned rawChunkBytes;
+    unsigned long long *rawBar, *hdrFull, *empty, *cTma;
+    unsigned char *rawRing, *cRing;
+    const unsigned char *pStream, *cStream;
+};
+
+template <int MODE>
+__device__ __forceinline__ void split_issue_raw(const SplitCtx& C, const double* a, const double* b, int blk, int st)
+{
+    unsigned char* dst = C.rawRing + (size_t)st * C.stageBytes;
+    mbar_expect_tx(&C.rawBar[st], C.rawChunkBytes);
+    const unsigned pBytes = (unsigned)(kNH * C.pRec);
+    bulk_g2s(dst, C.pStream + (size_t)blk * pBytes, pBytes, &C.rawBar[st]);
+    const long long s0 = C.dir > 0 ? ((long long)C.base + (long long)blk * kNH) * 32 : ((long long)C.base + C.nT - (long long)(blk + 1) * kNH) * 32;
+    bulk_g2s(dst + pBytes, a + s0, kNH * 256, &C.rawBar[st]);
+    if (MODE == 0) bulk_g2s(dst + pBytes + kNH * 256, b + s0, kNH * 256, &C.rawBar[st]);
+}
+
+__device__ __forceinline__ void split_issue_c(const SplitCtx& C, int blk, int slot)
+{
+    const unsigned bytes = (unsigned)(kNH * C.cRec);
+    mbar_expect_tx(&C.cTma[slot], bytes);
+    bulk_g2s(C.cRing + (size_t)slot * C.cBlockBytes, C.cStream + (size_t)blk * bytes, bytes, &C.cTma[slot]);
+}
+
+// ------------------------------------------------------------------------------------------ consumer
+template <int MODE, int RG>
+__device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx& C, const int g, const int lane, const double* a,
+                                               const double* b, double* out)
 {
     constexpr unsigned FULL = 0xffffffffu;
-    // ---- shared memory: [0,128) raw-stage barriers | [128,256) crec full/empty barriers | raw ring | crec ring
-    unsigned long long* rawBar = reinterpret_cast<unsigned long long*>(smem);
-    unsigned long long* crecFull = reinterpret_cast<unsigned long long*>(smem + 128);
-    unsigned long long* crecEmpty = crecFull + kRB;
-    SweepRing R;
-    R.W = W;
-    R.CHg = S.gCH[g];
-    R.nT = S.gNT[g];
-    R.base = S.gBase[g];
-    R.shflMask = 0;
-    R.nChunks = R.nT / R.CHg;
-    R.recBytes = W * 384;
-    R.schedBytes = R.CHg * R.recBytes;
-    R.NS = S.nStages;
-    R.dir = S.dir;
-    R.stageBytes = S.stageBytes;
-    R.bars = rawBar;
-    R.stages = smem + 256;
-    R.gstream = S.stream + 12ll * S.gTermOff[g];
-    R.vecBytes = (unsigned)(R.CHg * 256);
-    R.chunkBytes = (unsigned)R.schedBytes + R.vecBytes * (MODE == 0 ? 2u : 1u);
-    unsigned char* crecRing = R.stages + (size_t)R.NS * R.stageBytes;
-    constexpr int stepBytes = 512 + W * 768; // 512 (hdr) + W*512 (terms) + W*256 (const values)
-    constexpr int termOff = 512, cvalOff = 512 + W * 512;
-    const int CHg = R.CHg, nT = R.nT, NS = R.NS, dir = R.dir;
-    const int nBlocks = nT / kNH;
-
-    if (warp == 0 && lane == 0)
+    const int dir = C.dir, nT = C.nT;
+    double* outPtr = out + ((long long)C.base + (dir > 0 ? 0 : nT - 1)) * 32 + lane;
+    const long long outStride = dir > 0 ? 32 : -32;
+    const int hdrOff = kNH * C.cRec; // hdr part of a ring block follows its C-records
+    double prev = 0.0;
+    int slot = 0;
+    unsigned par = 0u;
+    long long tWait = 0, t0 = 0, g0 = 0, tTma = 0, tTail = 0;
+    if (S.stats)
     {
-        for (int st = 0; st < NS; st++) mbar_init(&rawBar[st], 1);
-        for (int i = 0; i < kRB; i++)
-        {
-            mbar_init(&crecFull[i], kNH);
-            mbar_init(&crecEmpty[i], 1);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int c = 0; c < NS && c < R.nChunks; c++) ring_issue<MODE>(R, a, b, c, c);
+        t0 = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
     }
-    __syncthreads();
-
-    if (warp == 0)
+    for (int blk = 0; blk < C.nBlocks; blk++)
     {
-        // ================================================================= consumer: the recurrence
-        double* outPtr = out + ((long long)R.base + (dir > 0 ? 0 : nT - 1)) * 32 + lane;
-        const long long outStride = dir > 0 ? 32 : -32;
-        double prev = 0.0;
-        int slot = 0;
-        unsigned par = 0u;
-        int stepsInChunk = 0, chunk = 0, stRefill = 0;
-        for (int blk = 0; blk < nBlocks; blk++)
+        const unsigned char* blkBase = C.cRing + (size_t)slot * C.cBlockBytes;
+        if (S.stats)
         {
-            mbar_wait(&crecFull[slot], par);
-            const unsigned char* rec = crecRing + (size_t)slot * (kNH * stepBytes) + lane * 16;
-            // operands are read four steps at a time, up front; terms below a step's common leading count are
-            // padding for every lane, so all W terms are always executed: no branch inside the chain
+            const long long w0 = clock64();
+            mbar_wait(&C.cTma[slot], par);
+            tTma += clock64() - w0;
+        }
+        else
+            mbar_wait(&C.cTma[slot], par);
 #pragma unroll
-            for (int hb = 0; hb < kNH; hb += 4)
+        for (int hb = 0; hb < kNH; hb += 4)
+        {
+            if (S.stats)
             {
-                const unsigned char* rb = rec + hb * stepBytes;
-                double2 hdr[4], tm[4][W];
+                const long long w0 = clock64();
+                mbar_wait(&C.hdrFull[slot * 2 + (hb >> 2)], par);
+                tWait += clock64() - w0;
+            }
+            else
+                mbar_wait(&C.hdrFull[slot * 2 + (hb >> 2)], par);
+            double acc0[4], cf[4][RG];
+            unsigned long long meta[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                const unsigned char* rec = blkBase + (size_t)(hb + q) * C.cRec;
+                acc0[q] = *reinterpret_cast<const double*>(blkBase + hdrOff + (size_t)(hb + q) * C.hdrStep + lane * 8);
+                meta[q] = *reinterpret_cast<const unsigned long long*>(rec + lane * 8);
+#pragma unroll
+                for (int r = 0; r < RG; r++) cf[q][r] = *reinterpret_cast<const double*>(rec + 256 + r * 256 + lane * 8);
+            }
+            unsigned flags = 0, rmax = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                flags |= (unsigned)(meta[q] >> 56) & 1u;
+                rmax = max(rmax, (unsigned)(meta[q] >> 48) & 0xffu);
+            }
+            if (MODE != 2 && !flags && !(S.debugFlags & 1))
+            {
+                // R = number of terms to run for these 4 steps (uniform); terms beyond a lane's own are padding
+                auto run = [&](auto RR) {
+                    constexpr int R = decltype(RR)::value;
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                    {
+                        double sh[R > 0 ? R : 1];
+#pragma unroll
+                        for (int r = 0; r < R; r++) sh[r] = __shfl_sync(FULL, prev, (int)(meta[q] >> (8 * r)) & 31);
+                        double acc = acc0[q];
+#pragma unroll
+                        for (int r = 0; r < R; r++) acc -= cf[q][r] * sh[r];
+                        st_relaxed(outPtr, acc);
+                        prev = acc;
+                        outPtr += outStride;
+                    }
+                };
+                if (RG >= 2 && rmax == RG - 1)
+                    run(std::integral_constant<int, (RG >= 2 ? RG - 1 : RG)>());
+                else if (RG >= 3 && rmax == RG - 2)
+                    run(std::integral_constant<int, (RG >= 3 ? RG - 2 : RG)>());
+                else
+                    run(std::integral_constant<int, RG>());
+            }
+            else
+            {
 #pragma unroll
                 for (int q = 0; q < 4; q++)
                 {
-                    hdr[q] = *reinterpret_cast<const double2*>(rb + q * stepBytes); // {acc0, info}
+                    const unsigned char* hd = blkBase + hdrOff + (size_t)(hb + q) * C.hdrStep + lane * 8;
+                    const double cv0 = *reinterpret_cast<const double*>(hd + 256);
+                    const double cv1 = C.Kg > 1 ? *reinterpret_cast<const double*>(hd + 512) : 0.0;
+                    double acc = acc0[q];
 #pragma unroll
-                    for (int j = 0; j < W; j++) tm[q][j] = *reinterpret_cast<const double2*>(rb + q * stepBytes + termOff + j * 512); // {coef, src}
-                }
-                int fastAll = 0x100;
-#pragma unroll
-                for (int q = 0; q < 4; q++) fastAll &= __double2loint(hdr[q].y);
-                if (MODE != 2 && fastAll)
-                {
-#pragma unroll
-                    for (int q = 0; q < 4; q++)
+                    for (int r = 0; r < RG; r++)
                     {
-                        double sh[W];
-#pragma unroll
-                        for (int j = 0; j < W; j++) sh[j] = __shfl_sync(FULL, prev, __double2loint(tm[q][j].y));
-                        double acc = hdr[q].x;
-#pragma unroll
-                        for (int j = 0; j < W; j++) acc -= tm[q][j].x * sh[j];
-                        st_relaxed(outPtr, acc);
-                        prev = acc;
-                        outPtr += outStride;
+                        const unsigned byte = (unsigned)(meta[q] >> (8 * r)) & 0xffu;
+                        const double sh = __shfl_sync(FULL, prev, (int)(byte & 31u));
+                        double v = (byte & 0x80u) ? ((byte & 0x20u) ? cv1 : cv0) : sh;
+                        if (byte & 0x40u) v = MODE == 2 ? 1.0 : 0.0; // padding term (coefficient 0)
+                        acc = sweep_apply<MODE>(acc, cf[q][r], v);
                     }
-                }
-                else
-                {
-#pragma unroll
-                    for (int q = 0; q < 4; q++)
-                    {
-                        double acc = hdr[q].x;
-#pragma unroll
-                        for (int j = 0; j < W; j++)
-                        {
-                            const int src = __double2loint(tm[q][j].y);
-                            const double cv = *reinterpret_cast<const double*>(rb - lane * 16 + q * stepBytes + cvalOff + j * 256 + lane * 8);
-                            const double sh = __shfl_sync(FULL, prev, src < 0 ? lane : src);
-                            acc = sweep_apply<MODE>(acc, tm[q][j].x, src < 0 ? cv : sh);
-                        }
-                        st_relaxed(outPtr, acc);
-                        prev = acc;
-                        outPtr += outStride;
-                    }
+                    st_relaxed(outPtr, acc);
+                    prev = acc;
+                    outPtr += outStride;
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&crecEmpty[slot]);
-            if (++slot == kRB)
+        }
+        const long long w1 = S.stats ? clock64() : 0;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&C.empty[slot]); // block done: producers may reuse its hdr, the loader warp refills
+        if (++slot == kRB)
+        {
+            slot = 0;
+            par ^= 1u;
+        }
+        if (S.stats) tTail += clock64() - w1;
+    }
+    if (S.stats && lane == 0)
+    {
+        long long g1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+        long long* st = S.stats + 8ll * g;
+        st[0] = clock64() - t0;
+        st[1] = tWait;
+        st[2] = g0;
+        st[3] = g1;
+        st[5] = nT;
+        st[6] = tTma;
+        st[7] = tTail;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ producers
+template <int MODE, int LG>
+__device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx& C, const int g, const int h, const int lane, double* out,
+                                               int* err)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int LGA = LG > 0 ? LG : 1;
+    const int dir = C.dir;
+    const int codeOff = LG * 256 + lane * 4, constOff = LG * 384 + lane * 4;
+    const int vecIdx = (dir > 0 ? h : kNH - 1 - h) * 32 + lane; // this producer's step inside a raw chunk
+    const double neutral = MODE == 2 ? 1.0 : 0.0;
+    const int hdrOff = kNH * C.cRec;
+    int codes[LGA], codesN[LGA], cc[2], ccN[2];
+    double mv[LGA], mvN[LGA], mc[2], mcN[2];
+    auto fetch = [&](const unsigned char* rec, int* cd, double* vals, int* kc, double* kv) {
+#pragma unroll
+        for (int i = 0; i < LG; i++)
+        {
+            cd[i] = *reinterpret_cast<const int*>(rec + codeOff + i * 128);
+            vals[i] = neutral;
+            if (cd[i] >= 0) vals[i] = ld_relaxed(out + cd[i]);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+        {
+            kc[k] = (k < C.Kg) ? *reinterpret_cast<const int*>(rec + constOff + k * 128) : -1;
+            kv[k] = 0.0;
+            if (kc[k] >= 0) kv[k] = ld_relaxed(out + kc[k]);
+        }
+    };
+    int st = 0, slot = 0;
+    unsigned parRaw = 0u, parC = 0u;
+    mbar_wait(&C.rawBar[0], 0u);
+    fetch(C.rawRing + (size_t)h * C.pRec, codes, mv, cc, mc);
+    for (int blk = 0; blk < C.nBlocks; blk++)
+    {
+        const unsigned char* sb = C.rawRing + (size_t)st * C.stageBytes;
+        const unsigned char* rec = sb + (size_t)h * C.pRec;
+        const double* aP = reinterpret_cast<const double*>(sb + kNH * C.pRec) + vecIdx;
+        // ---- prefetch the codes / cross-group values of this producer's step in the next block
+        int stN = st + 1;
+        unsigned parN = parRaw;
+        if (stN == C.NS)
+        {
+            stN = 0;
+            parN ^= 1u;
+        }
+        if (blk + 1 < C.nBlocks)
+        {
+            mbar_wait(&C.rawBar[stN], parN);
+            fetch(C.rawRing + (size_t)stN * C.stageBytes + (size_t)h * C.pRec, codesN, mvN, ccN, mcN);
+        }
+        // ---- operands of the current step first, the (possibly late) cross-group values last
+        double acc = *aP;
+        if (MODE == 0) acc *= aP[kNH * 32];
+        double cf[LGA];
+#pragma unroll
+        for (int i = 0; i < LG; i++) cf[i] = *reinterpret_cast<const double*>(rec + lane * 8 + i * 256);
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < LG; i++) bad |= codes[i] >= 0 && is_sentinel(mv[i]);
+#pragma unroll
+        for (int k = 0; k < 2; k++) bad |= cc[k] >= 0 && is_sentinel(mc[k]);
+        if (__any_sync(FULL, bad))
+        { // a value had not arrived when it was prefetched: poll for it
+            if (S.stats && lane == 0) atomicAdd((unsigned long long*)(S.stats + 8ll * g + 4), 1ull);
+#pragma unroll
+            for (int i = 0; i < LG; i++)
+                if (codes[i] >= 0 && is_sentinel(mv[i])) mv[i] = sweep_spin(out + codes[i], err);
+#pragma unroll
+            for (int k = 0; k < 2; k++)
+                if (cc[k] >= 0 && is_sentinel(mc[k])) mc[k] = sweep_spin(out + cc[k], err);
+        }
+#pragma unroll
+        for (int i = 0; i < LG; i++) acc = sweep_apply<MODE>(acc, cf[i], mv[i]); // padding: coefficient 0, neutral value
+        // ---- hand over once the consumer has released the ring block
+        if (blk >= kRB) mbar_wait(&C.empty[slot], parC ^ 1u);
+        unsigned char* hd = C.cRing + (size_t)slot * C.cBlockBytes + hdrOff + (size_t)h * C.hdrStep + lane * 8;
+        *reinterpret_cast<double*>(hd) = acc;
+        *reinterpret_cast<double*>(hd + 256) = mc[0];
+        if (C.Kg > 1) *reinterpret_cast<double*>(hd + 512) = mc[1];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&C.hdrFull[slot * 2 + (h >> 2)]);
+        if (++slot == kRB)
+        {
+            slot = 0;
+            parC ^= 1u;
+        }
+        st = stN;
+        parRaw = parN;
+#pragma unroll
+        for (int i = 0; i < LG; i++)
+        {
+            codes[i] = codesN[i];
+            mv[i] = mvN[i];
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+        {
+            cc[k] = ccN[k];
+            mc[k] = mcN[k];
+        }
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void sweep_group_split(const PipeDev& S, const int g, const int warp, const int lane, const double* __restrict__ a,
+                                                  const double* __restrict__ b, double* out, int* err, unsigned char* smem)
+{
+    SplitCtx C;
+    C.nT = S.gNT[g];
+    C.base = S.gBase[g];
+    C.dir = S.dir;
+    C.nBlocks = C.nT / kNH;
+    C.NS = S.nStages;
+    C.stageBytes = S.stageBytes;
+    C.Lg = S.gLg[g];
+    C.Rg = S.gRg[g];
+    C.Kg = S.gKg[g];
+    C.pRec = C.Lg * 384 + C.Kg * 128;
+    C.cRec = 256 + C.Rg * 256;
+    C.hdrStep = 256 * (1 + C.Kg);
+    C.cBlockBytes = S.cBlockBytes;
+    C.rawChunkBytes = (unsigned)(kNH * C.pRec + kNH * 256 * (MODE == 0 ? 2 : 1));
+    C.rawBar = reinterpret_cast<unsigned long long*>(smem);
+    C.hdrFull = reinterpret_cast<unsigned long long*>(smem + 128);
+    C.empty = C.hdrFull + 2 * kRB;
+    C.cTma = C.empty + kRB;
+    C.rawRing = smem + 256;
+    C.cRing = C.rawRing + (size_t)C.NS * C.stageBytes;
+    C.pStream = S.pStream + S.gPOff[g];
+    C.cStream = S.cStream + S.gCOff[g];
+    if (warp == 0 && lane == 0)
+    {
+        for (int st = 0; st < C.NS; st++) mbar_init(&C.rawBar[st], 1);
+        for (int i = 0; i < 2 * kRB; i++) mbar_init(&C.hdrFull[i], kNH / 2);
+        for (int i = 0; i < kRB; i++)
+        {
+            mbar_init(&C.empty[i], 1);
+            mbar_init(&C.cTma[i], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int c = 0; c < C.NS && c < C.nBlocks; c++) split_issue_raw<MODE>(C, a, b, c, c);
+        for (int c = 0; c < kRB && c < C.nBlocks; c++) split_issue_c(C, c, c);
+    }
+    __syncthreads();
+    if (warp == 0)
+    {
+        switch (C.Rg)
+        {
+            case 1: split_consumer<MODE, 1>(S, C, g, lane, a, b, out); break;
+            case 2: split_consumer<MODE, 2>(S, C, g, lane, a, b, out); break;
+            case 3: split_consumer<MODE, 3>(S, C, g, lane, a, b, out); break;
+            case 4: split_consumer<MODE, 4>(S, C, g, lane, a, b, out); break;
+            case 5: split_consumer<MODE, 5>(S, C, g, lane, a, b, out); break;
+            default: split_consumer<MODE, 6>(S, C, g, lane, a, b, out); break;
+        }
+    }
+    else if (warp == 1 + kNH)
+    {
+        // loader: one thread refills the rings as soon as the consumer has released a block
+        if (lane == 0)
+        {
+            int slot = 0, stRaw = 0;
+            unsigned par = 0u;
+            for (int blk = 0; blk < C.nBlocks; blk++)
             {
-                slot = 0;
-                par ^= 1u;
-            }
-            // raw chunk fully consumed (the producers are ahead of this warp) -> refill its stage
-            stepsInChunk += kNH;
-            if (stepsInChunk == CHg)
-            {
-                stepsInChunk = 0;
-                if (lane == 0 && chunk + NS < R.nChunks) ring_issue<MODE>(R, a, b, chunk + NS, stRefill);
-                chunk++;
-                if (++stRefill == NS) stRefill = 0;
+                if (blk + kRB >= C.nBlocks && blk + C.NS >= C.nBlocks) break;
+                mbar_wait(&C.empty[slot], par);
+                if (blk + kRB < C.nBlocks) split_issue_c(C, blk + kRB, slot);
+                if (blk + C.NS < C.nBlocks) split_issue_raw<MODE>(C, a, b, blk + C.NS, stRaw);
+                if (++slot == kRB)
+                {
+                    slot = 0;
+                    par ^= 1u;
+                }
+                if (++stRaw == C.NS) stRaw = 0;
             }
         }
     }
     else
     {
-        // ================================================================= producers
-        const int h = warp - 1; // step within a block
-        const int codeOff = W * 256 + lane * 4;
-        const int coefOff = lane * 8;
-        const int vecStart = dir > 0 ? lane : (CHg - 1) * 32 + lane;
-        const int vecStride = dir > 0 ? 32 : -32;
-        const double neutral = MODE == 2 ? 1.0 : 0.0;
-        int codes[W], codesN[W];
-        double mv[W], mvN[W];
-        int q = h;            // step index inside the current raw chunk
-        int st = 0;           // raw stage of the current chunk
-        unsigned parRaw = 0u; // parity of that stage's barrier
-        int chunk = 0, chunksWaited = 0;
-        auto wait_chunk = [&](int cidx, int stg, unsigned parity) {
-            if (cidx >= chunksWaited)
-            {
-                mbar_wait(&rawBar[stg], parity);
-                chunksWaited = cidx + 1;
-            }
-        };
-        auto fetch = [&](const unsigned char* rec, int* cd, double* vals) {
-#pragma unroll
-            for (int j = 0; j < W; j++)
-            {
-                cd[j] = *reinterpret_cast<const int*>(rec + codeOff + j * 128);
-                vals[j] = 0.0;
-                if (cd[j] >= 0) vals[j] = ld_relaxed(out + cd[j]);
-            }
-        };
-        wait_chunk(0, 0, 0u);
-        fetch(R.stages + (size_t)q * R.recBytes, codes, mv);
-        int slot = 0;
-        unsigned parC = 0u;
-        for (int blk = 0; blk < nBlocks; blk++)
+        const int h = warp - 1;
+        switch (C.Lg)
         {
-            const unsigned char* sb = R.stages + (size_t)st * R.stageBytes;
-            const unsigned char* rec = sb + (size_t)q * R.recBytes;
-            const double* aP = reinterpret_cast<const double*>(sb + R.schedBytes) + vecStart + q * vecStride;
-            // ---- prefetch the codes / cross-warp values of this producer's next step (next block)
-            int qN = q + kNH, stN = st, chunkN = chunk;
-            unsigned parN = parRaw;
-            if (qN >= CHg)
-            {
-                qN -= CHg;
-                chunkN++;
-                if (++stN == NS)
-                {
-                    stN = 0;
-                    parN ^= 1u;
-                }
-            }
-            if (blk + 1 < nBlocks)
-            {
-                wait_chunk(chunkN, stN, parN);
-                fetch(R.stages + (size_t)stN * R.stageBytes + (size_t)qN * R.recBytes, codesN, mvN);
-            }
-            // ---- prepare the current step
-            bool bad = false;
-#pragma unroll
-            for (int j = 0; j < W; j++) bad |= codes[j] >= 0 && is_sentinel(mv[j]);
-            if (__any_sync(FULL, bad))
-            { // a cross-warp value had not arrived when it was prefetched: poll for it
-#pragma unroll
-                for (int j = 0; j < W; j++)
-                    if (codes[j] >= 0 && is_sentinel(mv[j])) mv[j] = sweep_spin(out + codes[j], err);
-            }
-            double acc = *aP;
-            if (MODE == 0) acc *= aP[CHg * 32];
-            double cf[W];
-            int ld = 0;
-            bool still = true;
-#pragma unroll
-            for (int j = 0; j < W; j++)
-            {
-                cf[j] = *reinterpret_cast<const double*>(rec + coefOff + j * 256);
-                still = still && (codes[j] >= 0 || codes[j] == kCodeNone);
-                if (still)
-                {
-                    ld = j + 1;
-                    acc = sweep_apply<MODE>(acc, cf[j], codes[j] >= 0 ? mv[j] : neutral);
-                }
-            }
-            const int leadMin = __reduce_min_sync(FULL, ld);
-            bool fastOk = true;
-#pragma unroll
-            for (int j = 0; j < W; j++) fastOk = fastOk && !(j >= ld && codes[j] >= 0);
-            const int allFast = __all_sync(FULL, fastOk) ? 0x100 : 0;
-            // ---- write the prepared record once the consumer has released the ring slot
-            if (blk >= kRB) mbar_wait(&crecEmpty[slot], parC ^ 1u);
-            unsigned char* cr = crecRing + (size_t)slot * (kNH * stepBytes) + (size_t)h * stepBytes;
-            *reinterpret_cast<double2*>(cr + lane * 16) = make_double2(acc, __hiloint2double(0, leadMin | allFast));
-#pragma unroll
-            for (int j = 0; j < W; j++)
-            {
-                double coef = cf[j], cval = neutral;
-                int src = lane;
-                if (j < ld || codes[j] == kCodeNone)
-                { // already applied by this lane / padding term: exact no-op
-                    coef = 0.0;
-                    if (MODE == 2) src = -1;
-                }
-                else if (codes[j] >= 0)
-                {
-                    src = -1;
-                    cval = mv[j];
-                }
-                else if (codes[j] <= kCodeShfl)
-                    src = kCodeShfl - codes[j];
-                *reinterpret_cast<double2*>(cr + termOff + j * 512 + lane * 16) = make_double2(coef, __hiloint2double(0, src));
-                *reinterpret_cast<double*>(cr + cvalOff + j * 256 + lane * 8) = cval;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&crecFull[slot]);
-            if (++slot == kRB)
-            {
-                slot = 0;
-                parC ^= 1u;
-            }
-            // ---- advance
-            q = qN;
-            st = stN;
-            parRaw = parN;
-            chunk = chunkN;
-#pragma unroll
-            for (int j = 0; j < W; j++)
-            {
-                codes[j] = codesN[j];
-                mv[j] = mvN[j];
-            }
+            case 0: split_producer<MODE, 0>(S, C, g, h, lane, out, err); break;
+            case 1: split_producer<MODE, 1>(S, C, g, h, lane, out, err); break;
+            case 2: split_producer<MODE, 2>(S, C, g, h, lane, out, err); break;
+            case 3: split_producer<MODE, 3>(S, C, g, h, lane, out, err); break;
+            case 4: split_producer<MODE, 4>(S, C, g, h, lane, out, err); break;
+            case 5: split_producer<MODE, 5>(S, C, g, h, lane, out, err); break;
+            default: split_producer<MODE, 6>(S, C, g, h, lane, out, err); break;
         }
     }
 }
@@ -867,9 +981,9 @@ __device__ __noinline__ void sweep_group_generic(const PipeDev& S, const int g, 
     }
 }
 
-// One CTA (1 consumer + kNH producer warps) per group; CTAs take tickets so that groups start in a
+// One CTA (1 consumer + kNH producer warps + 1 loader warp) per group; CTAs take tickets so that groups start in a
 // topological order of the group graph: a group only ever waits for groups that are already running.
-constexpr int kSweepThreads = 32 * (1 + kNH);
+constexpr int kSweepThreads = 32 * (2 + kNH); // consumer + producers + loader
 template <int MODE>
 __global__ void __launch_bounds__(kSweepThreads) k_sweep(PipeDev S, const double* __restrict__ a, const double* __restrict__ b,
                                                           double* out, unsigned* ticket, unsigned ticketBase, int* err,
@@ -884,19 +998,10 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep(PipeDev S, const double
     if (sc->done && !force) return;
     if ((int)t >= S.nGroups) return;
     const int g = S.order ? S.order[t] : (int)t;
-    const int W = (S.gShflMask[g] < 0) ? 0 : S.gW[g];
-    switch (W)
-    {
-        case 1: sweep_group_fast<MODE, 1>(S, g, warp, lane, a, b, out, err, smem); break;
-        case 2: sweep_group_fast<MODE, 2>(S, g, warp, lane, a, b, out, err, smem); break;
-        case 3: sweep_group_fast<MODE, 3>(S, g, warp, lane, a, b, out, err, smem); break;
-        case 4: sweep_group_fast<MODE, 4>(S, g, warp, lane, a, b, out, err, smem); break;
-        case 5: sweep_group_fast<MODE, 5>(S, g, warp, lane, a, b, out, err, smem); break;
-        case 6: sweep_group_fast<MODE, 6>(S, g, warp, lane, a, b, out, err, smem); break;
-        default:
-            if (warp == 0) sweep_group_generic<MODE>(S, g, lane, a, b, out, err, smem);
-            break;
-    }
+    if (S.gFast[g])
+        sweep_group_split<MODE>(S, g, warp, lane, a, b, out, err, smem);
+    else if (warp == 0)
+        sweep_group_generic<MODE>(S, g, lane, a, b, out, err, smem);
 }
 
 // Fill the coefficient part of a sweep stream from the face coefficients (once per solve).
@@ -906,28 +1011,54 @@ __global__ void __launch_bounds__(256) k_pack_stream(PipeDev S, const double* __
 {
     const int g = blockIdx.x;
     if (g >= S.nGroups) return;
-    const int W = S.gW[g], nT = S.gNT[g], base = S.gBase[g];
-    const long long off = S.gTermOff[g];
-    const int perStep = W * 32;
-    const long long n = (long long)nT * perStep;
-    unsigned char* gs = S.stream + 12ll * off;
-    for (long long e = threadIdx.x; e < n; e += blockDim.x)
+    const int nT = S.gNT[g], base = S.gBase[g];
+    auto value = [&](int f, int step, int lane) -> double {
+        if (f < 0) return 0.0;
+        if (prodMode) return c1[f] * c2[f];
+        const long long slot = ((long long)base + (S.dir > 0 ? step : nT - 1 - step)) * 32 + lane;
+        return rD[slot] * c1[f];
+    };
+    const int tid = blockIdx.y * blockDim.x + threadIdx.x, nth = gridDim.y * blockDim.x;
+    if (!S.gFast[g])
     {
-        const int step = (int)(e / perStep);
-        const int rem = (int)(e - (long long)step * perStep);
-        const int f = S.face[off + e];
-        double v = 0.0;
-        if (f >= 0)
+        const int W = S.gW[g];
+        const long long off = S.gTermOff[g];
+        const int perStep = W * 32;
+        const long long n = (long long)nT * perStep;
+        unsigned char* gs = S.stream + 12ll * off;
+        for (long long e = tid; e < n; e += nth)
         {
-            if (prodMode)
-                v = c1[f] * c2[f];
-            else
-            {
-                const long long slot = ((long long)base + (S.dir > 0 ? step : nT - 1 - step)) * 32 + (rem & 31);
-                v = rD[slot] * c1[f];
-            }
+            const int step = (int)(e / perStep);
+            const int rem = (int)(e - (long long)step * perStep);
+            reinterpret_cast<double*>(gs + (size_t)step * perStep * 12)[rem] = value(S.face[off + e], step, rem & 31);
         }
-        reinterpret_cast<double*>(gs + (size_t)step * perStep * 12)[rem] = v;
+        return;
+    }
+    const int Lg = S.gLg[g], Rg = S.gRg[g], Kg = S.gKg[g];
+    const int pRec = Lg * 384 + Kg * 128, cRec = 256 + Rg * 256;
+    if (Lg > 0)
+    {
+        const long long n = (long long)nT * Lg * 32;
+        const int* face = S.pFace + S.gPFaceOff[g];
+        unsigned char* ps = S.pStream + S.gPOff[g];
+        for (long long e = tid; e < n; e += nth)
+        {
+            const int step = (int)(e / (Lg * 32));
+            const int rem = (int)(e - (long long)step * (Lg * 32));
+            reinterpret_cast<double*>(ps + (size_t)step * pRec)[rem] = value(face[e], step, rem & 31);
+        }
+    }
+    if (Rg > 0)
+    {
+        const long long n = (long long)nT * Rg * 32;
+        const int* face = S.cFace + S.gCFaceOff[g];
+        unsigned char* cs = S.cStream + S.gCOff[g];
+        for (long long e = tid; e < n; e += nth)
+        {
+            const int step = (int)(e / (Rg * 32));
+            const int rem = (int)(e - (long long)step * (Rg * 32));
+            reinterpret_cast<double*>(cs + (size_t)step * cRec + 256)[rem] = value(face[e], step, rem & 31);
+        }
     }
 }
 

@@ -126,6 +126,7 @@ struct PipeSchedule
     static constexpr int CH = 16;              // time steps per group are padded to a multiple of CH
     static constexpr int kStageBudget = 24576; // shared-memory bytes of one pipeline stage of the sweep kernel
     static constexpr int kLineModeMinAvgChain = 8;
+    bool forceGeneric = false; // debug: every group takes the single-warp generic path
 
     int64_t N = 0, nSlots = 0;
     int nGroups = 0;
@@ -140,6 +141,25 @@ struct PipeSchedule
         std::vector<int32_t> code, face; // [nTerms] index = gTermOff[g] + (step*W + j)*32 + lane, step in PROCESSING order
         int64_t nTerms = 0;
         int maxW = 0, maxStageBytes = 0, nLevels = 0;
+        // ---- split streams of the fast path (groups with gFast != 0).  Everything about a row's terms that
+        //      does not depend on the coefficient VALUES is decided here, once, on the host:
+        //  P-stream (producer warps), per step:  coef[Lg][32] f64 | code[Lg][32] i32 | constCode[Kg][32] i32
+        //      the LEADING terms of each row: its first run of cross-group (memory) terms, in reference order;
+        //      constCode[k] = slot of the k-th cross-group value the row's remaining terms need (-1: none)
+        //  C-stream (consumer warp), per step:   meta[32] u64 | coef[Rg][32] f64
+        //      the REMAINING terms, in reference order.  meta byte r < 6 describes term r: bits 0-4 source lane
+        //      (own lane for the register-carried value), 0x40 = padding term (coefficient 0), 0x80 = the
+        //      term takes the value of constCode[bit 5] instead of a shuffle; byte 6 = number of terms of this
+        //      step (uniform over the lanes); byte 7 bit 0 = some lane of this step has a 0x80 term (uniform).
+        std::vector<uint8_t> gFast;
+        std::vector<int32_t> gLg, gRg, gKg;
+        std::vector<int64_t> gPOff, gCOff;           // [nGroups+1] byte offsets into pStream / cStream
+        std::vector<int64_t> gPFaceOff, gCFaceOff;   // [nGroups+1] offsets into pFace / cFace
+        std::vector<unsigned char> pStream, cStream; // host images: codes / meta filled in, coefficients zero
+        std::vector<int32_t> pFace, cFace;           // face of every coefficient slot (-1: none)
+        std::vector<int64_t> gGenOff;                // [nGroups+1] term offsets of the unified stream: generic groups only
+        int64_t nGenTerms = 0;
+        int maxPStage = 0, maxCStep = 0, maxGenStage = 0, nFastGroups = 0;
     } fwd, bwd;
 
     // statistics
@@ -198,6 +218,8 @@ struct PipeSchedule
         order_and_number(g, P, grpNT);
         build_terms(g, +1, fwd);
         build_terms(g, -1, bwd);
+        build_split(+1, fwd);
+        build_split(-1, bwd);
     }
 
   private:
@@ -619,7 +641,153 @@ struct PipeSchedule
                 for (int32_t f = g.ownerStart[c + 1] - 1; f >= g.ownerStart[c]; f--) put(f, g.U[f]); // DESCENDING upper column
         }
     }
+    // ------------------------------------------------------------------ split streams (fast path)
+  public:
+    static constexpr int kMaxConst = 2; // cross-group values a row's remaining terms may need on the fast path
+    static int p_rec_bytes(int Lg, int Kg) { return Lg * 384 + Kg * 128; }
+    static int c_rec_bytes(int Rg) { return 256 + Rg * 256; }
+    static int c_ring_step_bytes(int Rg, int Kg) { return 256 * (1 + Kg) + c_rec_bytes(Rg); } // hdr acc0[32], cval[Kg][32] + record
+
+  private:
+    void build_split(int dir, Dir& D)
+    {
+        const int nG = nGroups;
+        const int nVec = dir > 0 ? 2 : 1;
+        D.gFast.assign(nG, 0);
+        D.gLg.assign(nG, 0);
+        D.gRg.assign(nG, 0);
+        D.gKg.assign(nG, 0);
+        D.gPOff.assign(nG + 1, 0);
+        D.gCOff.assign(nG + 1, 0);
+        D.gPFaceOff.assign(nG + 1, 0);
+        D.gCFaceOff.assign(nG + 1, 0);
+        D.gGenOff.assign(nG + 1, 0);
+        D.maxPStage = D.maxCStep = D.maxGenStage = D.nFastGroups = 0;
+        // pass 1: eligibility, Lg, Rg
+        for (int gI = 0; gI < nG; gI++)
+        {
+            const int W = D.gW[gI], nT = gNT[gI];
+            bool fast = W >= 1 && W <= 6 && D.gShflMask[gI] >= 0 && !forceGeneric;
+            int Lg = 0, Rg = 0, Kg = 1;
+            for (int step = 0; step < nT && fast; step++)
+                for (int lane = 0; lane < 32; lane++)
+                {
+                    const int64_t b0 = D.gTermOff[gI] + int64_t(step) * W * 32 + lane;
+                    int ld = 0, nTerms = 0, nConst = 0;
+                    for (int j = 0; j < W; j++)
+                        if (D.code[b0 + int64_t(j) * 32] != kCodeNone) nTerms = j + 1;
+                    while (ld < nTerms && D.code[b0 + int64_t(ld) * 32] >= 0) ld++;
+                    for (int j = ld; j < nTerms; j++)
+                        if (D.code[b0 + int64_t(j) * 32] >= 0) nConst++;
+                    if (nConst > kMaxConst) fast = false;
+                    Kg = std::max(Kg, nConst);
+                    Lg = std::max(Lg, ld);
+                    Rg = std::max(Rg, nTerms - ld);
+                }
+            D.gFast[gI] = fast ? 1 : 0;
+            D.gLg[gI] = fast ? Lg : 0;
+            Rg = std::max(Rg, 1); // at least one (padding) plane: the consumer is compiled for 1..6 remaining terms
+            D.gRg[gI] = fast ? Rg : 0;
+            D.gKg[gI] = fast ? Kg : 0;
+            if (fast)
+            {
+                D.nFastGroups++;
+                D.gCH[gI] = kSweepBlock;
+                D.gPOff[gI + 1] = D.gPOff[gI] + int64_t(nT) * p_rec_bytes(Lg, Kg);
+                D.gCOff[gI + 1] = D.gCOff[gI] + int64_t(nT) * c_rec_bytes(Rg);
+                D.gPFaceOff[gI + 1] = D.gPFaceOff[gI] + int64_t(nT) * Lg * 32;
+                D.gCFaceOff[gI + 1] = D.gCFaceOff[gI] + int64_t(nT) * Rg * 32;
+                D.gGenOff[gI + 1] = D.gGenOff[gI];
+                D.maxPStage = std::max(D.maxPStage, kSweepBlock * (p_rec_bytes(Lg, Kg) + nVec * 256));
+                D.maxCStep = std::max(D.maxCStep, c_ring_step_bytes(Rg, Kg));
+            }
+            else
+            {
+                D.gPOff[gI + 1] = D.gPOff[gI];
+                D.gCOff[gI + 1] = D.gCOff[gI];
+                D.gPFaceOff[gI + 1] = D.gPFaceOff[gI];
+                D.gCFaceOff[gI + 1] = D.gCFaceOff[gI];
+                D.gGenOff[gI + 1] = D.gGenOff[gI] + int64_t(nT) * W * 32;
+                D.maxGenStage = std::max(D.maxGenStage, D.gCH[gI] * (W * 384 + nVec * 256));
+            }
+        }
+        D.nGenTerms = D.gGenOff[nG];
+        D.pStream.assign(size_t(D.gPOff[nG]), 0);
+        D.cStream.assign(size_t(D.gCOff[nG]), 0);
+        D.pFace.assign(size_t(D.gPFaceOff[nG]), -1);
+        D.cFace.assign(size_t(D.gCFaceOff[nG]), -1);
+        // pass 2: fill
+        for (int gI = 0; gI < nG; gI++)
+        {
+            if (!D.gFast[gI]) continue;
+            const int W = D.gW[gI], nT = gNT[gI], Lg = D.gLg[gI], Rg = D.gRg[gI], Kg = D.gKg[gI];
+            const int pRec = p_rec_bytes(Lg, Kg), cRec = c_rec_bytes(Rg);
+            for (int step = 0; step < nT; step++)
+            {
+                unsigned char* pr = D.pStream.data() + D.gPOff[gI] + int64_t(step) * pRec;
+                unsigned char* cr = D.cStream.data() + D.gCOff[gI] + int64_t(step) * cRec;
+                int32_t* pCode = reinterpret_cast<int32_t*>(pr + Lg * 256);
+                int32_t* pConst = reinterpret_cast<int32_t*>(pr + Lg * 384);
+                uint64_t* meta = reinterpret_cast<uint64_t*>(cr);
+                int Rt = 0;
+                bool anyConst = false;
+                int ldOf[32], nOf[32];
+                for (int lane = 0; lane < 32; lane++)
+                {
+                    const int64_t b0 = D.gTermOff[gI] + int64_t(step) * W * 32 + lane;
+                    int ld = 0, nTerms = 0;
+                    for (int j = 0; j < W; j++)
+                        if (D.code[b0 + int64_t(j) * 32] != kCodeNone) nTerms = j + 1;
+                    while (ld < nTerms && D.code[b0 + int64_t(ld) * 32] >= 0) ld++;
+                    ldOf[lane] = ld;
+                    nOf[lane] = nTerms;
+                    Rt = std::max(Rt, nTerms - ld);
+                }
+                for (int lane = 0; lane < 32; lane++)
+                {
+                    const int64_t b0 = D.gTermOff[gI] + int64_t(step) * W * 32 + lane;
+                    const int ld = ldOf[lane], nTerms = nOf[lane];
+                    for (int i = 0; i < Lg; i++)
+                    {
+                        pCode[i * 32 + lane] = i < ld ? D.code[b0 + int64_t(i) * 32] : kCodeNone;
+                        D.pFace[D.gPFaceOff[gI] + (int64_t(step) * Lg + i) * 32 + lane] = i < ld ? D.face[b0 + int64_t(i) * 32] : -1;
+                    }
+                    for (int k = 0; k < Kg; k++) pConst[k * 32 + lane] = -1;
+                    int nc = 0;
+                    uint64_t m = 0;
+                    for (int r = 0; r < 6; r++)
+                    {
+                        unsigned byte = unsigned(lane) | 0x40u; // padding: coefficient 0, source = own lane
+                        const int j = ld + r;
+                        if (r < Rg && j < nTerms)
+                        {
+                            const int32_t code = D.code[b0 + int64_t(j) * 32];
+                            D.cFace[D.gCFaceOff[gI] + (int64_t(step) * Rg + r) * 32 + lane] = D.face[b0 + int64_t(j) * 32];
+                            if (code >= 0)
+                            {
+                                byte = unsigned(lane) | 0x80u | (nc ? 0x20u : 0u);
+                                pConst[nc * 32 + lane] = code;
+                                nc++;
+                                anyConst = true;
+                            }
+                            else if (code == kCodeOwn)
+                                byte = unsigned(lane);
+                            else
+                                byte = unsigned(kCodeShfl - code);
+                        }
+                        m |= uint64_t(byte) << (8 * r);
+                    }
+                    meta[lane] = m;
+                }
+                for (int lane = 0; lane < 32; lane++)
+                    meta[lane] |= (uint64_t(Rt) << 48) | (uint64_t(anyConst ? 1 : 0) << 56);
+            }
+        }
+    }
+
+  public:
 };
+
 
 // ------------------------------------------------------------------------------------------
 // Row-packed Amul layout over slots: slice s = the 32 slots of one (group, time step);

@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "b200_solve", "b200_upload", "b200_solve_resident", "b200_download",
     "b200_x_save", "b200_x_restore", "b200_host_register", "b200_host_unregister",
     "b200_amul", "b200_precondition", "b200_get_rD", "b200_reduce",
-    "b200_set_profiling", "b200_get_kernel_times", "b200_launch_count",
+    "b200_set_profiling", "b200_get_kernel_times", "b200_launch_count", "b200_debug_sweep_stats",
     "b200_ggi_interpolate", "b200_patch_face_to_global", "b200_global_face_to_patch",
 ]
 
@@ -93,6 +93,7 @@ def load():
     L.b200_reduce.argtypes = [vp, dpp, dpp, dp]
     L.b200_set_profiling.argtypes = [vp, C.c_int]
     L.b200_get_kernel_times.argtypes = [vp, dp, C.POINTER(C.c_int64), C.c_int]
+    L.b200_debug_sweep_stats.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.c_int]
     L.b200_launch_count.argtypes = [vp]
     L.b200_launch_count.restype = C.c_int64
     L.b200_ggi_interpolate.argtypes = [vp, C.c_int32, C.c_int32, ip, ip, dp, dp, C.c_int, dp]
@@ -331,6 +332,14 @@ class LduSystem:
         n = np.zeros(len(KERNEL_CLASSES), dtype=np.int64)
         self.ctx.check(load().b200_get_kernel_times(self.h, _dp(ms), n.ctypes.data_as(C.POINTER(C.c_int64)), int(reset)))
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(KERNEL_CLASSES)}
+
+    def sweep_stats(self, direction: int, enable: bool = True) -> np.ndarray:
+        """Debug counters of the sweep kernel per group: columns {consumer cycles, wait cycles, start ns, end ns,
+        producer polls, nT, -, -}; returns what the sweeps since the previous call recorded and (re)arms."""
+        n = self.ctx.check(load().b200_debug_sweep_stats(self.h, direction, 0, None, 0))
+        out = np.zeros((max(n, 1), 8), dtype=np.int64)
+        self.ctx.check(load().b200_debug_sweep_stats(self.h, direction, int(enable), out.ctypes.data_as(C.POINTER(C.c_longlong)), out.size))
+        return out[:n]
 
     def close(self):
         if self.h:

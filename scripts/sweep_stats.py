@@ -23,9 +23,9 @@ S.precondition(ldu.PRECOND_DILU, r)
 st = S.sweep_stats(+1, False)
 t0 = st[:, 2].min()
 print("groups", len(st), "sweep span us", (st[:, 3].max() - t0) / 1e3)
-print("ticket start_us end_us dur_us consumer_cycles wait_frac polls nT ns/step")
+print("ticket start_us end_us dur_us consumer_cycles wait_frac polls nT ns/step tma_frac tail_frac")
 sel = list(range(0, len(st), max(1, len(st) // 24)))
 for i in sel:
-    c, w, a, b, polls, nT = st[i, :6]
-    print(f"{i:5d} {(a-t0)/1e3:8.1f} {(b-t0)/1e3:8.1f} {(b-a)/1e3:8.1f} {c:10d} {w/max(c,1):6.2f} {polls:6d} {nT:5d} {(b-a)/max(nT,1):6.0f}")
+    c, w, a, b, polls, nT, tma, tail = st[i, :8]
+    print(f"{i:5d} {(a-t0)/1e3:8.1f} {(b-t0)/1e3:8.1f} {(b-a)/1e3:8.1f} {c:10d} {w/max(c,1):6.2f} {polls:6d} {nT:5d} {(b-a)/max(nT,1):6.0f} {tma/max(c,1):6.2f} {tail/max(c,1):6.2f}")
 print("mean wait frac", float((st[:, 1] / np.maximum(st[:, 0], 1)).mean()), "mean ns/step", float(((st[:, 3] - st[:, 2]) / np.maximum(st[:, 5], 1)).mean()))

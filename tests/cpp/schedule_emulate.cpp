@@ -26,34 +26,77 @@ int walk(const PipeSchedule& S, const PipeSchedule::Dir& D, int dir, int mode, c
         const int W = D.gW[g], nT = S.gNT[g];
         double prev[32], cur[32];
         for (int l = 0; l < 32; l++) prev[l] = 0.0;
+        const bool fast = D.gFast[g] != 0;
+        const int Lg = D.gLg[g], Rg = D.gRg[g], Kg = D.gKg[g];
         for (int step = 0; step < nT; step++)
         {
             const int t = dir > 0 ? step : nT - 1 - step;
+            auto coefOf = [&](int32_t f, int64_t slot) { return mode == 2 ? cA[f] * cB[f] : rD[slot] * cA[f]; };
             for (int lane = 0; lane < 32; lane++)
             {
                 const int64_t slot = (int64_t(S.gBase[g]) + t) * 32 + lane;
                 double acc = mode == 0 ? a[slot] * b[slot] : a[slot];
-                for (int j = 0; j < W; j++)
+                if (fast)
                 {
-                    const int64_t idx = D.gTermOff[g] + (int64_t(step) * W + j) * 32 + lane;
-                    const int32_t code = D.code[idx];
-                    if (code == kCodeNone) continue;
-                    const int32_t f = D.face[idx];
-                    double v;
-                    if (code >= 0)
+                    // producer part: leading cross-group terms from the P-stream
+                    const unsigned char* pr = D.pStream.data() + D.gPOff[g] + int64_t(step) * PipeSchedule::p_rec_bytes(Lg, Kg);
+                    const int32_t* pCode = reinterpret_cast<const int32_t*>(pr + Lg * 256);
+                    const int32_t* pConstArr = reinterpret_cast<const int32_t*>(pr + Lg * 384);
+                    for (int i = 0; i < Lg; i++)
                     {
-                        v = out[code];
-                        if (v == NOTSET) return -10; // dependency not produced yet: ticket order broken
+                        const int32_t code = pCode[i * 32 + lane];
+                        const int32_t f = D.pFace[D.gPFaceOff[g] + (int64_t(step) * Lg + i) * 32 + lane];
+                        if ((code >= 0) != (f >= 0)) return -20;
+                        if (code < 0) continue;
+                        if (out[code] == NOTSET) return -10;
+                        acc = mode == 2 ? acc - coefOf(f, slot) / out[code] : acc - coefOf(f, slot) * out[code];
                     }
-                    else if (code == kCodeOwn)
-                        v = prev[lane];
-                    else
-                        v = prev[kCodeShfl - code];
-                    if (mode == 2)
-                        acc -= cA[f] * cB[f] / v;
-                    else
-                        acc -= rD[slot] * cA[f] * v;
+                    // consumer part: remaining terms from the C-stream
+                    const unsigned char* cr = D.cStream.data() + D.gCOff[g] + int64_t(step) * PipeSchedule::c_rec_bytes(Rg);
+                    const uint64_t meta = reinterpret_cast<const uint64_t*>(cr)[lane];
+                    const int Rt = int((meta >> 48) & 0xff);
+                    if (Rt > Rg) return -21;
+                    for (int r = 0; r < Rg; r++)
+                    {
+                        const unsigned byte = unsigned((meta >> (8 * r)) & 0xff);
+                        const int32_t f = D.cFace[D.gCFaceOff[g] + (int64_t(step) * Rg + r) * 32 + lane];
+                        if (byte & 0x40u)
+                        {
+                            if (f >= 0) return -22;
+                            continue; // padding
+                        }
+                        if (r >= Rt || f < 0) return -23;
+                        double v;
+                        if (byte & 0x80u)
+                        {
+                            const int32_t pConst = pConstArr[((byte & 0x20u) ? 1 : 0) * 32 + lane];
+                            if (!(meta >> 56 & 1) || pConst < 0 || out[pConst] == NOTSET) return -24;
+                            v = out[pConst];
+                        }
+                        else
+                            v = prev[byte & 31u];
+                        acc = mode == 2 ? acc - coefOf(f, slot) / v : acc - coefOf(f, slot) * v;
+                    }
                 }
+                else
+                    for (int j = 0; j < W; j++)
+                    {
+                        const int64_t idx = D.gTermOff[g] + (int64_t(step) * W + j) * 32 + lane;
+                        const int32_t code = D.code[idx];
+                        if (code == kCodeNone) continue;
+                        const int32_t f = D.face[idx];
+                        double v;
+                        if (code >= 0)
+                        {
+                            v = out[code];
+                            if (v == NOTSET) return -10; // dependency not produced yet: ticket order broken
+                        }
+                        else if (code == kCodeOwn)
+                            v = prev[lane];
+                        else
+                            v = prev[kCodeShfl - code];
+                        acc = mode == 2 ? acc - coefOf(f, slot) / v : acc - coefOf(f, slot) * v;
+                    }
                 if (S.cellOfSlot[slot] < 0 && acc != 0.0) return -12; // padding slots must stay zero
                 cur[lane] = acc;
             }
@@ -148,6 +191,8 @@ int emu_run(int nCells, int nFaces, const int* l, const int* u, const double* di
         stats[9] = int(S.nMemTermsF);
         stats[10] = int(S.nShflTermsF);
         stats[11] = int(S.nOwnTermsF);
+        stats[12] = S.fwd.nFastGroups;
+        stats[13] = S.bwd.nFastGroups;
         return 0;
     }
     catch (const std::exception& e)
@@ -337,4 +382,46 @@ int emu_sys_amul(void* h, const double* xCells, const double* recv, double* yCel
     for (int64_t c = 0; c < s->g.N; c++) yCells[c] = y[s->S.slotOfCell[c]];
     return 0;
 }
+}
+
+// placement and per-group classification of a single-region system (debug / tests)
+extern "C" int emu_placement(int nCells, int nFaces, const int* l, const int* u, int* grp, int* tim, int* lan, int* gInfo /* 8 per group */,
+                             int capGroups)
+{
+    try
+    {
+        std::vector<RegionHost> regs(1);
+        regs[0].nCells = nCells;
+        regs[0].nFaces = nFaces;
+        regs[0].l.assign(l, l + nFaces);
+        regs[0].u.assign(u, u + nFaces);
+        regs[0].set = true;
+        GlobalLdu g;
+        g.build(regs);
+        PipeSchedule S;
+        S.build(g, regs);
+        for (int c = 0; c < nCells; c++)
+        {
+            grp[c] = S.place_.grp[c];
+            tim[c] = S.place_.tim[c];
+            lan[c] = S.place_.lan[c];
+        }
+        for (int i = 0; i < S.nGroups && i < capGroups; i++)
+        {
+            gInfo[8 * i + 0] = S.fwd.gW[i];
+            gInfo[8 * i + 1] = S.fwd.gFast[i];
+            gInfo[8 * i + 2] = S.fwd.gLg[i];
+            gInfo[8 * i + 3] = S.fwd.gRg[i];
+            gInfo[8 * i + 4] = S.fwd.gKg[i];
+            gInfo[8 * i + 5] = S.gNT[i];
+            gInfo[8 * i + 6] = S.bwd.gFast[i];
+            gInfo[8 * i + 7] = S.fwd.gShflMask[i] < 0;
+        }
+        return S.nGroups;
+    }
+    catch (const std::exception& e)
+    {
+        fprintf(stderr, "emu_placement: %s\n", e.what());
+        return -1;
+    }
 }

@@ -25,7 +25,7 @@ def run_emu(L, reg, dilu, x, r):
     n = reg.nCells
     l, u = np.ascontiguousarray(reg.lowerAddr, np.int32), np.ascontiguousarray(reg.upperAddr, np.int32)
     y, w, rD = np.empty(n), np.empty(n), np.empty(n)
-    stats = np.zeros(12, np.int32)
+    stats = np.zeros(16, np.int32)
     P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
     I = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
     lower = None if reg.lower is None else P(np.ascontiguousarray(reg.lower))
@@ -71,6 +71,7 @@ def test_line_structure_on_structured_mesh(emu):
     assert stats[11] == (nx - 1) * ny * nz           # own-lane terms: i-1 neighbours (incl. seams)
     assert stats[10] == nx * (ny - 2) * nz           # shuffle terms: j-1 neighbours inside a warp
     assert stats[9] == nx * ny * (nz - 1) + nx * nz  # memory terms: k-1 neighbours + the j-1 of each warp's lane 0
+    assert stats[12] == stats[0] and stats[13] == stats[0]   # every group takes the fast split-stream path
     assert stats[7] == nz * 32 * (368 + 352)  # 41 lines = 32 + 9 lanes per layer; (332 + skew) steps rounded up to 16
 
 
