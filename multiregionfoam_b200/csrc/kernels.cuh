@@ -457,7 +457,7 @@ __device__ __noinline__ double sweep_spin(const double* p, int* err)
     {
         const double v = ld_relaxed(p);
         if (!is_sentinel(v)) return v;
-        __nanosleep(tries > 4096 ? 400 : 64); // a busy-spinning warp would steal issue slots from the consumer warps
+        if (tries >= 16) __nanosleep(tries > 4096 ? 400 : 64); // later: a busy-spinning warp steals issue slots from the consumer warps
         if ((tries & 4095) == 4095 && *(volatile int*)err) break;
     }
     atomicExch(err, 1);
@@ -985,7 +985,7 @@ __device__ __noinline__ void sweep_group_generic(const PipeDev& S, const int g, 
 // topological order of the group graph: a group only ever waits for groups that are already running.
 constexpr int kSweepThreads = 32 * (2 + kNH); // consumer + producers + loader
 template <int MODE>
-__global__ void __launch_bounds__(kSweepThreads) k_sweep(PipeDev S, const double* __restrict__ a, const double* __restrict__ b,
+__global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(PipeDev S, const double* __restrict__ a, const double* __restrict__ b,
                                                           double* out, unsigned* ticket, unsigned ticketBase, int* err,
                                                           const DevScalars* sc, int force)
 {

@@ -29,3 +29,7 @@ for i in sel:
     c, w, a, b, polls, nT, tma, tail = st[i, :8]
     print(f"{i:5d} {(a-t0)/1e3:8.1f} {(b-t0)/1e3:8.1f} {(b-a)/1e3:8.1f} {c:10d} {w/max(c,1):6.2f} {polls:6d} {nT:5d} {(b-a)/max(nT,1):6.0f} {tma/max(c,1):6.2f} {tail/max(c,1):6.2f}")
 print("mean wait frac", float((st[:, 1] / np.maximum(st[:, 0], 1)).mean()), "mean ns/step", float(((st[:, 3] - st[:, 2]) / np.maximum(st[:, 5], 1)).mean()))
+print("end_us by ticket (fluid nT=1040 only):")
+ends = [(i, (st[i, 3] - t0) / 1e3, st[i, 1] / max(st[i, 0], 1)) for i in range(len(st)) if st[i, 5] >= 1024]
+for k in range(0, len(ends), 8):
+    print("  ".join(f"{i:3d}:{e:6.1f}/{w:.2f}" for i, e, w in ends[k:k + 8]))
