@@ -155,7 +155,11 @@ struct PipeDirMem
     DevBuf<unsigned char> stream, gFast, pStream, cStream;
     PipeDev dev{};
     int smemBytes = 0;
-    int packedFor = -1; // 0: plain coefficients packed, 1: transposed, -1: none
+    // second set of stream buffers holding the TRANSPOSED coefficients (preconditionT of PBiCG), created on first use
+    DevBuf<unsigned char> streamT, pStreamT, cStreamT;
+    PipeDev devT{};
+    bool haveT = false;
+    bool packed[2] = {false, false}; // [0]: dev holds the plain coefficients of the current matrix, [1]: devT the transposed ones
 };
 
 // ------------------------------------------------------------------------------------------ system
@@ -513,7 +517,8 @@ static int upload_pipe_dir(b200_sys* s, const PipeSchedule& S, const PipeSchedul
     M.dev.cBlockBytes = cBlockBytes;
     M.dev.stats = nullptr;
     M.dev.debugFlags = getenv("B200_SWEEP_DEBUG") ? atoi(getenv("B200_SWEEP_DEBUG")) : 0;
-    M.packedFor = -1;
+    M.packed[0] = M.packed[1] = false;
+    M.haveT = false;
     return B200_OK;
 }
 
@@ -678,7 +683,7 @@ extern "C" int b200_sys_set_coeffs(b200_sys* s, int r, const double* diag, const
     s->regionHasCoeffs[r] = 1;
     s->sellDirty = s->sellTDirty = true;
     s->precondValid = -1;
-    s->fwd.packedFor = s->bwd.packedFor = -1;
+    s->fwd.packed[0] = s->fwd.packed[1] = s->bwd.packed[0] = s->bwd.packed[1] = false;
     return B200_OK;
 }
 
@@ -820,12 +825,13 @@ static int launch_amul(b200_sys* s, const double* x, double* y, int nd, const do
 }
 
 template <int MODE>
-static int launch_sweep(b200_sys* s, PipeDirMem& M, const double* a, const double* b, double* out, int force)
+static int launch_sweep(b200_sys* s, PipeDirMem& M, PipeDev dev, const double* a, const double* b, double* out, int force)
 {
     b200_ctx* ctx = s->ctx;
     if (s->nGroups == 0) return B200_OK;
-    KScope k(s, M.dev.dir > 0 ? B200_K_SWEEP_FWD : B200_K_SWEEP_BWD);
-    k_sweep<MODE><<<s->nGroups, kSweepThreads, M.smemBytes, ctx->stream>>>(M.dev, a, b, out, s->ticket.p, s->ticketBase, s->devErr.p, s->sc.p,
+    dev.stats = M.dev.stats;
+    KScope k(s, dev.dir > 0 ? B200_K_SWEEP_FWD : B200_K_SWEEP_BWD);
+    k_sweep<MODE><<<s->nGroups, kSweepThreads, M.smemBytes, ctx->stream>>>(dev, a, b, out, s->ticket.p, s->ticketBase, s->devErr.p, s->sc.p,
                                                                           force);
     s->ticketBase += (unsigned)s->nGroups;
     CK(ctx, cudaGetLastError());
@@ -841,25 +847,48 @@ static int fill_sentinel(b200_sys* s, double* a, double* b, int force)
     return B200_OK;
 }
 
-static int pack_stream(b200_sys* s, PipeDirMem& M, const double* c1, const double* c2, const double* rD, int prodMode)
+static int pack_stream(b200_sys* s, const PipeDev& dev, const double* c1, const double* c2, const double* rD, int prodMode)
 {
     if (s->nGroups == 0) return B200_OK;
     KScope k(s, B200_K_PACK);
-    k_pack_stream<<<dim3(s->nGroups, 8), 256, 0, s->ctx->stream>>>(M.dev, c1, c2, rD, prodMode);
+    k_pack_stream<<<dim3(s->nGroups, 8), 256, 0, s->ctx->stream>>>(dev, c1, c2, rD, prodMode);
     CK(s->ctx, cudaGetLastError());
+    return B200_OK;
+}
+
+static int ensure_transposed_buffers(b200_sys* s, PipeDirMem& M)
+{
+    if (M.haveT) return B200_OK;
+    b200_ctx* ctx = s->ctx;
+    auto clone = [&](DevBuf<unsigned char>& dst, const DevBuf<unsigned char>& src) -> cudaError_t {
+        cudaError_t e = dst.alloc(src.n);
+        if (e != cudaSuccess || src.n == 0) return e;
+        return cudaMemcpyAsync(dst.p, src.p, src.n, cudaMemcpyDeviceToDevice, ctx->stream); // static codes / meta
+    };
+    CK(ctx, clone(M.streamT, M.stream));
+    CK(ctx, clone(M.pStreamT, M.pStream));
+    CK(ctx, clone(M.cStreamT, M.cStream));
+    M.devT = M.dev;
+    M.devT.stream = M.streamT.p;
+    M.devT.pStream = M.pStreamT.p;
+    M.devT.cStream = M.cStreamT.p;
+    M.haveT = true;
+    M.packed[1] = false;
     return B200_OK;
 }
 
 // Preconditioner construction: calcReciprocalD as a forward sweep in division mode, then the
 // pre-multiplied sweep coefficients rD[row]*lower[f] / rD[row]*upper[f] packed into the streams.
+// transposed: preconditionT swaps the roles of upper and lower (DILUPreconditioner::preconditionT);
+// its coefficients live in a second set of stream buffers so that PBiCG can alternate.
 static int ensure_precond(b200_sys* s, int precond, bool transposed)
 {
     b200_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
     if (precond == B200_PRECOND_NONE) return B200_OK;
-    const int want = transposed ? 1 : 0;
+    const int v = transposed ? 1 : 0;
     const bool sweeps = precond >= B200_PRECOND_DIC;
-    if (s->precondValid == precond && (!sweeps || (s->fwd.packedFor == want && s->bwd.packedFor == want))) return B200_OK;
+    if (s->precondValid == precond && (!sweeps || (s->fwd.packed[v] && s->bwd.packed[v]))) return B200_OK;
     if (s->nSlots == 0)
     {
         s->precondValid = precond;
@@ -878,31 +907,38 @@ static int ensure_precond(b200_sys* s, int precond, bool transposed)
         }
         else
         {
-            if ((rc = pack_stream(s, s->fwd, cU, cL, nullptr, 1))) return rc;
-            s->fwd.packedFor = -1;
+            if ((rc = pack_stream(s, s->fwd.dev, cU, cL, nullptr, 1))) return rc;
             if ((rc = fill_sentinel(s, s->rDraw.p, nullptr, 1))) return rc;
-            if ((rc = launch_sweep<2>(s, s->fwd, s->diag.p, nullptr, s->rDraw.p, 1))) return rc;
+            if ((rc = launch_sweep<2>(s, s->fwd, s->fwd.dev, s->diag.p, nullptr, s->rDraw.p, 1))) return rc;
             {
                 KScope k(s, B200_K_VECTOR);
                 k_invert<<<s->vecBlocks, 256, 0, st>>>((size_t)s->nSlots, s->rDraw.p, s->rD.p, s->cellOfSlot.p);
             }
         }
         s->precondValid = precond;
+        s->fwd.packed[0] = s->fwd.packed[1] = s->bwd.packed[0] = s->bwd.packed[1] = false;
     }
-    if (sweeps && (s->fwd.packedFor != want || s->bwd.packedFor != want))
+    if (sweeps && !(s->fwd.packed[v] && s->bwd.packed[v]))
     {
-        // preconditionT swaps the roles of upper and lower (DILUPreconditioner::preconditionT)
-        if ((rc = pack_stream(s, s->fwd, transposed ? cU : cL, nullptr, s->rD.p, 0))) return rc;
-        if ((rc = pack_stream(s, s->bwd, transposed ? cL : cU, nullptr, s->rD.p, 0))) return rc;
-        s->fwd.packedFor = s->bwd.packedFor = want;
+        if (transposed)
+        {
+            if ((rc = ensure_transposed_buffers(s, s->fwd))) return rc;
+            if ((rc = ensure_transposed_buffers(s, s->bwd))) return rc;
+        }
+        const PipeDev& fdev = transposed ? s->fwd.devT : s->fwd.dev;
+        const PipeDev& bdev = transposed ? s->bwd.devT : s->bwd.dev;
+        if ((rc = pack_stream(s, fdev, transposed ? cU : cL, nullptr, s->rD.p, 0))) return rc;
+        if ((rc = pack_stream(s, bdev, transposed ? cL : cU, nullptr, s->rD.p, 0))) return rc;
+        s->fwd.packed[v] = s->bwd.packed[v] = true;
     }
     CK(ctx, cudaGetLastError());
     return B200_OK;
 }
 
-// w = M^-1 r.  tmp: scratch for the forward result.  If prefilled, the caller already wrote the
-// sentinel into tmp and w (fused into the preceding vector kernel).
-static int launch_precondition(b200_sys* s, int precond, const double* r, double* w, double* tmp, bool prefilled, int force)
+// w = M^-1 r (transposed: M^-T r).  tmp: scratch for the forward result.  If prefilled, the caller
+// already wrote the sentinel into tmp and w (fused into the preceding vector kernel).
+static int launch_precondition(b200_sys* s, int precond, const double* r, double* w, double* tmp, bool prefilled, int force,
+                               bool transposed = false)
 {
     b200_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
@@ -923,8 +959,8 @@ static int launch_precondition(b200_sys* s, int precond, const double* r, double
     }
     int rc;
     if (!prefilled && (rc = fill_sentinel(s, tmp, w, force))) return rc;
-    if ((rc = launch_sweep<0>(s, s->fwd, s->rD.p, r, tmp, force))) return rc;
-    if ((rc = launch_sweep<1>(s, s->bwd, tmp, nullptr, w, force))) return rc;
+    if ((rc = launch_sweep<0>(s, s->fwd, transposed ? s->fwd.devT : s->fwd.dev, s->rD.p, r, tmp, force))) return rc;
+    if ((rc = launch_sweep<1>(s, s->bwd, transposed ? s->bwd.devT : s->bwd.dev, tmp, nullptr, w, force))) return rc;
     return B200_OK;
 }
 
@@ -1292,7 +1328,7 @@ extern "C" int b200_precondition(b200_sys* s, int precond, const double* const* 
         if (!s->regionHasCoeffs[q]) return set_err(s->ctx, B200_ESTATE, "region %zu has no coefficients", q);
     if ((rc = upload_vec(s, V_S, r))) return rc;
     if ((rc = ensure_precond(s, precond, transpose != 0))) return rc;
-    if ((rc = launch_precondition(s, precond, s->vec[V_S].p, s->vec[V_SH].p, s->vec[V_TMP2].p, false, 1))) return rc;
+    if ((rc = launch_precondition(s, precond, s->vec[V_S].p, s->vec[V_SH].p, s->vec[V_TMP2].p, false, 1, transpose != 0))) return rc;
     if ((rc = download_vec(s, s->vec[V_SH].p, w))) return rc;
     CK(s->ctx, cudaStreamSynchronize(s->ctx->stream));
     if (s->profiling) harvest_events(s);
