@@ -167,8 +167,9 @@ int b200_reduce(b200_sys* sys, const double* const* a, const double* const* b, d
 int b200_set_profiling(b200_sys* sys, int enable);
 /* accumulated device ms and launch counts per kernel class since the last reset */
 int b200_get_kernel_times(b200_sys* sys, double* msPerClass, int64_t* launchesPerClass, int reset);
-/* Debug: per-group counters of the sweep kernel of one direction (dir > 0 forward): 8 int64 per group
- * {consumer cycles, consumer wait cycles, start ns, end ns, producer polls, nT, 0, 0}.  enable != 0 arms the
+/* Debug: per-group counters of the sweep kernel of one direction (dir > 0 forward): 16 int64 per group
+ * {consumer cycles, consumer wait cycles, start ns, end ns, producer polls, nT, general blocks, blocks,
+ *  producer-0 cycles, its stage-wait / value-wait / spin cycles, 0...}.  enable != 0 arms the
  * counters for the following sweeps; out (may be NULL) receives the counters of the previous ones.
  * Returns the number of groups. */
 int b200_debug_sweep_stats(b200_sys* sys, int dir, int enable, long long* out, int cap);

@@ -482,13 +482,15 @@ static int upload_pipe_dir(b200_sys* s, const PipeSchedule& S, const PipeSchedul
     CK(ctx, M.cFace.upload(D.cFace, st));
     if (dir < 0) CK(ctx, M.order.upload(S.orderB, st));
     CK(ctx, cudaStreamSynchronize(st)); // host vectors go out of scope after return
-    // shared memory: 256 B of barriers | raw ring (nStages stages) | consumer ring (kRB blocks); the generic
-    // single-warp path uses its own layout inside the same allocation.  About 90 KB per CTA for a 3-D
-    // structured mesh, so that two groups are co-resident per SM.
-    const int nStages = 4;
-    const int stageBytes = (std::max(D.maxPStage, D.maxGenStage) + 127) / 128 * 128;
-    const int cBlockBytes = (kNH * D.maxCStep + 127) / 128 * 128;
-    M.smemBytes = 256 + nStages * stageBytes + kRB * cBlockBytes;
+    // shared memory: 256 B of barriers / counters | nStages stages, each one block of kNH steps (records, input
+    // vectors, hdr); the generic single-warp path uses its own layout inside the same allocation.  At most
+    // ~110 KB per CTA so that two groups are co-resident per SM.
+    const int stageBytes = (std::max(D.maxFastStage, D.maxGenStage) + 127) / 128 * 128;
+    int nStages = getenv("B200_SWEEP_STAGES") ? atoi(getenv("B200_SWEEP_STAGES")) : 4;
+    nStages = std::max(2, std::min(nStages, 8));
+    const int smemCapKB = getenv("B200_SWEEP_SMEM_KB") ? atoi(getenv("B200_SWEEP_SMEM_KB")) : 110;
+    while (nStages > 2 && 256 + nStages * stageBytes > smemCapKB * 1024) nStages--;
+    M.smemBytes = 256 + nStages * stageBytes;
     M.dev.nGroups = S.nGroups;
     M.dev.dir = dir;
     M.dev.nStages = nStages;
@@ -514,7 +516,6 @@ static int upload_pipe_dir(b200_sys* s, const PipeSchedule& S, const PipeSchedul
     M.dev.cStream = M.cStream.p;
     M.dev.pFace = M.pFace.p;
     M.dev.cFace = M.cFace.p;
-    M.dev.cBlockBytes = cBlockBytes;
     M.dev.stats = nullptr;
     M.dev.debugFlags = getenv("B200_SWEEP_DEBUG") ? atoi(getenv("B200_SWEEP_DEBUG")) : 0;
     M.packed[0] = M.packed[1] = false;
@@ -1379,7 +1380,7 @@ extern "C" int b200_debug_sweep_stats(b200_sys* s, int dir, int enable, long lon
     PipeDirMem& M = dir > 0 ? s->fwd : s->bwd;
     CK(ctx, cudaSetDevice(ctx->device));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
-    const size_t n = 8 * (size_t)s->nGroups;
+    const size_t n = (size_t)kStatsStride * (size_t)s->nGroups;
     if (out && M.stats.p)
         CK(ctx, cudaMemcpy(out, M.stats.p, sizeof(long long) * std::min<size_t>(n, (size_t)cap), cudaMemcpyDeviceToHost));
     if (enable)

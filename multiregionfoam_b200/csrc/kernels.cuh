@@ -395,7 +395,7 @@ __global__ void k_pack_sell(size_t nSlots, const int* __restrict__ src, const do
 // streamed into a shared-memory ring by bulk asynchronous copies (TMA, cp.async.bulk + mbarrier);
 // in-warp dependencies travel through one warp shuffle per time step, the own-lane dependency
 // stays in a register, dependencies on other warps are read from the output vector, which
-// doubles as its own ready flag (sentinel until written), and are prefetched kPF steps ahead.
+// doubles as its own ready flag (sentinel until written), and are prefetched a block of steps ahead.
 struct PipeDev
 {
     int nGroups;
@@ -424,12 +424,10 @@ struct PipeDev
     unsigned char* cStream;
     const int* pFace;
     const int* cFace;
-    int cBlockBytes;  // bytes of one block of the consumer ring (max over the fast groups)
-    int debugFlags;   // bit 0: consumer always takes the select path (debug)
-    long long* stats; // optional [8 * nGroups]: consumer cycles, wait cycles, start ns, end ns, producer polls, nT (debug)
+    int debugFlags;   // bit 0: consumer always takes the general (descriptor-driven) path (debug)
+    long long* stats; // optional [8 * nGroups]: consumer cycles, wait cycles, start ns, end ns, producer polls, nT, general blocks, blocks (debug)
 };
 
-constexpr int kPF = 4; // prefetch distance (time steps) of cross-warp values
 
 // MODE 0: forward  : acc = a[slot]*b[slot]; acc -= c * w[nbr]   (a = rD, b = rA, c = rD[row]*lower[f])
 // MODE 1: backward : acc = a[slot];         acc -= c * w[nbr]   (a = forward result, c = rD[row]*upper[f])
@@ -545,68 +543,114 @@ __device__ __forceinline__ SweepRing ring_setup(const PipeDev& S, int g, int lan
 
 // ================================================================================================
 // Fast path: warp-specialised CTA over the SPLIT streams (schedule.hpp, build_split).
-// A lone warp issues one instruction every ~5 cycles and the recurrence is serial, so the consumer
-// warp must execute as little as possible per time step.  Everything static (which terms lead, which
-// lane a term shuffles from, how many terms a step has) was decided on the host:
-//   * kNH = 8 producer warps (producer h prepares step 8b+h of block b): read the P-stream record and
-//     the input vectors from the TMA-fed raw ring, fetch the cross-group values (prefetched one block
-//     ahead, verified against the sentinel), apply the row's LEADING terms in reference order and
-//     hand {acc0, cval[]} to the consumer through the hdr part of the consumer ring;
-//   * the C-stream records {meta, remaining coefficients} go by TMA straight into the consumer ring;
-//   * the consumer warp runs only the recurrence: per remaining term  v = shfl(prev, lane from meta);
-//     acc -= coef * v;  then one store.  Steps whose remaining terms need a cross-group value (block
-//     seams) and calcReciprocalD (division) take a select path.
+// The recurrence of a group is serial, so what sits on the dependent chain of a time step decides the
+// speed of the whole sweep (measured on B200: DADD 8, DMUL 8, 64-bit SHFL 31, LDS 29, mbarrier try_wait 90
+// cycles).  Everything static was decided on the host, and the CTA is organised so that the consumer
+// warp's chain per step is ONE multiply and ONE subtract:
+//   * lanes are skewed by kSkew = 2 steps, so the neighbour-lane value a step needs is already two steps
+//     old: its shuffle and its product are issued a step ahead, off the chain;
+//   * a loader thread streams the records and the input vectors of a block of kNH = 8 steps into one of
+//     NS shared-memory stages with bulk asynchronous copies (TMA: cp.async.bulk + mbarrier);
+//   * kNH producer warps (producer h prepares step h of every block) fetch the cross-group values
+//     (prefetched one block ahead, verified against the sentinel), apply the row's LEADING terms in
+//     reference order and leave {acc0, cval[]} in the hdr part of the stage; then they bump the stage's
+//     counter - bits 8.. of the increment say whether the step is canonical;
+//   * the consumer warp polls that counter with a plain load (no mbarrier wait, no fence on its path),
+//     loads the 8 steps' operands at once and runs  acc = (acc0 - c0*shfl(prev2)) - c1*prev1 ; one store
+//     per step.  Blocks with a non-canonical step (block seams) and calcReciprocalD (division) interpret
+//     the descriptor bytes instead (general path).  After a block it resets the counter and publishes its
+//     progress, which is what the loader polls before it refills the stage.
 constexpr int kNH = kSweepBlock; // producer warps = steps per block (8)
-constexpr int kRB = 3;           // blocks in the consumer ring
+constexpr int kStatsStride = 16;  // debug counters per group
+constexpr int kL2Ahead = 8;      // blocks the L2 prefetch runs ahead of the stage fill
 
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+// Flag words in shared memory.  A formal release/acquire pair costs a MEMBAR.ALL.CTA on the releasing side, which
+// also waits for the warp's outstanding GLOBAL accesses (the consumer's st.cg results, the producers' prefetches
+// of cross-group values): hundreds of cycles per block on the dependent path.  The handshakes below therefore use
+// relaxed accesses and rely on the shared-memory pipeline of an SM processing the accesses of a warp in program
+// order (STS data ... ATOMS flag on one side, LDS flag ... LDS data on the other); "memory" clobbers keep the
+// compiler from moving anything across them.
+__device__ __forceinline__ unsigned ld_flag_smem(const unsigned* p)
 {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+    unsigned v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_flag_smem(unsigned* p, unsigned v)
+{
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_flag_smem(unsigned* p, unsigned v)
+{
+    asm volatile("red.relaxed.cta.shared.add.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 
 struct SplitCtx
 {
-    int nT, base, dir, nBlocks, NS, stageBytes;
-    int Lg, Rg, Kg, pRec, cRec, hdrStep, cBlockBytes;
-    unsigned rawChunkBytes;
-    unsigned long long *rawBar, *hdrFull, *empty, *cTma;
-    unsigned char *rawRing, *cRing;
+    int nT, base, nBlocks, NS, stageBytes;
+    int Lg, Rg, Kg, pRec, cRec, hdrStep;
+    int offC, offA, offHdr; // byte offsets inside a stage: P-records at 0, then C-records, a (b), hdr
+    unsigned pBytes, cBytes, rawBytes;
+    unsigned long long* rawBar; // [NS] TMA completion
+    unsigned* cnt;              // [NS] producer arrivals of the block in the stage (+ 256 per non-canonical step)
+    unsigned* done;             // blocks the consumer has finished
+    unsigned char* stages;
     const unsigned char *pStream, *cStream;
 };
 
-template <int MODE>
-__device__ __forceinline__ void split_issue_raw(const SplitCtx& C, const double* a, const double* b, int blk, int st)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes)
 {
-    unsigned char* dst = C.rawRing + (size_t)st * C.stageBytes;
-    mbar_expect_tx(&C.rawBar[st], C.rawChunkBytes);
-    const unsigned pBytes = (unsigned)(kNH * C.pRec);
-    bulk_g2s(dst, C.pStream + (size_t)blk * pBytes, pBytes, &C.rawBar[st]);
-    const long long s0 = C.dir > 0 ? ((long long)C.base + (long long)blk * kNH) * 32 : ((long long)C.base + C.nT - (long long)(blk + 1) * kNH) * 32;
-    bulk_g2s(dst + pBytes, a + s0, kNH * 256, &C.rawBar[st]);
-    if (MODE == 0) bulk_g2s(dst + pBytes + kNH * 256, b + s0, kNH * 256, &C.rawBar[st]);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
-__device__ __forceinline__ void split_issue_c(const SplitCtx& C, int blk, int slot)
+// Pull the records and input vectors of block blk into L2 well ahead of the stage fill, so that the fill itself
+// sees L2 latency only: the few stages that fit in shared memory would not cover HBM latency at one block per
+// ~500 cycles.
+template <int MODE>
+__device__ __forceinline__ void split_prefetch(const SplitCtx& C, const double* a, const double* b, int blk)
 {
-    const unsigned bytes = (unsigned)(kNH * C.cRec);
-    mbar_expect_tx(&C.cTma[slot], bytes);
-    bulk_g2s(C.cRing + (size_t)slot * C.cBlockBytes, C.cStream + (size_t)blk * bytes, bytes, &C.cTma[slot]);
+    constexpr int dir = MODE == 1 ? -1 : 1;
+    if (blk >= C.nBlocks) return;
+    if (C.pBytes) bulk_prefetch_l2(C.pStream + (size_t)blk * C.pBytes, C.pBytes);
+    bulk_prefetch_l2(C.cStream + (size_t)blk * C.cBytes, C.cBytes);
+    const long long s0 = dir > 0 ? ((long long)C.base + (long long)blk * kNH) * 32 : ((long long)C.base + C.nT - (long long)(blk + 1) * kNH) * 32;
+    bulk_prefetch_l2(a + s0, kNH * 256);
+    if (MODE == 0) bulk_prefetch_l2(b + s0, kNH * 256);
+}
+
+template <int MODE>
+__device__ __forceinline__ void split_issue(const SplitCtx& C, const double* a, const double* b, int blk, int st)
+{
+    constexpr int dir = MODE == 1 ? -1 : 1;
+    unsigned char* dst = C.stages + (size_t)st * C.stageBytes;
+    mbar_expect_tx(&C.rawBar[st], C.rawBytes);
+    if (C.pBytes) bulk_g2s(dst, C.pStream + (size_t)blk * C.pBytes, C.pBytes, &C.rawBar[st]);
+    bulk_g2s(dst + C.offC, C.cStream + (size_t)blk * C.cBytes, C.cBytes, &C.rawBar[st]);
+    const long long s0 = dir > 0 ? ((long long)C.base + (long long)blk * kNH) * 32 : ((long long)C.base + C.nT - (long long)(blk + 1) * kNH) * 32;
+    bulk_g2s(dst + C.offA, a + s0, kNH * 256, &C.rawBar[st]);
+    if (MODE == 0) bulk_g2s(dst + C.offA + kNH * 256, b + s0, kNH * 256, &C.rawBar[st]);
 }
 
 // ------------------------------------------------------------------------------------------ consumer
 template <int MODE, int RG>
-__device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx& C, const int g, const int lane, const double* a,
-                                               const double* b, double* out)
+__device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx& C, const int g, const int lane, double* out)
 {
     constexpr unsigned FULL = 0xffffffffu;
-    const int dir = C.dir, nT = C.nT;
+    constexpr int dir = MODE == 1 ? -1 : 1;
+    constexpr long long outStride = dir > 0 ? 32 : -32;
+    const int nT = C.nT;
     double* outPtr = out + ((long long)C.base + (dir > 0 ? 0 : nT - 1)) * 32 + lane;
-    const long long outStride = dir > 0 ? 32 : -32;
-    const int hdrOff = kNH * C.cRec; // hdr part of a ring block follows its C-records
-    double prev = 0.0;
-    int slot = 0;
-    unsigned par = 0u;
-    long long tWait = 0, t0 = 0, g0 = 0, tTma = 0, tTail = 0;
+    const int srcLane = (lane - dir) & 31; // the linked neighbour lane of a canonical step
+    double h[kSkew];                       // h[k]: the value this lane produced k+1 steps ago
+#pragma unroll
+    for (int k = 0; k < kSkew; k++) h[k] = 0.0;
+    auto push = [&](double v) {
+#pragma unroll
+        for (int k = kSkew - 1; k > 0; k--) h[k] = h[k - 1];
+        h[0] = v;
+    };
+    int st = 0;
+    long long tWait = 0, t0 = 0, g0 = 0, nGeneral = 0;
     if (S.stats)
     {
         t0 = clock64();
@@ -614,116 +658,95 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
     }
     for (int blk = 0; blk < C.nBlocks; blk++)
     {
-        const unsigned char* blkBase = C.cRing + (size_t)slot * C.cBlockBytes;
+        const unsigned char* stage = C.stages + (size_t)st * C.stageBytes;
+        unsigned c;
         if (S.stats)
         {
             const long long w0 = clock64();
-            mbar_wait(&C.cTma[slot], par);
-            tTma += clock64() - w0;
+            do c = ld_flag_smem(&C.cnt[st]);
+            while ((c & 0xffu) != (unsigned)kNH);
+            tWait += clock64() - w0;
         }
         else
-            mbar_wait(&C.cTma[slot], par);
-#pragma unroll
-        for (int hb = 0; hb < kNH; hb += 4)
         {
-            if (S.stats)
+            do c = ld_flag_smem(&C.cnt[st]);
+            while ((c & 0xffu) != (unsigned)kNH);
+        }
+        const unsigned char* rec = stage + C.offC + lane * 8;
+        const unsigned char* hd = stage + C.offHdr + lane * 8;
+        if (S.stats && blk == C.nBlocks / 2 && lane == 0)
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(S.stats[(long long)kStatsStride * g + 12]));
+        if (MODE != 2 && (c >> 8) == 0u && !(S.debugFlags & 1))
+        {
+            double a0[kNH], c0[kNH], c1[kNH];
+#pragma unroll
+            for (int q = 0; q < kNH; q++)
             {
-                const long long w0 = clock64();
-                mbar_wait(&C.hdrFull[slot * 2 + (hb >> 2)], par);
-                tWait += clock64() - w0;
+                a0[q] = *reinterpret_cast<const double*>(hd + (size_t)q * C.hdrStep);
+                c0[q] = *reinterpret_cast<const double*>(rec + (size_t)q * C.cRec + 256);
+                c1[q] = *reinterpret_cast<const double*>(rec + (size_t)q * C.cRec + 512);
             }
-            else
-                mbar_wait(&C.hdrFull[slot * 2 + (hb >> 2)], par);
-            double acc0[4], cf[4][RG];
-            unsigned long long meta[4];
 #pragma unroll
-            for (int q = 0; q < 4; q++)
+            for (int q = 0; q < kNH; q++)
             {
-                const unsigned char* rec = blkBase + (size_t)(hb + q) * C.cRec;
-                acc0[q] = *reinterpret_cast<const double*>(blkBase + hdrOff + (size_t)(hb + q) * C.hdrStep + lane * 8);
-                meta[q] = *reinterpret_cast<const unsigned long long*>(rec + lane * 8);
-#pragma unroll
-                for (int r = 0; r < RG; r++) cf[q][r] = *reinterpret_cast<const double*>(rec + 256 + r * 256 + lane * 8);
+                const double sh = __shfl_sync(FULL, h[kSkew - 1], srcLane);
+                const double pre = a0[q] - c0[q] * sh;
+                const double acc = pre - c1[q] * h[0];
+                st_relaxed(outPtr + q * outStride, acc);
+                push(acc);
             }
-            unsigned flags = 0, rmax = 0;
-#pragma unroll
-            for (int q = 0; q < 4; q++)
+        }
+        else
+        {
+            nGeneral++;
+#pragma unroll 2
+            for (int q = 0; q < kNH; q++)
             {
-                flags |= (unsigned)(meta[q] >> 56) & 1u;
-                rmax = max(rmax, (unsigned)(meta[q] >> 48) & 0xffu);
-            }
-            if (MODE != 2 && !flags && !(S.debugFlags & 1))
-            {
-                // R = number of terms to run for these 4 steps (uniform); terms beyond a lane's own are padding
-                auto run = [&](auto RR) {
-                    constexpr int R = decltype(RR)::value;
+                const unsigned char* r0 = rec + (size_t)q * C.cRec;
+                const unsigned char* h0 = hd + (size_t)q * C.hdrStep;
+                const unsigned long long meta = *reinterpret_cast<const unsigned long long*>(r0);
+                double acc = *reinterpret_cast<const double*>(h0);
+                const double cv0 = C.Kg > 0 ? *reinterpret_cast<const double*>(h0 + 256) : 0.0;
+                const double cv1 = C.Kg > 1 ? *reinterpret_cast<const double*>(h0 + 512) : 0.0;
+                double cf[RG];
 #pragma unroll
-                    for (int q = 0; q < 4; q++)
-                    {
-                        double sh[R > 0 ? R : 1];
+                for (int r = 0; r < RG; r++) cf[r] = *reinterpret_cast<const double*>(r0 + 256 + r * 256);
 #pragma unroll
-                        for (int r = 0; r < R; r++) sh[r] = __shfl_sync(FULL, prev, (int)(meta[q] >> (8 * r)) & 31);
-                        double acc = acc0[q];
-#pragma unroll
-                        for (int r = 0; r < R; r++) acc -= cf[q][r] * sh[r];
-                        st_relaxed(outPtr, acc);
-                        prev = acc;
-                        outPtr += outStride;
-                    }
-                };
-                if (RG >= 2 && rmax == RG - 1)
-                    run(std::integral_constant<int, (RG >= 2 ? RG - 1 : RG)>());
-                else if (RG >= 3 && rmax == RG - 2)
-                    run(std::integral_constant<int, (RG >= 3 ? RG - 2 : RG)>());
-                else
-                    run(std::integral_constant<int, RG>());
-            }
-            else
-            {
-#pragma unroll
-                for (int q = 0; q < 4; q++)
+                for (int r = 0; r < RG; r++)
                 {
-                    const unsigned char* hd = blkBase + hdrOff + (size_t)(hb + q) * C.hdrStep + lane * 8;
-                    const double cv0 = *reinterpret_cast<const double*>(hd + 256);
-                    const double cv1 = C.Kg > 1 ? *reinterpret_cast<const double*>(hd + 512) : 0.0;
-                    double acc = acc0[q];
-#pragma unroll
-                    for (int r = 0; r < RG; r++)
-                    {
-                        const unsigned byte = (unsigned)(meta[q] >> (8 * r)) & 0xffu;
-                        const double sh = __shfl_sync(FULL, prev, (int)(byte & 31u));
-                        double v = (byte & 0x80u) ? ((byte & 0x20u) ? cv1 : cv0) : sh;
-                        if (byte & 0x40u) v = MODE == 2 ? 1.0 : 0.0; // padding term (coefficient 0)
-                        acc = sweep_apply<MODE>(acc, cf[q][r], v);
-                    }
-                    st_relaxed(outPtr, acc);
-                    prev = acc;
-                    outPtr += outStride;
+                    const unsigned byte = (unsigned)(meta >> (8 * r)) & 0xffu;
+                    const double sh = __shfl_sync(FULL, h[kSkew - 1], (int)(byte & kMetaLane));
+                    double v = (byte & kMetaConst) ? ((byte & 0x20u) ? cv1 : cv0) : ((byte & kMetaOwn) ? h[0] : sh);
+                    if (byte & kMetaPad) v = MODE == 2 ? 1.0 : 0.0; // padding term (coefficient 0)
+                    acc = sweep_apply<MODE>(acc, cf[r], v);
                 }
+                st_relaxed(outPtr + q * outStride, acc);
+                push(acc);
             }
         }
-        const long long w1 = S.stats ? clock64() : 0;
+        outPtr += kNH * outStride;
         __syncwarp();
-        if (lane == 0) mbar_arrive(&C.empty[slot]); // block done: producers may reuse its hdr, the loader warp refills
-        if (++slot == kRB)
-        {
-            slot = 0;
-            par ^= 1u;
+        if (S.stats && blk == C.nBlocks / 2 && lane == 0)
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(S.stats[(long long)kStatsStride * g + 13]));
+        if (lane == 0)
+        { // block done: the stage may be refilled
+            st_flag_smem(&C.cnt[st], 0u);
+            st_flag_smem(C.done, (unsigned)(blk + 1));
         }
-        if (S.stats) tTail += clock64() - w1;
+        if (++st == C.NS) st = 0;
     }
     if (S.stats && lane == 0)
     {
         long long g1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
-        long long* st = S.stats + 8ll * g;
-        st[0] = clock64() - t0;
-        st[1] = tWait;
-        st[2] = g0;
-        st[3] = g1;
-        st[5] = nT;
-        st[6] = tTma;
-        st[7] = tTail;
+        long long* sp = S.stats + (long long)kStatsStride * g;
+        sp[0] = clock64() - t0;
+        sp[1] = tWait;
+        sp[2] = g0;
+        sp[3] = g1;
+        sp[5] = nT;
+        sp[6] = nGeneral;
+        sp[7] = C.nBlocks;
     }
 }
 
@@ -734,13 +757,14 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
 {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int LGA = LG > 0 ? LG : 1;
-    const int dir = C.dir;
+    constexpr int dir = MODE == 1 ? -1 : 1;
     const int codeOff = LG * 256 + lane * 4, constOff = LG * 384 + lane * 4;
-    const int vecIdx = (dir > 0 ? h : kNH - 1 - h) * 32 + lane; // this producer's step inside a raw chunk
+    const int vecIdx = (dir > 0 ? h : kNH - 1 - h) * 32 + lane; // this producer's step inside the a / b chunk
     const double neutral = MODE == 2 ? 1.0 : 0.0;
-    const int hdrOff = kNH * C.cRec;
-    int codes[LGA], codesN[LGA], cc[2], ccN[2];
-    double mv[LGA], mvN[LGA], mc[2], mcN[2];
+    // two register sets for the prefetched codes / cross-group values: the block loop is unrolled by two and the
+    // sets swap roles, so that no register copy (which would wait for the prefetch to land) sits in the loop
+    int codesA[LGA], codesB[LGA], ccA[2], ccB[2];
+    double mvA[LGA], mvB[LGA], mcA[2], mcB[2];
     auto fetch = [&](const unsigned char* rec, int* cd, double* vals, int* kc, double* kv) {
 #pragma unroll
         for (int i = 0; i < LG; i++)
@@ -757,18 +781,17 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
             if (kc[k] >= 0) kv[k] = ld_relaxed(out + kc[k]);
         }
     };
-    int st = 0, slot = 0;
-    unsigned parRaw = 0u, parC = 0u;
-    mbar_wait(&C.rawBar[0], 0u);
-    fetch(C.rawRing + (size_t)h * C.pRec, codes, mv, cc, mc);
-    for (int blk = 0; blk < C.nBlocks; blk++)
-    {
-        const unsigned char* sb = C.rawRing + (size_t)st * C.stageBytes;
-        const unsigned char* rec = sb + (size_t)h * C.pRec;
-        const double* aP = reinterpret_cast<const double*>(sb + kNH * C.pRec) + vecIdx;
+    int st = 0;
+    unsigned par = 0u;
+    const bool timed = S.stats != nullptr && h == 0;
+    long long tStage = 0, tVal = 0, tSpin = 0, tAll = timed ? clock64() : 0;
+    auto step = [&](const int blk, int* codes, double* mv, int* cc, double* mc, int* codesN, double* mvN, int* ccN, double* mcN) {
+        unsigned char* stage = C.stages + (size_t)st * C.stageBytes;
+        const unsigned char* rec = stage + (size_t)h * C.pRec;
+        const double* aP = reinterpret_cast<const double*>(stage + C.offA) + vecIdx;
         // ---- prefetch the codes / cross-group values of this producer's step in the next block
         int stN = st + 1;
-        unsigned parN = parRaw;
+        unsigned parN = par;
         if (stN == C.NS)
         {
             stN = 0;
@@ -776,8 +799,10 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
         }
         if (blk + 1 < C.nBlocks)
         {
+            const long long w0 = timed ? clock64() : 0;
             mbar_wait(&C.rawBar[stN], parN);
-            fetch(C.rawRing + (size_t)stN * C.stageBytes + (size_t)h * C.pRec, codesN, mvN, ccN, mcN);
+            if (timed) tStage += clock64() - w0;
+            fetch(C.stages + (size_t)stN * C.stageBytes + (size_t)h * C.pRec, codesN, mvN, ccN, mcN);
         }
         // ---- operands of the current step first, the (possibly late) cross-group values last
         double acc = *aP;
@@ -785,14 +810,19 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
         double cf[LGA];
 #pragma unroll
         for (int i = 0; i < LG; i++) cf[i] = *reinterpret_cast<const double*>(rec + lane * 8 + i * 256);
+        const unsigned general =
+            MODE == 2 ? 1u : (unsigned)(*reinterpret_cast<const unsigned long long*>(stage + C.offC + (size_t)h * C.cRec + lane * 8) >> 56) & 1u;
+        const long long v0 = timed ? clock64() : 0;
         bool bad = false;
 #pragma unroll
         for (int i = 0; i < LG; i++) bad |= codes[i] >= 0 && is_sentinel(mv[i]);
 #pragma unroll
         for (int k = 0; k < 2; k++) bad |= cc[k] >= 0 && is_sentinel(mc[k]);
-        if (__any_sync(FULL, bad))
+        const bool anyBad = __any_sync(FULL, bad);
+        const long long v1 = timed ? clock64() : 0;
+        if (anyBad)
         { // a value had not arrived when it was prefetched: poll for it
-            if (S.stats && lane == 0) atomicAdd((unsigned long long*)(S.stats + 8ll * g + 4), 1ull);
+            if (S.stats && lane == 0) atomicAdd((unsigned long long*)(S.stats + (long long)kStatsStride * g + 4), 1ull);
 #pragma unroll
             for (int i = 0; i < LG; i++)
                 if (codes[i] >= 0 && is_sentinel(mv[i])) mv[i] = sweep_spin(out + codes[i], err);
@@ -800,35 +830,39 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
             for (int k = 0; k < 2; k++)
                 if (cc[k] >= 0 && is_sentinel(mc[k])) mc[k] = sweep_spin(out + cc[k], err);
         }
+        if (timed)
+        {
+            tVal += v1 - v0;
+            tSpin += clock64() - v1;
+            if (blk == C.nBlocks / 2 && lane == 0)
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(S.stats[(long long)kStatsStride * g + 14]));
+        }
 #pragma unroll
         for (int i = 0; i < LG; i++) acc = sweep_apply<MODE>(acc, cf[i], mv[i]); // padding: coefficient 0, neutral value
-        // ---- hand over once the consumer has released the ring block
-        if (blk >= kRB) mbar_wait(&C.empty[slot], parC ^ 1u);
-        unsigned char* hd = C.cRing + (size_t)slot * C.cBlockBytes + hdrOff + (size_t)h * C.hdrStep + lane * 8;
+        // ---- hand over: the hdr part of the stage is free because the stage was refilled after the consumer released it
+        unsigned char* hd = stage + C.offHdr + (size_t)h * C.hdrStep + lane * 8;
         *reinterpret_cast<double*>(hd) = acc;
-        *reinterpret_cast<double*>(hd + 256) = mc[0];
+        if (C.Kg > 0) *reinterpret_cast<double*>(hd + 256) = mc[0];
         if (C.Kg > 1) *reinterpret_cast<double*>(hd + 512) = mc[1];
         __syncwarp();
-        if (lane == 0) mbar_arrive(&C.hdrFull[slot * 2 + (h >> 2)]);
-        if (++slot == kRB)
-        {
-            slot = 0;
-            parC ^= 1u;
-        }
+        if (lane == 0) red_flag_smem(&C.cnt[st], 1u + (general << 8));
         st = stN;
-        parRaw = parN;
-#pragma unroll
-        for (int i = 0; i < LG; i++)
-        {
-            codes[i] = codesN[i];
-            mv[i] = mvN[i];
-        }
-#pragma unroll
-        for (int k = 0; k < 2; k++)
-        {
-            cc[k] = ccN[k];
-            mc[k] = mcN[k];
-        }
+        par = parN;
+    };
+    mbar_wait(&C.rawBar[0], 0u);
+    fetch(C.stages + (size_t)h * C.pRec, codesA, mvA, ccA, mcA);
+    for (int blk = 0; blk < C.nBlocks; blk += 2)
+    {
+        step(blk, codesA, mvA, ccA, mcA, codesB, mvB, ccB, mcB);
+        if (blk + 1 < C.nBlocks) step(blk + 1, codesB, mvB, ccB, mcB, codesA, mvA, ccA, mcA);
+    }
+    if (timed && lane == 0)
+    {
+        long long* sp = S.stats + (long long)kStatsStride * g;
+        sp[8] = clock64() - tAll;
+        sp[9] = tStage;
+        sp[10] = tVal;
+        sp[11] = tSpin;
     }
 }
 
@@ -839,7 +873,6 @@ __device__ __forceinline__ void sweep_group_split(const PipeDev& S, const int g,
     SplitCtx C;
     C.nT = S.gNT[g];
     C.base = S.gBase[g];
-    C.dir = S.dir;
     C.nBlocks = C.nT / kNH;
     C.NS = S.nStages;
     C.stageBytes = S.stageBytes;
@@ -849,61 +882,55 @@ __device__ __forceinline__ void sweep_group_split(const PipeDev& S, const int g,
     C.pRec = C.Lg * 384 + C.Kg * 128;
     C.cRec = 256 + C.Rg * 256;
     C.hdrStep = 256 * (1 + C.Kg);
-    C.cBlockBytes = S.cBlockBytes;
-    C.rawChunkBytes = (unsigned)(kNH * C.pRec + kNH * 256 * (MODE == 0 ? 2 : 1));
+    C.pBytes = (unsigned)(kNH * C.pRec);
+    C.cBytes = (unsigned)(kNH * C.cRec);
+    C.offC = (int)C.pBytes;
+    C.offA = C.offC + (int)C.cBytes;
+    C.offHdr = C.offA + kNH * 256 * (MODE == 0 ? 2 : 1);
+    C.rawBytes = C.pBytes + C.cBytes + (unsigned)(kNH * 256 * (MODE == 0 ? 2 : 1));
     C.rawBar = reinterpret_cast<unsigned long long*>(smem);
-    C.hdrFull = reinterpret_cast<unsigned long long*>(smem + 128);
-    C.empty = C.hdrFull + 2 * kRB;
-    C.cTma = C.empty + kRB;
-    C.rawRing = smem + 256;
-    C.cRing = C.rawRing + (size_t)C.NS * C.stageBytes;
+    C.cnt = reinterpret_cast<unsigned*>(smem + 128);
+    C.done = reinterpret_cast<unsigned*>(smem + 192);
+    C.stages = smem + 256;
     C.pStream = S.pStream + S.gPOff[g];
     C.cStream = S.cStream + S.gCOff[g];
     if (warp == 0 && lane == 0)
     {
-        for (int st = 0; st < C.NS; st++) mbar_init(&C.rawBar[st], 1);
-        for (int i = 0; i < 2 * kRB; i++) mbar_init(&C.hdrFull[i], kNH / 2);
-        for (int i = 0; i < kRB; i++)
+        for (int st = 0; st < C.NS; st++)
         {
-            mbar_init(&C.empty[i], 1);
-            mbar_init(&C.cTma[i], 1);
+            mbar_init(&C.rawBar[st], 1);
+            C.cnt[st] = 0u;
         }
+        *C.done = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int c = 0; c < C.NS && c < C.nBlocks; c++) split_issue_raw<MODE>(C, a, b, c, c);
-        for (int c = 0; c < kRB && c < C.nBlocks; c++) split_issue_c(C, c, c);
+        for (int c = 0; c < C.NS && c < C.nBlocks; c++) split_issue<MODE>(C, a, b, c, c);
+        for (int c = C.NS; c < C.NS + kL2Ahead; c++) split_prefetch<MODE>(C, a, b, c);
     }
     __syncthreads();
     if (warp == 0)
     {
         switch (C.Rg)
         {
-            case 1: split_consumer<MODE, 1>(S, C, g, lane, a, b, out); break;
-            case 2: split_consumer<MODE, 2>(S, C, g, lane, a, b, out); break;
-            case 3: split_consumer<MODE, 3>(S, C, g, lane, a, b, out); break;
-            case 4: split_consumer<MODE, 4>(S, C, g, lane, a, b, out); break;
-            case 5: split_consumer<MODE, 5>(S, C, g, lane, a, b, out); break;
-            default: split_consumer<MODE, 6>(S, C, g, lane, a, b, out); break;
+            case 2: split_consumer<MODE, 2>(S, C, g, lane, out); break;
+            case 3: split_consumer<MODE, 3>(S, C, g, lane, out); break;
+            case 4: split_consumer<MODE, 4>(S, C, g, lane, out); break;
+            case 5: split_consumer<MODE, 5>(S, C, g, lane, out); break;
+            default: split_consumer<MODE, 6>(S, C, g, lane, out); break;
         }
     }
     else if (warp == 1 + kNH)
     {
-        // loader: one thread refills the rings as soon as the consumer has released a block
+        // loader: one thread refills a stage as soon as the consumer has released the block it held
         if (lane == 0)
         {
-            int slot = 0, stRaw = 0;
-            unsigned par = 0u;
-            for (int blk = 0; blk < C.nBlocks; blk++)
+            int st = 0;
+            for (int blk = C.NS; blk < C.nBlocks; blk++)
             {
-                if (blk + kRB >= C.nBlocks && blk + C.NS >= C.nBlocks) break;
-                mbar_wait(&C.empty[slot], par);
-                if (blk + kRB < C.nBlocks) split_issue_c(C, blk + kRB, slot);
-                if (blk + C.NS < C.nBlocks) split_issue_raw<MODE>(C, a, b, blk + C.NS, stRaw);
-                if (++slot == kRB)
-                {
-                    slot = 0;
-                    par ^= 1u;
-                }
-                if (++stRaw == C.NS) stRaw = 0;
+                const unsigned need = (unsigned)(blk - C.NS + 1);
+                while (ld_flag_smem(C.done) < need) __nanosleep(20);
+                split_issue<MODE>(C, a, b, blk, st);
+                split_prefetch<MODE>(C, a, b, blk + kL2Ahead);
+                if (++st == C.NS) st = 0;
             }
         }
     }
@@ -938,7 +965,9 @@ __device__ __noinline__ void sweep_group_generic(const PipeDev& S, const int g, 
     double* outPtr = out + ((long long)R.base + (dir > 0 ? 0 : R.nT - 1)) * 32 + lane;
     const int vecStart = dir > 0 ? lane : (CHg - 1) * 32 + lane;
     const int vecStride = dir > 0 ? 32 : -32;
-    double prev = 0.0;
+    double hist[kSkew]; // hist[k]: the value this lane produced k+1 steps ago
+#pragma unroll
+    for (int k = 0; k < kSkew; k++) hist[k] = 0.0;
     int stCur = 0;
     unsigned par = 0u;
     for (int c = 0; c < R.nChunks; c++)
@@ -957,8 +986,12 @@ __device__ __noinline__ void sweep_group_generic(const PipeDev& S, const int g, 
             {
                 const int code = *reinterpret_cast<const int*>(recPtr + codeOff + j * 128);
                 const double cfj = *reinterpret_cast<const double*>(recPtr + coefOff + j * 256);
-                double v = prev;
-                if ((shflMask >> j) & 1u) v = __shfl_sync(FULL, prev, code <= kCodeShfl ? kCodeShfl - code : lane);
+                double v = hist[0];
+                if ((shflMask >> j) & 1u)
+                {
+                    const double sh = __shfl_sync(FULL, hist[kSkew - 1], code <= kCodeShfl ? kCodeShfl - code : lane);
+                    if (code <= kCodeShfl) v = sh;
+                }
                 if (code >= 0)
                 {
                     v = ld_relaxed(out + code);
@@ -967,7 +1000,9 @@ __device__ __noinline__ void sweep_group_generic(const PipeDev& S, const int g, 
                 if (code != kCodeNone) acc = sweep_apply<MODE>(acc, cfj, v);
             }
             st_relaxed(outPtr, acc);
-            prev = acc;
+#pragma unroll
+            for (int k = kSkew - 1; k > 0; k--) hist[k] = hist[k - 1];
+            hist[0] = acc;
             recPtr += recBytes;
             aP += vecStride;
             bP += vecStride;

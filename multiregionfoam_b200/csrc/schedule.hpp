@@ -9,9 +9,10 @@
 // time reversed.  Two ways of forming groups, chosen per region:
 //   LINE  mode (structured / blockMesh-like numbering): a lane walks a *path* of rows in which each
 //         row has the previous one as a neighbour (x-lines, continued across block seams); lanes
-//         of a warp are paths linked row-by-row (line j depends on line j-1) and are skewed by one
-//         time step per lane, so that every in-warp dependency is exactly one time step old and
-//         travels through a warp shuffle.  Only dependencies on other warps go through memory.
+//         of a warp are paths linked row-by-row (line j depends on line j-1) and are skewed by kSkew
+//         time steps per lane: the own-lane dependency is one step old and stays in a register, the
+//         neighbour-lane dependency is kSkew steps old and travels through a warp shuffle that is
+//         issued ahead of its use.  Only dependencies on other warps go through memory.
 //   BLOCK mode (unstructured numbering, no long lines): rows sorted by wavefront level are cut
 //         into blocks of 32 independent rows; a group is 16 consecutive blocks.
 // Cross-warp dependencies are resolved through the output vector itself: it is pre-filled with a
@@ -115,10 +116,18 @@ struct GlobalLdu
 
 // term codes of the sweep streams
 constexpr int kSweepBlock = 8;     // steps per producer/consumer block of the sweep kernel (= producer warps)
+constexpr int kSkew = 2;           // time steps between linked lanes of a warp: a value shuffled from another lane is kSkew
+                                   // steps old, so the shuffle is issued ahead and only mul+sub of the own-lane term
+                                   // remain on the dependent chain of a time step
 constexpr int32_t kCodeNone = -1; // padding term
 constexpr int32_t kCodeOwn = -2;  // value this lane produced in the previous time step (register)
-constexpr int32_t kCodeShfl = -3; // -3 - m: value lane m produced in the previous time step (shuffle)
+constexpr int32_t kCodeShfl = -3; // -3 - m: value lane m produced kSkew time steps ago (shuffle)
                                   // >= 0 : slot of a value produced elsewhere (memory, sentinel-guarded)
+// term descriptor bytes of the consumer records (C-stream meta)
+constexpr unsigned kMetaLane = 0x1fu;  // source lane of a shuffled term
+constexpr unsigned kMetaOwn = 0x20u;   // (without kMetaConst) own-lane value of the previous step
+constexpr unsigned kMetaPad = 0x40u;   // padding term (coefficient 0)
+constexpr unsigned kMetaConst = 0x80u; // cross-group value handed over by the producers: constCode[bit 5]
 
 // ------------------------------------------------------------------------------------------
 struct PipeSchedule
@@ -147,10 +156,10 @@ struct PipeSchedule
         //      the LEADING terms of each row: its first run of cross-group (memory) terms, in reference order;
         //      constCode[k] = slot of the k-th cross-group value the row's remaining terms need (-1: none)
         //  C-stream (consumer warp), per step:   meta[32] u64 | coef[Rg][32] f64
-        //      the REMAINING terms, in reference order.  meta byte r < 6 describes term r: bits 0-4 source lane
-        //      (own lane for the register-carried value), 0x40 = padding term (coefficient 0), 0x80 = the
-        //      term takes the value of constCode[bit 5] instead of a shuffle; byte 6 = number of terms of this
-        //      step (uniform over the lanes); byte 7 bit 0 = some lane of this step has a 0x80 term (uniform).
+        //      the REMAINING terms.  meta byte r < 6 describes the term of plane r: bits 0-4 source lane of a value
+        //      shuffled from kSkew steps ago, kMetaOwn = own-lane value of the previous step, kMetaPad = padding
+        //      (coefficient 0), kMetaConst = the value of constCode[bit 5]; byte 6 = number of planes in use;
+        //      byte 7 bit 0 = the step is not canonical (uniform over the lanes, see build_split).
         std::vector<uint8_t> gFast;
         std::vector<int32_t> gLg, gRg, gKg;
         std::vector<int64_t> gPOff, gCOff;           // [nGroups+1] byte offsets into pStream / cStream
@@ -159,7 +168,8 @@ struct PipeSchedule
         std::vector<int32_t> pFace, cFace;           // face of every coefficient slot (-1: none)
         std::vector<int64_t> gGenOff;                // [nGroups+1] term offsets of the unified stream: generic groups only
         int64_t nGenTerms = 0;
-        int maxPStage = 0, maxCStep = 0, maxGenStage = 0, nFastGroups = 0;
+        int maxPStage = 0, maxCStep = 0, maxGenStage = 0, maxFastStage = 0, nFastGroups = 0;
+        int64_t nGeneralSteps = 0; // steps of fast groups that are not canonical (see build_split)
     } fwd, bwd;
 
     // statistics
@@ -375,7 +385,7 @@ struct PipeSchedule
                     for (; j < seq.size() && lanes.size() < 32; j++)
                     {
                         // admit seq[j] as the next lane only if all its dependencies on lanes already in
-                        // this warp are exactly one time step old: the aligned link to the previous lane
+                        // this warp are exactly kSkew time steps old: the aligned link to the previous lane
                         const int q = seq[j];
                         bool okLane = true;
                         for (auto& e : preds[q])
@@ -418,7 +428,7 @@ struct PipeSchedule
                 for (size_t ln = 0; ln < groups[gi].size(); ln++)
                 {
                     const int p = groups[gi][ln];
-                    const int skew = skewed[gi] ? int(ln) : 0;
+                    const int skew = skewed[gi] ? kSkew * int(ln) : 0;
                     nT = std::max(nT, skew + pLen[p]);
                     int32_t pos = 0;
                     for (int b : pathChains[p])
@@ -604,19 +614,16 @@ struct PipeSchedule
             int j = 0;
             auto put = [&](int32_t f, int32_t nb) {
                 int32_t code;
-                if (place_.grp[nb] == gI && place_.tim[nb] == t - dir)
+                if (place_.grp[nb] == gI && place_.lan[nb] == ln && place_.tim[nb] == t - dir)
                 {
-                    if (place_.lan[nb] == ln)
-                    {
-                        code = kCodeOwn;
-                        if (dir > 0) nOwnTermsF++;
-                    }
-                    else
-                    {
-                        code = kCodeShfl - place_.lan[nb];
-                        if (j < 31) D.gShflMask[gI] |= (1 << j);
-                        if (dir > 0) nShflTermsF++;
-                    }
+                    code = kCodeOwn;
+                    if (dir > 0) nOwnTermsF++;
+                }
+                else if (place_.grp[nb] == gI && place_.tim[nb] == t - kSkew * dir && (kSkew > 1 || place_.lan[nb] != ln))
+                {
+                    code = kCodeShfl - place_.lan[nb];
+                    if (j < 31) D.gShflMask[gI] |= (1 << j);
+                    if (dir > 0) nShflTermsF++;
                 }
                 else
                 {
@@ -647,6 +654,13 @@ struct PipeSchedule
     static int p_rec_bytes(int Lg, int Kg) { return Lg * 384 + Kg * 128; }
     static int c_rec_bytes(int Rg) { return 256 + Rg * 256; }
     static int c_ring_step_bytes(int Rg, int Kg) { return 256 * (1 + Kg) + c_rec_bytes(Rg); } // hdr acc0[32], cval[Kg][32] + record
+    static int hdr_step_bytes(int Kg) { return 256 * (1 + Kg); }                              // acc0[32] | cval[Kg][32]
+    // one shared-memory stage of a fast group = one block of kSweepBlock steps:
+    //   P-records | C-records | a[steps][32] | b[steps][32] (forward only) | hdr[steps] (written by the producer warps)
+    static int fast_stage_bytes(int Lg, int Rg, int Kg, int nVec)
+    {
+        return kSweepBlock * (p_rec_bytes(Lg, Kg) + c_rec_bytes(Rg) + nVec * 256 + hdr_step_bytes(Kg));
+    }
 
   private:
     void build_split(int dir, Dir& D)
@@ -662,13 +676,14 @@ struct PipeSchedule
         D.gPFaceOff.assign(nG + 1, 0);
         D.gCFaceOff.assign(nG + 1, 0);
         D.gGenOff.assign(nG + 1, 0);
-        D.maxPStage = D.maxCStep = D.maxGenStage = D.nFastGroups = 0;
+        D.maxPStage = D.maxCStep = D.maxGenStage = D.maxFastStage = D.nFastGroups = 0;
+        D.nGeneralSteps = 0;
         // pass 1: eligibility, Lg, Rg
         for (int gI = 0; gI < nG; gI++)
         {
             const int W = D.gW[gI], nT = gNT[gI];
             bool fast = W >= 1 && W <= 6 && D.gShflMask[gI] >= 0 && !forceGeneric;
-            int Lg = 0, Rg = 0, Kg = 1;
+            int Lg = 0, Rg = 0, Kg = 0;
             for (int step = 0; step < nT && fast; step++)
                 for (int lane = 0; lane < 32; lane++)
                 {
@@ -686,7 +701,7 @@ struct PipeSchedule
                 }
             D.gFast[gI] = fast ? 1 : 0;
             D.gLg[gI] = fast ? Lg : 0;
-            Rg = std::max(Rg, 1); // at least one (padding) plane: the consumer is compiled for 1..6 remaining terms
+            Rg = std::max(Rg, 2); // planes 0 / 1 hold the shuffled / own-lane coefficient of a canonical step
             D.gRg[gI] = fast ? Rg : 0;
             D.gKg[gI] = fast ? Kg : 0;
             if (fast)
@@ -700,6 +715,7 @@ struct PipeSchedule
                 D.gGenOff[gI + 1] = D.gGenOff[gI];
                 D.maxPStage = std::max(D.maxPStage, kSweepBlock * (p_rec_bytes(Lg, Kg) + nVec * 256));
                 D.maxCStep = std::max(D.maxCStep, c_ring_step_bytes(Rg, Kg));
+                D.maxFastStage = std::max(D.maxFastStage, fast_stage_bytes(Lg, Rg, Kg, nVec));
             }
             else
             {
@@ -729,8 +745,14 @@ struct PipeSchedule
                 int32_t* pCode = reinterpret_cast<int32_t*>(pr + Lg * 256);
                 int32_t* pConst = reinterpret_cast<int32_t*>(pr + Lg * 384);
                 uint64_t* meta = reinterpret_cast<uint64_t*>(cr);
+                // A step is CANONICAL if the remaining terms of every lane are, in reference order, an optional
+                // term shuffled from the linked neighbour lane (lane - dir) followed by an optional own-lane term.
+                // Its record then holds the shuffle coefficient in plane 0 and the own-lane coefficient in plane 1
+                // (0 where the term is absent) and the consumer runs  acc = (acc0 - c0*shfl) - c1*own  without
+                // looking at the descriptors.  Any other step keeps its terms in reference order in planes 0.. and is
+                // flagged (meta byte 7 bit 0); the consumer then interprets the descriptor bytes.
                 int Rt = 0;
-                bool anyConst = false;
+                bool canonical = true;
                 int ldOf[32], nOf[32];
                 for (int lane = 0; lane < 32; lane++)
                 {
@@ -742,7 +764,12 @@ struct PipeSchedule
                     ldOf[lane] = ld;
                     nOf[lane] = nTerms;
                     Rt = std::max(Rt, nTerms - ld);
+                    int j = ld;
+                    if (j < nTerms && D.code[b0 + int64_t(j) * 32] == kCodeShfl - ((lane - dir) & 31) && lane - dir >= 0 && lane - dir < 32) j++;
+                    if (j < nTerms && D.code[b0 + int64_t(j) * 32] == kCodeOwn) j++;
+                    if (j != nTerms) canonical = false;
                 }
+                if (canonical) Rt = 2;
                 for (int lane = 0; lane < 32; lane++)
                 {
                     const int64_t b0 = D.gTermOff[gI] + int64_t(step) * W * 32 + lane;
@@ -755,32 +782,48 @@ struct PipeSchedule
                     for (int k = 0; k < Kg; k++) pConst[k * 32 + lane] = -1;
                     int nc = 0;
                     uint64_t m = 0;
-                    for (int r = 0; r < 6; r++)
-                    {
-                        unsigned byte = unsigned(lane) | 0x40u; // padding: coefficient 0, source = own lane
-                        const int j = ld + r;
-                        if (r < Rg && j < nTerms)
+                    int32_t* cFaceRow = &D.cFace[D.gCFaceOff[gI] + int64_t(step) * Rg * 32 + lane];
+                    auto describe = [&](int j) -> unsigned {
+                        const int32_t code = D.code[b0 + int64_t(j) * 32];
+                        if (code >= 0)
                         {
-                            const int32_t code = D.code[b0 + int64_t(j) * 32];
-                            D.cFace[D.gCFaceOff[gI] + (int64_t(step) * Rg + r) * 32 + lane] = D.face[b0 + int64_t(j) * 32];
-                            if (code >= 0)
-                            {
-                                byte = unsigned(lane) | 0x80u | (nc ? 0x20u : 0u);
-                                pConst[nc * 32 + lane] = code;
-                                nc++;
-                                anyConst = true;
-                            }
-                            else if (code == kCodeOwn)
-                                byte = unsigned(lane);
-                            else
-                                byte = unsigned(kCodeShfl - code);
+                            const unsigned byte = unsigned(lane) | kMetaConst | (nc ? 0x20u : 0u);
+                            pConst[nc * 32 + lane] = code;
+                            nc++;
+                            return byte;
                         }
-                        m |= uint64_t(byte) << (8 * r);
+                        if (code == kCodeOwn) return unsigned(lane) | kMetaOwn;
+                        return unsigned(kCodeShfl - code);
+                    };
+                    unsigned bytes[6];
+                    for (int r = 0; r < 6; r++) bytes[r] = unsigned(lane) | kMetaPad; // padding: coefficient 0
+                    if (canonical)
+                    {
+                        int j = ld;
+                        if (j < nTerms && D.code[b0 + int64_t(j) * 32] != kCodeOwn)
+                        {
+                            bytes[0] = describe(j);
+                            cFaceRow[0] = D.face[b0 + int64_t(j) * 32];
+                            j++;
+                        }
+                        if (j < nTerms)
+                        {
+                            bytes[1] = describe(j);
+                            cFaceRow[32] = D.face[b0 + int64_t(j) * 32];
+                        }
                     }
+                    else
+                        for (int r = 0; r < Rg && ld + r < nTerms; r++)
+                        {
+                            bytes[r] = describe(ld + r);
+                            cFaceRow[int64_t(r) * 32] = D.face[b0 + int64_t(ld + r) * 32];
+                        }
+                    for (int r = 0; r < 6; r++) m |= uint64_t(bytes[r]) << (8 * r);
                     meta[lane] = m;
                 }
                 for (int lane = 0; lane < 32; lane++)
-                    meta[lane] |= (uint64_t(Rt) << 48) | (uint64_t(anyConst ? 1 : 0) << 56);
+                    meta[lane] |= (uint64_t(Rt) << 48) | (uint64_t(canonical ? 0 : 1) << 56);
+                if (!canonical) D.nGeneralSteps++;
             }
         }
     }

@@ -334,10 +334,11 @@ class LduSystem:
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(KERNEL_CLASSES)}
 
     def sweep_stats(self, direction: int, enable: bool = True) -> np.ndarray:
-        """Debug counters of the sweep kernel per group: columns {consumer cycles, wait cycles, start ns, end ns,
-        producer polls, nT, -, -}; returns what the sweeps since the previous call recorded and (re)arms."""
+        """Debug counters of the sweep kernel per group, 16 columns: consumer {cycles, wait cycles, start ns, end ns},
+        producer polls, nT, general blocks, blocks, producer 0 {cycles, stage-wait, value-wait, spin cycles}, -;
+        returns what the sweeps since the previous call recorded and (re)arms."""
         n = self.ctx.check(load().b200_debug_sweep_stats(self.h, direction, 0, None, 0))
-        out = np.zeros((max(n, 1), 8), dtype=np.int64)
+        out = np.zeros((max(n, 1), 16), dtype=np.int64)
         self.ctx.check(load().b200_debug_sweep_stats(self.h, direction, int(enable), out.ctypes.data_as(C.POINTER(C.c_longlong)), out.size))
         return out[:n]
 

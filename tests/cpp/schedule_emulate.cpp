@@ -24,8 +24,12 @@ int walk(const PipeSchedule& S, const PipeSchedule::Dir& D, int dir, int mode, c
     {
         const int g = dir > 0 ? ticket : S.orderB[ticket];
         const int W = D.gW[g], nT = S.gNT[g];
-        double prev[32], cur[32];
-        for (int l = 0; l < 32; l++) prev[l] = 0.0;
+        // hist[k][lane]: value lane produced k+1 time steps ago (own-lane terms use k = 0, shuffled terms k = kSkew-1)
+        double hist[kSkew][32], cur[32];
+        for (int k = 0; k < kSkew; k++)
+            for (int l = 0; l < 32; l++) hist[k][l] = 0.0;
+        const double(&prev)[32] = hist[0];
+        const double(&prevS)[32] = hist[kSkew - 1];
         const bool fast = D.gFast[g] != 0;
         const int Lg = D.gLg[g], Rg = D.gRg[g], Kg = D.gKg[g];
         for (int step = 0; step < nT; step++)
@@ -55,27 +59,42 @@ int walk(const PipeSchedule& S, const PipeSchedule::Dir& D, int dir, int mode, c
                     const unsigned char* cr = D.cStream.data() + D.gCOff[g] + int64_t(step) * PipeSchedule::c_rec_bytes(Rg);
                     const uint64_t meta = reinterpret_cast<const uint64_t*>(cr)[lane];
                     const int Rt = int((meta >> 48) & 0xff);
+                    const bool general = (meta >> 56) & 1;
                     if (Rt > Rg) return -21;
+                    const double acc0 = acc;
                     for (int r = 0; r < Rg; r++)
                     {
                         const unsigned byte = unsigned((meta >> (8 * r)) & 0xff);
                         const int32_t f = D.cFace[D.gCFaceOff[g] + (int64_t(step) * Rg + r) * 32 + lane];
-                        if (byte & 0x40u)
+                        if (byte & kMetaPad)
                         {
                             if (f >= 0) return -22;
                             continue; // padding
                         }
                         if (r >= Rt || f < 0) return -23;
                         double v;
-                        if (byte & 0x80u)
+                        if (byte & kMetaConst)
                         {
                             const int32_t pConst = pConstArr[((byte & 0x20u) ? 1 : 0) * 32 + lane];
-                            if (!(meta >> 56 & 1) || pConst < 0 || out[pConst] == NOTSET) return -24;
+                            if (!general || pConst < 0 || out[pConst] == NOTSET) return -24;
                             v = out[pConst];
                         }
+                        else if (byte & kMetaOwn)
+                            v = prev[lane];
                         else
-                            v = prev[byte & 31u];
+                            v = prevS[byte & kMetaLane];
                         acc = mode == 2 ? acc - coefOf(f, slot) / v : acc - coefOf(f, slot) * v;
+                    }
+                    if (!general && mode != 2)
+                    {
+                        // the consumer's descriptor-free evaluation of a canonical step must give the same bits
+                        const int32_t f0 = D.cFace[D.gCFaceOff[g] + (int64_t(step) * Rg + 0) * 32 + lane];
+                        const int32_t f1 = D.cFace[D.gCFaceOff[g] + (int64_t(step) * Rg + 1) * 32 + lane];
+                        const double c0 = f0 >= 0 ? coefOf(f0, slot) : 0.0, c1 = f1 >= 0 ? coefOf(f1, slot) : 0.0;
+                        const double fastAcc = (acc0 - c0 * prevS[(lane - dir) & 31]) - c1 * prev[lane];
+                        if (std::memcmp(&fastAcc, &acc, 8) != 0 && !(fastAcc == 0.0 && acc == 0.0)) return -25;
+                        for (int r = 2; r < Rg; r++)
+                            if (D.cFace[D.gCFaceOff[g] + (int64_t(step) * Rg + r) * 32 + lane] >= 0) return -26;
                     }
                 }
                 else
@@ -94,7 +113,7 @@ int walk(const PipeSchedule& S, const PipeSchedule::Dir& D, int dir, int mode, c
                         else if (code == kCodeOwn)
                             v = prev[lane];
                         else
-                            v = prev[kCodeShfl - code];
+                            v = prevS[kCodeShfl - code];
                         acc = mode == 2 ? acc - coefOf(f, slot) / v : acc - coefOf(f, slot) * v;
                     }
                 if (S.cellOfSlot[slot] < 0 && acc != 0.0) return -12; // padding slots must stay zero
@@ -103,7 +122,8 @@ int walk(const PipeSchedule& S, const PipeSchedule::Dir& D, int dir, int mode, c
             for (int lane = 0; lane < 32; lane++)
             {
                 out[(int64_t(S.gBase[g]) + t) * 32 + lane] = cur[lane];
-                prev[lane] = cur[lane];
+                for (int k = kSkew - 1; k > 0; k--) hist[k][lane] = hist[k - 1][lane];
+                hist[0][lane] = cur[lane];
             }
         }
     }
@@ -193,6 +213,8 @@ int emu_run(int nCells, int nFaces, const int* l, const int* u, const double* di
         stats[11] = int(S.nOwnTermsF);
         stats[12] = S.fwd.nFastGroups;
         stats[13] = S.bwd.nFastGroups;
+        stats[14] = int(S.fwd.nGeneralSteps);
+        stats[15] = int(S.bwd.nGeneralSteps);
         return 0;
     }
     catch (const std::exception& e)
