@@ -455,7 +455,7 @@ __device__ __noinline__ double sweep_spin(const double* p, int* err)
     {
         const double v = ld_relaxed(p);
         if (!is_sentinel(v)) return v;
-        if (tries >= 16) __nanosleep(tries > 4096 ? 400 : 64); // later: a busy-spinning warp steals issue slots from the consumer warps
+        if (tries >= 64) __nanosleep(tries > 4096 ? 400 : 64); // later: a busy-spinning warp steals issue slots from the consumer warps
         if ((tries & 4095) == 4095 && *(volatile int*)err) break;
     }
     atomicExch(err, 1);
@@ -589,7 +589,7 @@ struct SplitCtx
 {
     int nT, base, nBlocks, NS, stageBytes;
     int Lg, Rg, Kg, pRec, cRec, hdrStep;
-    int offC, offA, offHdr; // byte offsets inside a stage: P-records at 0, then C-records, a (b), hdr
+    int offHdr, offP, offA; // byte offsets inside a stage: C-block at 0, then hdr, P-records, a (b)
     unsigned pBytes, cBytes, rawBytes;
     unsigned long long* rawBar; // [NS] TMA completion
     unsigned* cnt;              // [NS] producer arrivals of the block in the stage (+ 256 per non-canonical step)
@@ -624,24 +624,32 @@ __device__ __forceinline__ void split_issue(const SplitCtx& C, const double* a, 
     constexpr int dir = MODE == 1 ? -1 : 1;
     unsigned char* dst = C.stages + (size_t)st * C.stageBytes;
     mbar_expect_tx(&C.rawBar[st], C.rawBytes);
-    if (C.pBytes) bulk_g2s(dst, C.pStream + (size_t)blk * C.pBytes, C.pBytes, &C.rawBar[st]);
-    bulk_g2s(dst + C.offC, C.cStream + (size_t)blk * C.cBytes, C.cBytes, &C.rawBar[st]);
+    bulk_g2s(dst, C.cStream + (size_t)blk * C.cBytes, C.cBytes, &C.rawBar[st]);
+    if (C.pBytes) bulk_g2s(dst + C.offP, C.pStream + (size_t)blk * C.pBytes, C.pBytes, &C.rawBar[st]);
     const long long s0 = dir > 0 ? ((long long)C.base + (long long)blk * kNH) * 32 : ((long long)C.base + C.nT - (long long)(blk + 1) * kNH) * 32;
     bulk_g2s(dst + C.offA, a + s0, kNH * 256, &C.rawBar[st]);
     if (MODE == 0) bulk_g2s(dst + C.offA + kNH * 256, b + s0, kNH * 256, &C.rawBar[st]);
 }
 
 // ------------------------------------------------------------------------------------------ consumer
+// The consumer warp executes every instruction of the group's critical path itself, so the block loop is kept
+// minimal: the C-block and the hdr part of a stage are plane-major (operands of step q of a plane at q * 256 from
+// the plane's base), which turns the 24 operand loads of a canonical block into loads at immediate offsets from
+// two base registers.
 template <int MODE, int RG>
 __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx& C, const int g, const int lane, double* out)
 {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int dir = MODE == 1 ? -1 : 1;
     constexpr long long outStride = dir > 0 ? 32 : -32;
+    constexpr int PL = kNH * 256; // bytes of one plane of a block
     const int nT = C.nT;
     double* outPtr = out + ((long long)C.base + (dir > 0 ? 0 : nT - 1)) * 32 + lane;
     const int srcLane = (lane - dir) & 31; // the linked neighbour lane of a canonical step
-    double h[kSkew];                       // h[k]: the value this lane produced k+1 steps ago
+    const bool statsOn = S.stats != nullptr;
+    const bool forceGeneral = MODE == 2 || (S.debugFlags & 1);
+    const int Kg = C.Kg;
+    double h[kSkew]; // h[k]: the value this lane produced k+1 steps ago
 #pragma unroll
     for (int k = 0; k < kSkew; k++) h[k] = 0.0;
     auto push = [&](double v) {
@@ -649,42 +657,41 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
         for (int k = kSkew - 1; k > 0; k--) h[k] = h[k - 1];
         h[0] = v;
     };
-    int st = 0;
+    const unsigned char* const stage0 = C.stages + lane * 8;
+    const unsigned char* const stageEnd = stage0 + (size_t)C.NS * C.stageBytes;
+    const unsigned char* sb = stage0; // C-block of the current stage (this lane's column)
+    unsigned* cntp = C.cnt;
     long long tWait = 0, t0 = 0, g0 = 0, nGeneral = 0;
-    if (S.stats)
+    if (statsOn)
     {
         t0 = clock64();
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
     }
     for (int blk = 0; blk < C.nBlocks; blk++)
     {
-        const unsigned char* stage = C.stages + (size_t)st * C.stageBytes;
         unsigned c;
-        if (S.stats)
+        if (statsOn)
         {
             const long long w0 = clock64();
-            do c = ld_flag_smem(&C.cnt[st]);
+            do c = ld_flag_smem(cntp);
             while ((c & 0xffu) != (unsigned)kNH);
             tWait += clock64() - w0;
         }
         else
         {
-            do c = ld_flag_smem(&C.cnt[st]);
+            do c = ld_flag_smem(cntp);
             while ((c & 0xffu) != (unsigned)kNH);
         }
-        const unsigned char* rec = stage + C.offC + lane * 8;
-        const unsigned char* hd = stage + C.offHdr + lane * 8;
-        if (S.stats && blk == C.nBlocks / 2 && lane == 0)
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(S.stats[(long long)kStatsStride * g + 12]));
-        if (MODE != 2 && (c >> 8) == 0u && !(S.debugFlags & 1))
+        const unsigned char* hd = sb + C.offHdr;
+        if (c == (unsigned)kNH && !forceGeneral)
         {
             double a0[kNH], c0[kNH], c1[kNH];
 #pragma unroll
             for (int q = 0; q < kNH; q++)
             {
-                a0[q] = *reinterpret_cast<const double*>(hd + (size_t)q * C.hdrStep);
-                c0[q] = *reinterpret_cast<const double*>(rec + (size_t)q * C.cRec + 256);
-                c1[q] = *reinterpret_cast<const double*>(rec + (size_t)q * C.cRec + 512);
+                a0[q] = *reinterpret_cast<const double*>(hd + q * 256);
+                c0[q] = *reinterpret_cast<const double*>(sb + PL + q * 256);
+                c1[q] = *reinterpret_cast<const double*>(sb + 2 * PL + q * 256);
             }
 #pragma unroll
             for (int q = 0; q < kNH; q++)
@@ -702,15 +709,13 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
 #pragma unroll 2
             for (int q = 0; q < kNH; q++)
             {
-                const unsigned char* r0 = rec + (size_t)q * C.cRec;
-                const unsigned char* h0 = hd + (size_t)q * C.hdrStep;
-                const unsigned long long meta = *reinterpret_cast<const unsigned long long*>(r0);
-                double acc = *reinterpret_cast<const double*>(h0);
-                const double cv0 = C.Kg > 0 ? *reinterpret_cast<const double*>(h0 + 256) : 0.0;
-                const double cv1 = C.Kg > 1 ? *reinterpret_cast<const double*>(h0 + 512) : 0.0;
+                const unsigned long long meta = *reinterpret_cast<const unsigned long long*>(sb + q * 256);
+                double acc = *reinterpret_cast<const double*>(hd + q * 256);
+                const double cv0 = Kg > 0 ? *reinterpret_cast<const double*>(hd + PL + q * 256) : 0.0;
+                const double cv1 = Kg > 1 ? *reinterpret_cast<const double*>(hd + 2 * PL + q * 256) : 0.0;
                 double cf[RG];
 #pragma unroll
-                for (int r = 0; r < RG; r++) cf[r] = *reinterpret_cast<const double*>(r0 + 256 + r * 256);
+                for (int r = 0; r < RG; r++) cf[r] = *reinterpret_cast<const double*>(sb + (1 + r) * PL + q * 256);
 #pragma unroll
                 for (int r = 0; r < RG; r++)
                 {
@@ -726,16 +731,20 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
         }
         outPtr += kNH * outStride;
         __syncwarp();
-        if (S.stats && blk == C.nBlocks / 2 && lane == 0)
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(S.stats[(long long)kStatsStride * g + 13]));
         if (lane == 0)
         { // block done: the stage may be refilled
-            st_flag_smem(&C.cnt[st], 0u);
+            st_flag_smem(cntp, 0u);
             st_flag_smem(C.done, (unsigned)(blk + 1));
         }
-        if (++st == C.NS) st = 0;
+        sb += C.stageBytes;
+        cntp++;
+        if (sb == stageEnd)
+        {
+            sb = stage0;
+            cntp = C.cnt;
+        }
     }
-    if (S.stats && lane == 0)
+    if (statsOn && lane == 0)
     {
         long long g1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
@@ -787,7 +796,7 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
     long long tStage = 0, tVal = 0, tSpin = 0, tAll = timed ? clock64() : 0;
     auto step = [&](const int blk, int* codes, double* mv, int* cc, double* mc, int* codesN, double* mvN, int* ccN, double* mcN) {
         unsigned char* stage = C.stages + (size_t)st * C.stageBytes;
-        const unsigned char* rec = stage + (size_t)h * C.pRec;
+        const unsigned char* rec = stage + C.offP + (size_t)h * C.pRec;
         const double* aP = reinterpret_cast<const double*>(stage + C.offA) + vecIdx;
         // ---- prefetch the codes / cross-group values of this producer's step in the next block
         int stN = st + 1;
@@ -802,7 +811,7 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
             const long long w0 = timed ? clock64() : 0;
             mbar_wait(&C.rawBar[stN], parN);
             if (timed) tStage += clock64() - w0;
-            fetch(C.stages + (size_t)stN * C.stageBytes + (size_t)h * C.pRec, codesN, mvN, ccN, mcN);
+            fetch(C.stages + (size_t)stN * C.stageBytes + C.offP + (size_t)h * C.pRec, codesN, mvN, ccN, mcN);
         }
         // ---- operands of the current step first, the (possibly late) cross-group values last
         double acc = *aP;
@@ -811,7 +820,7 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
 #pragma unroll
         for (int i = 0; i < LG; i++) cf[i] = *reinterpret_cast<const double*>(rec + lane * 8 + i * 256);
         const unsigned general =
-            MODE == 2 ? 1u : (unsigned)(*reinterpret_cast<const unsigned long long*>(stage + C.offC + (size_t)h * C.cRec + lane * 8) >> 56) & 1u;
+            MODE == 2 ? 1u : (unsigned)(*reinterpret_cast<const unsigned long long*>(stage + h * 256 + lane * 8) >> 56) & 1u;
         const long long v0 = timed ? clock64() : 0;
         bool bad = false;
 #pragma unroll
@@ -840,17 +849,17 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
 #pragma unroll
         for (int i = 0; i < LG; i++) acc = sweep_apply<MODE>(acc, cf[i], mv[i]); // padding: coefficient 0, neutral value
         // ---- hand over: the hdr part of the stage is free because the stage was refilled after the consumer released it
-        unsigned char* hd = stage + C.offHdr + (size_t)h * C.hdrStep + lane * 8;
+        unsigned char* hd = stage + C.offHdr + h * 256 + lane * 8; // hdr planes: acc0 | cval 0 | cval 1, each [kNH][32]
         *reinterpret_cast<double*>(hd) = acc;
-        if (C.Kg > 0) *reinterpret_cast<double*>(hd + 256) = mc[0];
-        if (C.Kg > 1) *reinterpret_cast<double*>(hd + 512) = mc[1];
+        if (C.Kg > 0) *reinterpret_cast<double*>(hd + kNH * 256) = mc[0];
+        if (C.Kg > 1) *reinterpret_cast<double*>(hd + 2 * kNH * 256) = mc[1];
         __syncwarp();
         if (lane == 0) red_flag_smem(&C.cnt[st], 1u + (general << 8));
         st = stN;
         par = parN;
     };
     mbar_wait(&C.rawBar[0], 0u);
-    fetch(C.stages + (size_t)h * C.pRec, codesA, mvA, ccA, mcA);
+    fetch(C.stages + C.offP + (size_t)h * C.pRec, codesA, mvA, ccA, mcA);
     for (int blk = 0; blk < C.nBlocks; blk += 2)
     {
         step(blk, codesA, mvA, ccA, mcA, codesB, mvB, ccB, mcB);
@@ -884,9 +893,9 @@ __device__ __forceinline__ void sweep_group_split(const PipeDev& S, const int g,
     C.hdrStep = 256 * (1 + C.Kg);
     C.pBytes = (unsigned)(kNH * C.pRec);
     C.cBytes = (unsigned)(kNH * C.cRec);
-    C.offC = (int)C.pBytes;
-    C.offA = C.offC + (int)C.cBytes;
-    C.offHdr = C.offA + kNH * 256 * (MODE == 0 ? 2 : 1);
+    C.offHdr = (int)C.cBytes;
+    C.offP = C.offHdr + kNH * C.hdrStep;
+    C.offA = C.offP + (int)C.pBytes;
     C.rawBytes = C.pBytes + C.cBytes + (unsigned)(kNH * 256 * (MODE == 0 ? 2 : 1));
     C.rawBar = reinterpret_cast<unsigned long long*>(smem);
     C.cnt = reinterpret_cast<unsigned*>(smem + 128);
@@ -1092,7 +1101,9 @@ __global__ void __launch_bounds__(256) k_pack_stream(PipeDev S, const double* __
         {
             const int step = (int)(e / (Rg * 32));
             const int rem = (int)(e - (long long)step * (Rg * 32));
-            reinterpret_cast<double*>(cs + (size_t)step * cRec + 256)[rem] = value(face[e], step, rem & 31);
+            const int r = rem >> 5; // plane-major inside a block of kNH steps (PipeSchedule::c_coef_off)
+            reinterpret_cast<double*>(cs + (size_t)(step / kNH) * kNH * cRec + (size_t)kNH * 256 * (1 + r) + (size_t)(step % kNH) * 256)[rem & 31] =
+                value(face[e], step, rem & 31);
         }
     }
 }

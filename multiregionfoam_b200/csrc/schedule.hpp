@@ -155,7 +155,7 @@ struct PipeSchedule
         //  P-stream (producer warps), per step:  coef[Lg][32] f64 | code[Lg][32] i32 | constCode[Kg][32] i32
         //      the LEADING terms of each row: its first run of cross-group (memory) terms, in reference order;
         //      constCode[k] = slot of the k-th cross-group value the row's remaining terms need (-1: none)
-        //  C-stream (consumer warp), per step:   meta[32] u64 | coef[Rg][32] f64
+        //  C-stream (consumer warp), per step:   meta[32] u64 | coef[Rg][32] f64  (plane-major per block, c_meta_off)
         //      the REMAINING terms.  meta byte r < 6 describes the term of plane r: bits 0-4 source lane of a value
         //      shuffled from kSkew steps ago, kMetaOwn = own-lane value of the previous step, kMetaPad = padding
         //      (coefficient 0), kMetaConst = the value of constCode[bit 5]; byte 6 = number of planes in use;
@@ -653,6 +653,18 @@ struct PipeSchedule
     static constexpr int kMaxConst = 2; // cross-group values a row's remaining terms may need on the fast path
     static int p_rec_bytes(int Lg, int Kg) { return Lg * 384 + Kg * 128; }
     static int c_rec_bytes(int Rg) { return 256 + Rg * 256; }
+    // The C-stream is PLANE-MAJOR inside a block of kSweepBlock steps: meta[steps][32] u64 | coef plane 0 [steps][32] |
+    // coef plane 1 [steps][32] | ... - the consumer warp then reaches the operands of all the steps of a block
+    // (plane 0 / plane 1 of a canonical step) at compile-time offsets from one base address, whatever Rg is.
+    static int64_t c_meta_off(int Rg, int step)
+    {
+        return int64_t(step / kSweepBlock) * kSweepBlock * c_rec_bytes(Rg) + int64_t(step % kSweepBlock) * 256;
+    }
+    static int64_t c_coef_off(int Rg, int step, int r)
+    {
+        return int64_t(step / kSweepBlock) * kSweepBlock * c_rec_bytes(Rg) + int64_t(kSweepBlock) * 256 * (1 + r) +
+               int64_t(step % kSweepBlock) * 256;
+    }
     static int c_ring_step_bytes(int Rg, int Kg) { return 256 * (1 + Kg) + c_rec_bytes(Rg); } // hdr acc0[32], cval[Kg][32] + record
     static int hdr_step_bytes(int Kg) { return 256 * (1 + Kg); }                              // acc0[32] | cval[Kg][32]
     // one shared-memory stage of a fast group = one block of kSweepBlock steps:
@@ -737,11 +749,11 @@ struct PipeSchedule
         {
             if (!D.gFast[gI]) continue;
             const int W = D.gW[gI], nT = gNT[gI], Lg = D.gLg[gI], Rg = D.gRg[gI], Kg = D.gKg[gI];
-            const int pRec = p_rec_bytes(Lg, Kg), cRec = c_rec_bytes(Rg);
+            const int pRec = p_rec_bytes(Lg, Kg);
             for (int step = 0; step < nT; step++)
             {
                 unsigned char* pr = D.pStream.data() + D.gPOff[gI] + int64_t(step) * pRec;
-                unsigned char* cr = D.cStream.data() + D.gCOff[gI] + int64_t(step) * cRec;
+                unsigned char* cr = D.cStream.data() + D.gCOff[gI] + c_meta_off(Rg, step);
                 int32_t* pCode = reinterpret_cast<int32_t*>(pr + Lg * 256);
                 int32_t* pConst = reinterpret_cast<int32_t*>(pr + Lg * 384);
                 uint64_t* meta = reinterpret_cast<uint64_t*>(cr);

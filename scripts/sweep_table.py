@@ -27,6 +27,13 @@ S = ldu.LduSystem(ctx, case.ranks[0])
 r = np.random.default_rng(0).standard_normal(S.nCells)
 for _ in range(3):
     S.precondition(ldu.PRECOND_DILU, r)
+S.set_profiling(True)
+S.kernel_times(reset=True)
+for _ in range(5):
+    S.precondition(ldu.PRECOND_DILU, r)
+kt = S.kernel_times()
+S.set_profiling(False)
+print(f"untimed-by-counters run: fwd {kt['sweep_fwd'][0] / 5 * 1e3:.1f} us, bwd {kt['sweep_bwd'][0] / 5 * 1e3:.1f} us per sweep")
 S.sweep_stats(+1, True)
 S.precondition(ldu.PRECOND_DILU, r)
 st = S.sweep_stats(+1, False)
@@ -39,12 +46,16 @@ for k in range(nz):
         g = [i for i in range(ng) if gj[i] == j0 and gk[i] == k]
         row.append(" ".join(f"{(st[i,3]-t0)/1e3:6.1f}/{st[i,1]/max(st[i,0],1):.2f}" for i in g))
     print(f"{k:3d}  " + "   ".join(row))
-print("producer 0 of selected groups: total cycles, stage-wait, value-wait, spin (fractions)")
-for i in list(range(0, ng, max(1, ng // 12))):
-    c = max(st[i, 8], 1)
-    print(f"  group {i:3d} (j0 {gj[i]:3d}, k {gk[i]:2d}): {st[i,8]:8d}  stage {st[i,9]/c:.2f}  value {st[i,10]/c:.2f}  spin {st[i,11]/c:.2f}   consumer wait {st[i,1]/max(st[i,0],1):.2f}")
-print("middle block, first j-group, by k: producer 0 has its value / consumer starts the block / consumer finished it (us)")
-for k in range(nz):
-    g = [i for i in range(ng) if gj[i] == js[0] and gk[i] == k][0]
-    print(f"  k {k:2d}: {(st[g,14]-t0)/1e3:8.2f} {(st[g,12]-t0)/1e3:8.2f} {(st[g,13]-t0)/1e3:8.2f}")
+if os.environ.get("B200_SWEEP_DEBUG") == "2":
+    print("progress of the first j-group by k: time (us) at which i/8 of the blocks were finished")
+    for k in range(nz):
+        g = [i for i in range(ng) if gj[i] == js[0] and gk[i] == k][0]
+        print(f"  k {k:2d}: " + " ".join(f"{(st[g, 8 + i] - t0) / 1e3:7.2f}" for i in range(8)))
+    print("SM of each group, rows k, columns j-group:")
+    for k in range(nz):
+        print(f"  k {k:2d}: " + " ".join(f"{st[[i for i in range(ng) if gj[i] == j0 and gk[i] == k][0], 6]:4d}" for j0 in js))
+    print("same for k = 5, by j-group")
+    for j0 in js:
+        g = [i for i in range(ng) if gj[i] == j0 and gk[i] == 5][0]
+        print(f"  j0 {j0:3d}: " + " ".join(f"{(st[g, 8 + i] - t0) / 1e3:7.2f}" for i in range(8)))
 print("sweep span us", (st[:, 3].max() - t0) / 1e3, " kernel ms", S.kernel_times())

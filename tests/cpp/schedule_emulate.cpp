@@ -56,7 +56,7 @@ int walk(const PipeSchedule& S, const PipeSchedule::Dir& D, int dir, int mode, c
                         acc = mode == 2 ? acc - coefOf(f, slot) / out[code] : acc - coefOf(f, slot) * out[code];
                     }
                     // consumer part: remaining terms from the C-stream
-                    const unsigned char* cr = D.cStream.data() + D.gCOff[g] + int64_t(step) * PipeSchedule::c_rec_bytes(Rg);
+                    const unsigned char* cr = D.cStream.data() + D.gCOff[g] + PipeSchedule::c_meta_off(Rg, step);
                     const uint64_t meta = reinterpret_cast<const uint64_t*>(cr)[lane];
                     const int Rt = int((meta >> 48) & 0xff);
                     const bool general = (meta >> 56) & 1;
