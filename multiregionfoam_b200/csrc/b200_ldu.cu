@@ -548,6 +548,7 @@ extern "C" int b200_sys_finalize(b200_sys* s)
         s->F = g.F;
         PipeSchedule S;
         S.forceGeneric = getenv("B200_FORCE_GENERIC") != nullptr;
+        if (getenv("B200_SWEEP_NO_SEAM_MERGE")) S.mergeSeams = false;
         S.build(g, s->regs);
         s->nSlots = S.nSlots;
         s->nGroups = S.nGroups;
@@ -1151,6 +1152,59 @@ static int throttle_mark(b200_sys* s, int it)
     return B200_OK;
 }
 
+// PBiCG::solve (foam/matrices/lduMatrix/solvers/PBiCG/PBiCG.C): PCG's scalar recurrences (rho = (wA, rT),
+// alpha = rho / (wA, pT)) over a primal and a shadow (transposed) system: Tmul and preconditionT next to Amul and
+// precondition.
+static int solve_pbicg(b200_sys* s, const b200_solver_opts* o)
+{
+    b200_ctx* ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    const size_t n = (size_t)s->nSlots;
+    double *x = s->vec[V_X].p, *rA = s->vec[V_R].p, *rT = s->vec[V_RW].p, *pA = s->vec[V_P].p, *pT = s->vec[V_PH].p;
+    double *wA = s->vec[V_V].p, *wT = s->vec[V_T].p, *zA = s->vec[V_S].p, *zT = s->vec[V_SH].p, *tmp = s->vec[V_TMP2].p;
+    int rc;
+    if ((rc = solve_head(s, OP_NORM_INIT_PCG, wA, rA, nullptr, pA, pT))) return rc;
+    if ((rc = launch_amul(s, x, wT, 0, nullptr, true, 1, nullptr))) return rc; // wT = A^T x
+    if (n)
+    {
+        KScope k(s, B200_K_VECTOR);
+        k_sub<<<s->vecBlocks, 256, 0, st>>>(n, s->vec[V_B].p, wT, rT);
+    }
+    if ((rc = ensure_precond(s, o->precond, false))) return rc;
+    if ((rc = ensure_precond(s, o->precond, true))) return rc;
+    PartCounts cnt;
+    for (int it = 0; it < o->maxIter; it++)
+    {
+        if (*(volatile int*)&s->hostFlags[0]) break;
+        if ((rc = throttle_wait(s, it))) return rc;
+        if ((rc = launch_precondition(s, o->precond, rA, zA, tmp, false, 0, false))) return rc; // wA = M^-1 rA
+        if ((rc = launch_precondition(s, o->precond, rT, zT, tmp, false, 0, true))) return rc;  // wT = M^-T rT
+        if (n)
+        {
+            KScope k(s, B200_K_VECTOR);
+            k_dot<<<s->vecBlocks, 256, 0, st>>>(n, zA, rT, s->partials.p, s->pstride, s->sc.p); // wArT
+        }
+        if ((rc = reduce_finish(s, vec_counts(s), 1, OP_PCG_RHO, 0))) return rc;
+        if (n)
+        {
+            KScope k(s, B200_K_VECTOR);
+            k_pbicg_p<<<s->vecBlocks, 256, 0, st>>>(n, zA, pA, zT, pT, s->sc.p);
+        }
+        if ((rc = launch_amul(s, pT, wT, 0, nullptr, true, 0, nullptr))) return rc; // wT = A^T pT
+        if ((rc = launch_amul(s, pA, wA, 1, pT, false, 0, &cnt))) return rc;       // wA = A pA, wApT
+        if ((rc = reduce_finish(s, cnt, 1, OP_PCG_ALPHA, 0))) return rc;
+        if (n)
+        {
+            KScope k(s, B200_K_VECTOR);
+            k_pbicg_xr<<<s->vecBlocks, 256, 0, st>>>(n, x, pA, rA, wA, rT, wT, s->partials.p, s->pstride, s->sc.p);
+        }
+        if ((rc = reduce_finish(s, vec_counts(s), 1, OP_PCG_RESIDUAL, 0))) return rc;
+        if ((rc = throttle_mark(s, it))) return rc;
+    }
+    CK(ctx, cudaGetLastError());
+    return B200_OK;
+}
+
 static int solve_bicgstab(b200_sys* s, const b200_solver_opts* o)
 {
     b200_ctx* ctx = s->ctx;
@@ -1252,8 +1306,8 @@ extern "C" int b200_solve_resident(b200_sys* s, const b200_solver_opts* o, b200_
     if (!s || !o || !perf) return s ? set_err(s->ctx, B200_EINVAL, "b200_solve: null argument") : B200_EINVAL;
     b200_ctx* ctx = s->ctx;
     if (!s->finalized) return set_err(ctx, B200_ESTATE, "solve before finalize");
-    if (o->solver == B200_SOLVER_PBICG) return set_err(ctx, B200_EUNSUPPORTED, "PBiCG is not built in this round; use BiCGStab");
-    if (o->solver != B200_SOLVER_PCG && o->solver != B200_SOLVER_BICGSTAB) return set_err(ctx, B200_EINVAL, "unknown solver %d", o->solver);
+    if (o->solver != B200_SOLVER_PCG && o->solver != B200_SOLVER_BICGSTAB && o->solver != B200_SOLVER_PBICG)
+        return set_err(ctx, B200_EINVAL, "unknown solver %d", o->solver);
     if (o->precond < B200_PRECOND_NONE || o->precond > B200_PRECOND_CHOLESKY)
         return set_err(ctx, B200_EINVAL, "unknown preconditioner %d", o->precond);
     if (o->maxIter < 0 || o->minIter < 0) return set_err(ctx, B200_EINVAL, "negative iteration bounds");
@@ -1264,7 +1318,7 @@ extern "C" int b200_solve_resident(b200_sys* s, const b200_solver_opts* o, b200_
     s->precondValid = -1;
     if ((rc = upload_scalars(s, o, history ? historyCap : 0))) return rc;
     CK(ctx, cudaEventRecord(s->evSolveA, ctx->stream));
-    rc = (o->solver == B200_SOLVER_PCG) ? solve_pcg(s, o) : solve_bicgstab(s, o);
+    rc = (o->solver == B200_SOLVER_PCG) ? solve_pcg(s, o) : (o->solver == B200_SOLVER_PBICG) ? solve_pbicg(s, o) : solve_bicgstab(s, o);
     if (rc) return rc;
     CK(ctx, cudaEventRecord(s->evSolveB, ctx->stream));
     DevScalars h;

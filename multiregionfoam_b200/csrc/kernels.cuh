@@ -1290,6 +1290,41 @@ __global__ void __launch_bounds__(256) k_pcg_p(size_t n, const double* __restric
 }
 
 // PCG: x += alpha*pA ; rA -= alpha*wA ; partial [0] sum |rA| ; sentinel fills for the next precondition
+// PBiCG (foam/matrices/lduMatrix/solvers/PBiCG/PBiCG.C): the shadow system runs next to the primal one
+__global__ void __launch_bounds__(256) k_sub(size_t n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out)
+{
+    B200_GRID_STRIDE(i, n) out[i] = a[i] - b[i];
+}
+__global__ void __launch_bounds__(256) k_pbicg_p(size_t n, const double* __restrict__ wA, double* __restrict__ pA,
+                                                  const double* __restrict__ wT, double* __restrict__ pT, const DevScalars* sc)
+{
+    if (sc->done) return;
+    const int first = sc->first;
+    const double beta = sc->beta;
+    B200_GRID_STRIDE(i, n)
+    {
+        pA[i] = first ? wA[i] : wA[i] + beta * pA[i];
+        pT[i] = first ? wT[i] : wT[i] + beta * pT[i];
+    }
+}
+__global__ void __launch_bounds__(256) k_pbicg_xr(size_t n, double* __restrict__ x, const double* __restrict__ pA,
+                                                   double* __restrict__ rA, const double* __restrict__ wA,
+                                                   double* __restrict__ rT, const double* __restrict__ wT, double* partials,
+                                                   int pstride, const DevScalars* sc)
+{
+    if (sc->done) return;
+    const double alpha = sc->alpha;
+    double d[1] = {0.0};
+    B200_GRID_STRIDE(i, n)
+    {
+        x[i] += alpha * pA[i];
+        const double ri = rA[i] - alpha * wA[i];
+        rA[i] = ri;
+        rT[i] -= alpha * wT[i];
+        d[0] += fabs(ri);
+    }
+    block_reduce_store<1>(d, partials, pstride, blockIdx.x);
+}
 __global__ void __launch_bounds__(256) k_pcg_xr(size_t n, double* __restrict__ x, const double* __restrict__ pA,
                                                  double* __restrict__ rA, const double* __restrict__ wA,
                                                  double* __restrict__ fillA, double* __restrict__ fillB,

@@ -136,6 +136,7 @@ struct PipeSchedule
     static constexpr int kStageBudget = 24576; // shared-memory bytes of one pipeline stage of the sweep kernel
     static constexpr int kLineModeMinAvgChain = 8;
     bool forceGeneric = false; // debug: every group takes the single-warp generic path
+    bool mergeSeams = true;    // continue a lane's path across block seams (head of a chain has the tail of another as neighbour)
 
     int64_t N = 0, nSlots = 0;
     int nGroups = 0;
@@ -260,7 +261,7 @@ struct PipeSchedule
         const int nCh = int(cFirst.size());
         // merge chains into paths across seams: head(B) has tail(A) as a lower neighbour
         std::vector<int32_t> nextCh(nCh, -1), prevCh(nCh, -1);
-        for (int b = 0; b < nCh; b++)
+        for (int b = 0; b < nCh && mergeSeams; b++)
         {
             const int32_t h = cFirst[b];
             for (int32_t k = g.losortStart[h + 1] - 1; k >= g.losortStart[h]; k--)

@@ -31,11 +31,14 @@ SOLVER_TABLE: Dict[str, tuple] = {
     # names registered by the drop-in library (north_star)
     "cudaPCG": (ldu.SOLVER_PCG, True),
     "cudaPBiCGStab": (ldu.SOLVER_BICGSTAB, False),
+    "cudaPBiCG": (ldu.SOLVER_PBICG, False),
     # names used by the shipped dictionaries; the adapter registers aliases so existing cases run unchanged
     "PCG": (ldu.SOLVER_PCG, True),
     "CG": (ldu.SOLVER_PCG, True),
     "BiCGStab": (ldu.SOLVER_BICGSTAB, False),
     "PBiCGStab": (ldu.SOLVER_BICGSTAB, False),
+    "PBiCG": (ldu.SOLVER_PBICG, False),
+    "BiCG": (ldu.SOLVER_PBICG, False),
 }
 
 PRECOND_TABLE: Dict[str, int] = {

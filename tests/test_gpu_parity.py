@@ -24,7 +24,7 @@ FIELD_RTOL = 1e-8   # north_star: converged fields within 1e-8 relative L2
 
 PRECOND_ID = {"none": ldu.PRECOND_NONE, "diagonal": ldu.PRECOND_DIAGONAL, "DIC": ldu.PRECOND_DIC,
               "DILU": ldu.PRECOND_DILU, "Cholesky": ldu.PRECOND_CHOLESKY}
-SOLVER_ID = {"PCG": ldu.SOLVER_PCG, "BiCGStab": ldu.SOLVER_BICGSTAB}
+SOLVER_ID = {"PCG": ldu.SOLVER_PCG, "BiCGStab": ldu.SOLVER_BICGSTAB, "PBiCG": ldu.SOLVER_PBICG}
 
 
 def make_cases(golden_addr):
@@ -80,6 +80,10 @@ def test_precondition_bit_exact(gpu_ctx, cases, name, precond):
         # repeated application reuses the packed coefficients: same bits
         r2 = random_vec(O.n, 4)
         assert np.array_equal(S.precondition(PRECOND_ID[precond], r2), O.precondition(r2))
+        # preconditionT (PBiCG's shadow system) keeps its own packed coefficients: alternate the two
+        assert np.array_equal(S.precondition(PRECOND_ID[precond], r, transpose=True), O.preconditionT(r))
+        assert np.array_equal(S.precondition(PRECOND_ID[precond], r2), O.precondition(r2))
+        assert np.array_equal(S.precondition(PRECOND_ID[precond], r2, transpose=True), O.preconditionT(r2))
     finally:
         S.close()
 
@@ -109,6 +113,11 @@ SOLVES = [
     ("duineveld1_asym", "BiCGStab", "DILU", 1e-12, 500),
     ("duineveld1_asym", "BiCGStab", "none", 1e-10, 2000),
     ("chain_asym", "BiCGStab", "DILU", 1e-12, 50),
+    ("cht_r1", "PBiCG", "DILU", 1e-12, 300),            # PBiCG + DILU: the U solver of the shipped FSI cases
+    ("cht_r1_L5", "PBiCG", "DILU", 1e-12, 400),
+    ("duineveld1_asym", "PBiCG", "DILU", 1e-12, 500),
+    ("duineveld0_sym", "PBiCG", "DIC", 1e-12, 500),
+    ("chain_asym", "PBiCG", "DILU", 1e-12, 50),
     ("one_cell", "PCG", "DIC", 1e-12, 10),
     ("no_faces", "BiCGStab", "DILU", 1e-12, 10),
 ]
