@@ -167,6 +167,9 @@ def main():
                    "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000)] + sys.argv
             os.execv(sys.executable, cmd)
         raise SystemExit(f"WORLD_SIZE={world} but --gpus {args.gpus}")
+    # Keep stdout for the ONE JSON line: libraries (NCCL prints its version banner there) write to fd 1 too
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     uid = None
     if world > 1:
@@ -337,7 +340,8 @@ def main():
             "kernels": kernels, "wall_ms_per_step": wall_ms / args.steps, "finalize_s": finalize_s,
             "final_residual": final_res,
         }
-        print(json.dumps(out))
+        real_stdout.write(json.dumps(out) + "\n")
+        real_stdout.flush()
     S.close()
     ctx.close()
     if world > 1:

@@ -126,6 +126,7 @@ WORKLOADS = {
     "C2-2D": (14, 1),    # 2-D-faithful, 4 275 152 cells
     "C3": (4, 183),      # 3-D, 63 865 536 cells
     "C3-2D": (54, 1),
+    "C3-slab8": (4, 23), # one of the 8 z-slabs of C3 (r = 4, 8 x 23 = 184 layers: 64 234 496 cells on 8 ranks), 8 029 312 cells per rank
 }
 
 
