@@ -93,18 +93,37 @@ def build_rank_system(workload: str, rank: int, nranks: int):
     return cht_rank_slab(r, L, rank, nranks), (r, L)
 
 
-def oracle_sample(workload: str, iters: int):
-    """The CPU port on the N=1 workload for `iters` BiCGStab+DILU iterations (serial)."""
+def oracle_sample(workload: str, iters: int, nsub: int = 1, threads: int = 1):
+    """The CPU port on the N=1 workload for `iters` BiCGStab+DILU iterations.  nsub > 1: the case is decomposed into
+    nsub z-slab sub-domains (foam-extend's processor decomposition, block-Jacobi preconditioner) worked on by
+    `threads` threads standing in for the MPI ranks of a decomposed foam-extend run on the same host."""
+    from multiregionfoam_b200.assembly import WORKLOADS, cht_rank_slab
     from multiregionfoam_b200.case import Case
     from oracle import pyoracle
-    rs, _ = build_rank_system(workload, 0, 1)
-    case = Case(workload, [rs])
+    r, L = WORKLOADS[workload]
+    if nsub > 1:
+        assert L % nsub == 0
+        case = Case(workload, [cht_rank_slab(r, L // nsub, g, nsub) for g in range(nsub)])
+    else:
+        case = Case(workload, [cht_rank_slab(r, L, 0, 1)])
     O = pyoracle.OracleSystem(case)
+    pyoracle.set_threads(threads)
     x0, b = case.concat("psi"), case.concat("source")
     t = time.perf_counter()
     _, info = O.solve(x0, b, "BiCGStab", "DILU", tolerance=0.0, minIter=iters, maxIter=iters)
     dt = time.perf_counter() - t
+    pyoracle.set_threads(1)
     return case.nCells * info["nIterations"] / dt, dt, case.nCells, case.nFaces, info["nIterations"]
+
+
+def host_decomposition(workload: str):
+    """(sub-domains, threads) of the decomposed CPU arm: the largest divisor of the layer count that the host's
+    cores can take one thread each."""
+    from multiregionfoam_b200.assembly import WORKLOADS
+    _, L = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    nsub = max(d for d in range(1, L + 1) if L % d == 0 and d <= cores)
+    return nsub, nsub
 
 
 def run_reference(args):
@@ -114,20 +133,23 @@ def run_reference(args):
     vals, times = [], []
     it = max(1, min(args.iters, args.ref_iters))
     nCells = nFaces = 0
+    nsub, threads = host_decomposition(args.workload)
     for s in range(args.warmup + args.steps):
-        v, dt, nCells, nFaces, _ = oracle_sample(args.workload, it)
+        v, dt, nCells, nFaces, _ = oracle_sample(args.workload, it, nsub, threads)
         if s >= args.warmup:
             vals.append(v)
             times.append(dt)
     total = nCells * it * len(times) / sum(times)
-    sample = f"{it} BiCGStab+DILU iterations per step on the full {args.workload} system ({nCells} cells), serial oracle port"
+    sample = (f"{it} BiCGStab+DILU iterations per step on the full {args.workload} system ({nCells} cells) decomposed into {nsub} "
+              f"z-slab sub-domains (block-Jacobi DILU, as foam-extend's MPI run), {threads} threads of the CPU oracle port")
     out = {
         "impl": "reference", "metric": METRIC, "value": total, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "cells": nCells, "faces": nFaces, "solver": "BiCGStab", "preconditioner": "DILU",
-                   "iterations_per_step": it},
-        "cpu_baseline": {"value": total, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+                   "iterations_per_step": it, "decomposition": f"simple (1 1 {nsub})"},
+        "cpu_baseline": {"value": total, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "host_cores_available": os.cpu_count()},
         "e2e": {"value": total, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "reference = CPU oracle port of foam-extend's coupled BiCGStab/DILU (foam-extend 4.1 is not in the reference tree; oracle/_ref unbuildable)",
@@ -319,9 +341,14 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         it = max(1, min(args.iters, args.cpu_baseline_iters))
-        v, dt, nc, nf, _ = oracle_sample(args.workload, it)
-        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"{it} BiCGStab+DILU iterations on the full {args.workload} system ({nc} cells) with the serial CPU oracle port, {dt:.1f} s",
+        nsub, threads = host_decomposition(args.workload)
+        v, dt, nc, nf, _ = oracle_sample(args.workload, it, nsub, threads)
+        it1 = max(1, it // 3)
+        v1, dt1, _, _, _ = oracle_sample(args.workload, it1)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{it} BiCGStab+DILU iterations on the full {args.workload} system ({nc} cells) decomposed into {nsub} z-slab "
+                         f"sub-domains (block-Jacobi DILU, as foam-extend's MPI run), {threads} threads of the CPU oracle port, {dt:.1f} s",
+               "serial": {"value": v1, "cores": 1, "sample": f"{it1} iterations, undecomposed, {dt1:.1f} s"},
                "host_cores_available": os.cpu_count()}
 
     if rank == 0:

@@ -7,6 +7,8 @@
 #include "ldu_oracle.h"
 
 #include <math.h>
+#include <pthread.h>
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -53,6 +55,7 @@ struct orc_sys
     int total;
     int precond;
     double* rankPartial;
+    double* rowPartial; /* [nRows] scratch of the threaded reductions */
     int redMode; /* 0: sequential sums (the reference); 1: pairwise sums -- only to MEASURE how sensitive a
                     residual history is to the summation order (tests), never the parity target */
 };
@@ -68,6 +71,7 @@ orc_sys* orc_create(int nRows, int nRanks)
     s->nRanks = nRanks > 0 ? nRanks : 1;
     s->rows = (orc_row*)calloc((size_t)nRows, sizeof(orc_row));
     s->rankPartial = (double*)calloc((size_t)s->nRanks, sizeof(double));
+    s->rowPartial = (double*)calloc((size_t)(s->nRows > 0 ? s->nRows : 1), sizeof(double));
     s->precond = -1;
     return s;
 }
@@ -100,6 +104,7 @@ void orc_destroy(orc_sys* s)
     }
     free(s->rows);
     free(s->rankPartial);
+    free(s->rowPartial);
     free(s);
 }
 
@@ -245,23 +250,142 @@ static double red_rows(const orc_sys* s, int kind, const double* a, const double
 }
 void orc_set_reduction_mode(orc_sys* s, int mode) { s->redMode = mode; }
 
+/* Threads stand in for the MPI ranks of a decomposed foam-extend run: the loops over the
+ * rows (= sub-domain matrices) and the element-wise vector updates are shared out; every sum keeps its order
+ * (per-row partial sums, combined in row / rank order), so the results do not depend on the thread count. */
+static int g_threads = 1;
+typedef void (*orc_job)(int i, void* ctx);
+static struct
+{
+    pthread_t th[64];
+    int nWorkers;                 /* started worker threads (the caller works too) */
+    pthread_mutex_t mu;
+    pthread_cond_t cv;
+    unsigned long gen;            /* job generation */
+    orc_job fn;
+    void* ctx;
+    int n;
+    volatile int next, finished;  /* next index to hand out; workers that left the current job */
+} g_pool = {.nWorkers = 0, .mu = PTHREAD_MUTEX_INITIALIZER, .cv = PTHREAD_COND_INITIALIZER};
+
+static void pool_run_items(void)
+{
+    for (;;)
+    {
+        int i = __atomic_fetch_add(&g_pool.next, 1, __ATOMIC_RELAXED);
+        if (i >= g_pool.n) break;
+        g_pool.fn(i, g_pool.ctx);
+    }
+}
+static void* pool_worker(void* arg)
+{
+    unsigned long seen = 0;
+    (void)arg;
+    for (;;)
+    {
+        pthread_mutex_lock(&g_pool.mu);
+        while (g_pool.gen == seen) pthread_cond_wait(&g_pool.cv, &g_pool.mu);
+        seen = g_pool.gen;
+        pthread_mutex_unlock(&g_pool.mu);
+        pool_run_items();
+        __atomic_fetch_add(&g_pool.finished, 1, __ATOMIC_RELEASE);
+    }
+    return NULL;
+}
+/* f(i, ctx) for i in [0, n): items are handed out dynamically; the caller takes part */
+static void par_for(int n, orc_job f, void* ctx)
+{
+    if (g_threads <= 1 || n <= 1)
+    {
+        for (int i = 0; i < n; i++) f(i, ctx);
+        return;
+    }
+    while (g_pool.nWorkers < g_threads - 1 && g_pool.nWorkers < 64)
+    {
+        if (pthread_create(&g_pool.th[g_pool.nWorkers], NULL, pool_worker, NULL)) break;
+        g_pool.nWorkers++;
+    }
+    pthread_mutex_lock(&g_pool.mu);
+    g_pool.fn = f;
+    g_pool.ctx = ctx;
+    g_pool.n = n;
+    g_pool.next = 0;
+    g_pool.finished = 0;
+    g_pool.gen++;
+    pthread_cond_broadcast(&g_pool.cv);
+    pthread_mutex_unlock(&g_pool.mu);
+    pool_run_items();
+    while (__atomic_load_n(&g_pool.finished, __ATOMIC_ACQUIRE) < g_pool.nWorkers) sched_yield();
+}
+void orc_set_threads(int n) { g_threads = n > 0 ? (n > 65 ? 65 : n) : 1; }
+int orc_get_threads(void) { return g_threads; }
+
+/* element-wise vector updates: chunk i of nChunks */
+typedef struct
+{
+    int kind, n, nChunks;
+    double *y, *y2;
+    const double *a, *b, *c;
+    double s1, s2;
+} vec_job;
+static void vec_chunk(int ch, void* vctx)
+{
+    vec_job* J = (vec_job*)vctx;
+    const int lo = (int)((long long)J->n * ch / J->nChunks), hi = (int)((long long)J->n * (ch + 1) / J->nChunks);
+    double* y = J->y;
+    const double *a = J->a, *b = J->b, *c = J->c;
+    const double s1 = J->s1, s2 = J->s2;
+    switch (J->kind)
+    {
+        case 0: for (int i = lo; i < hi; i++) y[i] = a[i] + s1 * y[i] - s1 * s2 * b[i]; break; /* p = r + beta p - beta omega v */
+        case 1: for (int i = lo; i < hi; i++) y[i] = a[i] - s1 * b[i]; break;                    /* s = r - alpha v */
+        case 2: for (int i = lo; i < hi; i++) y[i] = y[i] + s1 * a[i] + s2 * b[i]; break;        /* x += alpha ph + omega sh */
+        default: for (int i = lo; i < hi; i++) y[i] = a[i] - s1 * b[i]; break;
+    }
+    (void)c;
+}
+static void vec_op(int kind, int n, double* y, const double* a, const double* b, double s1, double s2)
+{
+    vec_job J = {.kind = kind, .n = n, .nChunks = g_threads > 1 ? 4 * g_threads : 1, .y = y, .a = a, .b = b, .s1 = s1, .s2 = s2};
+    par_for(J.nChunks, vec_chunk, &J);
+}
+
 /* gSumProd / gSumMag / gSum over a FieldField: per rank, rows in list order,
  * cells sequentially (FieldFunctions.C sumProd / FieldFieldFunctions.C), then
  * reduce(sum) over ranks (taken in ascending rank order). */
+
+typedef struct
+{
+    const orc_sys* s;
+    const double *a, *b;
+} red_job;
+static void row_sumprod(int r, void* ctx)
+{
+    const red_job* J = (const red_job*)ctx;
+    const orc_row* R = &J->s->rows[r];
+    const double* pa = J->a + R->offset;
+    const double* pb = J->b + R->offset;
+    double sum = 0.0;
+    for (int c = 0; c < R->nCells; c++) sum += pa[c] * pb[c];
+    J->s->rowPartial[r] = sum;
+}
+static void row_summag(int r, void* ctx)
+{
+    const red_job* J = (const red_job*)ctx;
+    const orc_row* R = &J->s->rows[r];
+    const double* pa = J->a + R->offset;
+    double sum = 0.0;
+    for (int c = 0; c < R->nCells; c++) sum += fabs(pa[c]);
+    J->s->rowPartial[r] = sum;
+}
 
 double orc_gsumprod(const orc_sys* s, const double* a, const double* b)
 {
     if (s->redMode) return red_rows(s, 0, a, b, NULL);
     for (int k = 0; k < s->nRanks; k++) s->rankPartial[k] = 0.0;
-    for (int r = 0; r < s->nRows; r++)
-    {
-        const orc_row* R = &s->rows[r];
-        const double* pa = a + R->offset;
-        const double* pb = b + R->offset;
-        double sum = 0.0;
-        for (int c = 0; c < R->nCells; c++) sum += pa[c] * pb[c];
-        s->rankPartial[R->rank] += sum;
-    }
+    red_job J = {s, a, b};
+    par_for(s->nRows, row_sumprod, &J);
+    for (int r = 0; r < s->nRows; r++) s->rankPartial[s->rows[r].rank] += s->rowPartial[r];
     double tot = s->rankPartial[0];
     for (int k = 1; k < s->nRanks; k++) tot += s->rankPartial[k];
     return tot;
@@ -271,14 +395,9 @@ double orc_gsummag(const orc_sys* s, const double* a)
 {
     if (s->redMode) return red_rows(s, 1, a, NULL, NULL);
     for (int k = 0; k < s->nRanks; k++) s->rankPartial[k] = 0.0;
-    for (int r = 0; r < s->nRows; r++)
-    {
-        const orc_row* R = &s->rows[r];
-        const double* pa = a + R->offset;
-        double sum = 0.0;
-        for (int c = 0; c < R->nCells; c++) sum += fabs(pa[c]);
-        s->rankPartial[R->rank] += sum;
-    }
+    red_job J = {s, a, NULL};
+    par_for(s->nRows, row_summag, &J);
+    for (int r = 0; r < s->nRows; r++) s->rankPartial[s->rows[r].rank] += s->rowPartial[r];
     double tot = s->rankPartial[0];
     for (int k = 1; k < s->nRanks; k++) tot += s->rankPartial[k];
     return tot;
@@ -420,24 +539,48 @@ static void update_interfaces(orc_sys* s, double* y, int useInt, int switchToLhs
 
 /* --------------------------------------------------------------- products */
 
+typedef struct
+{
+    orc_sys* s;
+    const double* x;
+    double* y;
+} mul_job;
+static void row_amul(int r, void* ctx)
+{
+    /* lduMatrix::AmulCore (lduMatrixATmul.C) */
+    const mul_job* J = (const mul_job*)ctx;
+    const orc_row* R = &J->s->rows[r];
+    const double* psi = J->x + R->offset;
+    double* Apsi = J->y + R->offset;
+    for (int c = 0; c < R->nCells; c++) Apsi[c] = R->diag[c] * psi[c];
+    for (int f = 0; f < R->nFaces; f++)
+    {
+        Apsi[R->u[f]] += R->lower[f] * psi[R->l[f]];
+        Apsi[R->l[f]] += R->upper[f] * psi[R->u[f]];
+    }
+}
+static void row_tmul(int r, void* ctx)
+{
+    /* lduMatrix::TmulCore */
+    const mul_job* J = (const mul_job*)ctx;
+    const orc_row* R = &J->s->rows[r];
+    const double* psi = J->x + R->offset;
+    double* Tpsi = J->y + R->offset;
+    for (int c = 0; c < R->nCells; c++) Tpsi[c] = R->diag[c] * psi[c];
+    for (int f = 0; f < R->nFaces; f++)
+    {
+        Tpsi[R->u[f]] += R->upper[f] * psi[R->l[f]];
+        Tpsi[R->l[f]] += R->lower[f] * psi[R->u[f]];
+    }
+}
+
 int orc_amul(orc_sys* s, const double* x, double* y)
 {
     for (int i = 0; i < s->total; i++) y[i] = 0.0; /* coupledLduMatrix::Amul: result = 0 */
     int rc = init_interfaces(s, x);
     if (rc) return rc;
-    for (int r = 0; r < s->nRows; r++)
-    {
-        /* lduMatrix::AmulCore (lduMatrixATmul.C) */
-        const orc_row* R = &s->rows[r];
-        const double* psi = x + R->offset;
-        double* Apsi = y + R->offset;
-        for (int c = 0; c < R->nCells; c++) Apsi[c] = R->diag[c] * psi[c];
-        for (int f = 0; f < R->nFaces; f++)
-        {
-            Apsi[R->u[f]] += R->lower[f] * psi[R->l[f]];
-            Apsi[R->l[f]] += R->upper[f] * psi[R->u[f]];
-        }
-    }
+    mul_job J = {s, x, y};
+    par_for(s->nRows, row_amul, &J);
     update_interfaces(s, y, 0, 0);
     return 0;
 }
@@ -447,19 +590,8 @@ int orc_tmul(orc_sys* s, const double* x, double* y)
     for (int i = 0; i < s->total; i++) y[i] = 0.0;
     int rc = init_interfaces(s, x);
     if (rc) return rc;
-    for (int r = 0; r < s->nRows; r++)
-    {
-        /* lduMatrix::TmulCore */
-        const orc_row* R = &s->rows[r];
-        const double* psi = x + R->offset;
-        double* Tpsi = y + R->offset;
-        for (int c = 0; c < R->nCells; c++) Tpsi[c] = R->diag[c] * psi[c];
-        for (int f = 0; f < R->nFaces; f++)
-        {
-            Tpsi[R->u[f]] += R->upper[f] * psi[R->l[f]];
-            Tpsi[R->l[f]] += R->lower[f] * psi[R->u[f]];
-        }
-    }
+    mul_job J = {s, x, y};
+    par_for(s->nRows, row_tmul, &J);
     update_interfaces(s, y, 1, 0);
     return 0;
 }
@@ -552,50 +684,60 @@ int orc_get_rD(orc_sys* s, double* out)
     return 0;
 }
 
-static int precondition_impl(orc_sys* s, const double* rIn, double* wOut, int transpose)
+typedef struct
 {
-    if (s->precond < 0) return -1;
-    for (int r = 0; r < s->nRows; r++)
+    orc_sys* s;
+    const double* rIn;
+    double* wOut;
+    int transpose;
+} pre_job;
+static void row_precondition(int r, void* ctx)
+{
+    const pre_job* J = (const pre_job*)ctx;
+    const orc_row* R = &J->s->rows[r];
+    const double* rA = J->rIn + R->offset;
+    double* wA = J->wOut + R->offset;
+    const double* rD = R->rD;
+    const int nF = R->nFaces;
+    if (R->precond == ORC_PRECOND_NONE)
     {
-        const orc_row* R = &s->rows[r];
-        const double* rA = rIn + R->offset;
-        double* wA = wOut + R->offset;
-        const double* rD = R->rD;
-        const int nF = R->nFaces;
-        if (R->precond == ORC_PRECOND_NONE)
+        for (int c = 0; c < R->nCells; c++) wA[c] = rA[c];
+        return;
+    }
+    for (int c = 0; c < R->nCells; c++) wA[c] = rD[c] * rA[c];
+    if (R->precond == ORC_PRECOND_DIC)
+    {
+        for (int f = 0; f < nF; f++) wA[R->u[f]] -= rD[R->u[f]] * R->upper[f] * wA[R->l[f]];
+        for (int f = nF - 1; f >= 0; f--) wA[R->l[f]] -= rD[R->l[f]] * R->upper[f] * wA[R->u[f]];
+    }
+    else if (R->precond == ORC_PRECOND_DILU)
+    {
+        if (!J->transpose)
         {
-            for (int c = 0; c < R->nCells; c++) wA[c] = rA[c];
-            continue;
-        }
-        for (int c = 0; c < R->nCells; c++) wA[c] = rD[c] * rA[c];
-        if (R->precond == ORC_PRECOND_DIC)
-        {
-            for (int f = 0; f < nF; f++) wA[R->u[f]] -= rD[R->u[f]] * R->upper[f] * wA[R->l[f]];
+            for (int k = 0; k < nF; k++)
+            {
+                int sf = R->losort[k];
+                wA[R->u[sf]] -= rD[R->u[sf]] * R->lower[sf] * wA[R->l[sf]];
+            }
             for (int f = nF - 1; f >= 0; f--) wA[R->l[f]] -= rD[R->l[f]] * R->upper[f] * wA[R->u[f]];
         }
-        else if (R->precond == ORC_PRECOND_DILU)
+        else
         {
-            if (!transpose)
+            /* DILUPreconditioner::preconditionT: roles of upper/lower swapped */
+            for (int f = 0; f < nF; f++) wA[R->u[f]] -= rD[R->u[f]] * R->upper[f] * wA[R->l[f]];
+            for (int k = nF - 1; k >= 0; k--)
             {
-                for (int k = 0; k < nF; k++)
-                {
-                    int sf = R->losort[k];
-                    wA[R->u[sf]] -= rD[R->u[sf]] * R->lower[sf] * wA[R->l[sf]];
-                }
-                for (int f = nF - 1; f >= 0; f--) wA[R->l[f]] -= rD[R->l[f]] * R->upper[f] * wA[R->u[f]];
-            }
-            else
-            {
-                /* DILUPreconditioner::preconditionT: roles of upper/lower swapped */
-                for (int f = 0; f < nF; f++) wA[R->u[f]] -= rD[R->u[f]] * R->upper[f] * wA[R->l[f]];
-                for (int k = nF - 1; k >= 0; k--)
-                {
-                    int sf = R->losort[k];
-                    wA[R->l[sf]] -= rD[R->l[sf]] * R->lower[sf] * wA[R->u[sf]];
-                }
+                int sf = R->losort[k];
+                wA[R->l[sf]] -= rD[R->l[sf]] * R->lower[sf] * wA[R->u[sf]];
             }
         }
     }
+}
+static int precondition_impl(orc_sys* s, const double* rIn, double* wOut, int transpose)
+{
+    if (s->precond < 0) return -1;
+    pre_job J = {s, rIn, wOut, transpose};
+    par_for(s->nRows, row_precondition, &J);
     return 0;
 }
 
@@ -737,16 +879,16 @@ static int solve_bicgstab(orc_sys* s, const orc_opts* o, double* x, const double
                 omega = 0;
                 beta = 0;
             }
-            for (int i = 0; i < n; i++) p[i] = r[i] + beta * p[i] - beta * omega * v[i];
+            vec_op(0, n, p, r, v, beta, omega);
             orc_precondition(s, p, ph);
             orc_amul(s, ph, v);
             alpha = rho / orc_gsumprod(s, rw, v);
-            for (int i = 0; i < n; i++) sv[i] = r[i] - alpha * v[i];
+            vec_op(1, n, sv, r, v, alpha, 0.0);
             orc_precondition(s, sv, sh);
             orc_amul(s, sh, t);
             omega = orc_gsumprod(s, t, sv) / orc_gsumprod(s, t, t);
-            for (int i = 0; i < n; i++) x[i] = x[i] + alpha * ph[i] + omega * sh[i];
-            for (int i = 0; i < n; i++) r[i] = sv[i] - omega * t[i];
+            vec_op(2, n, x, ph, sh, alpha, omega);
+            vec_op(3, n, r, sv, t, omega, 0.0);
             perf->finalResidual = orc_gsummag(s, r) / nf;
             perf->nIterations++;
             HIST(perf->nIterations, perf->finalResidual);

@@ -135,6 +135,9 @@ double orc_gsummag(const orc_sys*, const double* a);
 /* mode 0 (default): the reference's sequential sums.  mode 1: pairwise sums -- used by the tests only to
  * MEASURE how sensitive a residual history is to the summation order; never the parity target. */
 void orc_set_reduction_mode(orc_sys*, int mode);
+/* threads standing in for the MPI ranks of a decomposed run (results do not depend on the count); default 1 */
+void orc_set_threads(int n);
+int orc_get_threads(void);
 
 /* ---- partitioned-coupling face transfer ---- */
 /* GGIInterpolation::interpolate: result[i] = sum_k ff[addr[k]]*w[k], zero-initialised, list order */

@@ -40,6 +40,11 @@ def build(force: bool = False) -> str:
 _lib = None
 
 
+def set_threads(n: int) -> None:
+    """Threads of the oracle's row loops (stand-ins for MPI ranks); results are independent of the count."""
+    lib().orc_set_threads(int(n))
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -66,6 +71,8 @@ def lib():
         L.orc_gsummag.restype = C.c_double
         L.orc_gsummag.argtypes = [C.c_void_p, dp]
         L.orc_set_reduction_mode.argtypes = [C.c_void_p, C.c_int]
+        L.orc_set_threads.argtypes = [C.c_int]
+        L.orc_set_threads(1)
         L.orc_ggi_interpolate.argtypes = [C.c_int, ip, ip, dp, dp, C.c_int, dp]
         L.orc_patch_face_to_global.argtypes = [C.c_int, ip, ip, dp, C.c_int, C.c_int, dp]
         L.orc_global_face_to_patch.argtypes = [C.c_int, ip, dp, C.c_int, dp]

@@ -212,3 +212,24 @@ def test_face_transfer_functions():
     assert np.array_equal(g[perm], pf)
     assert np.array_equal(pyoracle.global_face_to_patch(perm[4:], g), pf[4:])
     assert np.array_equal(pyoracle.direct_map(perm, pf), pf[perm])
+
+
+def test_threaded_oracle_is_independent_of_thread_count():
+    """The worker pool standing in for MPI ranks (bench.py's decomposed CPU arm) must not change a single bit:
+    per-row partial sums are combined in row / rank order whatever thread produced them."""
+    from multiregionfoam_b200.assembly import cht_rank_slab
+    from multiregionfoam_b200.case import Case
+    case = Case("slabs", [cht_rank_slab(1, 2, g, 4) for g in range(4)])
+    O = pyoracle.OracleSystem(case)
+    x0, b = case.concat("psi"), case.concat("source")
+    ref = None
+    try:
+        for th in (1, 3, 8):
+            pyoracle.set_threads(th)
+            x, info = O.solve(x0.copy(), b, "BiCGStab", "DILU", tolerance=1e-12, maxIter=60)
+            if ref is None:
+                ref = (x, info["history"])
+            else:
+                assert np.array_equal(x, ref[0]) and np.array_equal(info["history"], ref[1])
+    finally:
+        pyoracle.set_threads(1)
