@@ -60,5 +60,25 @@ def full(path: str) -> None:
         print(f"| `{short(r[idx['Kernel Name']])}` | " + " | ".join(r[idx[m]] for m, _ in want) + " |")
 
 
+def traffic(path: str) -> None:
+    """Mean DRAM bytes (read + write) per launch of every kernel class of a --set full capture, as JSON on stdout
+    (bench.py reports it as roofline.traffic)."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    head, units = rows[0], rows[1]
+    idx = {n: i for i, n in enumerate(head)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    cls = {"k_sweep<0>": "sweep_fwd", "k_sweep<1>": "sweep_bwd", "k_amul": "amul", "k_bicg": "vector"}
+    agg = {}
+    for r in rows[2:]:
+        name = short(r[idx["Kernel Name"]])
+        key = next((v for k, v in cls.items() if name.startswith(k)), name)
+        b = sum(float(r[idx[m]].replace(",", "")) * scale[units[idx[m]]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        agg.setdefault(key, []).append(b)
+    print(json.dumps({"source": path, "dram_bytes_per_launch": {k: sum(v) / len(v) for k, v in agg.items()},
+                      "launches_captured": {k: len(v) for k, v in agg.items()}}, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
