@@ -319,3 +319,80 @@ def test_full_size_properties(gpu_ctx):
         assert np.max(np.abs(w - v)) < 1e-9
     finally:
         S.close()
+
+
+def test_partitioned_fsi_style_coupling_loop(gpu_ctx, golden_addr):
+    """BASELINE config 4 in miniature: PARTITIONED coupling.  Per Dirichlet-Neumann iteration the
+    fluid's vector equation is solved component by component with PBiCG + DILU (HronTurekFsi3 system/fluid/fvSolution
+    `U`), its interface field is transferred to the solid through the GGI weighted gather
+    (ggiInterfaceToInterfaceMapping::transferFacesZoneToZone), the solid's vector equation is solved with PCG + DIC
+    (`D`: PCG + FDIC) and its interface field goes back.  Every solve and every transfer runs through the C ABI
+    and is compared with the oracle doing the same loop."""
+    rng = np.random.default_rng(11)
+    A = golden_region(golden_addr, "bubbleA", symmetric=False, seed=21)   # "fluid"
+    B = golden_region(golden_addr, "bubbleB", symmetric=True, seed=22)    # "solid"
+    fcA = golden_addr["bubbleA_patch_interface"].astype(np.int32)
+    fcB = golden_addr["bubbleB_patch_interfaceShadow"].astype(np.int32)
+    nA, nB = fcA.size, fcB.size
+
+    def csr(nTo, nFrom):
+        cnt = rng.integers(1, 4, nTo)
+        offs = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+        addr = np.concatenate([np.sort(rng.choice(nFrom, k, replace=False)) for k in cnt]).astype(np.int32)
+        w = rng.random(offs[-1]) + 0.1
+        for i in range(nTo):
+            w[offs[i]:offs[i + 1]] /= w[offs[i]:offs[i + 1]].sum()
+        return offs, addr, w
+
+    a2b, b2a = csr(nB, nA), csr(nA, nB)
+    SA = ldu.LduSystem(gpu_ctx, single_region_case(A).ranks[0])
+    SB = ldu.LduSystem(gpu_ctx, single_region_case(B).ranks[0])
+    OA = pyoracle.OracleSystem(single_region_case(A))
+    OB = pyoracle.OracleSystem(single_region_case(B))
+    try:
+        srcA = rng.standard_normal((3, A.nCells))
+        srcB = rng.standard_normal((3, B.nCells))
+
+        def loop(solveA, solveB, interp):
+            U = np.zeros((3, A.nCells))
+            D = np.zeros((3, B.nCells))
+            dispOnA = np.zeros((nA, 3))
+            its = []
+            for _ in range(3):
+                for c in range(3):      # fluid: interface motion enters the source at the interface cells
+                    b = srcA[c].copy()
+                    np.add.at(b, fcA, 0.3 * dispOnA[:, c])
+                    U[c], n = solveA(U[c], b)
+                    its.append(n)
+                traction = interp(*a2b, np.ascontiguousarray(U[:, fcA].T))        # fluid -> solid faces (vector field)
+                for c in range(3):
+                    b = srcB[c].copy()
+                    np.add.at(b, fcB, 0.2 * traction[:, c])
+                    D[c], n = solveB(D[c], b)
+                    its.append(n)
+                dispOnA = interp(*b2a, np.ascontiguousarray(D[:, fcB].T))         # solid -> fluid faces
+            return U, D, its
+
+        def gA(x, b):
+            x, i = SA.solve(x, b, ldu.SOLVER_PBICG, ldu.PRECOND_DILU, tolerance=1e-11, maxIter=400)
+            return x, i["nIterations"]
+
+        def gB(x, b):
+            x, i = SB.solve(x, b, ldu.SOLVER_PCG, ldu.PRECOND_DIC, tolerance=1e-11, maxIter=400)
+            return x, i["nIterations"]
+
+        def oA(x, b):
+            x, i = OA.solve(x, b, "PBiCG", "DILU", tolerance=1e-11, maxIter=400)
+            return x, i["nIterations"]
+
+        def oB(x, b):
+            x, i = OB.solve(x, b, "PCG", "DIC", tolerance=1e-11, maxIter=400)
+            return x, i["nIterations"]
+
+        Ug, Dg, ig = loop(gA, gB, lambda o, a, w, f: gpu_ctx.ggi_interpolate(o, a, w, f))
+        Uo, Do, io = loop(oA, oB, lambda o, a, w, f: pyoracle.ggi_interpolate(o, a, w, f, 3))
+        assert rel_l2(Ug, Uo) < FIELD_RTOL and rel_l2(Dg, Do) < FIELD_RTOL
+        assert all(abs(a - b) <= 2 for a, b in zip(ig, io)), (ig, io)
+    finally:
+        SA.close()
+        SB.close()
