@@ -150,3 +150,47 @@ def synthetic_coeffs(nCells: int, l: np.ndarray, u: np.ndarray, *, symmetric: bo
 
 def single_region_case(reg: Region, name: str = "single") -> Case:
     return Case(name, [RankSystem(0, 1, [reg])])
+
+
+def pu_block_matrix(nCells: int, l: np.ndarray, u: np.ndarray, *, seed: int = 2024, coupling: float = 0.05,
+                    name: str = "Up"):
+    """Synthetic pressure-velocity block system (BASELINE config 5) on a given LDU addressing, assembled through the
+    ``fvBlockMatrix<vector4>`` mirror the way ``pUCoupledIcoFluid::setCoupledEqns`` does
+    (/root/reference/src/regions/pUCoupledIcoFluid/pUCoupledIcoFluid.C:584-621): ``insertEquation(0, UEqn)``
+    (asymmetric momentum matrix shared by the three components), ``insertEquation(3, pEqn)`` (symmetric pressure
+    Laplacian), ``insertBlockCoupling(0, 3, grad p, true)`` and ``insertBlockCoupling(3, 0, div U, false)``: 10 of the
+    16 entries of every block are structurally non-zero.  Seeded, diagonally dominant; the source is
+    ``A x*`` for a known ``x*`` (returned as ``M.xstar``) and the initial guess is zero."""
+    from .blockldu import BlockCoupling, ScalarEqn, fvBlockMatrix
+    rng = np.random.default_rng(seed)
+    F = l.size
+    l = np.ascontiguousarray(l, np.int32)
+    u = np.ascontiguousarray(u, np.int32)
+    upU = -(0.5 + rng.random(F))
+    loU = upU * (1.0 + 0.2 * (2.0 * rng.random(F) - 1.0))
+    dU = 0.5 - np.bincount(l, weights=upU, minlength=nCells) - np.bincount(u, weights=loU, minlength=nCells)
+    upP = -(0.1 + 0.2 * rng.random(F))
+    dP = 0.02 - np.bincount(l, weights=upP, minlength=nCells) - np.bincount(u, weights=upP, minlength=nCells)
+    Sf = coupling * rng.standard_normal((F, 3))
+    w = 0.3 + 0.4 * rng.random(F)
+    # fvm::grad(p): owner gets +w Sf p_P + (1-w) Sf p_N, neighbour the opposite sign
+    gUp = (1.0 - w)[:, None] * Sf
+    gLo = -w[:, None] * Sf
+    gD = np.zeros((nCells, 3))
+    for c in range(3):
+        gD[:, c] = np.bincount(l, weights=w * Sf[:, c], minlength=nCells) - np.bincount(u, weights=(1.0 - w) * Sf[:, c], minlength=nCells)
+    # fvm::UDiv(U): the same stencil acting on U, feeding the p row
+    M = fvBlockMatrix(l, u, nCells, name=name)
+    M.insertEquation(0, ScalarEqn(dU, np.zeros((nCells, 3)), upU, loU), nCmpts=3)
+    M.insertEquation(3, ScalarEqn(dP, np.zeros(nCells), upP, None))
+    M.insertBlockCoupling(0, 3, BlockCoupling(gD, gUp, gLo), True)
+    M.insertBlockCoupling(3, 0, BlockCoupling(gD, gUp, gLo), False)
+    xstar = np.empty((nCells, 4))
+    xstar[:, :3] = 1.0 + 0.1 * rng.standard_normal((nCells, 3))
+    xstar[:, 3] = 10.0 + rng.standard_normal(nCells)
+    b = np.einsum("nij,nj->ni", M.diag, xstar)
+    np.add.at(b, u, np.einsum("fij,fj->fi", M.lower, xstar[l]))
+    np.add.at(b, l, np.einsum("fij,fj->fi", M.upper, xstar[u]))
+    M.source[...] = b
+    M.xstar = xstar
+    return M

@@ -1564,3 +1564,6 @@ extern "C" int b200_global_face_to_patch(b200_ctx* ctx, int32_t nLocal, const in
     CK(ctx, cudaStreamSynchronize(st));
     return B200_OK;
 }
+
+// block-coupled (vector4) systems: include/b200_blk.h
+#include "blk_system.cuh"

@@ -27,6 +27,19 @@ def test_header_symbols_are_exported(lib_path):
     assert sorted(ldu.ABI_SYMBOLS) == declared
 
 
+def test_block_header_symbols_are_exported(lib_path):
+    """include/b200_blk.h: the block-coupled (vector4) entry points."""
+    from multiregionfoam_b200 import blockldu
+    hdr = open(os.path.join(ROOT, "include", "b200_blk.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(b200_blk_[a-z_0-9A-Z]+)\s*\(", hdr)))
+    assert declared, "no declarations found"
+    L = C.CDLL(lib_path)
+    missing = [s for s in declared if not hasattr(L, s)]
+    assert not missing, missing
+    assert sorted(blockldu.ABI_SYMBOLS) == declared
+
+
 def test_version_and_error_text(lib_path):
     L = ldu.load()
     assert L.b200_version() >= 100
@@ -49,4 +62,4 @@ def test_product_package_does_not_import_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 bad = [ln for ln in txt.splitlines() if re.search(r"^\s*(#include|import|from)\b.*oracle", ln) or "dlopen" in ln and "oracle" in ln]
                 assert not bad, (f, bad)
-                assert "pyoracle" not in txt and "ldu_oracle" not in txt, f
+                assert "pyoracle" not in txt and "ldu_oracle" not in txt and "pyblk" not in txt, f
