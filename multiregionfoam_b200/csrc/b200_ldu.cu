@@ -617,9 +617,12 @@ extern "C" int b200_sys_finalize(b200_sys* s)
     {
         const int maxSmem = std::max(s->fwd.smemBytes, s->bwd.smemBytes);
         if (maxSmem > 227 * 1024) return set_err(ctx, B200_EUNSUPPORTED, "sweep stage needs %d bytes of shared memory", maxSmem);
-        CK(ctx, cudaFuncSetAttribute(k_sweep<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
-        CK(ctx, cudaFuncSetAttribute(k_sweep<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
-        CK(ctx, cudaFuncSetAttribute(k_sweep<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        CK(ctx, cudaFuncSetAttribute(k_sweep<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        CK(ctx, cudaFuncSetAttribute(k_sweep<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        CK(ctx, cudaFuncSetAttribute(k_sweep<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        CK(ctx, cudaFuncSetAttribute(k_sweep<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        CK(ctx, cudaFuncSetAttribute(k_sweep<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        CK(ctx, cudaFuncSetAttribute(k_sweep<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
     }
     CK(ctx, s->sc.alloc(1));
     CK(ctx, cudaMemsetAsync(s->sc.p, 0, sizeof(DevScalars), st));
@@ -833,8 +836,12 @@ static int launch_sweep(b200_sys* s, PipeDirMem& M, PipeDev dev, const double* a
     if (s->nGroups == 0) return B200_OK;
     dev.stats = M.dev.stats;
     KScope k(s, dev.dir > 0 ? B200_K_SWEEP_FWD : B200_K_SWEEP_BWD);
-    k_sweep<MODE><<<s->nGroups, kSweepThreads, M.smemBytes, ctx->stream>>>(dev, a, b, out, s->ticket.p, s->ticketBase, s->devErr.p, s->sc.p,
-                                                                          force);
+    if (dev.stats) // debug counters and time stamps: a separately compiled instantiation, the product path carries none
+        k_sweep<MODE, true><<<s->nGroups, kSweepThreads, M.smemBytes, ctx->stream>>>(dev, a, b, out, s->ticket.p, s->ticketBase, s->devErr.p,
+                                                                                    s->sc.p, force);
+    else
+        k_sweep<MODE, false><<<s->nGroups, kSweepThreads, M.smemBytes, ctx->stream>>>(dev, a, b, out, s->ticket.p, s->ticketBase, s->devErr.p,
+                                                                                     s->sc.p, force);
     s->ticketBase += (unsigned)s->nGroups;
     CK(ctx, cudaGetLastError());
     return B200_OK;

@@ -561,7 +561,10 @@ __device__ __forceinline__ SweepRing ring_setup(const PipeDev& S, int g, int lan
 //     the descriptor bytes instead (general path).  After a block it resets the counter and publishes its
 //     progress, which is what the loader polls before it refills the stage.
 constexpr int kNH = kSweepBlock; // producer warps = steps per block (8)
-constexpr int kStatsStride = 16;  // debug counters per group
+constexpr int kTraceBlocks = 142; // debug: per-block time stamps (clock64 of the group's SM) of the first blocks
+constexpr int kStatsStride = 16 + 8 * kTraceBlocks; // debug counters per group: 16 totals, then per block 8 stamps:
+// consumer {ready seen, done}, loader issue, producer 0 {step start, next stage landed, values checked, delivered},
+// producer 7 delivered
 constexpr int kL2Ahead = 8;      // blocks the L2 prefetch runs ahead of the stage fill
 
 // Flag words in shared memory.  A formal release/acquire pair costs a MEMBAR.ALL.CTA on the releasing side, which
@@ -636,7 +639,7 @@ __device__ __forceinline__ void split_issue(const SplitCtx& C, const double* a, 
 // minimal: the C-block and the hdr part of a stage are plane-major (operands of step q of a plane at q * 256 from
 // the plane's base), which turns the 24 operand loads of a canonical block into loads at immediate offsets from
 // two base registers.
-template <int MODE, int RG>
+template <int MODE, int RG, bool STATS>
 __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx& C, const int g, const int lane, double* out)
 {
     constexpr unsigned FULL = 0xffffffffu;
@@ -646,7 +649,7 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
     const int nT = C.nT;
     double* outPtr = out + ((long long)C.base + (dir > 0 ? 0 : nT - 1)) * 32 + lane;
     const int srcLane = (lane - dir) & 31; // the linked neighbour lane of a canonical step
-    const bool statsOn = S.stats != nullptr;
+    constexpr bool statsOn = STATS;
     const bool forceGeneral = MODE == 2 || (S.debugFlags & 1);
     const int Kg = C.Kg;
     double h[kSkew]; // h[k]: the value this lane produced k+1 steps ago
@@ -682,6 +685,7 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
             do c = ld_flag_smem(cntp);
             while ((c & 0xffu) != (unsigned)kNH);
         }
+        if (statsOn && lane == 0 && blk < kTraceBlocks) S.stats[(long long)kStatsStride * g + 16 + blk * 8 + 0] = clock64();
         const unsigned char* hd = sb + C.offHdr;
         if (c == (unsigned)kNH && !forceGeneral)
         {
@@ -705,28 +709,60 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
         }
         else
         {
+            // Blocks with a non-canonical step (block seams: the own-lane term comes first in the reference order and
+            // the skew of the lanes spreads one seam over 62 steps, i.e. 9 blocks per seam of every group): the terms
+            // stay in reference order and are selected by their descriptor bytes, but the operands of HW steps are
+            // loaded at once and - when every shuffled term of the step comes from the linked neighbour lane (meta
+            // bit 57, set on the host) - a single shuffle is issued ahead of the dependent chain, as in the canonical path.
             nGeneral++;
-#pragma unroll 2
-            for (int q = 0; q < kNH; q++)
+            constexpr int HW = RG <= 3 ? 4 : 2;
+#pragma unroll 1
+            for (int q0 = 0; q0 < kNH; q0 += HW)
             {
-                const unsigned long long meta = *reinterpret_cast<const unsigned long long*>(sb + q * 256);
-                double acc = *reinterpret_cast<const double*>(hd + q * 256);
-                const double cv0 = Kg > 0 ? *reinterpret_cast<const double*>(hd + PL + q * 256) : 0.0;
-                const double cv1 = Kg > 1 ? *reinterpret_cast<const double*>(hd + 2 * PL + q * 256) : 0.0;
-                double cf[RG];
+                unsigned long long meta[HW];
+                double a0[HW], cv0[HW], cv1[HW], cf[HW][RG];
 #pragma unroll
-                for (int r = 0; r < RG; r++) cf[r] = *reinterpret_cast<const double*>(sb + (1 + r) * PL + q * 256);
-#pragma unroll
-                for (int r = 0; r < RG; r++)
+                for (int u = 0; u < HW; u++)
                 {
-                    const unsigned byte = (unsigned)(meta >> (8 * r)) & 0xffu;
-                    const double sh = __shfl_sync(FULL, h[kSkew - 1], (int)(byte & kMetaLane));
-                    double v = (byte & kMetaConst) ? ((byte & 0x20u) ? cv1 : cv0) : ((byte & kMetaOwn) ? h[0] : sh);
-                    if (byte & kMetaPad) v = MODE == 2 ? 1.0 : 0.0; // padding term (coefficient 0)
-                    acc = sweep_apply<MODE>(acc, cf[r], v);
+                    const int q = q0 + u;
+                    meta[u] = *reinterpret_cast<const unsigned long long*>(sb + q * 256);
+                    a0[u] = *reinterpret_cast<const double*>(hd + q * 256);
+                    cv0[u] = Kg > 0 ? *reinterpret_cast<const double*>(hd + PL + q * 256) : 0.0;
+                    cv1[u] = Kg > 1 ? *reinterpret_cast<const double*>(hd + 2 * PL + q * 256) : 0.0;
+#pragma unroll
+                    for (int r = 0; r < RG; r++) cf[u][r] = *reinterpret_cast<const double*>(sb + (1 + r) * PL + q * 256);
                 }
-                st_relaxed(outPtr + q * outStride, acc);
-                push(acc);
+#pragma unroll
+                for (int u = 0; u < HW; u++)
+                {
+                    double acc = a0[u];
+                    if ((meta[u] >> 57) & 1ull)
+                    { // warp-uniform: all shuffled terms of this step read the linked lane
+                        const double sh = __shfl_sync(FULL, h[kSkew - 1], srcLane);
+#pragma unroll
+                        for (int r = 0; r < RG; r++)
+                        {
+                            const unsigned byte = (unsigned)(meta[u] >> (8 * r)) & 0xffu;
+                            double v = (byte & kMetaConst) ? ((byte & 0x20u) ? cv1[u] : cv0[u]) : ((byte & kMetaOwn) ? h[0] : sh);
+                            if (byte & kMetaPad) v = MODE == 2 ? 1.0 : 0.0; // padding term (coefficient 0)
+                            acc = sweep_apply<MODE>(acc, cf[u][r], v);
+                        }
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int r = 0; r < RG; r++)
+                        {
+                            const unsigned byte = (unsigned)(meta[u] >> (8 * r)) & 0xffu;
+                            const double sh = __shfl_sync(FULL, h[kSkew - 1], (int)(byte & kMetaLane));
+                            double v = (byte & kMetaConst) ? ((byte & 0x20u) ? cv1[u] : cv0[u]) : ((byte & kMetaOwn) ? h[0] : sh);
+                            if (byte & kMetaPad) v = MODE == 2 ? 1.0 : 0.0; // padding term (coefficient 0)
+                            acc = sweep_apply<MODE>(acc, cf[u][r], v);
+                        }
+                    }
+                    st_relaxed(outPtr + (q0 + u) * outStride, acc);
+                    push(acc);
+                }
             }
         }
         outPtr += kNH * outStride;
@@ -735,6 +771,7 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
         { // block done: the stage may be refilled
             st_flag_smem(cntp, 0u);
             st_flag_smem(C.done, (unsigned)(blk + 1));
+            if (statsOn && blk < kTraceBlocks) S.stats[(long long)kStatsStride * g + 16 + blk * 8 + 1] = clock64();
         }
         sb += C.stageBytes;
         cntp++;
@@ -760,67 +797,117 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
 }
 
 // ------------------------------------------------------------------------------------------ producers
-template <int MODE, int LG>
+// A block is ready when its slowest producer has delivered, and a producer's step is one long chain of dependent
+// shared-memory loads, checks and flag operations executed by a single warp: measured (per-block time stamps), that
+// chain - not the memory system and not the consumer - set the pace of a group.  The loop is therefore written for a
+// short chain: 32-bit shared-memory addresses stepped from stage to stage (no 64-bit address arithmetic), the
+// operand loads of the current block issued before the wait for the next stage so that their latency overlaps it,
+// no instrumentation in the product instantiation (STATS = false).
+__device__ __forceinline__ double lds_f64(unsigned a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int lds_s32(unsigned a)
+{
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ unsigned lds_u8(unsigned a)
+{
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void mbar_wait_u32(unsigned bar, unsigned parity)
+{
+    unsigned ok = 0;
+    while (!ok)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+}
+
+template <int MODE, int LG, bool STATS>
 __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx& C, const int g, const int h, const int lane, double* out,
                                                int* err)
 {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int LGA = LG > 0 ? LG : 1;
     constexpr int dir = MODE == 1 ? -1 : 1;
-    const int codeOff = LG * 256 + lane * 4, constOff = LG * 384 + lane * 4;
     const int vecIdx = (dir > 0 ? h : kNH - 1 - h) * 32 + lane; // this producer's step inside the a / b chunk
     const double neutral = MODE == 2 ? 1.0 : 0.0;
+    const int Kg = C.Kg;
+    // byte offsets of this producer's (step h) and this lane's operands inside a stage
+    const unsigned offCoef = (unsigned)(C.offP + h * C.pRec + lane * 8);              // coef i at + i * 256
+    const unsigned offCode = (unsigned)(C.offP + h * C.pRec + LG * 256 + lane * 4);   // code i at + i * 128
+    const unsigned offConst = (unsigned)(C.offP + h * C.pRec + LG * 384 + lane * 4);  // const code k at + k * 128
+    const unsigned offA = (unsigned)(C.offA + vecIdx * 8);                            // a; b at + kNH * 256
+    const unsigned offGen = (unsigned)(h * 256 + lane * 8 + 7);                       // top byte of the step's meta word
+    const unsigned offHd = (unsigned)(C.offHdr + h * 256 + lane * 8);                 // hdr planes acc0 | cval 0 | cval 1
+    const unsigned stage0 = smem_u32(C.stages), stageBytes = (unsigned)C.stageBytes;
+    const unsigned stageEnd = stage0 + (unsigned)C.NS * stageBytes;
+    const unsigned bar0 = smem_u32(C.rawBar), barEnd = bar0 + 8u * (unsigned)C.NS;
+    const unsigned cnt0 = smem_u32(C.cnt);
     // two register sets for the prefetched codes / cross-group values: the block loop is unrolled by two and the
     // sets swap roles, so that no register copy (which would wait for the prefetch to land) sits in the loop
     int codesA[LGA], codesB[LGA], ccA[2], ccB[2];
     double mvA[LGA], mvB[LGA], mcA[2], mcB[2];
-    auto fetch = [&](const unsigned char* rec, int* cd, double* vals, int* kc, double* kv) {
+    auto fetch = [&](const unsigned sg, int* cd, double* vals, int* kc, double* kv) {
+#pragma unroll
+        for (int i = 0; i < LG; i++) cd[i] = lds_s32(sg + offCode + i * 128);
+#pragma unroll
+        for (int k = 0; k < 2; k++) kc[k] = (k < Kg) ? lds_s32(sg + offConst + k * 128) : -1;
 #pragma unroll
         for (int i = 0; i < LG; i++)
         {
-            cd[i] = *reinterpret_cast<const int*>(rec + codeOff + i * 128);
             vals[i] = neutral;
             if (cd[i] >= 0) vals[i] = ld_relaxed(out + cd[i]);
         }
 #pragma unroll
         for (int k = 0; k < 2; k++)
         {
-            kc[k] = (k < C.Kg) ? *reinterpret_cast<const int*>(rec + constOff + k * 128) : -1;
             kv[k] = 0.0;
             if (kc[k] >= 0) kv[k] = ld_relaxed(out + kc[k]);
         }
     };
-    int st = 0;
-    unsigned par = 0u;
-    const bool timed = S.stats != nullptr && h == 0;
+    unsigned sg = stage0, bar = bar0, cnt = cnt0, par = 0u;
+    const bool timed = STATS && h == 0;
     long long tStage = 0, tVal = 0, tSpin = 0, tAll = timed ? clock64() : 0;
     auto step = [&](const int blk, int* codes, double* mv, int* cc, double* mc, int* codesN, double* mvN, int* ccN, double* mcN) {
-        unsigned char* stage = C.stages + (size_t)st * C.stageBytes;
-        const unsigned char* rec = stage + C.offP + (size_t)h * C.pRec;
-        const double* aP = reinterpret_cast<const double*>(stage + C.offA) + vecIdx;
-        // ---- prefetch the codes / cross-group values of this producer's step in the next block
-        int stN = st + 1;
-        unsigned parN = par;
-        if (stN == C.NS)
-        {
-            stN = 0;
-            parN ^= 1u;
-        }
-        if (blk + 1 < C.nBlocks)
-        {
-            const long long w0 = timed ? clock64() : 0;
-            mbar_wait(&C.rawBar[stN], parN);
-            if (timed) tStage += clock64() - w0;
-            fetch(C.stages + (size_t)stN * C.stageBytes + C.offP + (size_t)h * C.pRec, codesN, mvN, ccN, mcN);
-        }
-        // ---- operands of the current step first, the (possibly late) cross-group values last
-        double acc = *aP;
-        if (MODE == 0) acc *= aP[kNH * 32];
+        long long* const tr = (STATS && lane == 0 && blk < kTraceBlocks) ? S.stats + (long long)kStatsStride * g + 16 + blk * 8 : nullptr;
+        if (STATS && tr && h == 0) tr[3] = clock64();
+        // ---- operands of the current step (its stage landed: waited for one block ago)
+        double acc = lds_f64(sg + offA);
+        double bb = 0.0;
+        if (MODE == 0) bb = lds_f64(sg + offA + kNH * 256);
         double cf[LGA];
 #pragma unroll
-        for (int i = 0; i < LG; i++) cf[i] = *reinterpret_cast<const double*>(rec + lane * 8 + i * 256);
-        const unsigned general =
-            MODE == 2 ? 1u : (unsigned)(*reinterpret_cast<const unsigned long long*>(stage + h * 256 + lane * 8) >> 56) & 1u;
+        for (int i = 0; i < LG; i++) cf[i] = lds_f64(sg + offCoef + i * 256);
+        const unsigned general = MODE == 2 ? 1u : (lds_u8(sg + offGen) & 1u);
+        // ---- prefetch the codes / cross-group values of this producer's step in the next block
+        unsigned sgN = sg + stageBytes, barN = bar + 8u, parN = par;
+        if (sgN == stageEnd)
+        {
+            sgN = stage0;
+            barN = bar0;
+            parN ^= 1u;
+        }
+        const bool haveNext = blk + 1 < C.nBlocks;
+        if (haveNext)
+        {
+            const long long w0 = timed ? clock64() : 0;
+            mbar_wait_u32(barN, parN);
+            if (timed) tStage += clock64() - w0;
+            if (STATS && tr && h == 0) tr[4] = clock64();
+            fetch(sgN, codesN, mvN, ccN, mcN);
+        }
+        if (MODE == 0) acc *= bb;
+        // ---- the (possibly late) cross-group values
         const long long v0 = timed ? clock64() : 0;
         bool bad = false;
 #pragma unroll
@@ -829,15 +916,48 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
         for (int k = 0; k < 2; k++) bad |= cc[k] >= 0 && is_sentinel(mc[k]);
         const bool anyBad = __any_sync(FULL, bad);
         const long long v1 = timed ? clock64() : 0;
+        if (STATS && tr && h == 0) tr[5] = v1;
         if (anyBad)
-        { // a value had not arrived when it was prefetched: poll for it
-            if (S.stats && lane == 0) atomicAdd((unsigned long long*)(S.stats + (long long)kStatsStride * g + 4), 1ull);
+        { // a value had not arrived when it was prefetched: poll for it.  A group that runs right behind the group
+          // it depends on gets here in every block: every polling round therefore re-reads, in one batch of
+          // independent loads, whatever is missing of this block AND of the next one, so that a producer falls straight
+          // through the next block when its values arrived in the meantime.
+            if (STATS && lane == 0) atomicAdd((unsigned long long*)(S.stats + (long long)kStatsStride * g + 4), 1ull);
+            int tries = 0;
+            bool still;
+            do
+            {
 #pragma unroll
-            for (int i = 0; i < LG; i++)
-                if (codes[i] >= 0 && is_sentinel(mv[i])) mv[i] = sweep_spin(out + codes[i], err);
+                for (int i = 0; i < LG; i++)
+                    if (codes[i] >= 0 && is_sentinel(mv[i])) mv[i] = ld_relaxed(out + codes[i]);
 #pragma unroll
-            for (int k = 0; k < 2; k++)
-                if (cc[k] >= 0 && is_sentinel(mc[k])) mc[k] = sweep_spin(out + cc[k], err);
+                for (int k = 0; k < 2; k++)
+                    if (cc[k] >= 0 && is_sentinel(mc[k])) mc[k] = ld_relaxed(out + cc[k]);
+                if (haveNext)
+                {
+#pragma unroll
+                    for (int i = 0; i < LG; i++)
+                        if (codesN[i] >= 0 && is_sentinel(mvN[i])) mvN[i] = ld_relaxed(out + codesN[i]);
+#pragma unroll
+                    for (int k = 0; k < 2; k++)
+                        if (ccN[k] >= 0 && is_sentinel(mcN[k])) mcN[k] = ld_relaxed(out + ccN[k]);
+                }
+                still = false;
+#pragma unroll
+                for (int i = 0; i < LG; i++) still |= codes[i] >= 0 && is_sentinel(mv[i]);
+#pragma unroll
+                for (int k = 0; k < 2; k++) still |= cc[k] >= 0 && is_sentinel(mc[k]);
+                if (++tries >= 64)
+                {
+                    __nanosleep(tries > 4096 ? 400 : 64);
+                    if ((tries & 4095) == 4095 && *(volatile int*)err) break;
+                    if (tries >= (1 << 24))
+                    {
+                        atomicExch(err, 1);
+                        break;
+                    }
+                }
+            } while (__any_sync(FULL, still));
         }
         if (timed)
         {
@@ -849,17 +969,21 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
 #pragma unroll
         for (int i = 0; i < LG; i++) acc = sweep_apply<MODE>(acc, cf[i], mv[i]); // padding: coefficient 0, neutral value
         // ---- hand over: the hdr part of the stage is free because the stage was refilled after the consumer released it
-        unsigned char* hd = stage + C.offHdr + h * 256 + lane * 8; // hdr planes: acc0 | cval 0 | cval 1, each [kNH][32]
-        *reinterpret_cast<double*>(hd) = acc;
-        if (C.Kg > 0) *reinterpret_cast<double*>(hd + kNH * 256) = mc[0];
-        if (C.Kg > 1) *reinterpret_cast<double*>(hd + 2 * kNH * 256) = mc[1];
+        sts_f64(sg + offHd, acc);
+        if (Kg > 0) sts_f64(sg + offHd + kNH * 256, mc[0]);
+        if (Kg > 1) sts_f64(sg + offHd + 2 * kNH * 256, mc[1]);
         __syncwarp();
-        if (lane == 0) red_flag_smem(&C.cnt[st], 1u + (general << 8));
-        st = stN;
+        if (lane == 0) asm volatile("red.relaxed.cta.shared.add.u32 [%0], %1;" ::"r"(cnt), "r"(1u + (general << 8)) : "memory");
+        if (STATS && tr && h == 0) tr[6] = clock64();
+        if (STATS && tr && h == kNH - 1) tr[7] = clock64();
+        cnt = (sgN == stage0) ? cnt0 : cnt + 4u;
+        sg = sgN;
+        bar = barN;
         par = parN;
     };
-    mbar_wait(&C.rawBar[0], 0u);
-    fetch(C.stages + C.offP + (size_t)h * C.pRec, codesA, mvA, ccA, mcA);
+    (void)barEnd;
+    mbar_wait_u32(bar0, 0u);
+    fetch(stage0, codesA, mvA, ccA, mcA);
     for (int blk = 0; blk < C.nBlocks; blk += 2)
     {
         step(blk, codesA, mvA, ccA, mcA, codesB, mvB, ccB, mcB);
@@ -875,7 +999,19 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
     }
 }
 
-template <int MODE>
+// Warp roles: consumer, kNH producers, loader.  (Measured on B200: giving the consumer a scheduler sub-partition of its
+// own - wid % 4, 11 warps - or the highest warp id of the CTA changes the sweep time by < 2 %: the consumer is not
+// short of issue slots.)
+constexpr int kRoleConsumer = -1, kRoleLoader = -2;
+constexpr int kSweepWarps = 2 + kNH;
+__device__ __forceinline__ int sweep_role(int warp)
+{
+    if (warp == 0) return kRoleConsumer;
+    if (warp == 1 + kNH) return kRoleLoader;
+    return warp - 1;
+}
+
+template <int MODE, bool STATS>
 __device__ __forceinline__ void sweep_group_split(const PipeDev& S, const int g, const int warp, const int lane, const double* __restrict__ a,
                                                   const double* __restrict__ b, double* out, int* err, unsigned char* smem)
 {
@@ -903,7 +1039,7 @@ __device__ __forceinline__ void sweep_group_split(const PipeDev& S, const int g,
     C.stages = smem + 256;
     C.pStream = S.pStream + S.gPOff[g];
     C.cStream = S.cStream + S.gCOff[g];
-    if (warp == 0 && lane == 0)
+    if (threadIdx.x == 0)
     {
         for (int st = 0; st < C.NS; st++)
         {
@@ -916,18 +1052,19 @@ __device__ __forceinline__ void sweep_group_split(const PipeDev& S, const int g,
         for (int c = C.NS; c < C.NS + kL2Ahead; c++) split_prefetch<MODE>(C, a, b, c);
     }
     __syncthreads();
-    if (warp == 0)
+    const int role = sweep_role(warp);
+    if (role == kRoleConsumer)
     {
         switch (C.Rg)
         {
-            case 2: split_consumer<MODE, 2>(S, C, g, lane, out); break;
-            case 3: split_consumer<MODE, 3>(S, C, g, lane, out); break;
-            case 4: split_consumer<MODE, 4>(S, C, g, lane, out); break;
-            case 5: split_consumer<MODE, 5>(S, C, g, lane, out); break;
-            default: split_consumer<MODE, 6>(S, C, g, lane, out); break;
+            case 2: split_consumer<MODE, 2, STATS>(S, C, g, lane, out); break;
+            case 3: split_consumer<MODE, 3, STATS>(S, C, g, lane, out); break;
+            case 4: split_consumer<MODE, 4, STATS>(S, C, g, lane, out); break;
+            case 5: split_consumer<MODE, 5, STATS>(S, C, g, lane, out); break;
+            default: split_consumer<MODE, 6, STATS>(S, C, g, lane, out); break;
         }
     }
-    else if (warp == 1 + kNH)
+    else if (role == kRoleLoader)
     {
         // loader: one thread refills a stage as soon as the consumer has released the block it held
         if (lane == 0)
@@ -937,24 +1074,25 @@ __device__ __forceinline__ void sweep_group_split(const PipeDev& S, const int g,
             {
                 const unsigned need = (unsigned)(blk - C.NS + 1);
                 while (ld_flag_smem(C.done) < need) __nanosleep(20);
+                if (STATS && blk < kTraceBlocks) S.stats[(long long)kStatsStride * g + 16 + blk * 8 + 2] = clock64();
                 split_issue<MODE>(C, a, b, blk, st);
                 split_prefetch<MODE>(C, a, b, blk + kL2Ahead);
                 if (++st == C.NS) st = 0;
             }
         }
     }
-    else
+    else if (role >= 0)
     {
-        const int h = warp - 1;
+        const int h = role;
         switch (C.Lg)
         {
-            case 0: split_producer<MODE, 0>(S, C, g, h, lane, out, err); break;
-            case 1: split_producer<MODE, 1>(S, C, g, h, lane, out, err); break;
-            case 2: split_producer<MODE, 2>(S, C, g, h, lane, out, err); break;
-            case 3: split_producer<MODE, 3>(S, C, g, h, lane, out, err); break;
-            case 4: split_producer<MODE, 4>(S, C, g, h, lane, out, err); break;
-            case 5: split_producer<MODE, 5>(S, C, g, h, lane, out, err); break;
-            default: split_producer<MODE, 6>(S, C, g, h, lane, out, err); break;
+            case 0: split_producer<MODE, 0, STATS>(S, C, g, h, lane, out, err); break;
+            case 1: split_producer<MODE, 1, STATS>(S, C, g, h, lane, out, err); break;
+            case 2: split_producer<MODE, 2, STATS>(S, C, g, h, lane, out, err); break;
+            case 3: split_producer<MODE, 3, STATS>(S, C, g, h, lane, out, err); break;
+            case 4: split_producer<MODE, 4, STATS>(S, C, g, h, lane, out, err); break;
+            case 5: split_producer<MODE, 5, STATS>(S, C, g, h, lane, out, err); break;
+            default: split_producer<MODE, 6, STATS>(S, C, g, h, lane, out, err); break;
         }
     }
 }
@@ -1027,8 +1165,8 @@ __device__ __noinline__ void sweep_group_generic(const PipeDev& S, const int g, 
 
 // One CTA (1 consumer + kNH producer warps + 1 loader warp) per group; CTAs take tickets so that groups start in a
 // topological order of the group graph: a group only ever waits for groups that are already running.
-constexpr int kSweepThreads = 32 * (2 + kNH); // consumer + producers + loader
-template <int MODE>
+constexpr int kSweepThreads = 32 * kSweepWarps;
+template <int MODE, bool STATS>
 __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(PipeDev S, const double* __restrict__ a, const double* __restrict__ b,
                                                           double* out, unsigned* ticket, unsigned ticketBase, int* err,
                                                           const DevScalars* sc, int force)
@@ -1043,8 +1181,8 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(PipeDev S, const dou
     if ((int)t >= S.nGroups) return;
     const int g = S.order ? S.order[t] : (int)t;
     if (S.gFast[g])
-        sweep_group_split<MODE>(S, g, warp, lane, a, b, out, err, smem);
-    else if (warp == 0)
+        sweep_group_split<MODE, STATS>(S, g, warp, lane, a, b, out, err, smem);
+    else if (sweep_role(warp) == kRoleConsumer)
         sweep_group_generic<MODE>(S, g, lane, a, b, out, err, smem);
 }
 

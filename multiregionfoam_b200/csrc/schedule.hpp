@@ -834,8 +834,18 @@ struct PipeSchedule
                     for (int r = 0; r < 6; r++) m |= uint64_t(bytes[r]) << (8 * r);
                     meta[lane] = m;
                 }
+                // bit 57: every shuffled term of this step reads the linked neighbour lane (lane - dir): the consumer
+                // then issues one shuffle per step instead of one per term
+                bool linked = true;
                 for (int lane = 0; lane < 32; lane++)
-                    meta[lane] |= (uint64_t(Rt) << 48) | (uint64_t(canonical ? 0 : 1) << 56);
+                    for (int r = 0; r < 6; r++)
+                    {
+                        const unsigned byte = unsigned(meta[lane] >> (8 * r)) & 0xffu;
+                        if (!(byte & (kMetaConst | kMetaOwn | kMetaPad)) && (lane - dir < 0 || lane - dir > 31 || int(byte & kMetaLane) != lane - dir))
+                            linked = false;
+                    }
+                for (int lane = 0; lane < 32; lane++)
+                    meta[lane] |= (uint64_t(Rt) << 48) | (uint64_t(canonical ? 0 : 1) << 56) | (uint64_t(linked ? 1 : 0) << 57);
                 if (!canonical) D.nGeneralSteps++;
             }
         }

@@ -49,6 +49,7 @@ class Perf(C.Structure):
 
 
 _lib = None
+SWEEP_STATS_STRIDE = 16 + 8 * 142  # kStatsStride of csrc/kernels.cuh: 16 totals + 8 time stamps per traced block
 
 
 def load():
@@ -56,11 +57,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("B200_LDU_LIB", LIB_PATH)  # developer knob: compare differently compiled builds
+    if not os.path.exists(path):
         raise FileNotFoundError(
-            f"{LIB_PATH} not built: run __graft_entry__.build() / python -m multiregionfoam_b200.build "
+            f"{path} not built: run __graft_entry__.build() / python -m multiregionfoam_b200.build "
             "(the CUDA library is the only compute path; there is no CPU fallback)")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     vp, ip, dp = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double)
     dpp = C.POINTER(dp)
     L.b200_nccl_unique_id.argtypes = [vp]
@@ -335,10 +337,12 @@ class LduSystem:
 
     def sweep_stats(self, direction: int, enable: bool = True) -> np.ndarray:
         """Debug counters of the sweep kernel per group, 16 columns: consumer {cycles, wait cycles, start ns, end ns},
-        producer polls, nT, general blocks, blocks, producer 0 {cycles, stage-wait, value-wait, spin cycles}, -;
+        producer polls, nT, general blocks, blocks, producer 0 {cycles, stage-wait, value-wait, spin cycles}, -; then per
+        block 8 clock64 stamps: consumer {ready seen, done}, loader issue, producer 0 {step start, next stage landed,
+        values checked, delivered}, producer 7 delivered;
         returns what the sweeps since the previous call recorded and (re)arms."""
         n = self.ctx.check(load().b200_debug_sweep_stats(self.h, direction, 0, None, 0))
-        out = np.zeros((max(n, 1), 16), dtype=np.int64)
+        out = np.zeros((max(n, 1), SWEEP_STATS_STRIDE), dtype=np.int64)
         self.ctx.check(load().b200_debug_sweep_stats(self.h, direction, int(enable), out.ctypes.data_as(C.POINTER(C.c_longlong)), out.size))
         return out[:n]
 
