@@ -14,6 +14,8 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <map>
+#include <tuple>
 #include <vector>
 
 #include "kernels.cuh"
@@ -517,7 +519,19 @@ static int upload_pipe_dir(b200_sys* s, const PipeSchedule& S, const PipeSchedul
     M.dev.pFace = M.pFace.p;
     M.dev.cFace = M.cFace.p;
     M.dev.stats = nullptr;
+    M.dev.l2Ahead = getenv("B200_SWEEP_L2AHEAD") ? std::max(0, atoi(getenv("B200_SWEEP_L2AHEAD"))) : kL2Ahead;
     M.dev.debugFlags = getenv("B200_SWEEP_DEBUG") ? atoi(getenv("B200_SWEEP_DEBUG")) : 0;
+    if (getenv("B200_SWEEP_INFO"))
+    { // developer print: shape of the split streams
+        std::map<std::tuple<int, int, int, int>, int> hist;
+        for (int g = 0; g < S.nGroups; g++) hist[std::make_tuple((int)D.gFast[g], D.gLg[g], D.gRg[g], D.gKg[g])]++;
+        fprintf(stderr, "[b200] sweep dir %+d: %d groups, %lld non-canonical steps (%lld linked, %lld dual), stage %d B x %d;", dir, S.nGroups,
+                (long long)D.nGeneralSteps, (long long)D.nLinkedGeneralSteps, (long long)D.nDualSteps, stageBytes, nStages);
+        for (auto& kv : hist)
+            fprintf(stderr, " fast=%d Lg=%d Rg=%d Kg=%d: %d groups;", std::get<0>(kv.first), std::get<1>(kv.first), std::get<2>(kv.first),
+                    std::get<3>(kv.first), kv.second);
+        fprintf(stderr, "\n");
+    }
     M.packed[0] = M.packed[1] = false;
     M.haveT = false;
     return B200_OK;
@@ -836,7 +850,8 @@ static int launch_sweep(b200_sys* s, PipeDirMem& M, PipeDev dev, const double* a
     if (s->nGroups == 0) return B200_OK;
     dev.stats = M.dev.stats;
     KScope k(s, dev.dir > 0 ? B200_K_SWEEP_FWD : B200_K_SWEEP_BWD);
-    if (dev.stats) // debug counters and time stamps: a separately compiled instantiation, the product path carries none
+    if (dev.stats && !(dev.debugFlags & 2)) // debug counters and time stamps: a separately compiled instantiation, the product path carries none
+                                           // (debug flag 2: the product instantiation, recording only each group's start / end time)
         k_sweep<MODE, true><<<s->nGroups, kSweepThreads, M.smemBytes, ctx->stream>>>(dev, a, b, out, s->ticket.p, s->ticketBase, s->devErr.p,
                                                                                     s->sc.p, force);
     else

@@ -53,6 +53,35 @@ enum ScalarOp
 };
 
 __device__ __forceinline__ double sentinel() { return __longlong_as_double((long long)B200_SENTINEL_BITS); }
+// L2 residency hints.  The sweeps exchange cross-group values through their output vector: a group polls slots
+// that were pre-filled with the sentinel by the vector kernel BEFORE the sweep, and the sweep then streams ~300 MB
+// (coefficient streams, input vectors) through the 126 MB L2.  Without hints the sentinel lines are the oldest
+// lines in L2 and are evicted first, so that the first touch of a not-yet-written slot goes to DRAM - on the
+// dependent path of every group that runs right behind its predecessor.  The fills are therefore stored evict_last
+// and the streams are loaded evict_first.
+#ifndef B200_L2_HINTS
+#define B200_L2_HINTS 1
+#endif
+__device__ __forceinline__ unsigned long long l2_evict_last()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_evict_first()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void st_keep(double* p, double v, unsigned long long pol)
+{
+#if B200_L2_HINTS == 1
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+#else
+    *p = v;
+#endif
+}
 __device__ __forceinline__ bool is_sentinel(double v)
 {
     return (unsigned long long)__double_as_longlong(v) == B200_SENTINEL_BITS;
@@ -424,6 +453,7 @@ struct PipeDev
     unsigned char* cStream;
     const int* pFace;
     const int* cFace;
+    int l2Ahead;      // blocks the L2 prefetch runs ahead of the stage fill
     int debugFlags;   // bit 0: consumer always takes the general (descriptor-driven) path (debug)
     long long* stats; // optional [8 * nGroups]: consumer cycles, wait cycles, start ns, end ns, producer polls, nT, general blocks, blocks (debug)
 };
@@ -477,6 +507,18 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+// streamed once: evict_first (see B200_L2_HINTS)
+__device__ __forceinline__ void bulk_g2s_stream(void* dst, const void* src, unsigned bytes, unsigned long long* bar, unsigned long long pol)
+{
+#if B200_L2_HINTS
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                 : "memory");
+#else
+    bulk_g2s(dst, src, bytes, bar);
+#endif
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
 {
@@ -565,7 +607,7 @@ constexpr int kTraceBlocks = 142; // debug: per-block time stamps (clock64 of th
 constexpr int kStatsStride = 16 + 8 * kTraceBlocks; // debug counters per group: 16 totals, then per block 8 stamps:
 // consumer {ready seen, done}, loader issue, producer 0 {step start, next stage landed, values checked, delivered},
 // producer 7 delivered
-constexpr int kL2Ahead = 8;      // blocks the L2 prefetch runs ahead of the stage fill
+constexpr int kL2Ahead = 4;      // default number of blocks the L2 prefetch runs ahead of the stage fill (PipeDev::l2Ahead)
 
 // Flag words in shared memory.  A formal release/acquire pair costs a MEMBAR.ALL.CTA on the releasing side, which
 // also waits for the warp's outstanding GLOBAL accesses (the consumer's st.cg results, the producers' prefetches
@@ -599,11 +641,16 @@ struct SplitCtx
     unsigned* done;             // blocks the consumer has finished
     unsigned char* stages;
     const unsigned char *pStream, *cStream;
+    unsigned long long polStream; // L2 evict_first policy of the streamed operands
 };
 
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes, unsigned long long pol)
 {
+#if B200_L2_HINTS
+    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(pol) : "memory");
+#else
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+#endif
 }
 
 // Pull the records and input vectors of block blk into L2 well ahead of the stage fill, so that the fill itself
@@ -614,11 +661,11 @@ __device__ __forceinline__ void split_prefetch(const SplitCtx& C, const double* 
 {
     constexpr int dir = MODE == 1 ? -1 : 1;
     if (blk >= C.nBlocks) return;
-    if (C.pBytes) bulk_prefetch_l2(C.pStream + (size_t)blk * C.pBytes, C.pBytes);
-    bulk_prefetch_l2(C.cStream + (size_t)blk * C.cBytes, C.cBytes);
+    if (C.pBytes) bulk_prefetch_l2(C.pStream + (size_t)blk * C.pBytes, C.pBytes, C.polStream);
+    bulk_prefetch_l2(C.cStream + (size_t)blk * C.cBytes, C.cBytes, C.polStream);
     const long long s0 = dir > 0 ? ((long long)C.base + (long long)blk * kNH) * 32 : ((long long)C.base + C.nT - (long long)(blk + 1) * kNH) * 32;
-    bulk_prefetch_l2(a + s0, kNH * 256);
-    if (MODE == 0) bulk_prefetch_l2(b + s0, kNH * 256);
+    bulk_prefetch_l2(a + s0, kNH * 256, C.polStream);
+    if (MODE == 0) bulk_prefetch_l2(b + s0, kNH * 256, C.polStream);
 }
 
 template <int MODE>
@@ -627,11 +674,11 @@ __device__ __forceinline__ void split_issue(const SplitCtx& C, const double* a, 
     constexpr int dir = MODE == 1 ? -1 : 1;
     unsigned char* dst = C.stages + (size_t)st * C.stageBytes;
     mbar_expect_tx(&C.rawBar[st], C.rawBytes);
-    bulk_g2s(dst, C.cStream + (size_t)blk * C.cBytes, C.cBytes, &C.rawBar[st]);
-    if (C.pBytes) bulk_g2s(dst + C.offP, C.pStream + (size_t)blk * C.pBytes, C.pBytes, &C.rawBar[st]);
+    bulk_g2s_stream(dst, C.cStream + (size_t)blk * C.cBytes, C.cBytes, &C.rawBar[st], C.polStream);
+    if (C.pBytes) bulk_g2s_stream(dst + C.offP, C.pStream + (size_t)blk * C.pBytes, C.pBytes, &C.rawBar[st], C.polStream);
     const long long s0 = dir > 0 ? ((long long)C.base + (long long)blk * kNH) * 32 : ((long long)C.base + C.nT - (long long)(blk + 1) * kNH) * 32;
-    bulk_g2s(dst + C.offA, a + s0, kNH * 256, &C.rawBar[st]);
-    if (MODE == 0) bulk_g2s(dst + C.offA + kNH * 256, b + s0, kNH * 256, &C.rawBar[st]);
+    bulk_g2s_stream(dst + C.offA, a + s0, kNH * 256, &C.rawBar[st], C.polStream);
+    if (MODE == 0) bulk_g2s_stream(dst + C.offA + kNH * 256, b + s0, kNH * 256, &C.rawBar[st], C.polStream);
 }
 
 // ------------------------------------------------------------------------------------------ consumer
@@ -707,6 +754,46 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
                 push(acc);
             }
         }
+        else if ((c & 0xff00u) == 0u && !forceGeneral)
+        {
+            // Blocks with DUAL steps (schedule.hpp): every lane is in canonical form or in seam form (own-lane term first,
+            // then cval 0, then a shuffled value or a cval).  Both forms are evaluated from the same operands, the lane's
+            // flag selects; what sits on the dependent chain is one multiply and three subtractions.
+            nGeneral++;
+#pragma unroll 1
+            for (int q0 = 0; q0 < kNH; q0 += 4)
+            {
+                unsigned fl[4];
+                double a0[4], c0[4], c1[4], c2[4], cv0[4], cv1[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                {
+                    const int q = q0 + u;
+                    fl[u] = *reinterpret_cast<const unsigned*>(sb + q * 256 + 4) >> 26; // meta bits 58..: seam form, selB
+                    a0[u] = *reinterpret_cast<const double*>(hd + q * 256);
+                    c0[u] = *reinterpret_cast<const double*>(sb + PL + q * 256);
+                    c1[u] = *reinterpret_cast<const double*>(sb + 2 * PL + q * 256);
+                    c2[u] = RG > 2 ? *reinterpret_cast<const double*>(sb + 3 * PL + q * 256) : 0.0;
+                    cv0[u] = Kg > 0 ? *reinterpret_cast<const double*>(hd + PL + q * 256) : 0.0;
+                    cv1[u] = Kg > 1 ? *reinterpret_cast<const double*>(hd + 2 * PL + q * 256) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                {
+                    const double sh = __shfl_sync(FULL, h[kSkew - 1], srcLane);
+                    const bool seam = fl[u] & 1u;
+                    const unsigned selB = (fl[u] >> 1) & 3u;
+                    const double vB = selB == 2u ? cv1[u] : (selB == 1u ? cv0[u] : sh);
+                    const double pSh = c0[u] * sh, pA = c2[u] * cv0[u], pB = c0[u] * vB;
+                    const double pOwn = c1[u] * h[0];
+                    const double nrm = (a0[u] - pSh) - pOwn;
+                    const double sm = ((a0[u] - pOwn) - pA) - pB;
+                    const double acc = seam ? sm : nrm;
+                    st_relaxed(outPtr + (q0 + u) * outStride, acc);
+                    push(acc);
+                }
+            }
+        }
         else
         {
             // Blocks with a non-canonical step (block seams: the own-lane term comes first in the reference order and
@@ -736,9 +823,17 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
                 for (int u = 0; u < HW; u++)
                 {
                     double acc = a0[u];
-                    if ((meta[u] >> 57) & 1ull)
-                    { // warp-uniform: all shuffled terms of this step read the linked lane
-                        const double sh = __shfl_sync(FULL, h[kSkew - 1], srcLane);
+                    // the linked-lane shuffle is issued by all lanes before any branch (a dual step splits the lanes)
+                    const double sh = __shfl_sync(FULL, h[kSkew - 1], srcLane);
+                    if ((meta[u] >> 58) & 1ull)
+                    { // seam-form lane of a dual step (only calcReciprocalD and the debug mode get here): planes 1, 2, 0
+                        const unsigned selB = (unsigned)(meta[u] >> 59) & 3u;
+                        acc = sweep_apply<MODE>(acc, cf[u][1], h[0]);
+                        if (RG > 2 && !((meta[u] >> 16) & kMetaPad)) acc = sweep_apply<MODE>(acc, cf[u][RG > 2 ? 2 : 0], cv0[u]);
+                        if (!(meta[u] & kMetaPad)) acc = sweep_apply<MODE>(acc, cf[u][0], selB == 2u ? cv1[u] : (selB == 1u ? cv0[u] : sh));
+                    }
+                    else if ((meta[u] >> 57) & 1ull)
+                    { // all shuffled terms of this step read the linked lane (dual steps always do)
 #pragma unroll
                         for (int r = 0; r < RG; r++)
                         {
@@ -754,12 +849,13 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
                         for (int r = 0; r < RG; r++)
                         {
                             const unsigned byte = (unsigned)(meta[u] >> (8 * r)) & 0xffu;
-                            const double sh = __shfl_sync(FULL, h[kSkew - 1], (int)(byte & kMetaLane));
-                            double v = (byte & kMetaConst) ? ((byte & 0x20u) ? cv1[u] : cv0[u]) : ((byte & kMetaOwn) ? h[0] : sh);
+                            const double shr = __shfl_sync(FULL, h[kSkew - 1], (int)(byte & kMetaLane));
+                            double v = (byte & kMetaConst) ? ((byte & 0x20u) ? cv1[u] : cv0[u]) : ((byte & kMetaOwn) ? h[0] : shr);
                             if (byte & kMetaPad) v = MODE == 2 ? 1.0 : 0.0; // padding term (coefficient 0)
                             acc = sweep_apply<MODE>(acc, cf[u][r], v);
                         }
                     }
+                    __syncwarp();
                     st_relaxed(outPtr + (q0 + u) * outStride, acc);
                     push(acc);
                 }
@@ -857,11 +953,15 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
     // sets swap roles, so that no register copy (which would wait for the prefetch to land) sits in the loop
     int codesA[LGA], codesB[LGA], ccA[2], ccB[2];
     double mvA[LGA], mvB[LGA], mcA[2], mcB[2];
-    auto fetch = [&](const unsigned sg, int* cd, double* vals, int* kc, double* kv) {
+    // codes of a step's cross-group terms (from the landed stage), and the loads of their values: issued separately,
+    // see the order of a step below
+    auto fetch_codes = [&](const unsigned sg, int* cd, int* kc) {
 #pragma unroll
         for (int i = 0; i < LG; i++) cd[i] = lds_s32(sg + offCode + i * 128);
 #pragma unroll
         for (int k = 0; k < 2; k++) kc[k] = (k < Kg) ? lds_s32(sg + offConst + k * 128) : -1;
+    };
+    auto fetch_values = [&](const int* cd, double* vals, const int* kc, double* kv) {
 #pragma unroll
         for (int i = 0; i < LG; i++)
         {
@@ -888,7 +988,8 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
         double cf[LGA];
 #pragma unroll
         for (int i = 0; i < LG; i++) cf[i] = lds_f64(sg + offCoef + i * 256);
-        const unsigned general = MODE == 2 ? 1u : (lds_u8(sg + offGen) & 1u);
+        const unsigned b7 = lds_u8(sg + offGen); // bit 0: descriptor-driven step, bit 5: dual step (schedule.hpp)
+        const unsigned stepKind = MODE == 2 ? 0x100u : (((b7 & 1u) << 8) | ((b7 & 0x20u) << 11));
         // ---- prefetch the codes / cross-group values of this producer's step in the next block
         unsigned sgN = sg + stageBytes, barN = bar + 8u, parN = par;
         if (sgN == stageEnd)
@@ -904,7 +1005,7 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
             mbar_wait_u32(barN, parN);
             if (timed) tStage += clock64() - w0;
             if (STATS && tr && h == 0) tr[4] = clock64();
-            fetch(sgN, codesN, mvN, ccN, mcN);
+            fetch_codes(sgN, codesN, ccN);
         }
         if (MODE == 0) acc *= bb;
         // ---- the (possibly late) cross-group values
@@ -919,9 +1020,8 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
         if (STATS && tr && h == 0) tr[5] = v1;
         if (anyBad)
         { // a value had not arrived when it was prefetched: poll for it.  A group that runs right behind the group
-          // it depends on gets here in every block: every polling round therefore re-reads, in one batch of
-          // independent loads, whatever is missing of this block AND of the next one, so that a producer falls straight
-          // through the next block when its values arrived in the meantime.
+          // it depends on gets here in every block; a polling round re-reads, in one batch of independent loads, whatever
+          // is still missing of this block.
             if (STATS && lane == 0) atomicAdd((unsigned long long*)(S.stats + (long long)kStatsStride * g + 4), 1ull);
             int tries = 0;
             bool still;
@@ -933,15 +1033,6 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
 #pragma unroll
                 for (int k = 0; k < 2; k++)
                     if (cc[k] >= 0 && is_sentinel(mc[k])) mc[k] = ld_relaxed(out + cc[k]);
-                if (haveNext)
-                {
-#pragma unroll
-                    for (int i = 0; i < LG; i++)
-                        if (codesN[i] >= 0 && is_sentinel(mvN[i])) mvN[i] = ld_relaxed(out + codesN[i]);
-#pragma unroll
-                    for (int k = 0; k < 2; k++)
-                        if (ccN[k] >= 0 && is_sentinel(mcN[k])) mcN[k] = ld_relaxed(out + ccN[k]);
-                }
                 still = false;
 #pragma unroll
                 for (int i = 0; i < LG; i++) still |= codes[i] >= 0 && is_sentinel(mv[i]);
@@ -973,9 +1064,14 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
         if (Kg > 0) sts_f64(sg + offHd + kNH * 256, mc[0]);
         if (Kg > 1) sts_f64(sg + offHd + 2 * kNH * 256, mc[1]);
         __syncwarp();
-        if (lane == 0) asm volatile("red.relaxed.cta.shared.add.u32 [%0], %1;" ::"r"(cnt), "r"(1u + (general << 8)) : "memory");
+        if (lane == 0) asm volatile("red.relaxed.cta.shared.add.u32 [%0], %1;" ::"r"(cnt), "r"(1u + stepKind) : "memory");
         if (STATS && tr && h == 0) tr[6] = clock64();
         if (STATS && tr && h == kNH - 1) tr[7] = clock64();
+        // ---- only now the loads of the next block's cross-group values.  ptxas tracks all of these loads with ONE
+        // scoreboard (checked in the SASS), so a check of older values also waits for whatever was issued since: issued
+        // here, the loads are the only ones outstanding at the next check, and their flight overlaps the loop back, the
+        // operand loads and the wait for the stage after next.
+        if (haveNext) fetch_values(codesN, mvN, ccN, mcN);
         cnt = (sgN == stage0) ? cnt0 : cnt + 4u;
         sg = sgN;
         bar = barN;
@@ -983,7 +1079,8 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
     };
     (void)barEnd;
     mbar_wait_u32(bar0, 0u);
-    fetch(stage0, codesA, mvA, ccA, mcA);
+    fetch_codes(stage0, codesA, ccA);
+    fetch_values(codesA, mvA, ccA, mcA);
     for (int blk = 0; blk < C.nBlocks; blk += 2)
     {
         step(blk, codesA, mvA, ccA, mcA, codesB, mvB, ccB, mcB);
@@ -1039,6 +1136,7 @@ __device__ __forceinline__ void sweep_group_split(const PipeDev& S, const int g,
     C.stages = smem + 256;
     C.pStream = S.pStream + S.gPOff[g];
     C.cStream = S.cStream + S.gCOff[g];
+    C.polStream = l2_evict_first();
     if (threadIdx.x == 0)
     {
         for (int st = 0; st < C.NS; st++)
@@ -1049,7 +1147,7 @@ __device__ __forceinline__ void sweep_group_split(const PipeDev& S, const int g,
         *C.done = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int c = 0; c < C.NS && c < C.nBlocks; c++) split_issue<MODE>(C, a, b, c, c);
-        for (int c = C.NS; c < C.NS + kL2Ahead; c++) split_prefetch<MODE>(C, a, b, c);
+        for (int c = C.NS; c < C.NS + S.l2Ahead; c++) split_prefetch<MODE>(C, a, b, c);
     }
     __syncthreads();
     const int role = sweep_role(warp);
@@ -1076,7 +1174,7 @@ __device__ __forceinline__ void sweep_group_split(const PipeDev& S, const int g,
                 while (ld_flag_smem(C.done) < need) __nanosleep(20);
                 if (STATS && blk < kTraceBlocks) S.stats[(long long)kStatsStride * g + 16 + blk * 8 + 2] = clock64();
                 split_issue<MODE>(C, a, b, blk, st);
-                split_prefetch<MODE>(C, a, b, blk + kL2Ahead);
+                split_prefetch<MODE>(C, a, b, blk + S.l2Ahead);
                 if (++st == C.NS) st = 0;
             }
         }
@@ -1180,10 +1278,17 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(PipeDev S, const dou
     if (sc->done && !force) return;
     if ((int)t >= S.nGroups) return;
     const int g = S.order ? S.order[t] : (int)t;
+    const bool stamp = !STATS && S.stats != nullptr && threadIdx.x == 0; // debug flag 2: start / end of the group only
+    if (stamp) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(S.stats[(long long)kStatsStride * g + 2]));
     if (S.gFast[g])
         sweep_group_split<MODE, STATS>(S, g, warp, lane, a, b, out, err, smem);
     else if (sweep_role(warp) == kRoleConsumer)
         sweep_group_generic<MODE>(S, g, lane, a, b, out, err, smem);
+    if (stamp)
+    { // thread 0 is the consumer's lane 0: the group's last result has been stored
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(S.stats[(long long)kStatsStride * g + 3]));
+        S.stats[(long long)kStatsStride * g + 5] = S.gNT[g];
+    }
 }
 
 // Fill the coefficient part of a sweep stream from the face coefficients (once per solve).
@@ -1273,10 +1378,11 @@ __global__ void k_fill2_sentinel(size_t n, double* __restrict__ a, double* __res
 {
     if (sc->done && !force) return;
     const double s = sentinel();
+    const unsigned long long keep = l2_evict_last();
     B200_GRID_STRIDE(i, n)
     {
-        a[i] = s;
-        if (b) b[i] = s;
+        st_keep(a + i, s, keep);
+        if (b) st_keep(b + i, s, keep);
     }
 }
 __global__ void k_fill_xref(size_t n, double* __restrict__ a, const DevScalars* sc)
@@ -1356,13 +1462,14 @@ __global__ void __launch_bounds__(256) k_bicg_p(size_t n, const double* __restri
     const double beta = sc->beta, bo = sc->betaOmega;
     const int restart = sc->restart;
     const double sen = sentinel();
+    const unsigned long long keep = l2_evict_last();
     double d[1] = {0.0};
     B200_GRID_STRIDE(i, n)
     {
         const double ri = r[i];
         p[i] = ri + beta * p[i] - bo * v[i];
-        if (fillA) fillA[i] = sen;
-        if (fillB) fillB[i] = sen;
+        if (fillA) st_keep(fillA + i, sen, keep);
+        if (fillB) st_keep(fillB + i, sen, keep);
         d[0] += ri * ri;
         if (restart) rw[i] = ri;
     }
@@ -1378,11 +1485,12 @@ __global__ void __launch_bounds__(256) k_bicg_s(size_t n, const double* __restri
     if (sc->done) return;
     const double alpha = sc->alpha;
     const double sen = sentinel();
+    const unsigned long long keep = l2_evict_last();
     B200_GRID_STRIDE(i, n)
     {
         s[i] = r[i] - alpha * v[i];
-        if (fillA) fillA[i] = sen;
-        if (fillB) fillB[i] = sen;
+        if (fillA) st_keep(fillA + i, sen, keep);
+        if (fillB) st_keep(fillB + i, sen, keep);
     }
 }
 
@@ -1471,6 +1579,7 @@ __global__ void __launch_bounds__(256) k_pcg_xr(size_t n, double* __restrict__ x
     if (sc->done) return;
     const double alpha = sc->alpha;
     const double sen = sentinel();
+    const unsigned long long keep = l2_evict_last();
     double d[1] = {0.0};
     B200_GRID_STRIDE(i, n)
     {
@@ -1478,8 +1587,8 @@ __global__ void __launch_bounds__(256) k_pcg_xr(size_t n, double* __restrict__ x
         const double ri = rA[i] - alpha * wA[i];
         rA[i] = ri;
         d[0] += fabs(ri);
-        if (fillA) fillA[i] = sen;
-        if (fillB) fillB[i] = sen;
+        if (fillA) st_keep(fillA + i, sen, keep);
+        if (fillB) st_keep(fillB + i, sen, keep);
     }
     block_reduce_store<1>(d, partials, pstride, blockIdx.x);
 }

@@ -160,7 +160,11 @@ struct PipeSchedule
         //      the REMAINING terms.  meta byte r < 6 describes the term of plane r: bits 0-4 source lane of a value
         //      shuffled from kSkew steps ago, kMetaOwn = own-lane value of the previous step, kMetaPad = padding
         //      (coefficient 0), kMetaConst = the value of constCode[bit 5]; byte 6 = number of planes in use;
-        //      byte 7 bit 0 = the step is not canonical (uniform over the lanes, see build_split).
+        //      byte 7 bit 0 = the step needs the descriptor-driven path (uniform over the lanes, see build_split);
+        //      bit 1 = every shuffled term of the step reads the linked lane; bit 5 = DUAL step (uniform): every lane is
+        //      either in canonical form or in SEAM form - own-lane term FIRST, then up to two more terms - flagged per
+        //      lane by bit 2, its planes then hold: 1 = own, 2 = first of two trailing terms (always cval 0), 0 = last
+        //      trailing term, whose value bits 3-4 select (0 shuffled from the linked lane, 1 cval 0, 2 cval 1).
         std::vector<uint8_t> gFast;
         std::vector<int32_t> gLg, gRg, gKg;
         std::vector<int64_t> gPOff, gCOff;           // [nGroups+1] byte offsets into pStream / cStream
@@ -171,6 +175,8 @@ struct PipeSchedule
         int64_t nGenTerms = 0;
         int maxPStage = 0, maxCStep = 0, maxGenStage = 0, maxFastStage = 0, nFastGroups = 0;
         int64_t nGeneralSteps = 0; // steps of fast groups that are not canonical (see build_split)
+        int64_t nDualSteps = 0;          // ... of which dual (canonical / seam form per lane, meta bit 61)
+        int64_t nLinkedGeneralSteps = 0; // ... of which every shuffled term reads the linked lane (meta bit 57)
     } fwd, bwd;
 
     // statistics
@@ -691,6 +697,8 @@ struct PipeSchedule
         D.gGenOff.assign(nG + 1, 0);
         D.maxPStage = D.maxCStep = D.maxGenStage = D.maxFastStage = D.nFastGroups = 0;
         D.nGeneralSteps = 0;
+        D.nLinkedGeneralSteps = 0;
+        D.nDualSteps = 0;
         // pass 1: eligibility, Lg, Rg
         for (int gI = 0; gI < nG; gI++)
         {
@@ -783,6 +791,47 @@ struct PipeSchedule
                     if (j != nTerms) canonical = false;
                 }
                 if (canonical) Rt = 2;
+                // DUAL step: not canonical, but every lane is in canonical form or in seam form (block seams of a
+                // multi-block mesh: the i-1 neighbour lies in the previous mesh block and has the lowest column, so
+                // the own-lane term comes first: own, k-1, j-1).  The skew of the lanes spreads one seam over 62
+                // steps, so these steps deserve a descriptor-free evaluation of their own.
+                bool dual = false;
+                int formOf[32], idxA[32], idxB[32];
+                if (!canonical)
+                {
+                    dual = true;
+                    for (int lane = 0; lane < 32 && dual; lane++)
+                    {
+                        const int64_t b0 = D.gTermOff[gI] + int64_t(step) * W * 32 + lane;
+                        const int ld = ldOf[lane], nTerms = nOf[lane];
+                        auto codeAt = [&](int j) { return D.code[b0 + int64_t(j) * 32]; };
+                        auto linkedShfl = [&](int32_t c) { return lane - dir >= 0 && lane - dir < 32 && c == kCodeShfl - (lane - dir); };
+                        formOf[lane] = 0;
+                        idxA[lane] = idxB[lane] = -1;
+                        int j = ld;
+                        if (j < nTerms && linkedShfl(codeAt(j))) j++;
+                        if (j < nTerms && codeAt(j) == kCodeOwn) j++;
+                        if (j == nTerms) continue; // canonical form
+                        j = ld;
+                        if (!(j < nTerms && codeAt(j) == kCodeOwn))
+                        {
+                            dual = false;
+                            break;
+                        }
+                        j++;
+                        int t[2], nt = 0;
+                        while (j < nTerms && nt < 2 && (codeAt(j) >= 0 || linkedShfl(codeAt(j)))) t[nt++] = j++;
+                        if (j != nTerms || (nt == 2 && (codeAt(t[0]) < 0 || Rg < 3))) dual = false;
+                        formOf[lane] = 1;
+                        if (nt == 2)
+                        {
+                            idxA[lane] = t[0];
+                            idxB[lane] = t[1];
+                        }
+                        else if (nt == 1)
+                            idxB[lane] = t[0];
+                    }
+                }
                 for (int lane = 0; lane < 32; lane++)
                 {
                     const int64_t b0 = D.gTermOff[gI] + int64_t(step) * W * 32 + lane;
@@ -810,7 +859,26 @@ struct PipeSchedule
                     };
                     unsigned bytes[6];
                     for (int r = 0; r < 6; r++) bytes[r] = unsigned(lane) | kMetaPad; // padding: coefficient 0
-                    if (canonical)
+                    uint64_t laneFlags = 0;
+                    if (dual && formOf[lane] == 1)
+                    { // seam form: own | A | B in reference order -> planes 1 | 2 | 0
+                        bytes[1] = describe(ld);
+                        cFaceRow[32] = D.face[b0 + int64_t(ld) * 32];
+                        if (idxA[lane] >= 0)
+                        {
+                            bytes[2] = describe(idxA[lane]); // a cross-group value: becomes cval 0
+                            cFaceRow[64] = D.face[b0 + int64_t(idxA[lane]) * 32];
+                        }
+                        uint64_t selB = 0;
+                        if (idxB[lane] >= 0)
+                        {
+                            if (D.code[b0 + int64_t(idxB[lane]) * 32] >= 0) selB = nc ? 2 : 1;
+                            bytes[0] = describe(idxB[lane]);
+                            cFaceRow[0] = D.face[b0 + int64_t(idxB[lane]) * 32];
+                        }
+                        laneFlags = (uint64_t(1) << 58) | (selB << 59);
+                    }
+                    else if (canonical || dual)
                     {
                         int j = ld;
                         if (j < nTerms && D.code[b0 + int64_t(j) * 32] != kCodeOwn)
@@ -832,7 +900,7 @@ struct PipeSchedule
                             cFaceRow[int64_t(r) * 32] = D.face[b0 + int64_t(ld + r) * 32];
                         }
                     for (int r = 0; r < 6; r++) m |= uint64_t(bytes[r]) << (8 * r);
-                    meta[lane] = m;
+                    meta[lane] = m | laneFlags;
                 }
                 // bit 57: every shuffled term of this step reads the linked neighbour lane (lane - dir): the consumer
                 // then issues one shuffle per step instead of one per term
@@ -845,8 +913,11 @@ struct PipeSchedule
                             linked = false;
                     }
                 for (int lane = 0; lane < 32; lane++)
-                    meta[lane] |= (uint64_t(Rt) << 48) | (uint64_t(canonical ? 0 : 1) << 56) | (uint64_t(linked ? 1 : 0) << 57);
+                    meta[lane] |= (uint64_t(Rt) << 48) | (uint64_t(canonical || dual ? 0 : 1) << 56) | (uint64_t(linked ? 1 : 0) << 57) |
+                                  (uint64_t(dual ? 1 : 0) << 61);
                 if (!canonical) D.nGeneralSteps++;
+                if (!canonical && linked) D.nLinkedGeneralSteps++;
+                if (dual) D.nDualSteps++;
             }
         }
     }

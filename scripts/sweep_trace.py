@@ -10,8 +10,12 @@ nx, ny, nz, grp = [int(a) for a in sys.argv[1:5]]
 first = int(sys.argv[5]) if len(sys.argv) > 5 else 40
 n = int(sys.argv[6]) if len(sys.argv) > 6 else 24
 ctx = ldu.Context(0)
-m = StructuredRegion("box", [Block(nx, 0.0, 1.0, 1.0)], ny=ny, nz=nz, y0=0.0, y1=1.0, grady=1.0).build()
-case = single_region_case(synthetic_coeffs(m.nCells, m.lowerAddr, m.upperAddr, symmetric=False))
+if nx == 0:  # C2
+    from multiregionfoam_b200.assembly import cht_case
+    case = cht_case(3, 22)[0]
+else:
+    m = StructuredRegion("box", [Block(nx, 0.0, 1.0, 1.0)], ny=ny, nz=nz, y0=0.0, y1=1.0, grady=1.0).build()
+    case = single_region_case(synthetic_coeffs(m.nCells, m.lowerAddr, m.upperAddr, symmetric=False))
 S = ldu.LduSystem(ctx, case.ranks[0])
 r = np.random.default_rng(0).standard_normal(S.nCells)
 for _ in range(3):

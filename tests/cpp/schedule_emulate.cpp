@@ -62,6 +62,52 @@ int walk(const PipeSchedule& S, const PipeSchedule::Dir& D, int dir, int mode, c
                     const bool general = (meta >> 56) & 1;
                     if (Rt > Rg) return -21;
                     const double acc0 = acc;
+                    const bool dualStep = (meta >> 61) & 1, seamLane = (meta >> 58) & 1;
+                    if (seamLane && !dualStep) return -27;
+                    if (dualStep && general) return -28;
+                    if (seamLane)
+                    {
+                        // seam form of a dual step: reference order own | A | B lives in planes 1 | 2 | 0
+                        const unsigned selB = unsigned(meta >> 59) & 3u;
+                        const int32_t fB = D.cFace[D.gCFaceOff[g] + (int64_t(step) * Rg + 0) * 32 + lane];
+                        const int32_t fO = D.cFace[D.gCFaceOff[g] + (int64_t(step) * Rg + 1) * 32 + lane];
+                        const int32_t fA = Rg > 2 ? D.cFace[D.gCFaceOff[g] + (int64_t(step) * Rg + 2) * 32 + lane] : -1;
+                        if (fO < 0 || acc != (mode == 0 ? a[slot] * b[slot] : a[slot])) return -29; // no leading terms before the own-lane term
+                        auto sub = [&](int32_t f, double v) { acc = mode == 2 ? acc - coefOf(f, slot) / v : acc - coefOf(f, slot) * v; };
+                        sub(fO, prev[lane]);
+                        if (fA >= 0)
+                        {
+                            const int32_t pc = pConstArr[lane];
+                            if (pc < 0 || out[pc] == NOTSET) return -30;
+                            sub(fA, out[pc]);
+                        }
+                        if (fB >= 0)
+                        {
+                            double v;
+                            if (selB == 0)
+                                v = prevS[(lane - dir) & 31];
+                            else
+                            {
+                                const int32_t pc = pConstArr[(selB - 1) * 32 + lane];
+                                if (pc < 0 || out[pc] == NOTSET) return -31;
+                                v = out[pc];
+                            }
+                            sub(fB, v);
+                        }
+                        else if (selB != 0)
+                            return -32;
+                        if (mode != 2)
+                        {
+                            // the consumer's select-free evaluation of the seam form must give the same bits
+                            const double cO = coefOf(fO, slot), cA = fA >= 0 ? coefOf(fA, slot) : 0.0, cB = fB >= 0 ? coefOf(fB, slot) : 0.0;
+                            const double cv0 = Kg > 0 && pConstArr[lane] >= 0 ? out[pConstArr[lane]] : 0.0;
+                            const double cv1 = Kg > 1 && pConstArr[32 + lane] >= 0 ? out[pConstArr[32 + lane]] : 0.0;
+                            const double vB = selB == 2 ? cv1 : (selB == 1 ? cv0 : prevS[(lane - dir) & 31]);
+                            const double fastAcc = ((acc0 - cO * prev[lane]) - cA * cv0) - cB * vB;
+                            if (std::memcmp(&fastAcc, &acc, 8) != 0 && !(fastAcc == 0.0 && acc == 0.0)) return -33;
+                        }
+                    }
+                    else
                     for (int r = 0; r < Rg; r++)
                     {
                         const unsigned byte = unsigned((meta >> (8 * r)) & 0xff);
@@ -85,7 +131,7 @@ int walk(const PipeSchedule& S, const PipeSchedule::Dir& D, int dir, int mode, c
                             v = prevS[byte & kMetaLane];
                         acc = mode == 2 ? acc - coefOf(f, slot) / v : acc - coefOf(f, slot) * v;
                     }
-                    if (!general && mode != 2)
+                    if (!general && !seamLane && mode != 2)
                     {
                         // the consumer's descriptor-free evaluation of a canonical step must give the same bits
                         const int32_t f0 = D.cFace[D.gCFaceOff[g] + (int64_t(step) * Rg + 0) * 32 + lane];
