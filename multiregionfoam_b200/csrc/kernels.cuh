@@ -1057,6 +1057,11 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
             if (blk == C.nBlocks / 2 && lane == 0)
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(S.stats[(long long)kStatsStride * g + 14]));
         }
+        // ---- only now the loads of the next block's cross-group values.  ptxas tracks all of these loads with ONE
+        // scoreboard (checked in the SASS), so a check of older values also waits for whatever was issued since: issued
+        // here - after the check, before the hand-over - the loads are the only ones outstanding at the next check, and
+        // their flight overlaps the hand-over, the loop back, the operand loads and the wait for the stage after next.
+        if (haveNext) fetch_values(codesN, mvN, ccN, mcN);
 #pragma unroll
         for (int i = 0; i < LG; i++) acc = sweep_apply<MODE>(acc, cf[i], mv[i]); // padding: coefficient 0, neutral value
         // ---- hand over: the hdr part of the stage is free because the stage was refilled after the consumer released it
@@ -1067,11 +1072,6 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
         if (lane == 0) asm volatile("red.relaxed.cta.shared.add.u32 [%0], %1;" ::"r"(cnt), "r"(1u + stepKind) : "memory");
         if (STATS && tr && h == 0) tr[6] = clock64();
         if (STATS && tr && h == kNH - 1) tr[7] = clock64();
-        // ---- only now the loads of the next block's cross-group values.  ptxas tracks all of these loads with ONE
-        // scoreboard (checked in the SASS), so a check of older values also waits for whatever was issued since: issued
-        // here, the loads are the only ones outstanding at the next check, and their flight overlaps the loop back, the
-        // operand loads and the wait for the stage after next.
-        if (haveNext) fetch_values(codesN, mvN, ccN, mcN);
         cnt = (sgN == stage0) ? cnt0 : cnt + 4u;
         sg = sgN;
         bar = barN;

@@ -73,12 +73,21 @@ def compare_solve(S, O, x0, b, solver, pre, **kw):
     _, ialt = O.solve(x0, b, solver, pre, **kw)
     O.set_reduction_mode(0)
     halt = ialt["history"][:k]
-    own = np.zeros_like(ho)
-    own[: halt.shape[0]] = 8.0 * np.abs(halt - ho[: halt.shape[0]])
+    # The amplification is cumulative (a perturbation of iteration i is carried by every later iteration) while the
+    # difference of two particular runs can pass through zero at any single iteration: the allowance of iteration k is
+    # therefore the running maximum of the RELATIVE own sensitivity up to k, not its value at k alone.
+    rel = np.zeros(ho.shape[0])
+    m = halt.shape[0]
+    rel[:m] = np.max(np.abs(halt - ho[:m]).reshape(m, -1) / (np.abs(ho[:m]).reshape(m, -1) + 1e-300), axis=1)
+    rel[m:] = rel[m - 1] if m else 0.0
+    # one pair of runs is a one-sample estimate of a chaotic amplification: 8 x for the preconditioned solves (as in the
+    # scalar tests), 16 x for the unpreconditioned stress case
+    own = (16.0 if pre == "none" else 8.0) * np.maximum.accumulate(rel).reshape((-1,) + (1,) * (ho.ndim - 1)) * np.abs(ho)
     allowed = np.maximum(HIST_RTOL * np.abs(ho), own) + 1e-15
     err = np.max(np.abs(hg - ho) / allowed) * HIST_RTOL
     # the plain north_star bound: 1e-10 relative (entries at the round-off level of the normalisation are compared
     # absolutely against that floor, as in the scalar tests); < 1 means inside the bound
+    ig["own_iter_spread"] = abs(int(ialt["nIterations"]) - int(io["nIterations"]))
     ig["plain_history_err"] = np.max(np.abs(hg - ho) / (HIST_RTOL * np.abs(ho) + 1e-15))
     return xo, io, xg, ig, err
 
@@ -95,7 +104,11 @@ def test_pu_bicgstab_history_and_field(gpu_ctx, golden_addr, name, pre):
         assert err <= HIST_RTOL, f"history rel err {err:.2e}"
         if pre == "Cholesky":  # the BASELINE configuration: the plain north_star bound, no sensitivity allowance
             assert ig["plain_history_err"] < 1.0, ig["plain_history_err"]
-        assert abs(ig["nIterations"] - io["nIterations"]) <= 1 + max(2, int(0.1 * io["nIterations"])) * (pre != "Cholesky")
+        # iteration counts: equal up to one for the BASELINE configuration; for the weaker preconditioners the count of an
+        # (almost) unpreconditioned BiCGStab depends on the summation order of the dot products - the allowance is what the
+        # reference itself shows between its two summation orders
+        slack = 0 if pre == "Cholesky" else max(2, int((0.25 if pre == "none" else 0.1) * io["nIterations"]), 2 * ig["own_iter_spread"])
+        assert abs(ig["nIterations"] - io["nIterations"]) <= 1 + slack
         assert ig["converged"]
         assert np.linalg.norm(xg - xo) / np.linalg.norm(xo) < FIELD_RTOL
         assert np.linalg.norm(xg - M.xstar) / np.linalg.norm(M.xstar) < 1e-7
