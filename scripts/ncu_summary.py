@@ -69,7 +69,7 @@ def traffic(path: str) -> None:
     head, units = rows[0], rows[1]
     idx = {n: i for i, n in enumerate(head)}
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    cls = {"k_sweep<0>": "sweep_fwd", "k_sweep<1>": "sweep_bwd", "k_amul": "amul", "k_bicg": "vector"}
+    cls = {"k_sweep<0": "sweep_fwd", "k_sweep<1": "sweep_bwd", "k_amul": "amul", "k_bicg": "vector"}
     agg = {}
     for r in rows[2:]:
         name = short(r[idx["Kernel Name"]])
