@@ -849,7 +849,8 @@ static int launch_sweep(b200_sys* s, PipeDirMem& M, PipeDev dev, const double* a
     b200_ctx* ctx = s->ctx;
     if (s->nGroups == 0) return B200_OK;
     dev.stats = M.dev.stats;
-    KScope k(s, dev.dir > 0 ? B200_K_SWEEP_FWD : B200_K_SWEEP_BWD);
+    // calcReciprocalD (MODE 2) is the once-per-solve preconditioner construction: accounted with the packing kernels
+    KScope k(s, MODE == 2 ? B200_K_PACK : (dev.dir > 0 ? B200_K_SWEEP_FWD : B200_K_SWEEP_BWD));
     if (dev.stats && !(dev.debugFlags & 2)) // debug counters and time stamps: a separately compiled instantiation, the product path carries none
                                            // (debug flag 2: the product instantiation, recording only each group's start / end time)
         k_sweep<MODE, true><<<s->nGroups, kSweepThreads, M.smemBytes, ctx->stream>>>(dev, a, b, out, s->ticket.p, s->ticketBase, s->devErr.p,

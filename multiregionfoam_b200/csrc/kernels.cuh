@@ -838,9 +838,10 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
                         for (int r = 0; r < RG; r++)
                         {
                             const unsigned byte = (unsigned)(meta[u] >> (8 * r)) & 0xffu;
-                            double v = (byte & kMetaConst) ? ((byte & 0x20u) ? cv1[u] : cv0[u]) : ((byte & kMetaOwn) ? h[0] : sh);
-                            if (byte & kMetaPad) v = MODE == 2 ? 1.0 : 0.0; // padding term (coefficient 0)
-                            acc = sweep_apply<MODE>(acc, cf[u][r], v);
+                            const double v = (byte & kMetaConst) ? ((byte & 0x20u) ? cv1[u] : cv0[u]) : ((byte & kMetaOwn) ? h[0] : sh);
+                            // padding terms are skipped: the reference has no such term, and calcReciprocalD's division is
+                            // ~100 instructions that a plane without a real term in any lane then never issues
+                            if (!(byte & kMetaPad)) acc = sweep_apply<MODE>(acc, cf[u][r], v);
                         }
                     }
                     else
@@ -850,9 +851,8 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
                         {
                             const unsigned byte = (unsigned)(meta[u] >> (8 * r)) & 0xffu;
                             const double shr = __shfl_sync(FULL, h[kSkew - 1], (int)(byte & kMetaLane));
-                            double v = (byte & kMetaConst) ? ((byte & 0x20u) ? cv1[u] : cv0[u]) : ((byte & kMetaOwn) ? h[0] : shr);
-                            if (byte & kMetaPad) v = MODE == 2 ? 1.0 : 0.0; // padding term (coefficient 0)
-                            acc = sweep_apply<MODE>(acc, cf[u][r], v);
+                            const double v = (byte & kMetaConst) ? ((byte & 0x20u) ? cv1[u] : cv0[u]) : ((byte & kMetaOwn) ? h[0] : shr);
+                            if (!(byte & kMetaPad)) acc = sweep_apply<MODE>(acc, cf[u][r], v);
                         }
                     }
                     __syncwarp();
