@@ -757,41 +757,40 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
         else if ((c & 0xff00u) == 0u && !forceGeneral)
         {
             // Blocks with DUAL steps (schedule.hpp): every lane is in canonical form or in seam form (own-lane term first,
-            // then cval 0, then a shuffled value or a cval).  Both forms are evaluated from the same operands, the lane's
-            // flag selects; what sits on the dependent chain is one multiply and three subtractions.
+            // then cval 0, then a shuffled value or a cval).  The canonical operands of the 8 steps are loaded at once as
+            // above; the arrival counter carries one bit per dual step, and only those steps (with lanes skewed by 2 steps,
+            // every other step of a seam crossing) load the flags and the extra operands and evaluate the seam form next
+            // to the canonical one - one multiply and three subtractions on the dependent chain.
             nGeneral++;
-#pragma unroll 1
-            for (int q0 = 0; q0 < kNH; q0 += 4)
+            const unsigned dualMask = c >> 16;
+            double a0[kNH], c0[kNH], c1[kNH];
+#pragma unroll
+            for (int q = 0; q < kNH; q++)
             {
-                unsigned fl[4];
-                double a0[4], c0[4], c1[4], c2[4], cv0[4], cv1[4];
+                a0[q] = *reinterpret_cast<const double*>(hd + q * 256);
+                c0[q] = *reinterpret_cast<const double*>(sb + PL + q * 256);
+                c1[q] = *reinterpret_cast<const double*>(sb + 2 * PL + q * 256);
+            }
 #pragma unroll
-                for (int u = 0; u < 4; u++)
+            for (int q = 0; q < kNH; q++)
+            {
+                const double sh = __shfl_sync(FULL, h[kSkew - 1], srcLane);
+                const double pSh = c0[q] * sh;
+                const double pOwn = c1[q] * h[0];
+                double acc = (a0[q] - pSh) - pOwn;
+                if (dualMask & (1u << q))
                 {
-                    const int q = q0 + u;
-                    fl[u] = *reinterpret_cast<const unsigned*>(sb + q * 256 + 4) >> 26; // meta bits 58..: seam form, selB
-                    a0[u] = *reinterpret_cast<const double*>(hd + q * 256);
-                    c0[u] = *reinterpret_cast<const double*>(sb + PL + q * 256);
-                    c1[u] = *reinterpret_cast<const double*>(sb + 2 * PL + q * 256);
-                    c2[u] = RG > 2 ? *reinterpret_cast<const double*>(sb + 3 * PL + q * 256) : 0.0;
-                    cv0[u] = Kg > 0 ? *reinterpret_cast<const double*>(hd + PL + q * 256) : 0.0;
-                    cv1[u] = Kg > 1 ? *reinterpret_cast<const double*>(hd + 2 * PL + q * 256) : 0.0;
+                    const unsigned fl = *reinterpret_cast<const unsigned*>(sb + q * 256 + 4) >> 26; // meta bits 58..: seam form, selB
+                    const double c2 = RG > 2 ? *reinterpret_cast<const double*>(sb + 3 * PL + q * 256) : 0.0;
+                    const double cv0 = Kg > 0 ? *reinterpret_cast<const double*>(hd + PL + q * 256) : 0.0;
+                    const double cv1 = Kg > 1 ? *reinterpret_cast<const double*>(hd + 2 * PL + q * 256) : 0.0;
+                    const unsigned selB = (fl >> 1) & 3u;
+                    const double vB = selB == 2u ? cv1 : (selB == 1u ? cv0 : sh);
+                    const double sm = ((a0[q] - pOwn) - c2 * cv0) - c0[q] * vB;
+                    if (fl & 1u) acc = sm;
                 }
-#pragma unroll
-                for (int u = 0; u < 4; u++)
-                {
-                    const double sh = __shfl_sync(FULL, h[kSkew - 1], srcLane);
-                    const bool seam = fl[u] & 1u;
-                    const unsigned selB = (fl[u] >> 1) & 3u;
-                    const double vB = selB == 2u ? cv1[u] : (selB == 1u ? cv0[u] : sh);
-                    const double pSh = c0[u] * sh, pA = c2[u] * cv0[u], pB = c0[u] * vB;
-                    const double pOwn = c1[u] * h[0];
-                    const double nrm = (a0[u] - pSh) - pOwn;
-                    const double sm = ((a0[u] - pOwn) - pA) - pB;
-                    const double acc = seam ? sm : nrm;
-                    st_relaxed(outPtr + (q0 + u) * outStride, acc);
-                    push(acc);
-                }
+                st_relaxed(outPtr + q * outStride, acc);
+                push(acc);
             }
         }
         else
@@ -989,7 +988,9 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
 #pragma unroll
         for (int i = 0; i < LG; i++) cf[i] = lds_f64(sg + offCoef + i * 256);
         const unsigned b7 = lds_u8(sg + offGen); // bit 0: descriptor-driven step, bit 5: dual step (schedule.hpp)
-        const unsigned stepKind = MODE == 2 ? 0x100u : (((b7 & 1u) << 8) | ((b7 & 0x20u) << 11));
+        // what the consumer learns with the arrival: bits 8-15 count the descriptor-driven steps, bit 16 + h says that
+        // step h is a dual step
+        const unsigned stepKind = MODE == 2 ? 0x100u : (((b7 & 1u) << 8) | (((b7 >> 5) & 1u) << (16 + h)));
         // ---- prefetch the codes / cross-group values of this producer's step in the next block
         unsigned sgN = sg + stageBytes, barN = bar + 8u, parN = par;
         if (sgN == stageEnd)
