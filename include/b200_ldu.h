@@ -129,6 +129,19 @@ int b200_sys_finalize(b200_sys* sys);
 int b200_sys_set_coeffs(b200_sys* sys, int r, const double* diag, const double* upper, const double* lower);
 /* boundaryCoeffs / internalCoeffs of interface iface of region r (intCoeffs may be NULL). */
 int b200_sys_set_interface_coeffs(b200_sys* sys, int r, int iface, const double* bouCoeffs, const double* intCoeffs);
+/* regionInterfaceType::attach() / detach() (src/regionInterfaces/regionInterface/regionInterfaceType.C:543-627) flip the
+ * regionCouple patches of an interface.  A detached patch must not take part in a coupled matrix-vector product:
+ * monolithicCouplingFvPatchField::initInterfaceMatrixUpdate is fatal for it (monolithicCouplingFvPatchField.C:406-413);
+ * while an interface of the system is detached, b200_solve / b200_amul return B200_ESTATE (the adapter turns that into
+ * the reference's FatalError).  Only kind B200_IFACE_REGION_COUPLE. */
+int b200_sys_set_interface_attached(b200_sys* sys, int r, int iface, int attached);
+/* attach() forces the interpolation weights to be re-computed (regionInterfaceType.C:551-558; the FSI cases rebuild the
+ * interpolator every interpolatorUpdateFrequency steps, :483-511): replace the GGI addressing / weights of interface
+ * iface of region r (arguments as in b200_sys_add_interface; ggiOffsets == NULL: identity).  Allowed before and after
+ * finalize; the cached device interface tables are rebuilt at the next use, the sweep / Amul layouts are kept.  The
+ * patch itself (nFaces, faceCells) cannot change: a topology change means destroy and re-create. */
+int b200_sys_set_interface_ggi(b200_sys* sys, int r, int iface, int32_t nPeerFaces, const int32_t* ggiOffsets,
+                               const int32_t* ggiAddr, const double* ggiWeights);
 int64_t b200_sys_num_cells(const b200_sys* sys);
 int64_t b200_sys_num_faces(const b200_sys* sys);
 

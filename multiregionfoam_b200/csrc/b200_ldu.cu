@@ -209,6 +209,9 @@ struct b200_sys
     int nTouched = 0;
     DevBuf<int> ifRows, ifRowStart, ifEntCoef, ifEntSrc, ifEntCnt, ifGSrc, sendCells;
     DevBuf<double> ifGW, sendBuf, recvBuf;
+    std::vector<int32_t> slotOfCellHost; // kept for rebuilding the interface plan (b200_sys_set_interface_ggi)
+    bool ifacePlanDirty = false;
+    int nDetached = 0; // regionCouple interfaces currently detached (regionInterfaceType::detach)
     std::vector<int> peers;
     std::vector<int32_t> sendOff, recvOff;
     int64_t nIfCoefs = 0;
@@ -537,6 +540,49 @@ static int upload_pipe_dir(b200_sys* s, const PipeSchedule& S, const PipeSchedul
     return B200_OK;
 }
 
+// Interface / halo plan of the system (schedule.hpp, IfacePlan): built at finalize, and rebuilt (first == false: the
+// coefficient arrays keep their contents) when the GGI interpolation of an interface was replaced.
+static int build_iface_plan(b200_sys* s, bool first)
+{
+    b200_ctx* ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    IfacePlan P;
+    try
+    {
+        P.build(s->regs, ctx->rank, s->slotOfCellHost, s->nSlots);
+    }
+    catch (const std::exception& e)
+    {
+        return set_err(ctx, B200_EINVAL, "interface plan: %s", e.what());
+    }
+    s->nTouched = (int)P.rows.size();
+    s->nIfCoefs = P.nCoefs;
+    s->peers = P.peers;
+    s->sendOff = P.sendOff;
+    s->recvOff = P.recvOff;
+    CK(ctx, s->ifRows.upload(P.rows, st));
+    CK(ctx, s->ifRowStart.upload(P.rowStart, st));
+    CK(ctx, s->ifEntCoef.upload(P.entCoef, st));
+    CK(ctx, s->ifEntSrc.upload(P.entSrc, st));
+    CK(ctx, s->ifEntCnt.upload(P.entCnt, st));
+    CK(ctx, s->ifGSrc.upload(P.gSrc, st));
+    CK(ctx, s->ifGW.upload(P.gW, st));
+    CK(ctx, s->ifaceMask.upload(P.sliceMask, st));
+    CK(ctx, s->sendCells.upload(P.sendCells, st));
+    CK(ctx, s->sendBuf.alloc(P.sendOff.back()));
+    CK(ctx, s->recvBuf.alloc(P.recvOff.back()));
+    if (first)
+    {
+        CK(ctx, s->ifCoefBou.alloc(P.nCoefs));
+        CK(ctx, s->ifCoefInt.alloc(P.nCoefs));
+        CK(ctx, cudaMemsetAsync(s->ifCoefBou.p, 0, (P.nCoefs ? P.nCoefs : 1) * sizeof(double), st));
+        CK(ctx, cudaMemsetAsync(s->ifCoefInt.p, 0, (P.nCoefs ? P.nCoefs : 1) * sizeof(double), st));
+    }
+    CK(ctx, cudaStreamSynchronize(st)); // host vectors go out of scope after return
+    s->ifacePlanDirty = false;
+    return B200_OK;
+}
+
 extern "C" int b200_sys_finalize(b200_sys* s)
 {
     if (!s) return B200_EINVAL;
@@ -581,30 +627,10 @@ extern "C" int b200_sys_finalize(b200_sys* s)
             CK(ctx, s->sellVal.alloc(sell.nEntries));
             CK(ctx, cudaStreamSynchronize(st));
         }
+        s->slotOfCellHost = S.slotOfCell;
         {
-            IfacePlan P;
-            P.build(s->regs, ctx->rank, S);
-            s->nTouched = (int)P.rows.size();
-            s->nIfCoefs = P.nCoefs;
-            s->peers = P.peers;
-            s->sendOff = P.sendOff;
-            s->recvOff = P.recvOff;
-            CK(ctx, s->ifRows.upload(P.rows, st));
-            CK(ctx, s->ifRowStart.upload(P.rowStart, st));
-            CK(ctx, s->ifEntCoef.upload(P.entCoef, st));
-            CK(ctx, s->ifEntSrc.upload(P.entSrc, st));
-            CK(ctx, s->ifEntCnt.upload(P.entCnt, st));
-            CK(ctx, s->ifGSrc.upload(P.gSrc, st));
-            CK(ctx, s->ifGW.upload(P.gW, st));
-            CK(ctx, s->ifaceMask.upload(P.sliceMask, st));
-            CK(ctx, s->sendCells.upload(P.sendCells, st));
-            CK(ctx, s->sendBuf.alloc(P.sendOff.back()));
-            CK(ctx, s->recvBuf.alloc(P.recvOff.back()));
-            CK(ctx, s->ifCoefBou.alloc(P.nCoefs));
-            CK(ctx, s->ifCoefInt.alloc(P.nCoefs));
-            CK(ctx, cudaMemsetAsync(s->ifCoefBou.p, 0, (P.nCoefs ? P.nCoefs : 1) * sizeof(double), st));
-            CK(ctx, cudaMemsetAsync(s->ifCoefInt.p, 0, (P.nCoefs ? P.nCoefs : 1) * sizeof(double), st));
-            CK(ctx, cudaStreamSynchronize(st));
+            const int rcI = build_iface_plan(s, true);
+            if (rcI) return rcI;
         }
         int rc = upload_pipe_dir(s, S, S.fwd, +1, s->fwd);
         if (rc) return rc;
@@ -724,12 +750,77 @@ extern "C" int b200_sys_set_interface_coeffs(b200_sys* s, int r, int iface, cons
     return B200_OK;
 }
 
+extern "C" int b200_sys_set_interface_attached(b200_sys* s, int r, int iface, int attached)
+{
+    if (!s) return B200_EINVAL;
+    b200_ctx* ctx = s->ctx;
+    if (r < 0 || r >= (int)s->regs.size() || iface < 0 || iface >= (int)s->regs[r].ifaces.size())
+        return set_err(ctx, B200_EINVAL, "b200_sys_set_interface_attached: bad arguments");
+    IfaceHost& I = s->regs[r].ifaces[iface];
+    if (I.kind != B200_IFACE_REGION_COUPLE) return set_err(ctx, B200_EINVAL, "only regionCouple interfaces attach / detach");
+    if (I.attached != (attached != 0))
+    {
+        I.attached = attached != 0;
+        s->nDetached += I.attached ? -1 : 1;
+    }
+    return B200_OK;
+}
+
+extern "C" int b200_sys_set_interface_ggi(b200_sys* s, int r, int iface, int32_t nPeerFaces, const int32_t* ggiOffsets,
+                                          const int32_t* ggiAddr, const double* ggiWeights)
+{
+    if (!s) return B200_EINVAL;
+    b200_ctx* ctx = s->ctx;
+    if (r < 0 || r >= (int)s->regs.size() || iface < 0 || iface >= (int)s->regs[r].ifaces.size())
+        return set_err(ctx, B200_EINVAL, "b200_sys_set_interface_ggi: bad arguments");
+    IfaceHost& I = s->regs[r].ifaces[iface];
+    if (I.kind != B200_IFACE_REGION_COUPLE) return set_err(ctx, B200_EINVAL, "only regionCouple interfaces carry a GGI interpolation");
+    if (!ggiOffsets)
+    {
+        if (nPeerFaces != I.nFaces) return set_err(ctx, B200_EINVAL, "identity interface needs nPeerFaces == nFaces");
+        I.identity = true;
+        I.ggiOffsets.clear();
+        I.ggiAddr.clear();
+        I.ggiWeights.clear();
+    }
+    else
+    {
+        if (!ggiAddr || !ggiWeights) return set_err(ctx, B200_EINVAL, "GGI interface needs addr and weights");
+        const int nnz = ggiOffsets[I.nFaces];
+        if (ggiOffsets[0] != 0 || nnz < 0) return set_err(ctx, B200_EINVAL, "bad GGI offsets");
+        for (int i = 0; i < I.nFaces; i++)
+            if (ggiOffsets[i + 1] < ggiOffsets[i]) return set_err(ctx, B200_EINVAL, "GGI offsets must not decrease");
+        for (int k = 0; k < nnz; k++)
+            if (ggiAddr[k] < 0 || ggiAddr[k] >= nPeerFaces) return set_err(ctx, B200_EINVAL, "GGI address %d out of range of the shadow patch", ggiAddr[k]);
+        I.identity = false;
+        I.ggiOffsets.assign(ggiOffsets, ggiOffsets + I.nFaces + 1);
+        I.ggiAddr.assign(ggiAddr, ggiAddr + nnz);
+        I.ggiWeights.assign(ggiWeights, ggiWeights + nnz);
+    }
+    I.nPeerFaces = nPeerFaces;
+    if (s->finalized) s->ifacePlanDirty = true; // rebuilt at the next use
+    return B200_OK;
+}
+
 // ------------------------------------------------------------------------------------------ launch helpers
 static int ensure_sell(b200_sys* s, bool transpose)
 {
     b200_ctx* ctx = s->ctx;
     for (size_t r = 0; r < s->regs.size(); r++)
         if (!s->regionHasCoeffs[r]) return set_err(ctx, B200_ESTATE, "region %zu has no coefficients", r);
+    if (s->nDetached)
+        for (size_t r = 0; r < s->regs.size(); r++)
+            for (size_t i = 0; i < s->regs[r].ifaces.size(); i++)
+                if (!s->regs[r].ifaces[i].attached)
+                    return set_err(ctx, B200_ESTATE,
+                                   "regionCouple interface %zu of region %zu is detached: the coupled matrix-vector product needs attached "
+                                   "patches (monolithicCouplingFvPatchField::initInterfaceMatrixUpdate is fatal for a detached patch)",
+                                   i, r);
+    if (s->ifacePlanDirty)
+    {
+        const int rc = build_iface_plan(s, false);
+        if (rc) return rc;
+    }
     if (s->nSlots == 0) return B200_OK;
     if (s->diagDirty)
     {

@@ -51,6 +51,7 @@ struct IfaceHost
     std::vector<int32_t> ggiOffsets, ggiAddr;
     std::vector<double> ggiWeights;
     int64_t coefOffset = 0; // into the concatenated interface-coefficient arrays
+    bool attached = true;   // regionInterfaceType::attach()/detach(): a detached regionCouple patch takes no part in a solve
 };
 
 struct RegionHost
@@ -996,8 +997,17 @@ struct IfacePlan
     std::vector<int32_t> sendCells;        // x slots packed into the send buffer
     int64_t nCoefs = 0;
 
-    void build(std::vector<RegionHost>& regs, int myRank, const PipeSchedule& S)
+    void build(std::vector<RegionHost>& regs, int myRank, const PipeSchedule& S) { build(regs, myRank, S.slotOfCell, S.nSlots); }
+    // (the plan needs the slot of every cell only: it can be rebuilt after finalize, when the GGI interpolation of an
+    // interface is replaced, without the sweep schedule)
+    struct SlotView
     {
+        const std::vector<int32_t>& slotOfCell;
+        int64_t nSlots;
+    };
+    void build(std::vector<RegionHost>& regs, int myRank, const std::vector<int32_t>& slotOfCell_, int64_t nSlots_)
+    {
+        const SlotView S{slotOfCell_, nSlots_};
         nCoefs = 0;
         for (auto& r : regs)
             for (auto& I : r.ifaces)

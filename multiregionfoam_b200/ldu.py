@@ -29,6 +29,7 @@ ABI_SYMBOLS = [
     "b200_amul", "b200_precondition", "b200_get_rD", "b200_reduce",
     "b200_set_profiling", "b200_get_kernel_times", "b200_launch_count", "b200_debug_sweep_stats",
     "b200_ggi_interpolate", "b200_patch_face_to_global", "b200_global_face_to_patch",
+    "b200_sys_set_interface_attached", "b200_sys_set_interface_ggi",
 ]
 
 
@@ -77,6 +78,8 @@ def load():
     L.b200_sys_finalize.argtypes = [vp]
     L.b200_sys_set_coeffs.argtypes = [vp, C.c_int, dp, dp, dp]
     L.b200_sys_set_interface_coeffs.argtypes = [vp, C.c_int, C.c_int, dp, dp]
+    L.b200_sys_set_interface_attached.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.b200_sys_set_interface_ggi.argtypes = [vp, C.c_int, C.c_int, C.c_int32, ip, ip, dp]
     L.b200_sys_num_cells.argtypes = [vp]
     L.b200_sys_num_cells.restype = C.c_int64
     L.b200_sys_num_faces.argtypes = [vp]
@@ -230,6 +233,20 @@ class LduSystem:
         b = _f64(bou)
         ic = None if int_ is None else _f64(int_)
         self.ctx.check(load().b200_sys_set_interface_coeffs(self.h, r, i, _dp(b), _dp(ic)))
+
+    def set_interface_attached(self, r: int, i: int, attached: bool):
+        """regionInterfaceType::attach()/detach() (regionInterfaceType.C:543-627): while a regionCouple interface is
+        detached, amul / solve raise (monolithicCouplingFvPatchField.C:406-413 is fatal for a detached patch)."""
+        self.ctx.check(load().b200_sys_set_interface_attached(self.h, r, i, int(bool(attached))))
+
+    def set_interface_ggi(self, r: int, i: int, nPeerFaces: int, offsets=None, addr=None, weights=None):
+        """Replace the GGI addressing / weights of a regionCouple interface (re-computed by attach() after mesh motion);
+        offsets None: identity pairing.  The device interface tables are rebuilt at the next use."""
+        if offsets is None:
+            self.ctx.check(load().b200_sys_set_interface_ggi(self.h, r, i, int(nPeerFaces), None, None, None))
+        else:
+            o, a, w = _i32(offsets), _i32(addr), _f64(weights)
+            self.ctx.check(load().b200_sys_set_interface_ggi(self.h, r, i, int(nPeerFaces), _ip(o), _ip(a), _dp(w)))
 
     def set_all_coeffs(self):
         for r, reg in enumerate(self.rs.regions):

@@ -396,3 +396,43 @@ def test_partitioned_fsi_style_coupling_loop(gpu_ctx, golden_addr):
     finally:
         SA.close()
         SB.close()
+
+
+def test_interface_attach_detach_and_ggi_update(gpu_ctx, golden_addr):
+    """regionInterfaceType::attach()/detach() (regionInterfaceType.C:543-627): a detached regionCouple patch makes the
+    coupled product / solve an error, as monolithicCouplingFvPatchField::initInterfaceMatrixUpdate is fatal for it
+    (.C:406-413); attach() re-computes the GGI interpolation, which replaces the cached device interface tables while the
+    Amul / sweep layouts are kept - checked against an oracle built with the new weights."""
+    import copy
+    case = ggi_case(golden_addr, seed=7)
+    S = ldu.LduSystem(gpu_ctx, case.ranks[0])
+    try:
+        x = case.concat("psi")
+        O = pyoracle.OracleSystem(case)
+        assert np.array_equal(S.amul(x), O.amul(x))
+        S.set_interface_attached(0, 0, False)
+        with pytest.raises(ldu.B200Error) as ei:
+            S.amul(x)
+        assert ei.value.code == -5 and "detached" in str(ei.value)      # B200_ESTATE
+        with pytest.raises(ldu.B200Error):
+            S.solve(x, case.concat("source"), ldu.SOLVER_BICGSTAB, ldu.PRECOND_DILU, tolerance=1e-10, maxIter=50)
+        S.set_interface_attached(0, 0, True)
+        assert np.array_equal(S.amul(x), O.amul(x))
+        # the same patches with another interpolation (other donors / weights) after re-attachment
+        case2 = ggi_case(golden_addr, seed=7)
+        other = ggi_case(golden_addr, seed=8)
+        for r in (0, 1):
+            src, dst = other.ranks[0].regions[r].interfaces[0], case2.ranks[0].regions[r].interfaces[0]
+            dst.ggiOffsets, dst.ggiAddr, dst.ggiWeights = src.ggiOffsets, src.ggiAddr, src.ggiWeights
+            S.set_interface_ggi(r, 0, dst.nPeerFaces, dst.ggiOffsets, dst.ggiAddr, dst.ggiWeights)
+        O2 = pyoracle.OracleSystem(case2)
+        y2 = S.amul(x)
+        assert np.array_equal(y2, O2.amul(x)) and not np.array_equal(y2, O.amul(x))
+        xo, io = O2.solve(x, case2.concat("source"), "BiCGStab", "DILU", tolerance=1e-11, maxIter=300)
+        xg, ig = S.solve(x, case2.concat("source"), ldu.SOLVER_BICGSTAB, ldu.PRECOND_DILU, tolerance=1e-11, maxIter=300)
+        assert rel_l2(xg, xo) < FIELD_RTOL
+        with pytest.raises(ldu.B200Error):
+            S.set_interface_ggi(0, 0, 96, np.array([0, 1], np.int32), np.array([500], np.int32), np.array([1.0]))
+    finally:
+        S.close()
+
