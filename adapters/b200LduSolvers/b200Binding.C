@@ -129,6 +129,11 @@ Foam::b200_sys* Foam::b200Binding::system
                 // see monolithicCouplingFvPatchField.C:183-187 (shadow lookup), :214-217, :401-404 (interpolate)
                 // -> b200_sys_add_interface(sys, r, B200_IFACE_REGION_COUPLE, nFaces, faceCells, myRank, shadowRow,
                 //                           shadowIface, nShadowFaces, ggiOffsets, ggiAddr, ggiWeights)
+                // Before every solve of a cached system: b200_sys_set_interface_attached(sys, r, iface,
+                // regionCouplePatch().attached()) (regionInterfaceType.C:543-627; a detached patch makes b200_solve return
+                // B200_ESTATE, which check() turns into the FatalError of monolithicCouplingFvPatchField.C:406-413), and, when
+                // the interpolator was rebuilt since (attach() after mesh motion), b200_sys_set_interface_ggi with the new
+                // addressing / weights.
                 notImplemented("regionCouple extraction: needs regionCoupleFvPatch::shadowRegion()/shadow() of the host tree");
             }
             else
