@@ -655,8 +655,13 @@ extern "C" int b200_sys_finalize(b200_sys* s)
         CK(ctx, cudaMemsetAsync(s->vec[v].p, 0, std::max<size_t>(1, s->nSlots) * sizeof(double), st));
     }
     {
-        const int maxSmem = std::max(s->fwd.smemBytes, s->bwd.smemBytes);
+        // the attribute is per kernel function, not per system: several systems may be alive (one per region in the
+        // partitioned loop), so it only ever grows (per device)
+        static int maxSmemSet[64] = {0};
+        int& seen = maxSmemSet[ctx->device & 63];
+        const int maxSmem = std::max(seen, std::max(s->fwd.smemBytes, s->bwd.smemBytes));
         if (maxSmem > 227 * 1024) return set_err(ctx, B200_EUNSUPPORTED, "sweep stage needs %d bytes of shared memory", maxSmem);
+        seen = maxSmem;
         CK(ctx, cudaFuncSetAttribute(k_sweep<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
         CK(ctx, cudaFuncSetAttribute(k_sweep<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
         CK(ctx, cudaFuncSetAttribute(k_sweep<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));

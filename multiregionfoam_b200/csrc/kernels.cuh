@@ -589,8 +589,10 @@ __device__ __forceinline__ SweepRing ring_setup(const PipeDev& S, int g, int lan
 // speed of the whole sweep (measured on B200: DADD 8, DMUL 8, 64-bit SHFL 31, LDS 29, mbarrier try_wait 90
 // cycles).  Everything static was decided on the host, and the CTA is organised so that the consumer
 // warp's chain per step is ONE multiply and ONE subtract:
-//   * lanes are skewed by kSkew = 2 steps, so the neighbour-lane value a step needs is already two steps
-//     old: its shuffle and its product are issued a step ahead, off the chain;
+//   * lanes are skewed by kSkew steps (schedule.hpp).  With kSkew = 2 the neighbour-lane value a step needs is two
+//     steps old and its shuffle and product are issued a step ahead, off the chain; with kSkew = 1 (the setting since
+//     the producers, not the consumer, were found to set the pace) the shuffle is on the chain again, but a group is
+//     31 steps shorter, a hop in j costs 31 instead of 62 steps of lag and a block seam spreads over 5 instead of 9 blocks;
 //   * a loader thread streams the records and the input vectors of a block of kNH = 8 steps into one of
 //     NS shared-memory stages with bulk asynchronous copies (TMA: cp.async.bulk + mbarrier);
 //   * kNH producer warps (producer h prepares step h of every block) fetch the cross-group values
@@ -759,7 +761,7 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
             // Blocks with DUAL steps (schedule.hpp): every lane is in canonical form or in seam form (own-lane term first,
             // then cval 0, then a shuffled value or a cval).  The canonical operands of the 8 steps are loaded at once as
             // above; the arrival counter carries one bit per dual step, and only those steps (with lanes skewed by 2 steps,
-            // every other step of a seam crossing) load the flags and the extra operands and evaluate the seam form next
+            // every other step of a seam crossing; every step with kSkew = 1) load the flags and the extra operands and evaluate the seam form next
             // to the canonical one - one multiply and three subtractions on the dependent chain.
             nGeneral++;
             const unsigned dualMask = c >> 16;

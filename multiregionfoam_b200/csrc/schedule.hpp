@@ -117,9 +117,11 @@ struct GlobalLdu
 
 // term codes of the sweep streams
 constexpr int kSweepBlock = 8;     // steps per producer/consumer block of the sweep kernel (= producer warps)
-constexpr int kSkew = 2;           // time steps between linked lanes of a warp: a value shuffled from another lane is kSkew
-                                   // steps old, so the shuffle is issued ahead and only mul+sub of the own-lane term
-                                   // remain on the dependent chain of a time step
+constexpr int kSkew = 1;           // time steps between linked lanes of a warp: a value shuffled from another lane is kSkew
+                                   // steps old.  2 takes the shuffle off the dependent chain of a time step (only mul+sub of
+                                   // the own-lane term remain); 1 keeps it on the chain but halves the lag of a hop in j and
+                                   // the spread of a block seam - measured faster on C2 (164.7 / 157.7 us per sweep against
+                                   // 170 / 162.5) once the producers, not the consumer, set the pace
 constexpr int32_t kCodeNone = -1; // padding term
 constexpr int32_t kCodeOwn = -2;  // value this lane produced in the previous time step (register)
 constexpr int32_t kCodeShfl = -3; // -3 - m: value lane m produced kSkew time steps ago (shuffle)

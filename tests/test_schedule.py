@@ -72,8 +72,12 @@ def test_line_structure_on_structured_mesh(emu):
     assert stats[10] == nx * (ny - 2) * nz           # shuffle terms: j-1 neighbours inside a warp
     assert stats[9] == nx * ny * (nz - 1) + nx * nz  # memory terms: k-1 neighbours + the j-1 of each warp's lane 0
     assert stats[12] == stats[0] and stats[13] == stats[0]   # every group takes the fast split-stream path
-    # 41 lines = 32 + 9 lanes per layer; (332 + 2 * (lanes - 1)) steps rounded up to 16 (lanes are skewed by kSkew = 2)
-    assert stats[7] == nz * 32 * (400 + 352)
+    # 41 lines = 32 + 9 lanes per layer; (332 + kSkew * (lanes - 1)) steps rounded up to 16 (lanes are skewed by kSkew steps)
+    import os, re
+    hpp = open(os.path.join(os.path.dirname(__file__), "..", "multiregionfoam_b200", "csrc", "schedule.hpp")).read()
+    skew = int(re.search(r"constexpr int kSkew = (\d+);", hpp).group(1))
+    up16 = lambda v: (v + 15) // 16 * 16
+    assert stats[7] == nz * 32 * (up16(nx + skew * 31) + up16(nx + skew * 8))
     # only the steps in which some lane crosses one of the two block seams leave the canonical (shuffle, own) form
     assert 0 < stats[14] <= 2 * 2 * 41 * nz and 0 < stats[15] <= 2 * 2 * 41 * nz
 
