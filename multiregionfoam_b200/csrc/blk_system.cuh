@@ -121,6 +121,32 @@ __device__ __forceinline__ void blk_load_row(int kind, const double* a, int i, d
         c[0] = kind == 4 ? a[i] : a[0];
 }
 
+// row i (tr: column i) of a coefficient into registers, for blk_mult_reg
+__device__ __forceinline__ void blk_load_row_tr(int kind, const double* __restrict__ a, bool tr, int i, double* c)
+{
+    if (kind != 16)
+    {
+        c[0] = kind == 4 ? __ldg(a + i) : __ldg(a);
+        c[1] = c[2] = c[3] = 0.0;
+    }
+    else if (tr)
+    {
+        c[0] = __ldg(a + i);
+        c[1] = __ldg(a + 4 + i);
+        c[2] = __ldg(a + 8 + i);
+        c[3] = __ldg(a + 12 + i);
+    }
+    else
+    {
+        const double2 p = __ldg(reinterpret_cast<const double2*>(a + 4 * i));
+        const double2 q = __ldg(reinterpret_cast<const double2*>(a + 4 * i + 2));
+        c[0] = p.x;
+        c[1] = p.y;
+        c[2] = q.x;
+        c[3] = q.y;
+    }
+}
+
 __device__ __forceinline__ void blk_load_x(const double* __restrict__ x, long long c, double* v)
 {
     const double2 p = __ldg(reinterpret_cast<const double2*>(x + 4 * c));
@@ -195,19 +221,66 @@ __global__ void __launch_bounds__(kBlkThreads)
         acc = a[4ll * row + i];
     const int k0 = BWD ? M.ownerStart[row] : M.losortStart[row], k1 = BWD ? M.ownerStart[row + 1] : M.losortStart[row + 1];
     const int nTerms = withFaces ? k1 - k0 : 0; // BlockDiagonalPrecon: x = mult(dDiag, b) only
-    for (int kk = 0; kk < nTerms; kk++)
+    // The rows of one wavefront level wait for the level before: what a row does AFTER its neighbours' values arrive is
+    // the critical path of the whole sweep.  Everything that does not depend on those values - face and neighbour
+    // indices, this thread's row of each coefficient block (from DRAM) - is therefore loaded for up to kChunk terms at
+    // once BEFORE the first poll; after a poll only multiply, quad shuffles and multiply remain (same order of the
+    // terms and of the operations as before).
+    constexpr int kChunk = 4;
+    const bool tr = !(BWD || M.lK);
+    const double* const coefBase = (BWD || !M.lK) ? M.upper : M.lower;
+    for (int kk0 = 0; kk0 < nTerms; kk0 += kChunk)
     {
-        const int f = BWD ? k1 - 1 - kk : M.losort[k0 + kk];
-        const int nb = BWD ? M.u[f] : M.l[f];
-        blk_poll<4>(out + 4ll * nb, xv, err);
-        double ti;
-        if (BWD || M.lK)
-            ti = blk_mult_row(M.uK, (BWD ? M.upper : M.lower) + (size_t)f * M.uK, false, xv, i);
-        else
-            ti = blk_mult_row(M.uK, M.upper + (size_t)f * M.uK, true, xv, i);
+        int nbv[kChunk];
+        double cf[kChunk][4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) tv[j] = __shfl_sync(qm, ti, qb + j);
-        acc -= blk_mult_reg(pK, d, tv, i);
+        for (int t = 0; t < kChunk; t++)
+            if (kk0 + t < nTerms)
+            {
+                const int f = BWD ? k1 - 1 - (kk0 + t) : M.losort[k0 + kk0 + t];
+                nbv[t] = BWD ? M.u[f] : M.l[f];
+                blk_load_row_tr(M.uK, coefBase + (size_t)f * M.uK, tr, i, cf[t]);
+            }
+        // the neighbours of a row mostly sit in the level just before it and arrive together: all of them are polled in
+        // one batch of independent loads per round instead of one after the other
+        double xn[kChunk][4];
+        bool have[kChunk];
+#pragma unroll
+        for (int t = 0; t < kChunk; t++) have[t] = !(kk0 + t < nTerms);
+        for (long long tries = 0;; tries++)
+        {
+#pragma unroll
+            for (int t = 0; t < kChunk; t++)
+                if (!have[t])
+                {
+                    ld_cg2(out + 4ll * nbv[t], xn[t][0], xn[t][1]);
+                    ld_cg2(out + 4ll * nbv[t] + 2, xn[t][2], xn[t][3]);
+                }
+            bool all = true;
+#pragma unroll
+            for (int t = 0; t < kChunk; t++)
+            {
+                if (!have[t]) have[t] = !is_sentinel(xn[t][0]) && !is_sentinel(xn[t][1]) && !is_sentinel(xn[t][2]) && !is_sentinel(xn[t][3]);
+                all = all && have[t];
+            }
+            if (all) break;
+            if (tries >= 32) __nanosleep(tries > 4096 ? 1000 : 100);
+            if ((tries & 1023) == 1023 && *(volatile int*)err) break;
+            if (tries >= (1ll << 22))
+            {
+                atomicExch(err, 1);
+                break;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < kChunk; t++)
+            if (kk0 + t < nTerms)
+            {
+                const double ti = blk_mult_reg(M.uK, cf[t], xn[t], i);
+#pragma unroll
+                for (int j = 0; j < 4; j++) tv[j] = __shfl_sync(qm, ti, qb + j);
+                acc -= blk_mult_reg(pK, d, tv, i);
+            }
     }
     st_relaxed(out + 4ll * row + i, acc);
 }
