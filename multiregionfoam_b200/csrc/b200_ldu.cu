@@ -726,9 +726,12 @@ extern "C" int b200_sys_set_coeffs(b200_sys* s, int r, const double* diag, const
     if (R.nFaces)
     {
         CK(ctx, cudaMemcpyAsync(s->coef.p + R.faceOffset, upper, sizeof(double) * R.nFaces, cudaMemcpyHostToDevice, st));
-        // symmetric matrix: lower aliases upper
-        CK(ctx, cudaMemcpyAsync(s->coef.p + s->F + R.faceOffset, lower ? lower : upper, sizeof(double) * R.nFaces,
-                                cudaMemcpyHostToDevice, st));
+        // symmetric matrix: lower aliases upper - filled on the device, the coefficients cross the bus once
+        if (lower)
+            CK(ctx, cudaMemcpyAsync(s->coef.p + s->F + R.faceOffset, lower, sizeof(double) * R.nFaces, cudaMemcpyHostToDevice, st));
+        else
+            CK(ctx, cudaMemcpyAsync(s->coef.p + s->F + R.faceOffset, s->coef.p + R.faceOffset, sizeof(double) * R.nFaces,
+                                    cudaMemcpyDeviceToDevice, st));
     }
     s->regionHasCoeffs[r] = 1;
     s->sellDirty = s->sellTDirty = true;
