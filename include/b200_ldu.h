@@ -142,6 +142,33 @@ int b200_sys_set_interface_attached(b200_sys* sys, int r, int iface, int attache
  * patch itself (nFaces, faceCells) cannot change: a topology change means destroy and re-create. */
 int b200_sys_set_interface_ggi(b200_sys* sys, int r, int iface, int32_t nPeerFaces, const int32_t* ggiOffsets,
                                const int32_t* ggiAddr, const double* ggiWeights);
+/* ---- device-side coefficient refresh of the temperature equations --------------------------- */
+/* The two T regions re-assemble their fvScalarMatrix every time step
+ *   B200_TEQN_CONDUCT    fvm::ddt(rho*cv, T) == fvm::laplacian(kappa, T)
+ *                        (src/regions/conductTemperature/conductTemperature.C:135-142)
+ *   B200_TEQN_TRANSPORT  rho*cp*(fvm::ddt(T) + fvm::div(phi, T)) == fvm::laplacian(kappa, T)
+ *                        (src/regions/transportTemperature/transportTemperature.C:129-140)
+ * (Euler ddt, Gauss upwind div, Gauss linear uncorrected laplacian, as in the tutorials' fvSchemes).  Instead of the
+ * host assembling diag / upper / lower / source and b200_sys_set_coeffs + b200_upload copying them (the whole matrix
+ * per step), the adapter hands over the static geometry once and the matrix is produced on the device from it and
+ * from the resident field; per step only what changed (phi, kappa_f) crosses the bus.
+ *
+ * b200_sys_set_fv_geometry (after finalize; region r in upper-triangular face order): V = mesh.V(), magSf and
+ * deltaCoeffs of the internal faces, and the boundary faces of the region in patch order (bCells = faceCells, their
+ * internalCoeffs and boundary-source contributions as fvMatrix::addBoundaryDiag / addBoundarySource would add them,
+ * coupled patches included). */
+#define B200_TEQN_CONDUCT 0
+#define B200_TEQN_TRANSPORT 1
+int b200_sys_set_fv_geometry(b200_sys* sys, int r, const double* V, const double* magSf, const double* deltaCoeffs,
+                             int32_t nBoundary, const int32_t* bCells, const double* bIntCoeffs, const double* bSrcCoeffs);
+/* Assemble region r on the device: coefficients as b200_sys_set_coeffs would have set them, and the region's part of
+ * the resident right-hand side b, with T.oldTime() = the resident x (b200_upload, or the result of the previous
+ * b200_solve_resident).  rhoC = rho*cv | rho*cp, rDeltaT = 1/deltaT, kappa uniform unless kappaFace (host, nFaces:
+ * the face-interpolated conductivity) is given; phi (host, nFaces) is the face flux of the transport form.  kappaFace
+ * / phi == NULL: keep the table of the previous call.  Interface coefficients still come through
+ * b200_sys_set_interface_coeffs. */
+int b200_sys_assemble_T(b200_sys* sys, int r, int form, double rhoC, double rDeltaT, double kappa,
+                        const double* kappaFace, const double* phi);
 int64_t b200_sys_num_cells(const b200_sys* sys);
 int64_t b200_sys_num_faces(const b200_sys* sys);
 

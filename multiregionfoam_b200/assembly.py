@@ -87,6 +87,45 @@ def assemble_cht(fluid: StructuredRegion, solid: StructuredRegion, *, dt: float 
     return Case(name, [RankSystem(0, 1, [reg_f, reg_s])])
 
 
+def cht_fv_tables(fluid: StructuredRegion, solid: StructuredRegion, *, dt: float = 1e-2, Ux: float = 1.0):
+    """What a foam-extend adapter hands to ``b200_sys_set_fv_geometry`` / ``b200_sys_assemble_T`` for the two T regions of
+    the CHT case (same physics and constants as :func:`assemble_cht`): per region a dict with the static geometry
+    (``V``, ``magSf``, ``deltaCoeffs``), the boundary faces in patch order (``bCells`` with their internalCoeffs ``bInt``
+    and boundary-source contributions ``bSrc``; the regionCouple patch contributes its internalCoeffs), the equation form
+    and constants, the face flux ``phi`` (fluid), the interface coefficients and the initial field."""
+    from .ldu import TEQN_CONDUCT, TEQN_TRANSPORT
+    rho_f, cp_f, k_f = 1.0, 250.0, 5.0
+    rho_s, cv_s, k_s = 1.0, 100.0, 100.0
+    T_f0, T_s0, T_in, T_bot = 300.0, 310.0, 300.0, 310.0
+    rc_f = rho_f * cp_f
+    fc_f, a_f, d_f = fluid.side_y(1, top=False)
+    fc_s, a_s, d_s = solid.side_y(0, top=True)
+    kOwn, kNei = k_f / d_f, k_s / d_s
+    cond = a_f * kOwn * kNei / (kOwn + kNei)
+    # fluid: inlet (fixedValue), outlet (zeroGradient), interface (regionCouple)
+    ci, ai, di = fluid.side_xmin()
+    co, ao, _ = fluid.side_xmax()
+    Db = k_f * ai / di
+    Fb = -rc_f * Ux * ai
+    bCells_f = np.concatenate([ci, co, fc_f]).astype(np.int32)
+    bInt_f = np.concatenate([Db + np.maximum(Fb, 0.0), np.maximum(rc_f * Ux * ao, 0.0), cond])
+    bSrc_f = np.concatenate([(Db - np.minimum(Fb, 0.0)) * T_in, np.zeros(co.size), np.zeros(fc_f.size)])
+    phi = np.where(fluid.faceDir == 0, Ux * fluid.faceArea, 0.0)  # volumetric flux U.S_f; rho*cp scales the operator
+    # solid: bottom (fixedValue), top (regionCouple)
+    cb, ab, db = solid.side_y(0, top=False)
+    Dbs = k_s * ab / db
+    bCells_s = np.concatenate([cb, fc_s]).astype(np.int32)
+    bInt_s = np.concatenate([Dbs, cond])
+    bSrc_s = np.concatenate([Dbs * T_bot, np.zeros(fc_s.size)])
+    tf = dict(form=TEQN_TRANSPORT, rhoC=rc_f, kappa=k_f, rDeltaT=1.0 / dt, V=fluid.volume, magSf=fluid.faceArea,
+              deltaCoeffs=1.0 / fluid.faceDelta, phi=phi, bCells=bCells_f, bInt=bInt_f, bSrc=bSrc_f,
+              ifaceCoeffs=cond.copy(), T0=np.full(fluid.nCells, T_f0))
+    ts = dict(form=TEQN_CONDUCT, rhoC=rho_s * cv_s, kappa=k_s, rDeltaT=1.0 / dt, V=solid.volume, magSf=solid.faceArea,
+              deltaCoeffs=1.0 / solid.faceDelta, phi=None, bCells=bCells_s, bInt=bInt_s, bSrc=bSrc_s,
+              ifaceCoeffs=cond.copy(), T0=np.full(solid.nCells, T_s0))
+    return tf, ts
+
+
 def cht_case(r: int = 1, layers: int = 1, z1: float = 0.4, **kw) -> Tuple[Case, StructuredRegion, StructuredRegion]:
     fluid, solid = flow_over_heated_plate(r, layers, z1)
     return assemble_cht(fluid, solid, name=f"cht_r{r}_L{layers}", **kw), fluid, solid

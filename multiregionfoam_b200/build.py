@@ -18,6 +18,8 @@ LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libb200ldu.so")
 EMU_SRC = os.path.join(ROOT, "tests", "cpp", "schedule_emulate.cpp")
 EMU_PATH = os.path.join(ROOT, "tests", "_build", "libschedule_emu.so")
+ASM_EMU_SRC = os.path.join(ROOT, "tests", "cpp", "assemble_emulate.cpp")
+ASM_EMU_PATH = os.path.join(ROOT, "tests", "_build", "libassemble_emu.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -65,6 +67,15 @@ def build_schedule_emulator(force: bool = False) -> str:
     return EMU_PATH
 
 
+def build_assemble_emulator(force: bool = False) -> str:
+    deps = [ASM_EMU_SRC, os.path.join(CSRC, "fv_assemble.hpp")]
+    if force or _stale(ASM_EMU_PATH, deps):
+        os.makedirs(os.path.dirname(ASM_EMU_PATH), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", ASM_EMU_PATH, ASM_EMU_SRC])
+    return ASM_EMU_PATH
+
+
 if __name__ == "__main__":
     print(build_library(force=True, verbose=True))
     print(build_schedule_emulator(force=True))
+    print(build_assemble_emulator(force=True))

@@ -164,6 +164,14 @@ struct PipeDirMem
     bool packed[2] = {false, false}; // [0]: dev holds the plain coefficients of the current matrix, [1]: devT the transposed ones
 };
 
+// static FV geometry of one region for the device-side coefficient refresh (fv_assemble.cuh)
+struct FvRegionDev
+{
+    DevBuf<double> V, magSf, delta, phi, kappaFace, bInt, bSrc;
+    DevBuf<int> ownerStart, losort, losortStart, bStart;
+    bool havePhi = false, haveKappaFace = false;
+};
+
 // ------------------------------------------------------------------------------------------ system
 enum VecId
 {
@@ -248,6 +256,8 @@ struct b200_sys
     int64_t clsLaunches[B200_K_NCLASSES] = {0};
     cudaEvent_t evSolveA = nullptr, evSolveB = nullptr;
     std::vector<cudaEvent_t> throttle;
+    // device-side coefficient refresh (fv_assemble.cuh): static FV geometry per region, set on demand
+    std::vector<std::unique_ptr<FvRegionDev>> fv;
 };
 
 struct KScope
@@ -739,6 +749,8 @@ extern "C" int b200_sys_set_coeffs(b200_sys* s, int r, const double* diag, const
     s->fwd.packed[0] = s->fwd.packed[1] = s->bwd.packed[0] = s->bwd.packed[1] = false;
     return B200_OK;
 }
+
+#include "fv_assemble.cuh"
 
 extern "C" int b200_sys_set_interface_coeffs(b200_sys* s, int r, int iface, const double* bouCoeffs, const double* intCoeffs)
 {

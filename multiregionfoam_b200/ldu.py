@@ -30,7 +30,10 @@ ABI_SYMBOLS = [
     "b200_set_profiling", "b200_get_kernel_times", "b200_launch_count", "b200_debug_sweep_stats",
     "b200_ggi_interpolate", "b200_patch_face_to_global", "b200_global_face_to_patch",
     "b200_sys_set_interface_attached", "b200_sys_set_interface_ggi",
+    "b200_sys_set_fv_geometry", "b200_sys_assemble_T",
 ]
+
+TEQN_CONDUCT, TEQN_TRANSPORT = 0, 1
 
 
 class B200Error(RuntimeError):
@@ -80,6 +83,8 @@ def load():
     L.b200_sys_set_interface_coeffs.argtypes = [vp, C.c_int, C.c_int, dp, dp]
     L.b200_sys_set_interface_attached.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.b200_sys_set_interface_ggi.argtypes = [vp, C.c_int, C.c_int, C.c_int32, ip, ip, dp]
+    L.b200_sys_set_fv_geometry.argtypes = [vp, C.c_int, dp, dp, dp, C.c_int32, ip, dp, dp]
+    L.b200_sys_assemble_T.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, dp, dp]
     L.b200_sys_num_cells.argtypes = [vp]
     L.b200_sys_num_cells.restype = C.c_int64
     L.b200_sys_num_faces.argtypes = [vp]
@@ -247,6 +252,25 @@ class LduSystem:
         else:
             o, a, w = _i32(offsets), _i32(addr), _f64(weights)
             self.ctx.check(load().b200_sys_set_interface_ggi(self.h, r, i, int(nPeerFaces), _ip(o), _ip(a), _dp(w)))
+
+    # ---- device-side coefficient refresh of the T equations
+    def set_fv_geometry(self, r: int, V, magSf, deltaCoeffs, bCells=None, bIntCoeffs=None, bSrcCoeffs=None):
+        """Static FV tables of region r: mesh.V(), magSf / deltaCoeffs of the internal faces and the boundary faces in
+        patch order with their internalCoeffs / boundary-source contributions (addBoundaryDiag / addBoundarySource)."""
+        v, a, d = _f64(V), _f64(magSf), _f64(deltaCoeffs)
+        nB = 0 if bCells is None else int(np.asarray(bCells).size)
+        bc = _i32(bCells) if nB else None
+        bi = _f64(bIntCoeffs) if nB else None
+        bs = _f64(bSrcCoeffs) if nB else None
+        self.ctx.check(load().b200_sys_set_fv_geometry(self.h, r, _dp(v), _dp(a), _dp(d), nB, _ip(bc), _dp(bi), _dp(bs)))
+
+    def assemble_T(self, r: int, form: int, rhoC: float, rDeltaT: float, kappa: float, kappaFace=None, phi=None):
+        """conductTemperature / transportTemperature::setCoupledEqns on the device (conductTemperature.C:135-142,
+        transportTemperature.C:129-140): coefficients of region r and its part of the resident b from the resident x
+        (= T.oldTime()).  kappaFace / phi None: keep the resident table."""
+        kf = None if kappaFace is None else _f64(kappaFace)
+        ph = None if phi is None else _f64(phi)
+        self.ctx.check(load().b200_sys_assemble_T(self.h, r, int(form), float(rhoC), float(rDeltaT), float(kappa), _dp(kf), _dp(ph)))
 
     def set_all_coeffs(self):
         for r, reg in enumerate(self.rs.regions):
