@@ -75,7 +75,20 @@ def build_assemble_emulator(force: bool = False) -> str:
     return ASM_EMU_PATH
 
 
+GGI_EMU_SRC = os.path.join(ROOT, "tests", "cpp", "ggi_emulate.cpp")
+GGI_EMU_PATH = os.path.join(ROOT, "tests", "_build", "libggi_emu.so")
+
+
+def build_ggi_emulator(force: bool = False) -> str:
+    deps = [GGI_EMU_SRC, os.path.join(CSRC, "ggi_build.hpp")]
+    if force or _stale(GGI_EMU_PATH, deps):
+        os.makedirs(os.path.dirname(GGI_EMU_PATH), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", GGI_EMU_PATH, GGI_EMU_SRC])
+    return GGI_EMU_PATH
+
+
 if __name__ == "__main__":
     print(build_library(force=True, verbose=True))
     print(build_schedule_emulator(force=True))
     print(build_assemble_emulator(force=True))
+    print(build_ggi_emulator(force=True))
