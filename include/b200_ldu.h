@@ -221,6 +221,21 @@ int64_t b200_launch_count(const b200_ctx* ctx);
 int b200_ggi_interpolate(b200_ctx* ctx, int32_t nTo, int32_t nFrom, const int32_t* offsets,
                          const int32_t* addr, const double* weights, const double* ff, int nComp,
                          double* result);
+/* GGI weight construction: what GGIInterpolation<standAlonePatch, standAlonePatch>(zoneA, zoneB, ...,
+ * SMALL, SMALL, rescale = true, BB_OCTREE) computes for the reference
+ * (src/numerics/interfaceToInterfaceMappings/ggiInterfaceToInterfaceMapping/ggiInterfaceToInterfaceMapping.C:62-77; rebuilt
+ * when the interface moves, src/regionInterfaces/regionInterface/regionInterfaceType.C:483-511, 551-558): for every master
+ * face the slave faces it overlaps and the weights (intersection area / master face area in the master plane, entries
+ * below nonOverlapTol dropped, rows rescaled to sum to one when rescale != 0).  Patches as standAlonePatch holds them:
+ * faces = CSR of point labels (3..8 points), points = xyz triples.  Candidate pairs come from a host bounding-box hash
+ * grid; clipping and rescaling run on the device.  Returns the number of addressing entries (>= 0) or an error code; the
+ * result (the arguments b200_ggi_interpolate / b200_sys_set_interface_ggi take, master = the receiving side) is kept in
+ * the context until the next build and copied out by b200_ggi_fetch.  For the other direction swap the patches. */
+int b200_ggi_build(b200_ctx* ctx, int32_t nMaster, const int32_t* mFaceOffsets, const int32_t* mFaceLabels,
+                   int32_t nMasterPoints, const double* mPoints, int32_t nSlave, const int32_t* sFaceOffsets,
+                   const int32_t* sFaceLabels, int32_t nSlavePoints, const double* sPoints, double nonOverlapTol, int rescale);
+/* offsets[nMaster+1], addr[nnz], weights[nnz] of the last b200_ggi_build */
+int b200_ggi_fetch(b200_ctx* ctx, int32_t nMaster, int32_t* offsets, int32_t* addr, double* weights);
 /* globalPolyPatch::patchFaceToGlobal: zone field = all-reduce(sum) of the zero-padded scatter of the
  * local patch values through faceToGlobalAddr (collective over the context's ranks). */
 int b200_patch_face_to_global(b200_ctx* ctx, int32_t nLocal, const int32_t* faceToGlobalAddr,

@@ -90,6 +90,9 @@ struct b200_ctx
     std::string err;
     int64_t launches = 0;
     int smCount = 148;
+    // result of the last b200_ggi_build (ggi_build.cuh), handed out by b200_ggi_fetch
+    std::vector<int32_t> ggiOff, ggiAddr;
+    std::vector<double> ggiW;
 };
 
 static int set_err(b200_ctx* ctx, int code, const char* fmt, ...)
@@ -1608,6 +1611,8 @@ extern "C" int b200_get_kernel_times(b200_sys* s, double* msPerClass, int64_t* l
     }
     return B200_OK;
 }
+
+#include "ggi_build.cuh"
 
 // ------------------------------------------------------------------------------------------ partitioned face transfer
 extern "C" int b200_ggi_interpolate(b200_ctx* ctx, int32_t nTo, int32_t nFrom, const int32_t* offsets, const int32_t* addr,

@@ -31,6 +31,7 @@ ABI_SYMBOLS = [
     "b200_ggi_interpolate", "b200_patch_face_to_global", "b200_global_face_to_patch",
     "b200_sys_set_interface_attached", "b200_sys_set_interface_ggi",
     "b200_sys_set_fv_geometry", "b200_sys_assemble_T",
+    "b200_ggi_build", "b200_ggi_fetch",
 ]
 
 TEQN_CONDUCT, TEQN_TRANSPORT = 0, 1
@@ -106,6 +107,8 @@ def load():
     L.b200_debug_sweep_stats.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.c_int]
     L.b200_launch_count.argtypes = [vp]
     L.b200_launch_count.restype = C.c_int64
+    L.b200_ggi_build.argtypes = [vp, C.c_int32, ip, ip, C.c_int32, dp, C.c_int32, ip, ip, C.c_int32, dp, C.c_double, C.c_int]
+    L.b200_ggi_fetch.argtypes = [vp, C.c_int32, ip, ip, dp]
     L.b200_ggi_interpolate.argtypes = [vp, C.c_int32, C.c_int32, ip, ip, dp, dp, C.c_int, dp]
     L.b200_patch_face_to_global.argtypes = [vp, C.c_int32, ip, dp, C.c_int, C.c_int32, dp]
     L.b200_global_face_to_patch.argtypes = [vp, C.c_int32, ip, dp, C.c_int, dp]
@@ -175,6 +178,19 @@ class Context:
             self.h = C.c_void_p()
 
     # ---- partitioned-coupling face transfer
+    def ggi_build(self, mFaceOffsets, mFaceLabels, mPoints, sFaceOffsets, sFaceLabels, sPoints, nonOverlapTol: float = 1e-15,
+                  rescale: bool = True):
+        """GGIInterpolation weights of the master faces from the slave patch (ggiInterfaceToInterfaceMapping.C:62-77:
+        tolerances SMALL, rescale true): -> offsets, addr, weights as ggi_interpolate / set_interface_ggi take them."""
+        mo, ml, so, sl = _i32(mFaceOffsets), _i32(mFaceLabels), _i32(sFaceOffsets), _i32(sFaceLabels)
+        mp, sp = _f64(mPoints), _f64(sPoints)
+        nM, nS = mo.size - 1, so.size - 1
+        nnz = self.check(load().b200_ggi_build(self.h, nM, _ip(mo), _ip(ml), mp.size // 3, _dp(mp), nS, _ip(so), _ip(sl),
+                                               sp.size // 3, _dp(sp), float(nonOverlapTol), int(bool(rescale))))
+        off, addr, w = np.zeros(nM + 1, np.int32), np.zeros(nnz, np.int32), np.zeros(nnz)
+        self.check(load().b200_ggi_fetch(self.h, nM, _ip(off), _ip(addr), _dp(w)))
+        return off, addr, w
+
     def ggi_interpolate(self, offsets, addr, weights, ff, nFrom: Optional[int] = None) -> np.ndarray:
         offsets, addr, weights = _i32(offsets), _i32(addr), _f64(weights)
         ff = _f64(ff)
