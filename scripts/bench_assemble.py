@@ -3,8 +3,7 @@ the two-region CHT case (default C2) driven (a) the way an unmodified caller doe
 b200_solve with host buffers - and (b) with b200_sys_assemble_T from the resident field + b200_solve_resident + the D2H
 of the solution.  Also times the two assembly kernels alone (CUDA events, 'pack' class) against their algorithmic bytes.
 usage: python scripts/bench_assemble.py [--workload C2] [--iters 50] [--steps 5]
-Prints one JSON line (not the driver's bench contract - a profile for profiles/).  NOT YET RUN ON A B200 (written after
-round 1's GPU minutes were spent)."""
+Prints one JSON line (not the driver's bench contract - a profile for profiles/)."""
 import argparse, json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
