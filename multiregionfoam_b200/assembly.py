@@ -126,6 +126,23 @@ def cht_fv_tables(fluid: StructuredRegion, solid: StructuredRegion, *, dt: float
     return tf, ts
 
 
+def cht_fv_tables_slab(r: int, layers_per_rank: int, rank: int, nranks: int):
+    """:func:`cht_fv_tables` for rank ``rank`` of the z-slab decomposition :func:`cht_rank_slab` builds: the processor
+    patches (after the regionCouple patch, ordered by neighbour rank) add their internalCoeffs to the boundary-face
+    list, exactly what ``processorFvPatchField`` contributes through ``addBoundaryDiag``; they carry no source."""
+    fluid, solid = flow_over_heated_plate(r, layers_per_rank)
+    tables = cht_fv_tables(fluid, solid)
+    for t, mesh in zip(tables, (fluid, solid)):
+        for nb in (rank - 1, rank + 1):
+            if 0 <= nb < nranks:
+                c, a, d = mesh.side_z(top=(nb > rank))
+                D = t["kappa"] * a / (2.0 * d)
+                t["bCells"] = np.concatenate([t["bCells"], c]).astype(np.int32)
+                t["bInt"] = np.concatenate([t["bInt"], D])
+                t["bSrc"] = np.concatenate([t["bSrc"], np.zeros(c.size)])
+    return tables, (fluid, solid)
+
+
 def cht_case(r: int = 1, layers: int = 1, z1: float = 0.4, **kw) -> Tuple[Case, StructuredRegion, StructuredRegion]:
     fluid, solid = flow_over_heated_plate(r, layers, z1)
     return assemble_cht(fluid, solid, name=f"cht_r{r}_L{layers}", **kw), fluid, solid

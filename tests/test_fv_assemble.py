@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 
 from multiregionfoam_b200 import build as b200build
-from multiregionfoam_b200.assembly import assemble_cht, cht_fv_tables
+from multiregionfoam_b200.assembly import assemble_cht, cht_fv_tables, cht_fv_tables_slab, cht_rank_slab
 from multiregionfoam_b200.mesh import flow_over_heated_plate
 from oracle import pyfv
 
@@ -140,3 +140,22 @@ def test_assembled_row_sums(emu):
     # columns: diag[c] + sum of the coefficients multiplying x[c] in other rows = ddt diagonal (div and lap are conservative)
     cols = d1 + np.bincount(t["u"], weights=up1, minlength=2000) + np.bincount(t["l"], weights=lo1, minlength=2000)
     np.testing.assert_allclose(cols, rhoC * rdt * t["V"], rtol=1e-9)
+
+
+@pytest.mark.parametrize("rank,nranks", [(0, 2), (1, 2), (1, 3)])
+def test_decomposed_slab_tables(emu, rank, nranks):
+    """N > 1: the tables of one z-slab rank (processor patches in the boundary-face list) reproduce the matrices
+    cht_rank_slab hands to the multi-GPU solve (1e-12), and the kernel arithmetic stays bit-exact against the oracle."""
+    rs = cht_rank_slab(1, 2, rank, nranks)
+    tables, meshes = cht_fv_tables_slab(1, 2, rank, nranks)
+    for reg, mesh, t in zip(rs.regions, meshes, tables):
+        kw = dict(phi=t["phi"], bCells=t["bCells"], bInt=t["bInt"], bSrc=t["bSrc"])
+        args = (t["form"], mesh.lowerAddr, mesh.upperAddr, t["rhoC"], t["rDeltaT"], t["kappa"], t["V"], t["magSf"],
+                t["deltaCoeffs"], t["T0"])
+        d, up, lo, src = pyfv.assemble_T(*args, **kw)
+        np.testing.assert_allclose(d, reg.diag, rtol=1e-12)
+        np.testing.assert_allclose(up, reg.upper, rtol=1e-12)
+        np.testing.assert_allclose(src, reg.source, rtol=1e-12)
+        nProc = sum(i.nFaces for i in reg.interfaces[1:])      # patch list: [regionCouple, processor patches...]
+        assert nProc > 0 and np.array_equal(t["bCells"][-nProc:], np.concatenate([i.faceCells for i in reg.interfaces[1:]]))
+        assert _all_equal(emulate(emu, *args, **kw), (d, up, lo, src))
