@@ -339,6 +339,55 @@ def main():
         for a in keep:
             ctx.host_unregister(a)
 
+        # ---- informational (N = 1): the same step with the T equations assembled on the device (b200_sys_assemble_T,
+        # SURVEY 8(f) rank 3): per step only the field crosses the bus (x in, solution out).  Reported beside, never instead
+        # of, the host-assembled e2e above (what an unmodified foam-extend caller does); a failure here cannot touch the
+        # contract line.
+        if world == 1:
+            try:
+                from multiregionfoam_b200.assembly import cht_fv_tables_slab
+                tables, _ = cht_fv_tables_slab(r, L, 0, 1)
+                S2 = ldu.LduSystem(ctx, rs, set_coeffs=False)
+                try:
+                    for ri, t in enumerate(tables):
+                        S2.set_fv_geometry(ri, t["V"], t["magSf"], t["deltaCoeffs"], t["bCells"], t["bInt"], t["bSrc"])
+                        for i, itf in enumerate(rs.regions[ri].interfaces):
+                            S2.set_interface_coeffs(ri, i, itf.bouCoeffs, itf.intCoeffs)
+                    hx0 = [np.ascontiguousarray(reg.psi.copy()) for reg in rs.regions]
+                    hx = [np.ascontiguousarray(reg.psi.copy()) for reg in rs.regions]
+                    for a in hx0 + hx:
+                        ctx.host_register(a)
+                    first = [True]
+
+                    def dev_step():
+                        ctx.check(Lib.b200_upload(S2.h, ldu._dpp(hx0), None))                      # T.oldTime(): H2D
+                        for ri, t in enumerate(tables):
+                            S2.assemble_T(ri, t["form"], t["rhoC"], t["rDeltaT"], t["kappa"], phi=t["phi"] if first[0] else None)
+                        first[0] = False
+                        ctx.check(Lib.b200_solve_resident(S2.h, C.byref(opts), C.byref(perf), None, 0))
+                        ctx.check(Lib.b200_download(S2.h, ldu._dpp(hx)))                            # solution: D2H
+                        return perf.nIterations
+
+                    for _ in range(2):
+                        dev_step()
+                    barrier()
+                    t1 = time.perf_counter()
+                    its_d = 0
+                    for _ in range(n_e):
+                        its_d += dev_step()
+                    barrier()
+                    d_s = time.perf_counter() - t1
+                    xbytes = sum(a.nbytes for a in hx0)
+                    e2e["device_assembled"] = {"value": nGlobal * its_d / d_s, "unit": UNIT, "ms_per_step": 1e3 * d_s / n_e,
+                                               "h2d_bytes_per_step": int(xbytes), "d2h_bytes_per_step": int(xbytes), "steps": n_e,
+                                               "note": "T equations assembled on the device from the uploaded field (b200_sys_assemble_T)"}
+                    for a in hx0 + hx:
+                        ctx.host_unregister(a)
+                finally:
+                    S2.close()
+            except Exception as ex:  # informational leg only
+                e2e["device_assembled"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+
     # ---- CPU baseline (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
