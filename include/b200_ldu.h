@@ -236,6 +236,20 @@ int b200_ggi_build(b200_ctx* ctx, int32_t nMaster, const int32_t* mFaceOffsets, 
                    const int32_t* sFaceLabels, int32_t nSlavePoints, const double* sPoints, double nonOverlapTol, int rescale);
 /* offsets[nMaster+1], addr[nnz], weights[nnz] of the last b200_ggi_build */
 int b200_ggi_fetch(b200_ctx* ctx, int32_t nMaster, int32_t* offsets, int32_t* addr, double* weights);
+/* Conformal interfaces, directMapInterfaceToInterfaceMapping (directMap variant).
+ * b200_direct_map_build = calcZone{A,B}ToZone{B,A}{Face,Point}Map
+ * (src/numerics/interfaceToInterfaceMappings/directMapInterfaceToInterfaceMapping/directMapInterfaceToInterfaceMapping.C:
+ * 147-168, 268-289, 389-410, 510-531): map[i] = the FIRST location j of the other zone with mag(to[i] - from[j]) < tol,
+ * -1 if there is none; locations are xyz triples (face centres or points), tol = relTol_ (0.001, :52) * min edge length
+ * of zone A (:153, :560-597), computed by the caller.  The reference's N^2 loop on one core becomes one thread per
+ * receiving location.  Returns the number of unmatched locations (>= 0; > 0 is the reference's "interfaces are not
+ * conformal" FatalError, :170-181) or an error code.
+ * b200_direct_map_transfer = transferFacesZoneToZone / transferPointsZoneToZone
+ * (.../directMapInterfaceToInterfaceMappingTemplates.C:37-86, 89-140): to[i] = from[map[i]]. */
+int b200_direct_map_build(b200_ctx* ctx, int32_t nTo, const double* toXyz, int32_t nFrom, const double* fromXyz, double tol,
+                          int32_t* map);
+int b200_direct_map_transfer(b200_ctx* ctx, int32_t nTo, const int32_t* map, int32_t nFrom, const double* from, int nComp,
+                             double* to);
 /* globalPolyPatch::patchFaceToGlobal: zone field = all-reduce(sum) of the zero-padded scatter of the
  * local patch values through faceToGlobalAddr (collective over the context's ranks). */
 int b200_patch_face_to_global(b200_ctx* ctx, int32_t nLocal, const int32_t* faceToGlobalAddr,

@@ -87,8 +87,21 @@ def build_ggi_emulator(force: bool = False) -> str:
     return GGI_EMU_PATH
 
 
+MAP_EMU_SRC = os.path.join(ROOT, "tests", "cpp", "direct_map_emulate.cpp")
+MAP_EMU_PATH = os.path.join(ROOT, "tests", "_build", "libdirect_map_emu.so")
+
+
+def build_direct_map_emulator(force: bool = False) -> str:
+    deps = [MAP_EMU_SRC, os.path.join(CSRC, "direct_map.hpp")]
+    if force or _stale(MAP_EMU_PATH, deps):
+        os.makedirs(os.path.dirname(MAP_EMU_PATH), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", MAP_EMU_PATH, MAP_EMU_SRC])
+    return MAP_EMU_PATH
+
+
 if __name__ == "__main__":
     print(build_library(force=True, verbose=True))
     print(build_schedule_emulator(force=True))
     print(build_assemble_emulator(force=True))
     print(build_ggi_emulator(force=True))
+    print(build_direct_map_emulator(force=True))

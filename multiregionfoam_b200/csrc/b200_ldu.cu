@@ -1704,5 +1704,7 @@ extern "C" int b200_global_face_to_patch(b200_ctx* ctx, int32_t nLocal, const in
     return B200_OK;
 }
 
+#include "direct_map.cuh"
+
 // block-coupled (vector4) systems: include/b200_blk.h
 #include "blk_system.cuh"

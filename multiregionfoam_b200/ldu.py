@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "b200_ggi_interpolate", "b200_patch_face_to_global", "b200_global_face_to_patch",
     "b200_sys_set_interface_attached", "b200_sys_set_interface_ggi",
     "b200_sys_set_fv_geometry", "b200_sys_assemble_T",
-    "b200_ggi_build", "b200_ggi_fetch",
+    "b200_ggi_build", "b200_ggi_fetch", "b200_direct_map_build", "b200_direct_map_transfer",
 ]
 
 TEQN_CONDUCT, TEQN_TRANSPORT = 0, 1
@@ -109,6 +109,8 @@ def load():
     L.b200_launch_count.restype = C.c_int64
     L.b200_ggi_build.argtypes = [vp, C.c_int32, ip, ip, C.c_int32, dp, C.c_int32, ip, ip, C.c_int32, dp, C.c_double, C.c_int]
     L.b200_ggi_fetch.argtypes = [vp, C.c_int32, ip, ip, dp]
+    L.b200_direct_map_build.argtypes = [vp, C.c_int32, dp, C.c_int32, dp, C.c_double, ip]
+    L.b200_direct_map_transfer.argtypes = [vp, C.c_int32, ip, C.c_int32, dp, C.c_int, dp]
     L.b200_ggi_interpolate.argtypes = [vp, C.c_int32, C.c_int32, ip, ip, dp, dp, C.c_int, dp]
     L.b200_patch_face_to_global.argtypes = [vp, C.c_int32, ip, dp, C.c_int, C.c_int32, dp]
     L.b200_global_face_to_patch.argtypes = [vp, C.c_int32, ip, dp, C.c_int, dp]
@@ -190,6 +192,26 @@ class Context:
         off, addr, w = np.zeros(nM + 1, np.int32), np.zeros(nnz, np.int32), np.zeros(nnz)
         self.check(load().b200_ggi_fetch(self.h, nM, _ip(off), _ip(addr), _dp(w)))
         return off, addr, w
+
+    def direct_map_build(self, to, from_, tol: float, require_conformal: bool = True) -> np.ndarray:
+        """directMapInterfaceToInterfaceMapping::calcZoneAToZoneBFaceMap & co. (directMapInterfaceToInterfaceMapping.C:147-181):
+        for every location of ``to`` (n x 3) the first location of ``from_`` closer than tol; an unmatched location is the
+        reference's FatalError ("Direct mapping can only be used with conformal interfaces!")."""
+        t, f = _f64(to).reshape(-1, 3), _f64(from_).reshape(-1, 3)
+        m = np.full(t.shape[0], -1, np.int32)
+        unmatched = self.check(load().b200_direct_map_build(self.h, t.shape[0], _dp(t), f.shape[0], _dp(f), float(tol), _ip(m)))
+        if unmatched and require_conformal:
+            raise B200Error(-1, f"Cannot calculate the map between interfaces: {unmatched} locations have no counterpart "
+                                "(direct mapping can only be used with conformal interfaces)")
+        return m
+
+    def direct_map_transfer(self, map_, from_) -> np.ndarray:
+        """transferFacesZoneToZone / transferPointsZoneToZone of the directMap mapping: to[i] = from[map[i]]."""
+        m, f = _i32(map_), _f64(from_)
+        nComp = 1 if f.ndim == 1 else f.shape[1]
+        out = np.empty((m.size, nComp))
+        self.check(load().b200_direct_map_transfer(self.h, m.size, _ip(m), f.shape[0], _dp(f), nComp, _dp(out)))
+        return out[:, 0] if f.ndim == 1 else out
 
     def ggi_interpolate(self, offsets, addr, weights, ff, nFrom: Optional[int] = None) -> np.ndarray:
         offsets, addr, weights = _i32(offsets), _i32(addr), _f64(weights)

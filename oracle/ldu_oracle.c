@@ -1026,6 +1026,31 @@ void orc_global_face_to_patch(int nLocal, const int* faceToGlobalAddr, const dou
         for (int d = 0; d < nComp; d++) pField[i * nComp + d] = gField[faceToGlobalAddr[i] * nComp + d];
 }
 
+/* directMapInterfaceToInterfaceMapping::calcZoneAToZoneBFaceMap, the N^2 search as written in the reference
+ * (src/numerics/interfaceToInterfaceMappings/directMapInterfaceToInterfaceMapping/directMapInterfaceToInterfaceMapping.C:
+ * 155-168; the same loop builds the B-to-A face map :276-289 and the two point maps :397-410, :518-531):
+ *   map = -1;  forAll(to, i) forAll(from, j) if (mag(to[i] - from[j]) < tol) { map[i] = j; break; }
+ * Returns the number of entries left at -1 (the reference is fatal when gMin(map) == -1, :170-181). */
+int orc_direct_map_build(int nTo, const double* to, int nFrom, const double* from, double tol, int* map)
+{
+    int unmatched = 0;
+    for (int i = 0; i < nTo; i++)
+    {
+        map[i] = -1;
+        for (int j = 0; j < nFrom; j++)
+        {
+            const double dx = to[3 * i] - from[3 * j], dy = to[3 * i + 1] - from[3 * j + 1], dz = to[3 * i + 2] - from[3 * j + 2];
+            if (sqrt(dx * dx + dy * dy + dz * dz) < tol)
+            {
+                map[i] = j;
+                break;
+            }
+        }
+        unmatched += map[i] < 0;
+    }
+    return unmatched;
+}
+
 void orc_direct_map(int nTo, const int* map, const double* from, int nComp, double* to)
 {
     for (int i = 0; i < nTo; i++)

@@ -152,6 +152,9 @@ void orc_global_face_to_patch(int nLocal, const int* faceToGlobalAddr, const dou
                               int nComp, double* pField);
 /* directMapInterfaceToInterfaceMapping: to[i] = from[map[i]] */
 void orc_direct_map(int nTo, const int* map, const double* from, int nComp, double* to);
+/* directMapInterfaceToInterfaceMapping.C:155-168 (and :276-289, :397-410, :518-531): map[i] = first j with
+ * mag(to[i] - from[j]) < tol, else -1; returns the number of -1 entries */
+int orc_direct_map_build(int nTo, const double* to, int nFrom, const double* from, double tol, int* map);
 
 const char* orc_version(void);
 

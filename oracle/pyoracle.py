@@ -244,6 +244,16 @@ def global_face_to_patch(faceToGlobalAddr, gField, nComp=1):
     return out.reshape(addr.size, nComp) if nComp > 1 else out
 
 
+def direct_map_build(to, from_, tol):
+    """directMapInterfaceToInterfaceMapping.C:155-168: -> map (first match, -1 if none), number unmatched."""
+    t, f = _f64(to), _f64(from_)
+    m = np.empty(t.size // 3, np.int32)
+    L = lib()
+    L.orc_direct_map_build.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_int)]
+    n = L.orc_direct_map_build(m.size, _dp(t), f.size // 3, _dp(f), float(tol), _ip(m))
+    return m, n
+
+
 def direct_map(map_, from_, nComp=1):
     m, f = _i32(map_), _f64(from_)
     out = np.empty(m.size * nComp)
