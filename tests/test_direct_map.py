@@ -1,7 +1,7 @@
 """CPU tests of the conformal-interface maps (directMap variant): oracle (the reference's N^2 loop,
 directMapInterfaceToInterfaceMapping.C:155-168, restated in oracle/ldu_oracle.c) against known answers, and the kernel's
 arithmetic + tiling / early-exit control flow (csrc/direct_map.hpp via tests/cpp/direct_map_emulate.cpp) against the oracle:
-index work, so everything is exact.  GPU leg: tests/test_gpu_zdirect_map.py."""
+index work, so everything is exact.  GPU leg: tests/test_gpu_zz_direct_map.py."""
 import ctypes as C
 
 import numpy as np
