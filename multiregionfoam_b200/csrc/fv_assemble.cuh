@@ -78,8 +78,8 @@ extern "C" int b200_sys_set_fv_geometry(b200_sys* s, int r, const double* V, con
         if (!fvasm::build_row_tables(N, F, R.l.data(), R.u.data(), nBoundary, bCells, bIntCoeffs, bSrcCoeffs, T))
             return set_err(ctx, B200_EUNSUPPORTED, "region %d: faces are not in upper-triangular (owner-sorted) order", r);
         if (s->fv.size() != s->regs.size()) s->fv.resize(s->regs.size());
-        s->fv[r].reset(new FvRegionDev);
-        FvRegionDev& G = *s->fv[r];
+        std::unique_ptr<FvRegionDev> fresh(new FvRegionDev); // installed only when every table is on the device
+        FvRegionDev& G = *fresh;
         const std::vector<double> hV(V, V + N), hMagSf(magSf, magSf + F), hDelta(deltaCoeffs, deltaCoeffs + F);
         CK(ctx, G.V.upload(hV, st));
         CK(ctx, G.magSf.upload(hMagSf, st));
@@ -93,6 +93,7 @@ extern "C" int b200_sys_set_fv_geometry(b200_sys* s, int r, const double* V, con
         CK(ctx, G.phi.alloc(F));
         CK(ctx, G.kappaFace.alloc(F));
         CK(ctx, cudaStreamSynchronize(st)); // the host vectors above die here
+        s->fv[r] = std::move(fresh);
     }
     catch (const std::exception& e)
     {
