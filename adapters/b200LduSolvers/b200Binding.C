@@ -1,23 +1,27 @@
 /*---------------------------------------------------------------------------*\
-  b200Binding.C -- see b200Binding.H.  NOT compiled in this repository (needs foam-extend 4.1).
+  b200Binding.C -- see b200Binding.H.
 \*---------------------------------------------------------------------------*/
 #include "b200Binding.H"
 #include "processorLduInterfaceField.H"
-#include "ggiLduInterfaceField.H"
-#include "regionCoupleLduInterfaceField.H"
 #include "regionCoupleFvPatch.H"
+#include "regionCouplePolyPatch.H"
+#include "fvMesh.H"
 #include "Pstream.H"
 #include "HashTable.H"
+
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
 
 namespace Foam
 {
     static b200_ctx* ctxPtr_ = NULL;
     // cache: first lduAddressing pointer of the system -> device system (topology change => new addressing)
-    static HashTable<b200_sys*, const void*, Hash<const void*> > sysCache_;
+    static HashTable<b200Binding::systemEntry*, const void*, Hash<const void*> > sysCache_;
 }
 
 
-Foam::b200_ctx* Foam::b200Binding::context()
+b200_ctx* Foam::b200Binding::context()
 {
     if (!ctxPtr_)
     {
@@ -58,12 +62,13 @@ int Foam::b200Binding::solverId(const word& typeName)
 {
     if (typeName == "cudaPCG" || typeName == "PCG" || typeName == "CG") return B200_SOLVER_PCG;
     if (typeName == "cudaPBiCGStab" || typeName == "BiCGStab" || typeName == "PBiCGStab") return B200_SOLVER_BICGSTAB;
+    if (typeName == "cudaPBiCG" || typeName == "PBiCG" || typeName == "BiCG") return B200_SOLVER_PBICG;
     FatalErrorIn("b200Binding::solverId(const word&)") << "Unknown solver " << typeName << abort(FatalError);
     return -1;
 }
 
 
-int Foam::b200Binding::precondId(const dictionary& dict)
+Foam::word Foam::b200Binding::precondName(const dictionary& dict)
 {
     word name("none");
     if (dict.found("preconditioner"))
@@ -71,88 +76,289 @@ int Foam::b200Binding::precondId(const dictionary& dict)
         if (dict.isDict("preconditioner")) dict.subDict("preconditioner").lookup("preconditioner") >> name;
         else dict.lookup("preconditioner") >> name;
     }
+    return name;
+}
+
+
+int Foam::b200Binding::precondId(const word& name)
+{
     if (name == "cudaDIC" || name == "DIC" || name == "FDIC") return B200_PRECOND_DIC;
     if (name == "cudaDILU" || name == "DILU") return B200_PRECOND_DILU;
     if (name == "Cholesky") return B200_PRECOND_CHOLESKY;
     if (name == "diagonal") return B200_PRECOND_DIAGONAL;
     if (name == "none") return B200_PRECOND_NONE;
-    FatalErrorIn("b200Binding::precondId(const dictionary&)")
+    FatalErrorIn("b200Binding::precondId(const word&)")
         << "Unknown preconditioner " << name << " (GAMG etc. are not provided by libb200ldu)" << abort(FatalError);
     return -1;
 }
 
 
-Foam::b200_sys* Foam::b200Binding::system
+// * * * * * * * * * * * * * * * interface extraction  * * * * * * * * * * * * * //
+
+namespace Foam
+{
+
+// ragged -> CSR
+static void flatten(const labelListList& addr, const scalarListList& w, labelList& offsets, labelList& flatAddr, scalarField& flatW)
+{
+    offsets.setSize(addr.size() + 1);
+    label n = 0;
+    forAll (addr, i)
+    {
+        offsets[i] = n;
+        n += addr[i].size();
+    }
+    offsets[addr.size()] = n;
+    flatAddr.setSize(n);
+    flatW.setSize(n);
+    n = 0;
+    forAll (addr, i)
+    {
+        forAll (addr[i], k)
+        {
+            flatAddr[n] = addr[i][k];
+            flatW[n++] = w[i][k];
+        }
+    }
+}
+
+// The tables regionCoupleFvPatch::interpolate() applies to the shadow's patchInternalField
+// (monolithicCouplingFvPatchField.C:214-217, 401-404): values of the shadow patch seen on the faces of rc.
+static void regionCoupleTables(const regionCoupleFvPatch& rc, b200Binding::ifaceInfo& I)
+{
+    const regionCouplePolyPatch& pp = refCast<const regionCouplePolyPatch>(rc.patch());
+    if (Pstream::parRun() && !rc.localParallel())
+    {
+        FatalErrorIn("b200Binding::describe(...)")
+            << "regionCouple patch " << pp.name() << " and its shadow are spread over several processors: "
+            << "this version of libb200ldu needs both sides of a regionCouple pair on one rank "
+            << "(decompose the two regions consistently along the interface)" << abort(FatalError);
+    }
+    I.nPeerFaces = rc.shadow().size();
+    if (pp.master())
+    {
+        // interpolate() = patchToPatch().slaveToMaster(): result[mf] = sum_k ff[masterAddr[mf][k]]*masterWeights[mf][k]
+        flatten(pp.patchToPatch().masterAddr(), pp.patchToPatch().masterWeights(), I.ggiOffsets, I.ggiAddr, I.ggiWeights);
+    }
+    else
+    {
+        // interpolate() = shadow().patchToPatch().masterToSlave(): the master owns the interpolator
+        flatten(pp.shadow().patchToPatch().slaveAddr(), pp.shadow().patchToPatch().slaveWeights(), I.ggiOffsets, I.ggiAddr, I.ggiWeights);
+    }
+}
+
+} // End namespace Foam
+
+
+void Foam::b200Binding::describe
 (
     const UPtrList<const lduMatrix>& matrices,
-    const List<lduInterfaceFieldPtrsList>& interfaces
+    const List<lduInterfaceFieldPtrsList>& interfaces,
+    List<List<ifaceInfo> >& ifaces
 )
 {
-    const void* key = &matrices[0].lduAddr();
-    if (sysCache_.found(key)) return sysCache_[key];
+    const label nRows = matrices.size();
+    ifaces.setSize(nRows);
 
-    b200_sys* sys = NULL;
-    check(b200_sys_create(context(), matrices.size(), &sys), "b200Binding::system(...)");
-    forAll (matrices, r)
-    {
-        const lduAddressing& addr = matrices[r].lduAddr();
-        check
-        (
-            b200_sys_set_region(sys, r, addr.size(), addr.lowerAddr().size(), addr.lowerAddr().begin(), addr.upperAddr().begin()),
-            "b200Binding::system(...)"
-        );
-    }
-    // patch index -> interface index of each row (only coupled patches are interfaces)
+    // ---- pass 1: which patches are interfaces, and of what kind
     forAll (matrices, r)
     {
         const lduInterfaceFieldPtrsList& ifs = interfaces[r];
+        label n = 0;
+        forAll (ifs, patchI) if (ifs.set(patchI)) n++;
+        ifaces[r].setSize(n);
+        n = 0;
         forAll (ifs, patchI)
         {
             if (!ifs.set(patchI)) continue;
             const lduInterfaceField& f = ifs[patchI];
-            const unallocLabelList& fc = matrices[r].lduAddr().patchAddr(patchI);
+            ifaceInfo& I = ifaces[r][n++];
+            I.patch = patchI;
             if (isA<processorLduInterfaceField>(f))
             {
-                const processorLduInterfaceField& pf = refCast<const processorLduInterfaceField>(f);
-                // the peer's interface index equals the rank of this patch among ITS coupled patches towards us;
-                // processor patches are created pairwise in the same order on both sides (decomposePar)
-                check
-                (
-                    b200_sys_add_interface(sys, r, B200_IFACE_PROCESSOR, fc.size(), fc.begin(), pf.neighbProcNo(), r,
-                                           /* peerIface, resolved by the binding's patch ordering */ -1, fc.size(), NULL, NULL, NULL),
-                    "b200Binding::system(...)"
-                );
+                I.kind = B200_IFACE_PROCESSOR;
+                I.peerRank = refCast<const processorLduInterfaceField>(f).neighbProcNo();
+                I.peerRegion = r;
+                I.nPeerFaces = matrices[r].lduAddr().patchAddr(patchI).size();
             }
-            else if (isA<regionCoupleLduInterfaceField>(f) || isA<ggiLduInterfaceField>(f))
+            else if (isA<regionCoupleFvPatch>(f.coupledInterface()))
             {
-                // shadow region / patch and the GGI addressing + weights of regionCouplePatch().interpolate:
-                // see monolithicCouplingFvPatchField.C:183-187 (shadow lookup), :214-217, :401-404 (interpolate)
-                // -> b200_sys_add_interface(sys, r, B200_IFACE_REGION_COUPLE, nFaces, faceCells, myRank, shadowRow,
-                //                           shadowIface, nShadowFaces, ggiOffsets, ggiAddr, ggiWeights)
-                // Before every solve of a cached system: b200_sys_set_interface_attached(sys, r, iface,
-                // regionCouplePatch().attached()) (regionInterfaceType.C:543-627; a detached patch makes b200_solve return
-                // B200_ESTATE, which check() turns into the FatalError of monolithicCouplingFvPatchField.C:406-413), and, when
-                // the interpolator was rebuilt since (attach() after mesh motion), b200_sys_set_interface_ggi with the new
-                // addressing / weights.
-                notImplemented("regionCouple extraction: needs regionCoupleFvPatch::shadowRegion()/shadow() of the host tree");
+                I.kind = B200_IFACE_REGION_COUPLE;
+                I.peerRank = Pstream::myProcNo();
             }
             else
             {
-                FatalErrorIn("b200Binding::system(...)")
+                FatalErrorIn("b200Binding::describe(...)")
                     << "lduInterfaceField of type " << f.type() << " on patch " << patchI
                     << " is not supported on the device (no CPU fallback)" << abort(FatalError);
             }
         }
     }
-    check(b200_sys_finalize(sys), "b200Binding::system(...)");
-    sysCache_.insert(key, sys);
-    return sys;
+
+    // ---- pass 2: regionCouple: shadow (row, interface) and the interpolation tables
+    forAll (matrices, r)
+    {
+        forAll (ifaces[r], i)
+        {
+            ifaceInfo& I = ifaces[r][i];
+            if (I.kind != B200_IFACE_REGION_COUPLE) continue;
+            const regionCoupleFvPatch& rc = refCast<const regionCoupleFvPatch>(interfaces[r][I.patch].coupledInterface());
+            // the row of the shadow region: the matrix that lives on shadowRegion()'s addressing
+            // (monolithicCouplingFvPatchField.C:183-187 looks the shadow FIELD up in shadowRegion(); the matrix of that
+            // field is a row of the same coupledLduMatrix, multiRegionSystem.C:143-145)
+            const lduAddressing* shadowAddr = &rc.shadowRegion().lduAddr();
+            I.peerRegion = -1;
+            forAll (matrices, q) if (&matrices[q].lduAddr() == shadowAddr) I.peerRegion = q;
+            if (I.peerRegion < 0)
+            {
+                FatalErrorIn("b200Binding::describe(...)")
+                    << "the shadow region of regionCouple patch " << rc.name() << " has no row in this coupled matrix"
+                    << abort(FatalError);
+            }
+            I.peerIface = -1;
+            forAll (ifaces[I.peerRegion], k) if (ifaces[I.peerRegion][k].patch == rc.shadowIndex()) I.peerIface = k;
+            if (I.peerIface < 0)
+            {
+                FatalErrorIn("b200Binding::describe(...)")
+                    << "shadow patch " << rc.shadowIndex() << " of regionCouple patch " << rc.name()
+                    << " is not a coupled patch of its row" << abort(FatalError);
+            }
+            regionCoupleTables(rc, I);
+        }
+    }
+
+    // ---- pass 3: processor patches: the peer's interface index.  Every rank publishes, per row, (neighbour rank,
+    // interface index) of its processor interfaces in patch order; the k-th patch of rank A towards rank B in a row
+    // pairs with the k-th patch of B towards A in the same row (decomposePar creates the two sides of a cut in the
+    // same order on both processors).
+    if (Pstream::parRun())
+    {
+        List<labelList> table(Pstream::nProcs());
+        {
+            DynamicList<label> mine;
+            forAll (ifaces, r) forAll (ifaces[r], i)
+            {
+                if (ifaces[r][i].kind != B200_IFACE_PROCESSOR) continue;
+                mine.append(r);
+                mine.append(ifaces[r][i].peerRank);
+                mine.append(i);
+            }
+            table[Pstream::myProcNo()] = labelList(mine);
+        }
+        Pstream::gatherList(table);
+        Pstream::scatterList(table);
+        forAll (ifaces, r) forAll (ifaces[r], i)
+        {
+            ifaceInfo& I = ifaces[r][i];
+            if (I.kind != B200_IFACE_PROCESSOR) continue;
+            label kMine = 0; // rank of this patch among my patches of row r towards the same neighbour
+            for (label j = 0; j < i; j++)
+                if (ifaces[r][j].kind == B200_IFACE_PROCESSOR && ifaces[r][j].peerRank == I.peerRank) kMine++;
+            const labelList& theirs = table[I.peerRank];
+            label k = 0;
+            for (label e = 0; e + 2 < theirs.size() + 0 && I.peerIface < 0; e += 3)
+            {
+                if (theirs[e] == r && theirs[e + 1] == Pstream::myProcNo())
+                {
+                    if (k == kMine) I.peerIface = theirs[e + 2];
+                    k++;
+                }
+            }
+            if (I.peerIface < 0)
+            {
+                FatalErrorIn("b200Binding::describe(...)")
+                    << "processor " << I.peerRank << " has no processor patch of row " << r << " towards processor "
+                    << Pstream::myProcNo() << " that matches patch " << I.patch << abort(FatalError);
+            }
+        }
+    }
+}
+
+
+Foam::b200Binding::systemEntry& Foam::b200Binding::system
+(
+    const UPtrList<const lduMatrix>& matrices,
+    const List<lduInterfaceFieldPtrsList>& interfaces
+)
+{
+    const char* where = "b200Binding::system(...)";
+    const void* key = &matrices[0].lduAddr();
+    if (sysCache_.found(key))
+    {
+        // cached: the patches cannot have changed (a topology change gives new lduAddressing objects), but attach() /
+        // detach() flip the regionCouple patches and re-compute the interpolation (regionInterfaceType.C:543-627)
+        systemEntry& E = *sysCache_[key];
+        forAll (E.ifaces, r) forAll (E.ifaces[r], i)
+        {
+            ifaceInfo& I = E.ifaces[r][i];
+            if (I.kind != B200_IFACE_REGION_COUPLE) continue;
+            const regionCoupleFvPatch& rc = refCast<const regionCoupleFvPatch>(interfaces[r][I.patch].coupledInterface());
+            check(b200_sys_set_interface_attached(E.sys, r, i, rc.coupled() ? 1 : 0), where);
+            if (!rc.coupled()) continue;
+            ifaceInfo now;
+            regionCoupleTables(rc, now);
+            if (now.ggiAddr != I.ggiAddr || now.ggiOffsets != I.ggiOffsets || now.ggiWeights != I.ggiWeights)
+            {
+                I.ggiOffsets = now.ggiOffsets;
+                I.ggiAddr = now.ggiAddr;
+                I.ggiWeights = now.ggiWeights;
+                I.nPeerFaces = now.nPeerFaces;
+                check
+                (
+                    b200_sys_set_interface_ggi(E.sys, r, i, I.nPeerFaces, I.ggiOffsets.begin(), I.ggiAddr.begin(), I.ggiWeights.begin()),
+                    where
+                );
+            }
+        }
+        return E;
+    }
+
+    systemEntry* Eptr = new systemEntry;
+    systemEntry& E = *Eptr;
+    describe(matrices, interfaces, E.ifaces);
+    check(b200_sys_create(context(), matrices.size(), &E.sys), where);
+    forAll (matrices, r)
+    {
+        const lduAddressing& addr = matrices[r].lduAddr();
+        check
+        (
+            b200_sys_set_region(E.sys, r, addr.size(), addr.lowerAddr().size(), addr.lowerAddr().begin(), addr.upperAddr().begin()),
+            where
+        );
+    }
+    forAll (matrices, r)
+    {
+        forAll (E.ifaces[r], i)
+        {
+            const ifaceInfo& I = E.ifaces[r][i];
+            const unallocLabelList& fc = matrices[r].lduAddr().patchAddr(I.patch);
+            const bool ggi = I.ggiOffsets.size() > 0;
+            const int idx = b200_sys_add_interface
+            (
+                E.sys, r, I.kind, fc.size(), fc.begin(), I.peerRank, I.peerRegion, I.peerIface, I.nPeerFaces,
+                ggi ? I.ggiOffsets.begin() : NULL, ggi ? I.ggiAddr.begin() : NULL, ggi ? I.ggiWeights.begin() : NULL
+            );
+            check(idx, where);
+            if (idx != i)
+            {
+                FatalErrorIn(where) << "interface numbering out of step: " << idx << " != " << i << abort(FatalError);
+            }
+            if (I.kind == B200_IFACE_REGION_COUPLE)
+            {
+                const regionCoupleFvPatch& rc = refCast<const regionCoupleFvPatch>(interfaces[r][I.patch].coupledInterface());
+                check(b200_sys_set_interface_attached(E.sys, r, i, rc.coupled() ? 1 : 0), where);
+            }
+        }
+    }
+    check(b200_sys_finalize(E.sys), where);
+    sysCache_.insert(key, Eptr);
+    return E;
 }
 
 
 void Foam::b200Binding::setCoeffs
 (
-    b200_sys* sys,
+    const systemEntry& E,
     const UPtrList<const lduMatrix>& matrices,
     const List<const FieldField<Field, scalar>*>& bouCoeffs,
     const List<const FieldField<Field, scalar>*>& intCoeffs
@@ -163,27 +369,123 @@ void Foam::b200Binding::setCoeffs
         const lduMatrix& m = matrices[r];
         check
         (
-            b200_sys_set_coeffs(sys, r, m.diag().begin(), m.upper().begin(), m.asymmetric() ? m.lower().begin() : NULL),
+            b200_sys_set_coeffs(E.sys, r, m.diag().begin(), m.upper().begin(), m.asymmetric() ? m.lower().begin() : NULL),
             "b200Binding::setCoeffs(...)"
         );
-        label ifaceI = 0;
-        forAll (*bouCoeffs[r], patchI)
+        forAll (E.ifaces[r], i)
         {
-            if ((*bouCoeffs[r])[patchI].size() && m.lduAddr().patchAddr(patchI).size() /* coupled patch */)
-            {
-                check
-                (
-                    b200_sys_set_interface_coeffs(sys, r, ifaceI++, (*bouCoeffs[r])[patchI].begin(), (*intCoeffs[r])[patchI].begin()),
-                    "b200Binding::setCoeffs(...)"
-                );
-            }
+            const label patchI = E.ifaces[r][i].patch;
+            check
+            (
+                b200_sys_set_interface_coeffs(E.sys, r, i, (*bouCoeffs[r])[patchI].begin(), (*intCoeffs[r])[patchI].begin()),
+                "b200Binding::setCoeffs(...)"
+            );
         }
     }
 }
 
 
-void Foam::b200Binding::dump(const fileName& dir, b200_sys*, const scalarField&, const scalarField&)
+// * * * * * * * * * * * * * * * * * * dump  * * * * * * * * * * * * * * * * * * //
+
+namespace Foam
 {
-    // format: INTEGRATION.md "LDU dump format"; written with OFstream in binary mode
-    notImplemented("b200Binding::dump: see INTEGRATION.md");
+    static void put(std::ofstream& os, const void* p, const size_t bytes) { os.write(reinterpret_cast<const char*>(p), bytes); }
+    static void putI(std::ofstream& os, const int v) { put(os, &v, sizeof(int)); }
+    static void putD(std::ofstream& os, const double v) { put(os, &v, sizeof(double)); }
+    static void putLabels(std::ofstream& os, const UList<label>& l)
+    {
+        // WM_LABEL_SIZE=32 in the reference build (compile_commands.json): label == int32
+        forAll (l, i) putI(os, l[i]);
+    }
+    static void putScalars(std::ofstream& os, const UList<scalar>& f)
+    {
+        forAll (f, i) putD(os, f[i]);
+    }
+    static void putName(std::ofstream& os, const word& w)
+    {
+        char buf[32];
+        memset(buf, 0, sizeof(buf));
+        strncpy(buf, w.c_str(), sizeof(buf) - 1);
+        put(os, buf, sizeof(buf));
+    }
+}
+
+
+void Foam::b200Binding::dump
+(
+    const fileName& file,
+    const UPtrList<const lduMatrix>& matrices,
+    const List<lduInterfaceFieldPtrsList>& interfaces,
+    const List<const FieldField<Field, scalar>*>& bouCoeffs,
+    const List<const FieldField<Field, scalar>*>& intCoeffs,
+    const UPtrList<const scalarField>& x,
+    const UPtrList<const scalarField>& b,
+    const word& solverName,
+    const word& preconName,
+    const scalar tolerance,
+    const scalar relTol,
+    const label minIter,
+    const label maxIter,
+    const scalarField& history
+)
+{
+    // layout: multiregionfoam_b200/dumpio.py (format "B200LDU1", little endian)
+    List<List<ifaceInfo> > ifaces;
+    describe(matrices, interfaces, ifaces);
+
+    std::ofstream os(file.c_str(), std::ios::binary);
+    if (!os.good())
+    {
+        FatalErrorIn("b200Binding::dump(...)") << "cannot open " << file << abort(FatalError);
+    }
+    put(os, "B200LDU1", 8);
+    putI(os, Pstream::myProcNo());
+    putI(os, Pstream::nProcs());
+    putI(os, matrices.size());
+    forAll (matrices, r)
+    {
+        const lduMatrix& m = matrices[r];
+        const lduAddressing& addr = m.lduAddr();
+        putI(os, addr.size());
+        putI(os, addr.lowerAddr().size());
+        putI(os, m.asymmetric() ? 0 : 1);
+        putI(os, ifaces[r].size());
+        putLabels(os, addr.lowerAddr());
+        putLabels(os, addr.upperAddr());
+        putScalars(os, m.diag());
+        putScalars(os, m.upper());
+        if (m.asymmetric()) putScalars(os, m.lower());
+        putScalars(os, b[r]);
+        putScalars(os, x[r]);
+        forAll (ifaces[r], i)
+        {
+            const ifaceInfo& I = ifaces[r][i];
+            const unallocLabelList& fc = addr.patchAddr(I.patch);
+            const bool ggi = I.ggiOffsets.size() > 0;
+            putI(os, I.kind);
+            putI(os, fc.size());
+            putI(os, I.peerRank);
+            putI(os, I.peerRegion);
+            putI(os, I.peerIface);
+            putI(os, I.nPeerFaces);
+            putI(os, ggi ? 1 : 0);
+            putLabels(os, fc);
+            putScalars(os, (*bouCoeffs[r])[I.patch]);
+            putScalars(os, (*intCoeffs[r])[I.patch]);
+            if (ggi)
+            {
+                putLabels(os, I.ggiOffsets);
+                putLabels(os, I.ggiAddr);
+                putScalars(os, I.ggiWeights);
+            }
+        }
+    }
+    putName(os, solverName);
+    putName(os, preconName);
+    putD(os, tolerance);
+    putD(os, relTol);
+    putI(os, minIter);
+    putI(os, maxIter);
+    putI(os, history.size());
+    putScalars(os, history);
 }

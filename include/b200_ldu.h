@@ -127,7 +127,9 @@ int b200_sys_add_interface(b200_sys* sys, int r, int kind, int32_t nFaces, const
 int b200_sys_finalize(b200_sys* sys);
 /* lduMatrix coefficients of region r (host -> device).  lower == NULL: symmetric matrix. */
 int b200_sys_set_coeffs(b200_sys* sys, int r, const double* diag, const double* upper, const double* lower);
-/* boundaryCoeffs / internalCoeffs of interface iface of region r (intCoeffs may be NULL). */
+/* boundaryCoeffs / internalCoeffs of interface iface of region r.  The transposed products (Tmul, PBiCG's shadow
+ * system) apply intCoeffs, as lduMatrix::Tmul passes interfaceIntCoeffs to updateMatrixInterfaces.  intCoeffs == NULL
+ * means "the same as bouCoeffs" (symmetric coupling); the CPU oracle follows the same rule (orc_add_iface). */
 int b200_sys_set_interface_coeffs(b200_sys* sys, int r, int iface, const double* bouCoeffs, const double* intCoeffs);
 /* regionInterfaceType::attach() / detach() (src/regionInterfaces/regionInterface/regionInterfaceType.C:543-627) flip the
  * regionCouple patches of an interface.  A detached patch must not take part in a coupled matrix-vector product:

@@ -1232,6 +1232,7 @@ static int upload_scalars(b200_sys* s, const b200_solver_opts* o, int histCap)
     h.histCap = std::min(histCap, (int)kHistOnDevice);
     s->hostFlags[0] = 0;
     s->hostFlags[1] = 0;
+    s->hostFlags[2] = 0;
     CK(s->ctx, cudaMemcpyAsync(s->sc.p, &h, sizeof(h), cudaMemcpyHostToDevice, s->ctx->stream));
     CK(s->ctx, cudaStreamSynchronize(s->ctx->stream)); // h is on the stack
     return B200_OK;
@@ -1269,24 +1270,50 @@ static int solve_head(b200_sys* s, int op, double* Ax, double* r, double* rw, do
     return B200_OK;
 }
 
-// keep the host at most kAhead iterations ahead of the device so that the done flag is seen soon
+// Keep the host at most kAhead iterations ahead of the device so that the done flag is seen soon.
+// Leaving the loop: a single rank breaks as soon as its host sees the mapped done flag.  With several ranks every
+// iteration enqueues NCCL calls (the all-reduce of reduce_finish, the halo exchange of launch_amul), so all hosts
+// must enqueue exactly the same number of iterations although each of them reads the flag at another moment:
+// the device publishes the loop iteration d that set done (hostFlags[2] = d + 2, identical on all ranks because it
+// follows from all-reduced scalars), the flag is certainly visible once the event of iteration d has been waited
+// for - which throttle_wait does at iteration d + kAhead - and every rank stops exactly there (or at maxIter).
+// Iterations enqueued after d are no-ops on the device (every kernel returns on sc->done) whose collectives still pair up.
+static int throttle_ahead(const b200_sys* s) { return s->ctx->nranks > 1 ? 3 : 8; }
 static int throttle_wait(b200_sys* s, int it)
 {
-    const int kAhead = 8;
-    if ((int)s->throttle.size() < kAhead)
+    const int kAhead = throttle_ahead(s);
+    if ((int)s->throttle.size() < 8)
     {
-        s->throttle.resize(kAhead, nullptr);
+        s->throttle.resize(8, nullptr);
         for (auto& e : s->throttle)
             if (!e) CK(s->ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
-    cudaEvent_t e = s->throttle[it % kAhead];
-    if (it >= kAhead) CK(s->ctx, cudaEventSynchronize(e));
+    if (it >= kAhead) CK(s->ctx, cudaEventSynchronize(s->throttle[(it - kAhead) % 8]));
     return B200_OK;
 }
 static int throttle_mark(b200_sys* s, int it)
 {
     CK(s->ctx, cudaEventRecord(s->throttle[it % 8], s->ctx->stream));
     return B200_OK;
+}
+// After solve_head: with several ranks wait for the head, so that "converged before the first iteration" is seen by
+// every host (the loop is then skipped everywhere).
+static int loop_enter(b200_sys* s, bool* skip)
+{
+    *skip = false;
+    if (s->ctx->nranks > 1)
+    {
+        CK(s->ctx, cudaStreamSynchronize(s->ctx->stream));
+        *skip = *(volatile int*)&s->hostFlags[2] != 0;
+    }
+    return B200_OK;
+}
+// top of a solver-loop iteration (after throttle_wait): true when this host has to leave the loop
+static bool loop_leave(const b200_sys* s, int it)
+{
+    if (s->ctx->nranks <= 1) return *(volatile int*)&s->hostFlags[0] != 0;
+    const int f = *(volatile int*)&s->hostFlags[2];
+    return f != 0 && it >= (f - 2) + throttle_ahead(s);
 }
 
 // PBiCG::solve (foam/matrices/lduMatrix/solvers/PBiCG/PBiCG.C): PCG's scalar recurrences (rho = (wA, rT),
@@ -1310,10 +1337,12 @@ static int solve_pbicg(b200_sys* s, const b200_solver_opts* o)
     if ((rc = ensure_precond(s, o->precond, false))) return rc;
     if ((rc = ensure_precond(s, o->precond, true))) return rc;
     PartCounts cnt;
-    for (int it = 0; it < o->maxIter; it++)
+    bool skipLoop;
+    if ((rc = loop_enter(s, &skipLoop))) return rc;
+    for (int it = 0; it < o->maxIter && !skipLoop; it++)
     {
-        if (*(volatile int*)&s->hostFlags[0]) break;
         if ((rc = throttle_wait(s, it))) return rc;
+        if (loop_leave(s, it)) break;
         if ((rc = launch_precondition(s, o->precond, rA, zA, tmp, false, 0, false))) return rc; // wA = M^-1 rA
         if ((rc = launch_precondition(s, o->precond, rT, zT, tmp, false, 0, true))) return rc;  // wT = M^-T rT
         if (n)
@@ -1360,10 +1389,12 @@ static int solve_bicgstab(b200_sys* s, const b200_solver_opts* o)
     if ((rc = ensure_precond(s, o->precond, false))) return rc;
     const bool sweeps = o->precond >= B200_PRECOND_DIC;
     PartCounts cnt;
-    for (int it = 0; it < o->maxIter; it++)
+    bool skipLoop;
+    if ((rc = loop_enter(s, &skipLoop))) return rc;
+    for (int it = 0; it < o->maxIter && !skipLoop; it++)
     {
-        if (*(volatile int*)&s->hostFlags[0]) break;
         if ((rc = throttle_wait(s, it))) return rc;
+        if (loop_leave(s, it)) break;
         if (n)
         {
             KScope k(s, B200_K_VECTOR);
@@ -1407,10 +1438,12 @@ static int solve_pcg(b200_sys* s, const b200_solver_opts* o)
     const bool sweeps = o->precond >= B200_PRECOND_DIC;
     if (sweeps && (rc = fill_sentinel(s, tmp, z, 1))) return rc;
     PartCounts cnt;
-    for (int it = 0; it < o->maxIter; it++)
+    bool skipLoop;
+    if ((rc = loop_enter(s, &skipLoop))) return rc;
+    for (int it = 0; it < o->maxIter && !skipLoop; it++)
     {
-        if (*(volatile int*)&s->hostFlags[0]) break;
         if ((rc = throttle_wait(s, it))) return rc;
+        if (loop_leave(s, it)) break;
         if ((rc = launch_precondition(s, o->precond, rA, z, tmp, true, 0))) return rc; // wA = M^-1 rA
         if (n)
         {

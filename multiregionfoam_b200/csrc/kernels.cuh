@@ -143,7 +143,13 @@ __device__ __forceinline__ void stop_check(DevScalars* sc, volatile int* hostFla
     if (hostFlags)
     {
         hostFlags[1] = sc->nIter;
-        if (sc->done) hostFlags[0] = 1;
+        if (sc->done)
+        {
+            // [2]: index of the solver-loop iteration that set done, + 2 (head of the solve: -1), in ONE word: with
+            // several ranks every host leaves its loop at the same iteration derived from it (b200_ldu.cu, solve loops)
+            hostFlags[2] = sc->nIter + 1;
+            hostFlags[0] = 1;
+        }
     }
 }
 
@@ -221,7 +227,11 @@ __device__ void scalar_op(DevScalars* sc, int op, double* history, volatile int*
             {
                 sc->singular = 1; // checkSingularity -> break before the update
                 sc->done = 1;
-                if (hostFlags) hostFlags[0] = 1;
+                if (hostFlags)
+                {
+                    hostFlags[2] = sc->nIter + 2; // set inside iteration nIter (stop_check runs after nIter++)
+                    hostFlags[0] = 1;
+                }
             }
             else
                 sc->alpha = sc->wArA / wApA;
@@ -479,9 +489,13 @@ __device__ __forceinline__ void st_relaxed(double* p, double v)
     asm volatile("st.global.cg.f64 [%0], %1;" ::"l"(p), "d"(v));
 }
 
+#ifndef B200_SWEEP_SPIN_LIMIT
+#define B200_SWEEP_SPIN_LIMIT (1 << 24)
+#endif
+constexpr int kSweepSpinLimit = B200_SWEEP_SPIN_LIMIT; // polling rounds before a group gives up (B200_EDEVICE)
 __device__ __noinline__ double sweep_spin(const double* p, int* err)
 {
-    for (long long tries = 0; tries < (1ll << 24); tries++)
+    for (long long tries = 0; tries < (long long)kSweepSpinLimit; tries++)
     {
         const double v = ld_relaxed(p);
         if (!is_sentinel(v)) return v;
@@ -1045,7 +1059,7 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
                 {
                     __nanosleep(tries > 4096 ? 400 : 64);
                     if ((tries & 4095) == 4095 && *(volatile int*)err) break;
-                    if (tries >= (1 << 24))
+                    if (tries >= kSweepSpinLimit)
                     {
                         atomicExch(err, 1);
                         break;
@@ -1099,15 +1113,197 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
     }
 }
 
+// Producer of the set organisation: this warp prepares steps h0 .. h0 + M - 1 of the blocks set, set + nSets, ...
+template <int MODE, int LG, int M, bool STATS>
+__device__ __forceinline__ void split_producer_sets(const PipeDev& S, const SplitCtx& C, const int g, const int set, const int nSets, const int h0,
+                                                    const int lane, double* out, int* err)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int LGA = LG > 0 ? LG : 1;
+    constexpr int dir = MODE == 1 ? -1 : 1;
+    const double neutral = MODE == 2 ? 1.0 : 0.0;
+    const int Kg = C.Kg;
+    // byte offsets of step h0's and this lane's operands inside a stage; step h0 + u at + u * (the step's stride)
+    const unsigned offCoef = (unsigned)(C.offP + h0 * C.pRec + lane * 8);             // coef i at + i * 256
+    const unsigned offCode = (unsigned)(C.offP + h0 * C.pRec + LG * 256 + lane * 4);  // code i at + i * 128
+    const unsigned offConst = (unsigned)(C.offP + h0 * C.pRec + LG * 384 + lane * 4); // const code k at + k * 128
+    const unsigned pRec = (unsigned)C.pRec;
+    const int vec0 = (dir > 0 ? h0 : kNH - 1 - h0) * 32 + lane; // step h0 inside the a / b chunk; step h0 + u at + u * dir * 32
+    const unsigned offA = (unsigned)(C.offA + vec0 * 8);
+    const int vecStep = dir * 256;
+    const unsigned offGen = (unsigned)(h0 * 256 + lane * 8 + 7); // top byte of the step's meta word
+    const unsigned offHd = (unsigned)(C.offHdr + h0 * 256 + lane * 8); // hdr planes acc0 | cval 0 | cval 1
+    const unsigned stage0 = smem_u32(C.stages), stageBytes = (unsigned)C.stageBytes;
+    const unsigned bar0 = smem_u32(C.rawBar), cnt0 = smem_u32(C.cnt);
+    const int NS = C.NS;
+    int st = set % NS;
+    unsigned par = (unsigned)(set / NS) & 1u;
+    const bool timed = STATS && set == 0 && h0 == 0;
+    long long tStage = 0, tVal = 0, tSpin = 0, tAll = timed ? clock64() : 0;
+    for (int blk = set; blk < C.nBlocks; blk += nSets)
+    {
+        const unsigned sg = stage0 + (unsigned)st * stageBytes;
+        long long* const tr = (STATS && lane == 0 && blk < kTraceBlocks) ? S.stats + (long long)kStatsStride * g + 16 + blk * 8 : nullptr;
+        if (STATS && tr && h0 == 0) tr[3] = clock64();
+        const long long w0 = timed ? clock64() : 0;
+        mbar_wait_u32(bar0 + 8u * (unsigned)st, par);
+        if (timed) tStage += clock64() - w0;
+        if (STATS && tr && h0 == 0) tr[4] = clock64();
+        // ---- codes of the cross-group terms, then their loads: the only global accesses of the step
+        int cd[M][LGA], kc[M][2];
+        double mv[M][LGA], mc[M][2];
+#pragma unroll
+        for (int u = 0; u < M; u++)
+        {
+#pragma unroll
+            for (int i = 0; i < LG; i++) cd[u][i] = lds_s32(sg + offCode + u * pRec + i * 128);
+#pragma unroll
+            for (int k = 0; k < 2; k++) kc[u][k] = (k < Kg) ? lds_s32(sg + offConst + u * pRec + k * 128) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < M; u++)
+        {
+#pragma unroll
+            for (int i = 0; i < LG; i++)
+            {
+                mv[u][i] = neutral;
+                if (cd[u][i] >= 0) mv[u][i] = ld_relaxed(out + cd[u][i]);
+            }
+#pragma unroll
+            for (int k = 0; k < 2; k++)
+            {
+                mc[u][k] = 0.0;
+                if (kc[u][k] >= 0) mc[u][k] = ld_relaxed(out + kc[u][k]);
+            }
+        }
+        // ---- operands from the stage while the loads fly
+        double acc[M];
+        unsigned kind = 0u;
+#pragma unroll
+        for (int u = 0; u < M; u++)
+        {
+            acc[u] = lds_f64(offA + sg + u * vecStep);
+            if (MODE == 0) acc[u] *= lds_f64(offA + sg + u * vecStep + kNH * 256);
+            const unsigned b7 = lds_u8(sg + offGen + u * 256); // bit 0: descriptor-driven step, bit 5: dual step (schedule.hpp)
+            kind += MODE == 2 ? 0x100u : (((b7 & 1u) << 8) | (((b7 >> 5) & 1u) << (16 + h0 + u)));
+        }
+        // ---- the cross-group values: poll for whatever had not been written yet
+        const long long v0 = timed ? clock64() : 0;
+        bool bad = false;
+#pragma unroll
+        for (int u = 0; u < M; u++)
+        {
+#pragma unroll
+            for (int i = 0; i < LG; i++) bad |= cd[u][i] >= 0 && is_sentinel(mv[u][i]);
+#pragma unroll
+            for (int k = 0; k < 2; k++) bad |= kc[u][k] >= 0 && is_sentinel(mc[u][k]);
+        }
+        const bool anyBad = __any_sync(FULL, bad);
+        const long long v1 = timed ? clock64() : 0;
+        if (STATS && tr && h0 == 0) tr[5] = v1;
+        if (anyBad)
+        {
+            if (STATS && lane == 0) atomicAdd((unsigned long long*)(S.stats + (long long)kStatsStride * g + 4), 1ull);
+            int tries = 0;
+            bool still;
+            do
+            {
+#pragma unroll
+                for (int u = 0; u < M; u++)
+                {
+#pragma unroll
+                    for (int i = 0; i < LG; i++)
+                        if (cd[u][i] >= 0 && is_sentinel(mv[u][i])) mv[u][i] = ld_relaxed(out + cd[u][i]);
+#pragma unroll
+                    for (int k = 0; k < 2; k++)
+                        if (kc[u][k] >= 0 && is_sentinel(mc[u][k])) mc[u][k] = ld_relaxed(out + kc[u][k]);
+                }
+                still = false;
+#pragma unroll
+                for (int u = 0; u < M; u++)
+                {
+#pragma unroll
+                    for (int i = 0; i < LG; i++) still |= cd[u][i] >= 0 && is_sentinel(mv[u][i]);
+#pragma unroll
+                    for (int k = 0; k < 2; k++) still |= kc[u][k] >= 0 && is_sentinel(mc[u][k]);
+                }
+                if (++tries >= 64)
+                {
+                    __nanosleep(tries > 4096 ? 400 : 64);
+                    if ((tries & 4095) == 4095 && *(volatile int*)err) break;
+                    if (tries >= kSweepSpinLimit)
+                    {
+                        atomicExch(err, 1);
+                        break;
+                    }
+                }
+            } while (__any_sync(FULL, still));
+        }
+        if (timed)
+        {
+            tVal += v1 - v0;
+            tSpin += clock64() - v1;
+            if (blk == (C.nBlocks / 2 / nSets) * nSets && lane == 0)
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(S.stats[(long long)kStatsStride * g + 14]));
+        }
+        // ---- leading terms in reference order, hand-over
+#pragma unroll
+        for (int u = 0; u < M; u++)
+        {
+#pragma unroll
+            for (int i = 0; i < LG; i++) acc[u] = sweep_apply<MODE>(acc[u], lds_f64(sg + offCoef + u * pRec + i * 256), mv[u][i]); // padding: coefficient 0, neutral value
+            sts_f64(sg + offHd + u * 256, acc[u]);
+            if (Kg > 0) sts_f64(sg + offHd + u * 256 + kNH * 256, mc[u][0]);
+            if (Kg > 1) sts_f64(sg + offHd + u * 256 + 2 * kNH * 256, mc[u][1]);
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("red.relaxed.cta.shared.add.u32 [%0], %1;" ::"r"(cnt0 + 4u * (unsigned)st), "r"((unsigned)M + kind) : "memory");
+        if (STATS && tr && h0 == 0) tr[6] = clock64();
+        if (STATS && tr && h0 + M == kNH) tr[7] = clock64();
+        st += nSets;
+        while (st >= NS)
+        {
+            st -= NS;
+            par ^= 1u;
+        }
+    }
+    if (timed && lane == 0)
+    {
+        long long* sp = S.stats + (long long)kStatsStride * g;
+        sp[8] = clock64() - tAll;
+        sp[9] = tStage;
+        sp[10] = tVal;
+        sp[11] = tSpin;
+    }
+}
+
 // Warp roles: consumer, kNH producers, loader.  (Measured on B200: giving the consumer a scheduler sub-partition of its
 // own - wid % 4, 11 warps - or the highest warp id of the CTA changes the sweep time by < 2 %: the consumer is not
 // short of issue slots.)
 constexpr int kRoleConsumer = -1, kRoleLoader = -2;
-constexpr int kSweepWarps = 2 + kNH;
+// Producer organisation (B200_PROD_SETS > 0): kProdSets sets of producer warps work on kProdSets consecutive blocks at
+// the same time (set s takes the blocks blk = s mod kProdSets); inside a set a producer prepares kProdM consecutive
+// steps of the block.  A producer's step is a chain of latencies (stage wait, code loads, the L2 round trip of the
+// cross-group values, the check, the hand-over) that no amount of tuning brought under ~850 cycles per block; with
+// one set that chain IS the block time of the group (106 cycles per step against the consumer's 61).  With several
+// sets the chains of consecutive blocks overlap, so the loads of the cross-group values can be issued when they are
+// needed (no prefetch a block ahead, no second register set) and a group's pace is the consumer's.
+#ifndef B200_PROD_SETS
+#define B200_PROD_SETS 4
+#endif
+#ifndef B200_PROD_M
+#define B200_PROD_M 4
+#endif
+constexpr int kProdSets = B200_PROD_SETS;
+constexpr int kProdM = B200_PROD_SETS > 0 ? B200_PROD_M : 1;
+constexpr int kProdPerSet = kNH / kProdM;
+constexpr int kProducers = B200_PROD_SETS > 0 ? kProdSets * kProdPerSet : kNH;
+static_assert(kNH % kProdM == 0, "a producer takes a whole number of steps of a block");
+constexpr int kSweepWarps = 2 + kProducers;
 __device__ __forceinline__ int sweep_role(int warp)
 {
     if (warp == 0) return kRoleConsumer;
-    if (warp == 1 + kNH) return kRoleLoader;
+    if (warp == 1 + kProducers) return kRoleLoader;
     return warp - 1;
 }
 
@@ -1182,6 +1378,22 @@ __device__ __forceinline__ void sweep_group_split(const PipeDev& S, const int g,
             }
         }
     }
+#if B200_PROD_SETS > 0
+    else if (role >= 0)
+    {
+        const int set = role / kProdPerSet, h0 = (role % kProdPerSet) * kProdM;
+        switch (C.Lg)
+        {
+            case 0: split_producer_sets<MODE, 0, kProdM, STATS>(S, C, g, set, kProdSets, h0, lane, out, err); break;
+            case 1: split_producer_sets<MODE, 1, kProdM, STATS>(S, C, g, set, kProdSets, h0, lane, out, err); break;
+            case 2: split_producer_sets<MODE, 2, kProdM, STATS>(S, C, g, set, kProdSets, h0, lane, out, err); break;
+            case 3: split_producer_sets<MODE, 3, kProdM, STATS>(S, C, g, set, kProdSets, h0, lane, out, err); break;
+            case 4: split_producer_sets<MODE, 4, kProdM, STATS>(S, C, g, set, kProdSets, h0, lane, out, err); break;
+            case 5: split_producer_sets<MODE, 5, kProdM, STATS>(S, C, g, set, kProdSets, h0, lane, out, err); break;
+            default: split_producer_sets<MODE, 6, kProdM, STATS>(S, C, g, set, kProdSets, h0, lane, out, err); break;
+        }
+    }
+#else
     else if (role >= 0)
     {
         const int h = role;
@@ -1196,6 +1408,7 @@ __device__ __forceinline__ void sweep_group_split(const PipeDev& S, const int g,
             default: split_producer<MODE, 6, STATS>(S, C, g, h, lane, out, err); break;
         }
     }
+#endif
 }
 
 // Generic path (any W): plain loops, cross-warp values read when consumed.

@@ -190,10 +190,9 @@ int orc_add_iface(orc_sys* s, int row, int kind, int nFaces, const int* faceCell
     I->nFaces = nFaces;
     I->faceCells = (int*)dupmem(faceCells, sizeof(int) * (size_t)nFaces);
     I->bouCoeffs = (double*)dupmem(bouCoeffs, sizeof(double) * (size_t)nFaces);
-    if (intCoeffs)
-        I->intCoeffs = (double*)dupmem(intCoeffs, sizeof(double) * (size_t)nFaces);
-    else
-        I->intCoeffs = (double*)calloc((size_t)(nFaces ? nFaces : 1), sizeof(double));
+    /* NULL internal coefficients: the boundary coefficients are used for the transposed product too
+       (b200_ldu.h, b200_sys_set_interface_coeffs; same rule in the device library) */
+    I->intCoeffs = (double*)dupmem(intCoeffs ? intCoeffs : bouCoeffs, sizeof(double) * (size_t)(nFaces ? nFaces : 1));
     I->peerRow = peerRow;
     I->peerIface = peerIface;
     if (ggiOffsets)
@@ -279,8 +278,9 @@ static void pool_run_items(void)
 }
 static void* pool_worker(void* arg)
 {
-    unsigned long seen = 0;
-    (void)arg;
+    /* a worker starts at the generation that was current when it was created (par_for creates workers before it
+       publishes a job), so it never takes part in - or reports completion of - a job older than itself */
+    unsigned long seen = (unsigned long)(size_t)arg;
     for (;;)
     {
         pthread_mutex_lock(&g_pool.mu);
@@ -302,7 +302,7 @@ static void par_for(int n, orc_job f, void* ctx)
     }
     while (g_pool.nWorkers < g_threads - 1 && g_pool.nWorkers < 64)
     {
-        if (pthread_create(&g_pool.th[g_pool.nWorkers], NULL, pool_worker, NULL)) break;
+        if (pthread_create(&g_pool.th[g_pool.nWorkers], NULL, pool_worker, (void*)(size_t)g_pool.gen)) break;
         g_pool.nWorkers++;
     }
     pthread_mutex_lock(&g_pool.mu);

@@ -321,6 +321,38 @@ def test_full_size_properties(gpu_ctx):
         S.close()
 
 
+@pytest.mark.parametrize("workload", ["C2", "C3-slab8"])
+def test_bench_config_history_against_oracle(gpu_ctx, workload):
+    """The bench configurations themselves against the oracle (not only through properties): BASELINE config C2
+    (4.3 M cells) and one z-slab of C3 as `bench.py --gpus 8` gives it to a GPU (8 M cells), monolithic BiCGStab + DILU,
+    20 iterations from the bench's initial guess: Amul and the preconditioner bit-exact, the residual history within
+    1e-10 relative, the field within 1e-8 relative L2 (north_star's bars)."""
+    from multiregionfoam_b200.assembly import WORKLOADS, cht_rank_slab
+    from multiregionfoam_b200.case import Case
+    r, L = WORKLOADS[workload]
+    case = Case(workload, [cht_rank_slab(r, L, 0, 1)])
+    O = pyoracle.OracleSystem(case)
+    pyoracle.set_threads(min(8, __import__("os").cpu_count() or 1))  # vector updates / Amul rows only: same bits for any count
+    S = ldu.LduSystem(gpu_ctx, case.ranks[0])
+    try:
+        x0, b = case.concat("psi"), case.concat("source")
+        v = random_vec(O.n, 11) * 10 + 300
+        assert np.array_equal(S.amul(v), O.amul(v))
+        O.precond_setup("DILU")
+        assert np.array_equal(S.rD(ldu.PRECOND_DILU), O.rD())
+        rr = random_vec(O.n, 12)
+        assert np.array_equal(S.precondition(ldu.PRECOND_DILU, rr), O.precondition(rr))
+        xo, io = O.solve(x0, b, "BiCGStab", "DILU", tolerance=0.0, minIter=20, maxIter=20)
+        xg, ig = S.solve(x0, b, ldu.SOLVER_BICGSTAB, ldu.PRECOND_DILU, tolerance=0.0, minIter=20, maxIter=20)
+        assert ig["nIterations"] == io["nIterations"] == 20
+        ho, hg = io["history"][:21], ig["history"][:21]
+        assert np.max(np.abs(hg - ho) / np.abs(ho)) < HIST_RTOL
+        assert rel_l2(xg, xo) < FIELD_RTOL
+    finally:
+        pyoracle.set_threads(1)
+        S.close()
+
+
 def test_partitioned_fsi_style_coupling_loop(gpu_ctx, golden_addr):
     """BASELINE config 4 in miniature: PARTITIONED coupling.  Per Dirichlet-Neumann iteration the
     fluid's vector equation is solved component by component with PBiCG + DILU (HronTurekFsi3 system/fluid/fvSolution
