@@ -197,6 +197,13 @@ int b200_host_unregister(b200_ctx* ctx, void* p);
 /* ---- test hooks (single operations through the same kernels) -------------------------------- */
 /* y = A x (transpose != 0: y = A^T x with internalCoeffs on interfaces) */
 int b200_amul(b200_sys* sys, const double* const* x, double* const* y, int transpose);
+/* lduMatrix::residual (foam/matrices/lduMatrix/lduMatrix/lduMatrixATmul.C; coupled rows: coupledLduMatrix): r = b - A x,
+ * every row rounded as the reference's loops do (rA = source - diag*psi, then -= lower*psi[l] / upper*psi[u] in face
+ * order, interfaces applied in the switchToLhs sense, monolithicCouplingFvPatchField.C:441-447). */
+int b200_residual(b200_sys* sys, const double* const* x, const double* const* b, double* const* r);
+/* lduMatrix::sumA: sumA[c] = diag[c] + the row's lower / upper coefficients, minus the boundaryCoeffs of the coupled
+ * patches at their faceCells (same file).  Uses the coefficients of the last b200_sys_set_coeffs. */
+int b200_sum_a(b200_sys* sys, double* const* sumA);
 /* w = M^-1 r with the given preconditioner (transpose != 0: preconditionT) */
 int b200_precondition(b200_sys* sys, int precond, const double* const* r, double* const* w, int transpose);
 /* reciprocal preconditioned diagonal of the last preconditioner setup */

@@ -503,12 +503,22 @@ static int upload_pipe_dir(b200_sys* s, const PipeSchedule& S, const PipeSchedul
     // shared memory: 256 B of barriers / counters | nStages stages, each one block of kNH steps (records, input
     // vectors, hdr); the generic single-warp path uses its own layout inside the same allocation.  At most
     // ~110 KB per CTA so that two groups are co-resident per SM.
-    const int stageBytes = (std::max(D.maxFastStage, D.maxGenStage) + 127) / 128 * 128;
-    int nStages = getenv("B200_SWEEP_STAGES") ? atoi(getenv("B200_SWEEP_STAGES")) : 4;
-    nStages = std::max(2, std::min(nStages, 8));
-    const int smemCapKB = getenv("B200_SWEEP_SMEM_KB") ? atoi(getenv("B200_SWEEP_SMEM_KB")) : 110;
-    while (nStages > 2 && 256 + nStages * stageBytes > smemCapKB * 1024) nStages--;
-    M.smemBytes = 256 + nStages * stageBytes;
+    // direct mode (kernels.cuh, B200_PROD_DIRECT): a stage holds the consumer's operands only (C-block + hdr)
+    const int fastStage = kProdDirect ? kSweepBlock * D.maxCStep : D.maxFastStage;
+    const int stageBytes = (std::max(fastStage, D.maxGenStage) + 127) / 128 * 128;
+    // two CTAs per SM, so that every group of up to 2 x SMs groups runs from the start: (228 KB - 2 x 1 KB reserved) / 2 =
+    // 113 KB each, static shared memory included.  (One CTA per SM with a ring twice as deep - B200_SWEEP_SMEM_KB=220
+    // B200_SWEEP_STAGES=8 - is 3-4 % faster for an isolated precondition() of C2, 176 groups on 148 SMs, but slower inside
+    // the Krylov loop: 173 / 168 us per sweep against 166 / 159.)
+    int nStages = getenv("B200_SWEEP_STAGES") ? atoi(getenv("B200_SWEEP_STAGES")) : (kProdDirect ? 8 : 4);
+    nStages = std::max(2, std::min(nStages, kSweepMaxStages));
+    const int smemCapKB = getenv("B200_SWEEP_SMEM_KB") ? atoi(getenv("B200_SWEEP_SMEM_KB")) : 113;
+    while (nStages > 2 && kSweepSmemHeader + 256 + nStages * stageBytes > smemCapKB * 1024) nStages--;
+    // the producers of the fast path work in kProdSets sets on consecutive blocks; a set must see every fill of "its"
+    // stages (kernels.cuh, split_producer_sets)
+    if (kProdSets > 1 && nStages >= kProdSets) nStages -= nStages % kProdSets;
+    if (kProdSets > 1 && nStages < kProdSets) return set_err(ctx, B200_ESTATE, "sweep ring: %d stages of %d B do not fit %d producer sets", nStages, stageBytes, kProdSets);
+    M.smemBytes = kSweepSmemHeader + nStages * stageBytes;
     M.dev.nGroups = S.nGroups;
     M.dev.dir = dir;
     M.dev.nStages = nStages;
@@ -895,8 +905,9 @@ static int reduce_finish(b200_sys* s, const PartCounts& cnt, int nd, int op, int
 
 // y = A x (or A^T x) with nd fused dots of y: nd=1: (y,d0); nd=2: (y,d0),(y,y).  Leaves the
 // partials of the dots in quantities 0..nd-1 with counts amulBlocks + ifaceBlocks.
+// op 0: y = A x (nd fused dots against d0).  op 1: y = d0 - A x as lduMatrix::residual rounds it.  op 2: y = sumA.
 static int launch_amul(b200_sys* s, const double* x, double* y, int nd, const double* d0, bool transpose, int force,
-                       PartCounts* cntOut)
+                       PartCounts* cntOut, int op = 0)
 {
     b200_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
@@ -927,7 +938,13 @@ static int launch_amul(b200_sys* s, const double* x, double* y, int nd, const do
     {
         KScope k(s, B200_K_AMUL);
         const unsigned* mask = s->nTouched ? s->ifaceMask.p : nullptr;
-        if (nd == 0)
+        if (op == 1)
+            k_amul<0, 1><<<s->amulBlocks, 256, 0, st>>>((int)s->nSlots, (int)s->nSlices, s->diag.p, s->sliceOff.p, s->sellCol.p, val, x, y,
+                                                        d0, mask, s->partials.p, s->pstride, s->sc.p, force);
+        else if (op == 2)
+            k_amul<0, 2><<<s->amulBlocks, 256, 0, st>>>((int)s->nSlots, (int)s->nSlices, s->diag.p, s->sliceOff.p, s->sellCol.p, val, x, y,
+                                                        nullptr, mask, s->partials.p, s->pstride, s->sc.p, force);
+        else if (nd == 0)
             k_amul<0><<<s->amulBlocks, 256, 0, st>>>((int)s->nSlots, (int)s->nSlices, s->diag.p, s->sliceOff.p, s->sellCol.p, val, x, y,
                                                      nullptr, mask, s->partials.p, s->pstride, s->sc.p, force);
         else if (nd == 1)
@@ -943,7 +960,11 @@ static int launch_amul(b200_sys* s, const double* x, double* y, int nd, const do
 #define IFACE_ARGS                                                                                                           \
     s->nTouched, s->ifRows.p, s->ifRowStart.p, s->ifEntCoef.p, s->ifEntSrc.p, s->ifEntCnt.p, s->ifGSrc.p, s->ifGW.p, ifc, x, \
         s->recvBuf.p, y, d0, s->partials.p, s->pstride, s->amulBlocks, s->sc.p, force
-        if (nd == 0)
+        if (op == 1)
+            k_iface<0, 1><<<s->ifaceBlocks, 128, 0, st>>>(IFACE_ARGS);
+        else if (op == 2)
+            k_iface<0, 2><<<s->ifaceBlocks, 128, 0, st>>>(IFACE_ARGS);
+        else if (nd == 0)
             k_iface<0><<<s->ifaceBlocks, 128, 0, st>>>(IFACE_ARGS);
         else if (nd == 1)
             k_iface<1><<<s->ifaceBlocks, 128, 0, st>>>(IFACE_ARGS);
@@ -1537,6 +1558,37 @@ extern "C" int b200_amul(b200_sys* s, const double* const* x, double* const* y, 
     if ((rc = upload_vec(s, V_P, x))) return rc;
     if ((rc = launch_amul(s, s->vec[V_P].p, s->vec[V_V].p, 0, nullptr, transpose != 0, 1, nullptr))) return rc;
     if ((rc = download_vec(s, s->vec[V_V].p, y))) return rc;
+    CK(s->ctx, cudaStreamSynchronize(s->ctx->stream));
+    if (s->profiling) harvest_events(s);
+    return B200_OK;
+}
+
+// lduMatrix::residual / lduMatrix::sumA: the operations a smoother or the GAMG agglomeration asks of the matrix
+extern "C" int b200_residual(b200_sys* s, const double* const* x, const double* const* b, double* const* r)
+{
+    if (!s || !x || !b || !r) return B200_EINVAL;
+    if (!s->finalized) return set_err(s->ctx, B200_ESTATE, "residual before finalize");
+    CK(s->ctx, cudaSetDevice(s->ctx->device));
+    int rc;
+    if ((rc = upload_vec(s, V_P, x))) return rc;
+    if ((rc = upload_vec(s, V_S, b))) return rc;
+    if ((rc = launch_amul(s, s->vec[V_P].p, s->vec[V_V].p, 0, s->vec[V_S].p, false, 1, nullptr, 1))) return rc;
+    if ((rc = download_vec(s, s->vec[V_V].p, r))) return rc;
+    CK(s->ctx, cudaStreamSynchronize(s->ctx->stream));
+    if (s->profiling) harvest_events(s);
+    return B200_OK;
+}
+
+extern "C" int b200_sum_a(b200_sys* s, double* const* sumA)
+{
+    if (!s || !sumA) return B200_EINVAL;
+    if (!s->finalized) return set_err(s->ctx, B200_ESTATE, "sumA before finalize");
+    CK(s->ctx, cudaSetDevice(s->ctx->device));
+    int rc;
+    // x is not read by the kernels of this mode, but the halo exchange of launch_amul still runs (and pairs up across
+    // ranks); V_P holds whatever the last operation left there
+    if ((rc = launch_amul(s, s->vec[V_P].p, s->vec[V_V].p, 0, nullptr, false, 1, nullptr, 2))) return rc;
+    if ((rc = download_vec(s, s->vec[V_V].p, sumA))) return rc;
     CK(s->ctx, cudaStreamSynchronize(s->ctx->stream));
     if (s->profiling) harvest_events(s);
     return B200_OK;

@@ -294,7 +294,10 @@ __global__ void k_scalar_op(DevScalars* sc, int op, int force, double* history, 
 // by ascending column: the order of lduMatrix::Amul's face loop.
 // ND fused dot products of the result: ND=1: (y,d0); ND=2: (y,d0),(y,y).  Rows touched by an
 // interface are excluded from the dots here (k_iface adds them once their value is final).
-template <int ND>
+// OP 0: y = A x.  OP 1: lduMatrix::residual, y = b - A x row by row as the reference's loops round it
+// (rA = source - diag*psi; rA[u] -= lower*psi[l]; rA[l] -= upper*psi[u]); b arrives through d0.  OP 2: lduMatrix::sumA,
+// y = diag + the row's off-diagonal coefficients (x is not read).
+template <int ND, int OP = 0>
 __global__ void __launch_bounds__(256) k_amul(int nRows, int nSlices, const double* __restrict__ diag,
                                                const int* __restrict__ sliceOff, const int* __restrict__ col,
                                                const double* __restrict__ val, const double* __restrict__ x,
@@ -316,8 +319,17 @@ __global__ void __launch_bounds__(256) k_amul(int nRows, int nSlices, const doub
         const int width = o1 - o0;
         if (row < nRows)
         {
-            double acc = diag[row] * x[row];
+            double acc = OP == 2 ? diag[row] : (OP == 1 ? d0[row] - diag[row] * x[row] : diag[row] * x[row]);
             int j = 0;
+            if (OP != 0)
+            {
+                for (; j < width; j++)
+                {
+                    const int c0 = col[base + (size_t)j * 32];
+                    const double v0 = val[base + (size_t)j * 32];
+                    if (c0 >= 0) acc = OP == 2 ? acc + v0 : acc - v0 * x[c0];
+                }
+            }
             for (; j + 4 <= width; j += 4)
             {
                 int c0 = col[base + (size_t)(j + 0) * 32], c1 = col[base + (size_t)(j + 1) * 32];
@@ -357,7 +369,9 @@ __global__ void __launch_bounds__(256) k_amul(int nRows, int nSlices, const doub
 // (non-processor, processor) x patch-list order:  y[row] -= coeff * pnf, where pnf is the
 // shadow side's patchInternalField (GGI-weighted when non-conformal) gathered on the fly from x
 // (same rank) or from the halo receive buffer (other rank).
-template <int ND>
+// OP 1 (residual): the update is applied in the switchToLhs sense, y[row] += coeff * pnf
+// (monolithicCouplingFvPatchField.C:441-447).  OP 2 (sumA): y[row] -= coeff (lduMatrix::sumA's interface loop).
+template <int ND, int OP = 0>
 __global__ void __launch_bounds__(128) k_iface(int nTouched, const int* __restrict__ rows,
                                                 const int* __restrict__ rowStart, const int* __restrict__ entCoef,
                                                 const int* __restrict__ entSrc, const int* __restrict__ entCnt,
@@ -380,6 +394,11 @@ __global__ void __launch_bounds__(128) k_iface(int nTouched, const int* __restri
         {
             const int cnt = entCnt[e];
             double pnf;
+            if (OP == 2)
+            {
+                acc -= coef[entCoef[e]];
+                continue;
+            }
             if (cnt == 0)
             {
                 const int s = entSrc[e];
@@ -396,7 +415,10 @@ __global__ void __launch_bounds__(128) k_iface(int nTouched, const int* __restri
                     pnf += f * gW[g0 + k];
                 }
             }
-            acc -= coef[entCoef[e]] * pnf;
+            if (OP == 1)
+                acc += coef[entCoef[e]] * pnf;
+            else
+                acc -= coef[entCoef[e]] * pnf;
         }
         y[row] = acc;
         if (ND > 0)
@@ -619,10 +641,62 @@ __device__ __forceinline__ SweepRing ring_setup(const PipeDev& S, int g, int lan
 //     the descriptor bytes instead (general path).  After a block it resets the counter and publishes its
 //     progress, which is what the loader polls before it refills the stage.
 constexpr int kNH = kSweepBlock; // producer warps = steps per block (8)
+// Producer organisation (B200_PROD_SETS > 0): kProdSets sets of producer warps work on kProdSets consecutive blocks at
+// the same time (set s takes the blocks blk = s mod kProdSets); inside a set a producer prepares kProdM consecutive
+// steps of the block.  A producer's step is a chain of latencies (stage wait, code loads, the L2 round trip of the
+// cross-group values, the check, the hand-over) that no amount of tuning brought under ~850 cycles per block; with
+// one set that chain IS the block time of the group (106 cycles per step against the consumer's 61).  With several
+// sets the chains of consecutive blocks overlap, so the loads of the cross-group values can be issued when they are
+// needed (no prefetch a block ahead, no second register set) and a group's pace is the consumer's.
+#ifndef B200_PROD_SETS
+#define B200_PROD_SETS 0
+#endif
+#ifndef B200_PROD_M
+#define B200_PROD_M 4
+#endif
+// B200_PROD_DIRECT (needs sets): the producers read THEIR operands - the P-records (coefficients and codes of the leading
+// cross-group terms) and the input vectors a, b - straight from global memory (coalesced 8-byte-per-lane loads of lines
+// the loader has pulled into L2), and only the consumer's operands (C-block) travel through the bulk-copy ring.  A stage
+// shrinks from P + C + a + b + hdr (26.6 KB on C2) to C + hdr (14.3 KB): eight stages instead of four fit next to a second
+// CTA on the SM.  Measured on B200 a refill lands ~1 900 cycles after its issue even on an otherwise idle GPU and
+// ~2 100 - 2 800 cycles under load; with four stages (three blocks of look-ahead, ~560 cycles of consumer work each) the
+// consumer of even the FIRST group - which depends on nobody - waited for its ring about a third of the time.
+#ifndef B200_PROD_DIRECT
+#define B200_PROD_DIRECT 1
+#endif
+#ifndef B200_PROD_PIPE
+#define B200_PROD_PIPE 1
+#endif
+constexpr bool kProdDirect = B200_PROD_SETS > 0 && B200_PROD_DIRECT;
+// B200_STORE_SMEM: the consumer leaves its results in shared memory (in the slot of the hdr plane it has just read acc0
+// from) and the loader warp writes a finished block to the output vector - 8 coalesced stores per lane - before it
+// refills the stage.  A global store costs the consumer ~16 cycles of issue per step (scripts/micro/consumer.cu: 43 ->
+// 59 cycles per step), a shared-memory store 3; followers need the whole block anyway, so they see it ~200 cycles later.
+#ifndef B200_STORE_SMEM
+#define B200_STORE_SMEM 0
+#endif
+constexpr bool kStoreSmem = B200_STORE_SMEM != 0;
+// B200_CONS_PIPE: canonical blocks are worked in two halves whose operand loads overlap the other half's recurrence
+// (the operands of steps 4-7 are loaded while steps 0-3 run, those of the next block's steps 0-3 - when it has been
+// delivered - while steps 4-7 run), instead of 24 loads in front of every block.
+#ifndef B200_CONS_PIPE
+#define B200_CONS_PIPE 0
+#endif
+#ifndef B200_PROBE
+#define B200_PROBE 0 // timing probes of the consumer loop (wrong results), see split_consumer
+#endif
+constexpr bool kConsPipe = B200_CONS_PIPE != 0;
+constexpr int kProdSets = B200_PROD_SETS;
+constexpr int kProdM = B200_PROD_SETS > 0 ? B200_PROD_M : 1;
+constexpr int kProdPerSet = kNH / kProdM;
+constexpr int kProducers = B200_PROD_SETS > 0 ? kProdSets * kProdPerSet : kNH;
+static_assert(kNH % kProdM == 0, "a producer takes a whole number of steps of a block");
 constexpr int kTraceBlocks = 142; // debug: per-block time stamps (clock64 of the group's SM) of the first blocks
 constexpr int kStatsStride = 16 + 8 * kTraceBlocks; // debug counters per group: 16 totals, then per block 8 stamps:
 // consumer {ready seen, done}, loader issue, producer 0 {step start, next stage landed, values checked, delivered},
 // producer 7 delivered
+constexpr int kSweepSmemHeader = 512; // bytes in front of the stages (barriers, counters)
+constexpr int kSweepMaxStages = 16;
 constexpr int kL2Ahead = 4;      // default number of blocks the L2 prefetch runs ahead of the stage fill (PipeDev::l2Ahead)
 
 // Flag words in shared memory.  A formal release/acquire pair costs a MEMBAR.ALL.CTA on the releasing side, which
@@ -691,10 +765,53 @@ __device__ __forceinline__ void split_issue(const SplitCtx& C, const double* a, 
     unsigned char* dst = C.stages + (size_t)st * C.stageBytes;
     mbar_expect_tx(&C.rawBar[st], C.rawBytes);
     bulk_g2s_stream(dst, C.cStream + (size_t)blk * C.cBytes, C.cBytes, &C.rawBar[st], C.polStream);
+    if (kProdDirect) return; // the producers fetch their operands themselves
     if (C.pBytes) bulk_g2s_stream(dst + C.offP, C.pStream + (size_t)blk * C.pBytes, C.pBytes, &C.rawBar[st], C.polStream);
     const long long s0 = dir > 0 ? ((long long)C.base + (long long)blk * kNH) * 32 : ((long long)C.base + C.nT - (long long)(blk + 1) * kNH) * 32;
     bulk_g2s_stream(dst + C.offA, a + s0, kNH * 256, &C.rawBar[st], C.polStream);
     if (MODE == 0) bulk_g2s_stream(dst + C.offA + kNH * 256, b + s0, kNH * 256, &C.rawBar[st], C.polStream);
+}
+
+__device__ __forceinline__ double lds_f64(unsigned a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int lds_s32(unsigned a)
+{
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ unsigned lds_u8(unsigned a)
+{
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+// operands streamed once from global memory by the producers (direct mode): L2 only
+__device__ __forceinline__ double ldg_stream_f64(const void* p)
+{
+    double v;
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ldg_stream_s32(const void* p)
+{
+    int v;
+    asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void mbar_wait_u32(unsigned bar, unsigned parity)
+{
+    unsigned ok = 0;
+    while (!ok)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
 }
 
 // ------------------------------------------------------------------------------------------ consumer
@@ -712,7 +829,9 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
     const int nT = C.nT;
     double* outPtr = out + ((long long)C.base + (dir > 0 ? 0 : nT - 1)) * 32 + lane;
     const int srcLane = (lane - dir) & 31; // the linked neighbour lane of a canonical step
-    constexpr bool statsOn = STATS;
+    // cheap accumulators (two clock reads per block, one write at the end) also run in the product instantiation when the
+    // caller armed the counters with debug flag 2; the per-block time stamps are in the STATS instantiation only
+    const bool statsOn = STATS || S.stats != nullptr;
     const bool forceGeneral = MODE == 2 || (S.debugFlags & 1);
     const int Kg = C.Kg;
     double h[kSkew]; // h[k]: the value this lane produced k+1 steps ago
@@ -727,7 +846,34 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
     const unsigned char* const stageEnd = stage0 + (size_t)C.NS * C.stageBytes;
     const unsigned char* sb = stage0; // C-block of the current stage (this lane's column)
     unsigned* cntp = C.cnt;
-    long long tWait = 0, t0 = 0, g0 = 0, nGeneral = 0;
+    // result of step q of the current block: to the output vector, or (kStoreSmem) into the acc0 slot of the hdr plane,
+    // which this lane has read before it gets here; the loader warp stores the block (sweep_group_split)
+    auto put = [&](const unsigned char* hdq, double* gp, double v) {
+        if (kStoreSmem)
+            sts_f64(smem_u32(hdq), v);
+        else
+            st_relaxed(gp, v);
+    };
+    auto wait_block = [&](unsigned* cp) -> unsigned {
+        unsigned cc;
+        do cc = ld_flag_smem(cp);
+        while ((cc & 0xffu) != (unsigned)kNH);
+        return cc;
+    };
+    constexpr int HB = kNH / 2;
+    double A0[HB], A1[HB], A2[HB]; // kConsPipe: a0, c0, c1 of steps 0 .. HB-1 of the block the loop is about to work on
+    auto loadA = [&](const unsigned char* s) {
+#pragma unroll
+        for (int q = 0; q < HB; q++)
+        {
+            A0[q] = *reinterpret_cast<const double*>(s + C.offHdr + q * 256);
+            A1[q] = *reinterpret_cast<const double*>(s + PL + q * 256);
+            A2[q] = *reinterpret_cast<const double*>(s + 2 * PL + q * 256);
+        }
+    };
+    unsigned cPre = 0u;
+    bool havePre = false; // kConsPipe: the next block's counter has been read (cPre) and its first half is in A
+    long long tWait = 0, t0 = 0, g0 = 0, nGeneral = 0, tCanon = 0, tOther = 0, nCanon = 0;
     if (statsOn)
     {
         t0 = clock64();
@@ -736,37 +882,99 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
     for (int blk = 0; blk < C.nBlocks; blk++)
     {
         unsigned c;
-        if (statsOn)
+        if (kConsPipe && havePre)
+            c = cPre;
+        else if (statsOn)
         {
             const long long w0 = clock64();
-            do c = ld_flag_smem(cntp);
-            while ((c & 0xffu) != (unsigned)kNH);
+            c = wait_block(cntp);
             tWait += clock64() - w0;
         }
         else
+            c = wait_block(cntp);
+        if (kConsPipe && !havePre) loadA(sb);
+        havePre = false;
+        // the stage after this one (kConsPipe looks ahead into it)
+        const unsigned char* sbN = sb + C.stageBytes;
+        unsigned* cntN = cntp + 1;
+        if (sbN == stageEnd)
         {
-            do c = ld_flag_smem(cntp);
-            while ((c & 0xffu) != (unsigned)kNH);
+            sbN = stage0;
+            cntN = C.cnt;
         }
-        if (statsOn && lane == 0 && blk < kTraceBlocks) S.stats[(long long)kStatsStride * g + 16 + blk * 8 + 0] = clock64();
+        if (STATS && lane == 0 && blk < kTraceBlocks) S.stats[(long long)kStatsStride * g + 16 + blk * 8 + 0] = clock64();
         const unsigned char* hd = sb + C.offHdr;
-        if (c == (unsigned)kNH && !forceGeneral)
+        const long long b0 = statsOn ? clock64() : 0;
+        const bool canon = c == (unsigned)kNH && !forceGeneral;
+        if (c == (unsigned)kNH && !forceGeneral && kConsPipe)
+        {
+            double B0[HB], B1[HB], B2[HB];
+#pragma unroll
+            for (int q = 0; q < HB; q++)
+            {
+                B0[q] = *reinterpret_cast<const double*>(hd + (HB + q) * 256);
+                B1[q] = *reinterpret_cast<const double*>(sb + PL + (HB + q) * 256);
+                B2[q] = *reinterpret_cast<const double*>(sb + 2 * PL + (HB + q) * 256);
+            }
+#pragma unroll
+            for (int q = 0; q < HB; q++)
+            {
+                const double sh = __shfl_sync(FULL, h[kSkew - 1], srcLane);
+                const double pre = A0[q] - A1[q] * sh;
+                const double acc = pre - A2[q] * h[0];
+                put(hd + q * 256, outPtr + q * outStride, acc);
+                push(acc);
+            }
+            if (blk + 1 < C.nBlocks)
+            { // the next block, if it has been delivered: its first half while the second half of this one runs
+                cPre = ld_flag_smem(cntN);
+                if ((cPre & 0xffu) == (unsigned)kNH)
+                {
+                    havePre = true;
+                    loadA(sbN);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < HB; q++)
+            {
+                const double sh = __shfl_sync(FULL, h[kSkew - 1], srcLane);
+                const double pre = B0[q] - B1[q] * sh;
+                const double acc = pre - B2[q] * h[0];
+                put(hd + (HB + q) * 256, outPtr + (HB + q) * outStride, acc);
+                push(acc);
+            }
+        }
+        else if (c == (unsigned)kNH && !forceGeneral)
         {
             double a0[kNH], c0[kNH], c1[kNH];
 #pragma unroll
             for (int q = 0; q < kNH; q++)
             {
+#if B200_PROBE == 4 // timing probe (wrong results): no operand loads
+                a0[q] = 1.0 + q;
+                c0[q] = 0.25;
+                c1[q] = 0.125;
+#else
                 a0[q] = *reinterpret_cast<const double*>(hd + q * 256);
                 c0[q] = *reinterpret_cast<const double*>(sb + PL + q * 256);
                 c1[q] = *reinterpret_cast<const double*>(sb + 2 * PL + q * 256);
+#endif
             }
 #pragma unroll
             for (int q = 0; q < kNH; q++)
             {
+#if B200_PROBE == 3 // timing probe (wrong results): no shuffle
+                const double sh = h[kSkew - 1];
+#else
                 const double sh = __shfl_sync(FULL, h[kSkew - 1], srcLane);
+#endif
                 const double pre = a0[q] - c0[q] * sh;
                 const double acc = pre - c1[q] * h[0];
-                st_relaxed(outPtr + q * outStride, acc);
+#if B200_PROBE == 2 // timing probe (wrong results): no store
+                if (acc == 1.2345e300) put(hd + q * 256, outPtr + q * outStride, acc);
+#else
+                put(hd + q * 256, outPtr + q * outStride, acc);
+#endif
                 push(acc);
             }
         }
@@ -805,7 +1013,7 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
                     const double sm = ((a0[q] - pOwn) - c2 * cv0) - c0[q] * vB;
                     if (fl & 1u) acc = sm;
                 }
-                st_relaxed(outPtr + q * outStride, acc);
+                put(hd + q * 256, outPtr + q * outStride, acc);
                 push(acc);
             }
         }
@@ -871,18 +1079,29 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
                         }
                     }
                     __syncwarp();
-                    st_relaxed(outPtr + (q0 + u) * outStride, acc);
+                    put(hd + (q0 + u) * 256, outPtr + (q0 + u) * outStride, acc);
                     push(acc);
                 }
             }
         }
         outPtr += kNH * outStride;
         __syncwarp();
+        if (statsOn)
+        {
+            const long long d = clock64() - b0;
+            if (canon)
+            {
+                tCanon += d;
+                nCanon++;
+            }
+            else
+                tOther += d;
+        }
         if (lane == 0)
         { // block done: the stage may be refilled
             st_flag_smem(cntp, 0u);
             st_flag_smem(C.done, (unsigned)(blk + 1));
-            if (statsOn && blk < kTraceBlocks) S.stats[(long long)kStatsStride * g + 16 + blk * 8 + 1] = clock64();
+            if (STATS && blk < kTraceBlocks) S.stats[(long long)kStatsStride * g + 16 + blk * 8 + 1] = clock64();
         }
         sb += C.stageBytes;
         cntp++;
@@ -904,6 +1123,12 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
         sp[5] = nT;
         sp[6] = nGeneral;
         sp[7] = C.nBlocks;
+        if (!STATS)
+        { // the per-block trace area is unused in the product instantiation: body cycles of canonical / other blocks
+            sp[16] = tCanon;
+            sp[17] = nCanon;
+            sp[18] = tOther;
+        }
     }
 }
 
@@ -914,34 +1139,6 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
 // short chain: 32-bit shared-memory addresses stepped from stage to stage (no 64-bit address arithmetic), the
 // operand loads of the current block issued before the wait for the next stage so that their latency overlaps it,
 // no instrumentation in the product instantiation (STATS = false).
-__device__ __forceinline__ double lds_f64(unsigned a)
-{
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ int lds_s32(unsigned a)
-{
-    int v;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ unsigned lds_u8(unsigned a)
-{
-    unsigned v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void sts_f64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
-__device__ __forceinline__ void mbar_wait_u32(unsigned bar, unsigned parity)
-{
-    unsigned ok = 0;
-    while (!ok)
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok)
-                     : "r"(bar), "r"(parity)
-                     : "memory");
-}
 
 template <int MODE, int LG, bool STATS>
 __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx& C, const int g, const int h, const int lane, double* out,
@@ -991,7 +1188,7 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
         }
     };
     unsigned sg = stage0, bar = bar0, cnt = cnt0, par = 0u;
-    const bool timed = STATS && h == 0;
+    const bool timed = (STATS || S.stats != nullptr) && h == 0;
     long long tStage = 0, tVal = 0, tSpin = 0, tAll = timed ? clock64() : 0;
     auto step = [&](const int blk, int* codes, double* mv, int* cc, double* mc, int* codesN, double* mvN, int* ccN, double* mcN) {
         long long* const tr = (STATS && lane == 0 && blk < kTraceBlocks) ? S.stats + (long long)kStatsStride * g + 16 + blk * 8 : nullptr;
@@ -1116,7 +1313,8 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
 // Producer of the set organisation: this warp prepares steps h0 .. h0 + M - 1 of the blocks set, set + nSets, ...
 template <int MODE, int LG, int M, bool STATS>
 __device__ __forceinline__ void split_producer_sets(const PipeDev& S, const SplitCtx& C, const int g, const int set, const int nSets, const int h0,
-                                                    const int lane, double* out, int* err)
+                                                    const int lane, double* out, int* err, const double* __restrict__ aVec,
+                                                    const double* __restrict__ bVec)
 {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int LGA = LG > 0 ? LG : 1;
@@ -1138,52 +1336,106 @@ __device__ __forceinline__ void split_producer_sets(const PipeDev& S, const Spli
     const int NS = C.NS;
     int st = set % NS;
     unsigned par = (unsigned)(set / NS) & 1u;
-    const bool timed = STATS && set == 0 && h0 == 0;
+    // direct mode: this lane's operands of step h0 of block 0 in global memory
+    const unsigned char* const pG0 = C.pStream + (size_t)h0 * C.pRec;
+    const double* const aG0 = aVec + ((long long)C.base + (dir > 0 ? h0 : C.nT - 1 - h0)) * 32 + lane;
+    const double* const bG0 = bVec ? bVec + ((long long)C.base + (dir > 0 ? h0 : C.nT - 1 - h0)) * 32 + lane : nullptr;
+    const bool timed = (STATS || S.stats != nullptr) && set == 0 && h0 == 0;
     long long tStage = 0, tVal = 0, tSpin = 0, tAll = timed ? clock64() : 0;
     for (int blk = set; blk < C.nBlocks; blk += nSets)
     {
         const unsigned sg = stage0 + (unsigned)st * stageBytes;
         long long* const tr = (STATS && lane == 0 && blk < kTraceBlocks) ? S.stats + (long long)kStatsStride * g + 16 + blk * 8 : nullptr;
         if (STATS && tr && h0 == 0) tr[3] = clock64();
+        // ---- direct mode: the operands of this block from global memory, issued before anything is waited for
+        int cd[M][LGA], kc[M][2];
+        double mv[M][LGA], mc[M][2];
+        double acc[M], bbv[M], cfv[M][LGA];
+        if (kProdDirect)
+        {
+            const unsigned char* pG = pG0 + (size_t)blk * C.pBytes;
+            const long long vOff = (long long)blk * kNH * 32 * dir;
+#pragma unroll
+            for (int u = 0; u < M; u++)
+            {
+#pragma unroll
+                for (int i = 0; i < LG; i++) cd[u][i] = ldg_stream_s32(pG + u * pRec + LG * 256 + i * 128 + lane * 4);
+#pragma unroll
+                for (int k = 0; k < 2; k++) kc[u][k] = (k < Kg) ? ldg_stream_s32(pG + u * pRec + LG * 384 + k * 128 + lane * 4) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < M; u++)
+            {
+                acc[u] = ldg_stream_f64(aG0 + vOff + u * dir * 32);
+                bbv[u] = MODE == 0 ? ldg_stream_f64(bG0 + vOff + u * dir * 32) : 0.0;
+#pragma unroll
+                for (int i = 0; i < LG; i++) cfv[u][i] = ldg_stream_f64(pG + u * pRec + i * 256 + lane * 8);
+            }
+            // the cross-group values as soon as their codes are here
+#pragma unroll
+            for (int u = 0; u < M; u++)
+            {
+#pragma unroll
+                for (int i = 0; i < LG; i++)
+                {
+                    mv[u][i] = neutral;
+                    if (cd[u][i] >= 0) mv[u][i] = ld_relaxed(out + cd[u][i]);
+                }
+#pragma unroll
+                for (int k = 0; k < 2; k++)
+                {
+                    mc[u][k] = 0.0;
+                    if (kc[u][k] >= 0) mc[u][k] = ld_relaxed(out + kc[u][k]);
+                }
+            }
+        }
         const long long w0 = timed ? clock64() : 0;
+        // A parity wait only tells the last two phases of a barrier apart, and bulk copies of different stages complete
+        // out of order.  The host therefore makes the stage count a multiple of the set count (upload_pipe_dir): every
+        // fill of a stage is then waited for by the same set, one after the other, and "phase par complete" cannot be
+        // answered for an older fill.
         mbar_wait_u32(bar0 + 8u * (unsigned)st, par);
         if (timed) tStage += clock64() - w0;
         if (STATS && tr && h0 == 0) tr[4] = clock64();
-        // ---- codes of the cross-group terms, then their loads: the only global accesses of the step
-        int cd[M][LGA], kc[M][2];
-        double mv[M][LGA], mc[M][2];
-#pragma unroll
-        for (int u = 0; u < M; u++)
+        // ---- ring mode: codes of the cross-group terms, then their loads: the only global accesses of the step
+        if (!kProdDirect)
         {
 #pragma unroll
-            for (int i = 0; i < LG; i++) cd[u][i] = lds_s32(sg + offCode + u * pRec + i * 128);
-#pragma unroll
-            for (int k = 0; k < 2; k++) kc[u][k] = (k < Kg) ? lds_s32(sg + offConst + u * pRec + k * 128) : -1;
-        }
-#pragma unroll
-        for (int u = 0; u < M; u++)
-        {
-#pragma unroll
-            for (int i = 0; i < LG; i++)
+            for (int u = 0; u < M; u++)
             {
-                mv[u][i] = neutral;
-                if (cd[u][i] >= 0) mv[u][i] = ld_relaxed(out + cd[u][i]);
+#pragma unroll
+                for (int i = 0; i < LG; i++) cd[u][i] = lds_s32(sg + offCode + u * pRec + i * 128);
+#pragma unroll
+                for (int k = 0; k < 2; k++) kc[u][k] = (k < Kg) ? lds_s32(sg + offConst + u * pRec + k * 128) : -1;
             }
 #pragma unroll
-            for (int k = 0; k < 2; k++)
+            for (int u = 0; u < M; u++)
             {
-                mc[u][k] = 0.0;
-                if (kc[u][k] >= 0) mc[u][k] = ld_relaxed(out + kc[u][k]);
+#pragma unroll
+                for (int i = 0; i < LG; i++)
+                {
+                    mv[u][i] = neutral;
+                    if (cd[u][i] >= 0) mv[u][i] = ld_relaxed(out + cd[u][i]);
+                }
+#pragma unroll
+                for (int k = 0; k < 2; k++)
+                {
+                    mc[u][k] = 0.0;
+                    if (kc[u][k] >= 0) mc[u][k] = ld_relaxed(out + kc[u][k]);
+                }
             }
         }
         // ---- operands from the stage while the loads fly
-        double acc[M];
         unsigned kind = 0u;
 #pragma unroll
         for (int u = 0; u < M; u++)
         {
-            acc[u] = lds_f64(offA + sg + u * vecStep);
-            if (MODE == 0) acc[u] *= lds_f64(offA + sg + u * vecStep + kNH * 256);
+            if (!kProdDirect)
+            {
+                acc[u] = lds_f64(offA + sg + u * vecStep);
+                bbv[u] = MODE == 0 ? lds_f64(offA + sg + u * vecStep + kNH * 256) : 0.0;
+            }
+            if (MODE == 0) acc[u] *= bbv[u];
             const unsigned b7 = lds_u8(sg + offGen + u * 256); // bit 0: descriptor-driven step, bit 5: dual step (schedule.hpp)
             kind += MODE == 2 ? 0x100u : (((b7 & 1u) << 8) | (((b7 >> 5) & 1u) << (16 + h0 + u)));
         }
@@ -1251,7 +1503,8 @@ __device__ __forceinline__ void split_producer_sets(const PipeDev& S, const Spli
         for (int u = 0; u < M; u++)
         {
 #pragma unroll
-            for (int i = 0; i < LG; i++) acc[u] = sweep_apply<MODE>(acc[u], lds_f64(sg + offCoef + u * pRec + i * 256), mv[u][i]); // padding: coefficient 0, neutral value
+            for (int i = 0; i < LG; i++)
+                acc[u] = sweep_apply<MODE>(acc[u], kProdDirect ? cfv[u][i] : lds_f64(sg + offCoef + u * pRec + i * 256), mv[u][i]); // padding: coefficient 0, neutral value
             sts_f64(sg + offHd + u * 256, acc[u]);
             if (Kg > 0) sts_f64(sg + offHd + u * 256 + kNH * 256, mc[u][0]);
             if (Kg > 1) sts_f64(sg + offHd + u * 256 + 2 * kNH * 256, mc[u][1]);
@@ -1277,28 +1530,190 @@ __device__ __forceinline__ void split_producer_sets(const PipeDev& S, const Spli
     }
 }
 
+// Software-pipelined producer of the direct mode (B200_PROD_PIPE): the static operands of a block (codes, coefficients,
+// a, b - always available) are requested one producer iteration ahead, so that the loads of the cross-group values - the
+// only ones that depend on another group's progress - go out as soon as this warp is done with its previous block, as in
+// the single-set producer (split_producer), and the two global round trips of a block do not add up on the path between
+// "the value exists" and "the block is handed to the consumer".
+template <int MODE, int LG, int M, bool STATS>
+__device__ __forceinline__ void split_producer_pipe(const PipeDev& S, const SplitCtx& C, const int g, const int set, const int nSets, const int h0,
+                                                    const int lane, double* out, int* err, const double* __restrict__ aVec,
+                                                    const double* __restrict__ bVec)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int LGA = LG > 0 ? LG : 1;
+    constexpr int dir = MODE == 1 ? -1 : 1;
+    const double neutral = MODE == 2 ? 1.0 : 0.0;
+    const int Kg = C.Kg;
+    const unsigned pRec = (unsigned)C.pRec;
+    const unsigned offGen = (unsigned)(h0 * 256 + lane * 8 + 7);       // top byte of the step's meta word
+    const unsigned offHd = (unsigned)(C.offHdr + h0 * 256 + lane * 8); // hdr planes acc0 | cval 0 | cval 1
+    const unsigned stage0 = smem_u32(C.stages), stageBytes = (unsigned)C.stageBytes;
+    const unsigned bar0 = smem_u32(C.rawBar), cnt0 = smem_u32(C.cnt);
+    const int NS = C.NS, nBlocks = C.nBlocks;
+    const unsigned char* const pG0 = C.pStream + (size_t)h0 * C.pRec;
+    const double* const aG0 = aVec + ((long long)C.base + (dir > 0 ? h0 : C.nT - 1 - h0)) * 32 + lane;
+    const double* const bG0 = bVec ? bVec + ((long long)C.base + (dir > 0 ? h0 : C.nT - 1 - h0)) * 32 + lane : nullptr;
+    const bool timed = (STATS || S.stats != nullptr) && set == 0 && h0 == 0;
+    long long tStage = 0, tVal = 0, tSpin = 0, tAll = timed ? clock64() : 0;
+    struct Ops
+    {
+        int cd[M][LGA], kc[M][2];
+        double acc[M], bb[M], cf[M][LGA];
+    };
+    double mv[M][LGA], mc[M][2]; // cross-group values of the block in work, then of the next one
+    auto load_static = [&](const int blk, Ops& o) {
+        if (blk >= nBlocks) return;
+        const unsigned char* pG = pG0 + (size_t)blk * C.pBytes;
+        const long long vOff = (long long)blk * kNH * 32 * dir;
+#pragma unroll
+        for (int u = 0; u < M; u++)
+        {
+#pragma unroll
+            for (int i = 0; i < LG; i++) o.cd[u][i] = ldg_stream_s32(pG + u * pRec + LG * 256 + i * 128 + lane * 4);
+#pragma unroll
+            for (int k = 0; k < 2; k++) o.kc[u][k] = (k < Kg) ? ldg_stream_s32(pG + u * pRec + LG * 384 + k * 128 + lane * 4) : -1;
+            o.acc[u] = ldg_stream_f64(aG0 + vOff + u * dir * 32);
+            o.bb[u] = MODE == 0 ? ldg_stream_f64(bG0 + vOff + u * dir * 32) : 0.0;
+#pragma unroll
+            for (int i = 0; i < LG; i++) o.cf[u][i] = ldg_stream_f64(pG + u * pRec + i * 256 + lane * 8);
+        }
+    };
+    auto load_values = [&](const Ops& o) {
+#pragma unroll
+        for (int u = 0; u < M; u++)
+        {
+#pragma unroll
+            for (int i = 0; i < LG; i++)
+            {
+                mv[u][i] = neutral;
+                if (o.cd[u][i] >= 0) mv[u][i] = ld_relaxed(out + o.cd[u][i]);
+            }
+#pragma unroll
+            for (int k = 0; k < 2; k++)
+            {
+                mc[u][k] = 0.0;
+                if (o.kc[u][k] >= 0) mc[u][k] = ld_relaxed(out + o.kc[u][k]);
+            }
+        }
+    };
+    int st = set % NS;
+    unsigned par = (unsigned)(set / NS) & 1u;
+    auto work = [&](const int blk, Ops& cur, const Ops& nxt) {
+        const unsigned sg = stage0 + (unsigned)st * stageBytes;
+        const long long w0 = timed ? clock64() : 0;
+        mbar_wait_u32(bar0 + 8u * (unsigned)st, par); // the stage of this block (its hdr part is free, its meta words are here)
+        if (timed) tStage += clock64() - w0;
+        unsigned kind = 0u;
+#pragma unroll
+        for (int u = 0; u < M; u++)
+        {
+            const unsigned b7 = lds_u8(sg + offGen + u * 256); // bit 0: descriptor-driven step, bit 5: dual step (schedule.hpp)
+            kind += MODE == 2 ? 0x100u : (((b7 & 1u) << 8) | (((b7 >> 5) & 1u) << (16 + h0 + u)));
+            if (MODE == 0) cur.acc[u] *= cur.bb[u];
+        }
+        // ---- the cross-group values (requested when the previous block of this warp was handed over)
+        const long long v0 = timed ? clock64() : 0;
+        bool bad = false;
+#pragma unroll
+        for (int u = 0; u < M; u++)
+        {
+#pragma unroll
+            for (int i = 0; i < LG; i++) bad |= cur.cd[u][i] >= 0 && is_sentinel(mv[u][i]);
+#pragma unroll
+            for (int k = 0; k < 2; k++) bad |= cur.kc[u][k] >= 0 && is_sentinel(mc[u][k]);
+        }
+        const bool anyBad = __any_sync(FULL, bad);
+        const long long v1 = timed ? clock64() : 0;
+        if (anyBad)
+        {
+            if (STATS && lane == 0) atomicAdd((unsigned long long*)(S.stats + (long long)kStatsStride * g + 4), 1ull);
+            int tries = 0;
+            bool still;
+            do
+            {
+#pragma unroll
+                for (int u = 0; u < M; u++)
+                {
+#pragma unroll
+                    for (int i = 0; i < LG; i++)
+                        if (cur.cd[u][i] >= 0 && is_sentinel(mv[u][i])) mv[u][i] = ld_relaxed(out + cur.cd[u][i]);
+#pragma unroll
+                    for (int k = 0; k < 2; k++)
+                        if (cur.kc[u][k] >= 0 && is_sentinel(mc[u][k])) mc[u][k] = ld_relaxed(out + cur.kc[u][k]);
+                }
+                still = false;
+#pragma unroll
+                for (int u = 0; u < M; u++)
+                {
+#pragma unroll
+                    for (int i = 0; i < LG; i++) still |= cur.cd[u][i] >= 0 && is_sentinel(mv[u][i]);
+#pragma unroll
+                    for (int k = 0; k < 2; k++) still |= cur.kc[u][k] >= 0 && is_sentinel(mc[u][k]);
+                }
+                if (++tries >= 64)
+                {
+                    __nanosleep(tries > 4096 ? 400 : 64);
+                    if ((tries & 4095) == 4095 && *(volatile int*)err) break;
+                    if (tries >= kSweepSpinLimit)
+                    {
+                        atomicExch(err, 1);
+                        break;
+                    }
+                }
+            } while (__any_sync(FULL, still));
+        }
+        if (timed)
+        {
+            tVal += v1 - v0;
+            tSpin += clock64() - v1;
+        }
+        // ---- leading terms in reference order, hand-over
+#pragma unroll
+        for (int u = 0; u < M; u++)
+        {
+#pragma unroll
+            for (int i = 0; i < LG; i++) cur.acc[u] = sweep_apply<MODE>(cur.acc[u], cur.cf[u][i], mv[u][i]); // padding: coefficient 0, neutral value
+            sts_f64(sg + offHd + u * 256, cur.acc[u]);
+            if (Kg > 0) sts_f64(sg + offHd + u * 256 + kNH * 256, mc[u][0]);
+            if (Kg > 1) sts_f64(sg + offHd + u * 256 + 2 * kNH * 256, mc[u][1]);
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("red.relaxed.cta.shared.add.u32 [%0], %1;" ::"r"(cnt0 + 4u * (unsigned)st), "r"((unsigned)M + kind) : "memory");
+        // ---- the next block of this warp: its values now (its codes came in during this block), its successor's static
+        // operands into the registers that have just become free
+        if (blk + nSets < nBlocks) load_values(nxt);
+        load_static(blk + 2 * nSets, cur);
+        st += nSets;
+        while (st >= NS)
+        {
+            st -= NS;
+            par ^= 1u;
+        }
+    };
+    Ops X, Y;
+    load_static(set, X);
+    load_static(set + nSets, Y);
+    if (set < nBlocks) load_values(X);
+    for (int blk = set; blk < nBlocks; blk += 2 * nSets)
+    {
+        work(blk, X, Y);
+        if (blk + nSets < nBlocks) work(blk + nSets, Y, X);
+    }
+    if (timed && lane == 0)
+    {
+        long long* sp = S.stats + (long long)kStatsStride * g;
+        sp[8] = clock64() - tAll;
+        sp[9] = tStage;
+        sp[10] = tVal;
+        sp[11] = tSpin;
+    }
+}
+
 // Warp roles: consumer, kNH producers, loader.  (Measured on B200: giving the consumer a scheduler sub-partition of its
 // own - wid % 4, 11 warps - or the highest warp id of the CTA changes the sweep time by < 2 %: the consumer is not
 // short of issue slots.)
 constexpr int kRoleConsumer = -1, kRoleLoader = -2;
-// Producer organisation (B200_PROD_SETS > 0): kProdSets sets of producer warps work on kProdSets consecutive blocks at
-// the same time (set s takes the blocks blk = s mod kProdSets); inside a set a producer prepares kProdM consecutive
-// steps of the block.  A producer's step is a chain of latencies (stage wait, code loads, the L2 round trip of the
-// cross-group values, the check, the hand-over) that no amount of tuning brought under ~850 cycles per block; with
-// one set that chain IS the block time of the group (106 cycles per step against the consumer's 61).  With several
-// sets the chains of consecutive blocks overlap, so the loads of the cross-group values can be issued when they are
-// needed (no prefetch a block ahead, no second register set) and a group's pace is the consumer's.
-#ifndef B200_PROD_SETS
-#define B200_PROD_SETS 4
-#endif
-#ifndef B200_PROD_M
-#define B200_PROD_M 4
-#endif
-constexpr int kProdSets = B200_PROD_SETS;
-constexpr int kProdM = B200_PROD_SETS > 0 ? B200_PROD_M : 1;
-constexpr int kProdPerSet = kNH / kProdM;
-constexpr int kProducers = B200_PROD_SETS > 0 ? kProdSets * kProdPerSet : kNH;
-static_assert(kNH % kProdM == 0, "a producer takes a whole number of steps of a block");
 constexpr int kSweepWarps = 2 + kProducers;
 __device__ __forceinline__ int sweep_role(int warp)
 {
@@ -1328,11 +1743,12 @@ __device__ __forceinline__ void sweep_group_split(const PipeDev& S, const int g,
     C.offHdr = (int)C.cBytes;
     C.offP = C.offHdr + kNH * C.hdrStep;
     C.offA = C.offP + (int)C.pBytes;
-    C.rawBytes = C.pBytes + C.cBytes + (unsigned)(kNH * 256 * (MODE == 0 ? 2 : 1));
+    C.rawBytes = kProdDirect ? C.cBytes : C.pBytes + C.cBytes + (unsigned)(kNH * 256 * (MODE == 0 ? 2 : 1));
+    // header of kSweepSmemHeader bytes: rawBar[16] | cnt[16] | done | (debug) issueClk[16]
     C.rawBar = reinterpret_cast<unsigned long long*>(smem);
     C.cnt = reinterpret_cast<unsigned*>(smem + 128);
     C.done = reinterpret_cast<unsigned*>(smem + 192);
-    C.stages = smem + 256;
+    C.stages = smem + kSweepSmemHeader;
     C.pStream = S.pStream + S.gPOff[g];
     C.cStream = S.cStream + S.gCOff[g];
     C.polStream = l2_evict_first();
@@ -1363,7 +1779,38 @@ __device__ __forceinline__ void sweep_group_split(const PipeDev& S, const int g,
     }
     else if (role == kRoleLoader)
     {
+        if (kStoreSmem)
+        {
+            // loader + storer: the whole warp writes a finished block from the hdr plane of its stage to the output vector
+            // (one coalesced store per step), then lane 0 refills the stage
+            constexpr int dir = MODE == 1 ? -1 : 1;
+            int st = 0;
+            double* op = out + ((long long)C.base + (dir > 0 ? 0 : C.nT - 1)) * 32 + lane;
+            for (int blk = 0; blk < C.nBlocks; blk++)
+            {
+                const unsigned need = (unsigned)(blk + 1);
+                while (ld_flag_smem(C.done) < need) __nanosleep(20);
+                const unsigned hdA = smem_u32(C.stages) + (unsigned)st * (unsigned)C.stageBytes + (unsigned)C.offHdr + (unsigned)lane * 8u;
+                double v[kNH];
+#pragma unroll
+                for (int q = 0; q < kNH; q++) v[q] = lds_f64(hdA + q * 256);
+#pragma unroll
+                for (int q = 0; q < kNH; q++) st_relaxed(op + (long long)q * dir * 32, v[q]);
+                op += (long long)kNH * dir * 32;
+                __syncwarp();
+                if (lane == 0 && blk + C.NS < C.nBlocks)
+                {
+                    if (STATS && blk + C.NS < kTraceBlocks) S.stats[(long long)kStatsStride * g + 16 + (blk + C.NS) * 8 + 2] = clock64();
+                    split_issue<MODE>(C, a, b, blk + C.NS, st);
+                    split_prefetch<MODE>(C, a, b, blk + C.NS + S.l2Ahead);
+                }
+                if (++st == C.NS) st = 0;
+            }
+            return;
+        }
         // loader: one thread refills a stage as soon as the consumer has released the block it held
+        const bool probe = S.stats != nullptr; // armed counters: lane 1 measures how long a refill takes to land
+        volatile long long* issueClk = reinterpret_cast<volatile long long*>(smem + 256); // [NS], debug part of the header
         if (lane == 0)
         {
             int st = 0;
@@ -1372,25 +1819,57 @@ __device__ __forceinline__ void sweep_group_split(const PipeDev& S, const int g,
                 const unsigned need = (unsigned)(blk - C.NS + 1);
                 while (ld_flag_smem(C.done) < need) __nanosleep(20);
                 if (STATS && blk < kTraceBlocks) S.stats[(long long)kStatsStride * g + 16 + blk * 8 + 2] = clock64();
+                if (probe) issueClk[st] = clock64();
                 split_issue<MODE>(C, a, b, blk, st);
                 split_prefetch<MODE>(C, a, b, blk + S.l2Ahead);
                 if (++st == C.NS) st = 0;
             }
         }
+        else if (lane == 1 && probe)
+        {
+            long long sum = 0, mx = 0;
+            int n = 0, st = 0;
+            unsigned par = 0u;
+            for (int blk = 0; blk < C.nBlocks; blk++)
+            {
+                mbar_wait(&C.rawBar[st], par);
+                if (blk >= C.NS)
+                {
+                    const long long d = clock64() - issueClk[st];
+                    sum += d;
+                    mx = d > mx ? d : mx;
+                    n++;
+                }
+                if (++st == C.NS)
+                {
+                    st = 0;
+                    par ^= 1u;
+                }
+            }
+            long long* sp = S.stats + (long long)kStatsStride * g;
+            sp[12] = sum;
+            sp[13] = n;
+            sp[15] = mx;
+        }
     }
 #if B200_PROD_SETS > 0
+#if B200_PROD_DIRECT && B200_PROD_PIPE
+#define PRODUCER_FN split_producer_pipe
+#else
+#define PRODUCER_FN split_producer_sets
+#endif
     else if (role >= 0)
     {
         const int set = role / kProdPerSet, h0 = (role % kProdPerSet) * kProdM;
         switch (C.Lg)
         {
-            case 0: split_producer_sets<MODE, 0, kProdM, STATS>(S, C, g, set, kProdSets, h0, lane, out, err); break;
-            case 1: split_producer_sets<MODE, 1, kProdM, STATS>(S, C, g, set, kProdSets, h0, lane, out, err); break;
-            case 2: split_producer_sets<MODE, 2, kProdM, STATS>(S, C, g, set, kProdSets, h0, lane, out, err); break;
-            case 3: split_producer_sets<MODE, 3, kProdM, STATS>(S, C, g, set, kProdSets, h0, lane, out, err); break;
-            case 4: split_producer_sets<MODE, 4, kProdM, STATS>(S, C, g, set, kProdSets, h0, lane, out, err); break;
-            case 5: split_producer_sets<MODE, 5, kProdM, STATS>(S, C, g, set, kProdSets, h0, lane, out, err); break;
-            default: split_producer_sets<MODE, 6, kProdM, STATS>(S, C, g, set, kProdSets, h0, lane, out, err); break;
+            case 0: PRODUCER_FN<MODE, 0, kProdM, STATS>(S, C, g, set, kProdSets, h0, lane, out, err, a, b); break;
+            case 1: PRODUCER_FN<MODE, 1, kProdM, STATS>(S, C, g, set, kProdSets, h0, lane, out, err, a, b); break;
+            case 2: PRODUCER_FN<MODE, 2, kProdM, STATS>(S, C, g, set, kProdSets, h0, lane, out, err, a, b); break;
+            case 3: PRODUCER_FN<MODE, 3, kProdM, STATS>(S, C, g, set, kProdSets, h0, lane, out, err, a, b); break;
+            case 4: PRODUCER_FN<MODE, 4, kProdM, STATS>(S, C, g, set, kProdSets, h0, lane, out, err, a, b); break;
+            case 5: PRODUCER_FN<MODE, 5, kProdM, STATS>(S, C, g, set, kProdSets, h0, lane, out, err, a, b); break;
+            default: PRODUCER_FN<MODE, 6, kProdM, STATS>(S, C, g, set, kProdSets, h0, lane, out, err, a, b); break;
         }
     }
 #else

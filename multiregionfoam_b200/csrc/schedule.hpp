@@ -117,7 +117,10 @@ struct GlobalLdu
 
 // term codes of the sweep streams
 constexpr int kSweepBlock = 8;     // steps per producer/consumer block of the sweep kernel (= producer warps)
-constexpr int kSkew = 1;           // time steps between linked lanes of a warp: a value shuffled from another lane is kSkew
+#ifndef B200_SKEW
+#define B200_SKEW 1
+#endif
+constexpr int kSkew = B200_SKEW;           // time steps between linked lanes of a warp: a value shuffled from another lane is kSkew
                                    // steps old.  2 takes the shuffle off the dependent chain of a time step (only mul+sub of
                                    // the own-lane term remain); 1 keeps it on the chain but halves the lag of a hop in j and
                                    // the spread of a block seam - measured faster on C2 (164.7 / 157.7 us per sweep against

@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "b200_sys_set_coeffs", "b200_sys_set_interface_coeffs", "b200_sys_num_cells", "b200_sys_num_faces",
     "b200_solve", "b200_upload", "b200_solve_resident", "b200_download",
     "b200_x_save", "b200_x_restore", "b200_host_register", "b200_host_unregister",
-    "b200_amul", "b200_precondition", "b200_get_rD", "b200_reduce",
+    "b200_amul", "b200_precondition", "b200_get_rD", "b200_reduce", "b200_residual", "b200_sum_a",
     "b200_set_profiling", "b200_get_kernel_times", "b200_launch_count", "b200_debug_sweep_stats",
     "b200_ggi_interpolate", "b200_patch_face_to_global", "b200_global_face_to_patch",
     "b200_sys_set_interface_attached", "b200_sys_set_interface_ggi",
@@ -100,6 +100,8 @@ def load():
     L.b200_host_unregister.argtypes = [vp, vp]
     L.b200_amul.argtypes = [vp, dpp, dpp, C.c_int]
     L.b200_precondition.argtypes = [vp, C.c_int, dpp, dpp, C.c_int]
+    L.b200_residual.argtypes = [vp, dpp, dpp, dpp]
+    L.b200_sum_a.argtypes = [vp, dpp]
     L.b200_get_rD.argtypes = [vp, C.c_int, dpp]
     L.b200_reduce.argtypes = [vp, dpp, dpp, dp]
     L.b200_set_profiling.argtypes = [vp, C.c_int]
@@ -340,6 +342,18 @@ class LduSystem:
         xs, ys = self.split(x), self._empty()
         self.ctx.check(load().b200_amul(self.h, _dpp(xs), _dpp(ys), int(transpose)))
         return np.concatenate(ys) if ys else np.empty(0)
+
+    def residual(self, x: np.ndarray, b: np.ndarray) -> np.ndarray:
+        """lduMatrix::residual: b - A x with the reference's per-row rounding (b200_residual)."""
+        xs, bs, rs_ = self.split(x), self.split(b), self._empty()
+        self.ctx.check(load().b200_residual(self.h, _dpp(xs), _dpp(bs), _dpp(rs_)))
+        return np.concatenate(rs_) if rs_ else np.empty(0)
+
+    def sumA(self) -> np.ndarray:
+        """lduMatrix::sumA (b200_sum_a)."""
+        out = self._empty()
+        self.ctx.check(load().b200_sum_a(self.h, _dpp(out)))
+        return np.concatenate(out) if out else np.empty(0)
 
     def precondition(self, precond: int, r: np.ndarray, transpose: bool = False) -> np.ndarray:
         rs_, ws = self.split(r), self._empty()

@@ -64,6 +64,22 @@ def test_amul_bit_exact(gpu_ctx, cases, name):
 
 
 @pytest.mark.parametrize("name", CASE_NAMES)
+def test_residual_and_sumA_bit_exact(gpu_ctx, cases, name):
+    """SURVEY a9: lduMatrix::residual (source - A psi, interfaces in the switchToLhs sense) and lduMatrix::sumA keep the
+    reference's per-row rounding order, so they equal the oracle's face loops bit for bit - they are NOT b - Amul(x)."""
+    case = cases[name]
+    O = pyoracle.OracleSystem(case)
+    S = ldu.LduSystem(gpu_ctx, case.ranks[0])
+    try:
+        x = random_vec(O.n, 7) * 10 + 300
+        b = random_vec(O.n, 8) * 1e3
+        assert np.array_equal(S.residual(x, b), O.residual(x, b))
+        assert np.array_equal(S.sumA(), O.sumA())
+    finally:
+        S.close()
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
 @pytest.mark.parametrize("precond", ["DIC", "DILU", "Cholesky", "diagonal", "none"])
 def test_precondition_bit_exact(gpu_ctx, cases, name, precond):
     case = cases[name]

@@ -75,7 +75,7 @@ def test_line_structure_on_structured_mesh(emu):
     # 41 lines = 32 + 9 lanes per layer; (332 + kSkew * (lanes - 1)) steps rounded up to 16 (lanes are skewed by kSkew steps)
     import os, re
     hpp = open(os.path.join(os.path.dirname(__file__), "..", "multiregionfoam_b200", "csrc", "schedule.hpp")).read()
-    skew = int(re.search(r"constexpr int kSkew = (\d+);", hpp).group(1))
+    skew = int(re.search(r"#define B200_SKEW (\d+)", hpp).group(1))  # the default the emulator is built with
     up16 = lambda v: (v + 15) // 16 * 16
     assert stats[7] == nz * 32 * (up16(nx + skew * 31) + up16(nx + skew * 8))
     # only the steps in which some lane crosses one of the two block seams leave the canonical (shuffle, own) form
