@@ -8,6 +8,9 @@
 #include <nccl.h>
 
 #include <chrono>
+#include <thread>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -82,11 +85,34 @@ static bool load_nccl(std::string& err)
 }
 
 // ------------------------------------------------------------------------------------------ context
+// Peer-to-peer transport of a context (nranks > 1): mailboxes for the fused all-reduce, an exchange area for the
+// zone all-reduce, and the rendezvous directory the ranks use to hand each other cudaIpc handles.
+struct PeerLink
+{
+    bool enabled = false;
+    std::string dir;                   // /dev/shm/b200_<first bytes of the unique id>
+    double* mbox = nullptr;            // [2][nranks][kMboxSlot]
+    std::vector<double*> peerMbox;     // per rank: mapped mailbox (own: mbox)
+    double** dPeerMbox = nullptr;      // the same on the device
+    unsigned long long arSeq = 0;
+    double* xbuf = nullptr;            // [2][nranks][kXchgCap + 8] exchange area (zone all-reduce without NCCL)
+    std::vector<double*> peerX;
+    double** dPeerX = nullptr;
+    unsigned long long xSeq = 0;
+    unsigned* counter = nullptr;       // last-block counter of the exchange kernels
+    int* err = nullptr;                // device word: 2 = a peer did not answer
+    int sysCount = 0;                  // systems finalized on this context (names the rendezvous files)
+    std::vector<void*> opened;         // cudaIpcOpenMemHandle results to close
+    std::vector<std::string> files;    // rendezvous files this rank wrote
+};
+constexpr int kXchgCap = 65536; // doubles per rank and parity in the exchange area
+
 struct b200_ctx
 {
     int device = 0, rank = 0, nranks = 1;
     cudaStream_t stream = nullptr;
     ncclComm_t comm = nullptr;
+    PeerLink peer;
     std::string err;
     int64_t launches = 0;
     int smCount = 148;
@@ -152,6 +178,64 @@ struct DevBuf
         return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st);
     }
 };
+
+// ------------------------------------------------------------------------------------------ peer-to-peer rendezvous
+// The C ABI hands every rank the same 128-byte unique id (b200_nccl_unique_id broadcast by rank 0; any 128 random bytes
+// do when NCCL is not used).  The ranks of one node meet in /dev/shm/b200_<id>: a rank publishes a record by writing
+// <name>.tmp and renaming it, and reads a peer's record by polling for the file.
+static std::string peer_dir(const void* uid)
+{
+    static const char* hex = "0123456789abcdef";
+    const unsigned char* b = static_cast<const unsigned char*>(uid);
+    std::string d = "/dev/shm/b200_";
+    for (int i = 0; i < 16; i++)
+    {
+        d.push_back(hex[b[i] >> 4]);
+        d.push_back(hex[b[i] & 15]);
+    }
+    return d;
+}
+static bool peer_publish(PeerLink& L, const std::string& name, const void* data, size_t n)
+{
+    const std::string path = L.dir + "/" + name, tmp = path + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return false;
+    const bool ok = fwrite(data, 1, n, f) == n;
+    fclose(f);
+    if (!ok || rename(tmp.c_str(), path.c_str()) != 0) return false;
+    L.files.push_back(path);
+    return true;
+}
+static bool peer_fetch(const PeerLink& L, const std::string& name, std::vector<unsigned char>& data, double timeoutSec = 120.0)
+{
+    const std::string path = L.dir + "/" + name;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;)
+    {
+        FILE* f = fopen(path.c_str(), "rb");
+        if (f)
+        {
+            fseek(f, 0, SEEK_END);
+            const long n = ftell(f);
+            fseek(f, 0, SEEK_SET);
+            data.resize((size_t)std::max(0l, n));
+            const bool ok = n >= 0 && fread(data.data(), 1, data.size(), f) == data.size();
+            fclose(f);
+            return ok;
+        }
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > timeoutSec) return false;
+        std::this_thread::sleep_for(std::chrono::microseconds(500));
+    }
+}
+// "p2p": the library's own transport only (no NCCL communicator: ranks may share a device); "nccl": NCCL only;
+// unset / "auto": peer-to-peer when the rendezvous and the mappings succeed, NCCL otherwise
+static int transport_mode()
+{
+    const char* e = getenv("B200_TRANSPORT");
+    if (e && !strcmp(e, "p2p")) return 1;
+    if (e && !strcmp(e, "nccl")) return 2;
+    return 0;
+}
 
 struct PipeDirMem
 {
@@ -225,6 +309,26 @@ struct b200_sys
     int nDetached = 0; // regionCouple interfaces currently detached (regionInterfaceType::detach)
     std::vector<int> peers;
     std::vector<int32_t> sendOff, recvOff;
+    // peer-to-peer halo (PeerLink of the context): one allocation [2 parities][recvTotal] doubles | [2][nPeers] flag words,
+    // mapped by the neighbours, which store their patchInternalField straight into it (k_halo_push)
+    struct HaloLink
+    {
+        bool enabled = false;
+        unsigned char* buf = nullptr;
+        size_t recvTotal = 0;
+        std::vector<double*> peerData;             // per peer: its buffer, at the offset of this rank's segment (parity 0)
+        std::vector<size_t> peerTotal;             // per peer: its recvTotal (parity stride)
+        std::vector<unsigned long long*> peerFlag; // per peer: this rank's flag word in its buffer (parity 0)
+        std::vector<int> peerNPeers;               // per peer: its number of peers (parity stride of the flags)
+        unsigned long long seq = 0;
+        unsigned* counters = nullptr;              // [nPeers] last-block counters of k_halo_push
+        std::vector<void*> opened;
+        double* data(int par) const { return reinterpret_cast<double*>(buf) + (size_t)par * recvTotal; }
+        unsigned long long* flags(int par, int nPeers) const
+        {
+            return reinterpret_cast<unsigned long long*>(buf + 2 * recvTotal * sizeof(double)) + (size_t)par * nPeers;
+        }
+    } halo;
     int64_t nIfCoefs = 0;
     // sweeps
     PipeDirMem fwd, bwd;
@@ -330,6 +434,91 @@ extern "C" int b200_nccl_unique_id(void* out128)
     return B200_OK;
 }
 
+// Map one buffer of every rank into this process: publish this rank's cudaIpc handle as <tag>, fetch the peers'.
+static bool peer_map_all(b200_ctx* c, const std::string& tag, void* mine, std::vector<double*>& mapped, std::string& why)
+{
+    PeerLink& L = c->peer;
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, mine) != cudaSuccess)
+    {
+        why = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(cudaGetLastError());
+        return false;
+    }
+    if (!peer_publish(L, "r" + std::to_string(c->rank) + "." + tag, &h, sizeof(h)))
+    {
+        why = "cannot write the rendezvous record in " + L.dir;
+        return false;
+    }
+    mapped.assign(c->nranks, nullptr);
+    mapped[c->rank] = static_cast<double*>(mine);
+    for (int r = 0; r < c->nranks; r++)
+    {
+        if (r == c->rank) continue;
+        std::vector<unsigned char> rec;
+        if (!peer_fetch(L, "r" + std::to_string(r) + "." + tag, rec) || rec.size() != sizeof(h))
+        {
+            why = "rank " + std::to_string(r) + " did not publish " + tag;
+            return false;
+        }
+        memcpy(&h, rec.data(), sizeof(h));
+        void* q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+        {
+            why = std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(r) + "): " + cudaGetErrorString(cudaGetLastError());
+            return false;
+        }
+        L.opened.push_back(q);
+        mapped[r] = static_cast<double*>(q);
+    }
+    return true;
+}
+
+static bool peer_setup(b200_ctx* c, const void* uid, std::string& why)
+{
+    PeerLink& L = c->peer;
+    L.dir = peer_dir(uid);
+    mkdir(L.dir.c_str(), 0700); // EEXIST: another rank was first
+    const size_t mboxDoubles = 2 * (size_t)c->nranks * kMboxSlot;
+    const size_t xDoubles = 2 * (size_t)c->nranks * (kXchgCap + 8);
+    if (cudaMalloc((void**)&L.mbox, mboxDoubles * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&L.xbuf, xDoubles * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&L.counter, 64) != cudaSuccess || cudaMalloc((void**)&L.err, 64) != cudaSuccess ||
+        cudaMalloc((void**)&L.dPeerMbox, sizeof(double*) * c->nranks) != cudaSuccess ||
+        cudaMalloc((void**)&L.dPeerX, sizeof(double*) * c->nranks) != cudaSuccess)
+    {
+        why = std::string("cudaMalloc: ") + cudaGetErrorString(cudaGetLastError());
+        return false;
+    }
+    cudaMemset(L.mbox, 0, mboxDoubles * sizeof(double));
+    cudaMemset(L.xbuf, 0, xDoubles * sizeof(double));
+    cudaMemset(L.counter, 0, 64);
+    cudaMemset(L.err, 0, 64);
+    cudaDeviceSynchronize(); // the zeros are in place before any peer can write
+    if (!peer_map_all(c, "mbox", L.mbox, L.peerMbox, why)) return false;
+    if (!peer_map_all(c, "xbuf", L.xbuf, L.peerX, why)) return false;
+    cudaMemcpy(L.dPeerMbox, L.peerMbox.data(), sizeof(double*) * c->nranks, cudaMemcpyHostToDevice);
+    cudaMemcpy(L.dPeerX, L.peerX.data(), sizeof(double*) * c->nranks, cudaMemcpyHostToDevice);
+    L.enabled = true;
+    return true;
+}
+
+static void peer_teardown(b200_ctx* c)
+{
+    PeerLink& L = c->peer;
+    for (void* q : L.opened) cudaIpcCloseMemHandle(q);
+    L.opened.clear();
+    for (const std::string& f : L.files) unlink(f.c_str());
+    L.files.clear();
+    if (!L.dir.empty()) rmdir(L.dir.c_str()); // succeeds for the last rank to leave
+    cudaFree(L.mbox);
+    cudaFree(L.xbuf);
+    cudaFree(L.counter);
+    cudaFree(L.err);
+    cudaFree(L.dPeerMbox);
+    cudaFree(L.dPeerX);
+    L = PeerLink();
+}
+
 extern "C" int b200_ctx_create(int device, int rank, int nranks, const void* ncclUniqueIdBytes, b200_ctx** out)
 {
     if (!out || nranks < 1 || rank < 0 || rank >= nranks) return set_err(nullptr, B200_EINVAL, "b200_ctx_create: bad arguments");
@@ -351,12 +540,28 @@ extern "C" int b200_ctx_create(int device, int rank, int nranks, const void* ncc
     if (nranks > 1)
     {
         std::string err;
-        if (!ncclUniqueIdBytes) return set_err(nullptr, B200_EINVAL, "nranks > 1 needs an NCCL unique id");
-        if (!load_nccl(err)) return set_err(nullptr, B200_ENCCL, "%s", err.c_str());
-        ncclUniqueId id;
-        memcpy(&id, ncclUniqueIdBytes, 128);
-        ncclResult_t r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
-        if (r != ncclSuccess) return set_err(nullptr, B200_ENCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+        if (!ncclUniqueIdBytes) return set_err(nullptr, B200_EINVAL, "nranks > 1 needs the 128-byte unique id all ranks share");
+        const int mode = transport_mode();
+        if (mode != 1)
+        { // NCCL communicator: the transport in "nccl" mode, the fall-back and the zone all-reduce otherwise
+            if (!load_nccl(err)) return set_err(nullptr, B200_ENCCL, "%s", err.c_str());
+            ncclUniqueId id;
+            memcpy(&id, ncclUniqueIdBytes, 128);
+            ncclResult_t r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+            if (r != ncclSuccess) return set_err(nullptr, B200_ENCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+        }
+        if (mode != 2)
+        {
+            std::string why;
+            if (!peer_setup(c.get(), ncclUniqueIdBytes, why))
+            {
+                peer_teardown(c.get());
+                if (mode == 1) return set_err(nullptr, B200_ECUDA, "B200_TRANSPORT=p2p: %s", why.c_str());
+                if (getenv("B200_TRANSPORT_INFO")) fprintf(stderr, "[b200] rank %d: peer-to-peer transport unavailable (%s), using NCCL\n", rank, why.c_str());
+            }
+            else if (getenv("B200_TRANSPORT_INFO"))
+                fprintf(stderr, "[b200] rank %d: peer-to-peer transport up (%s)\n", rank, c->peer.dir.c_str());
+        }
     }
     *out = c.release();
     return B200_OK;
@@ -366,6 +571,8 @@ extern "C" int b200_ctx_destroy(b200_ctx* ctx)
 {
     if (!ctx) return B200_OK;
     cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    peer_teardown(ctx);
     if (ctx->comm) g_nccl.CommDestroy(ctx->comm);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -397,6 +604,9 @@ extern "C" int b200_sys_destroy(b200_sys* s)
     if (s->evSolveA) cudaEventDestroy(s->evSolveA);
     if (s->evSolveB) cudaEventDestroy(s->evSolveB);
     if (s->hostFlags) cudaFreeHost(s->hostFlags);
+    for (void* q : s->halo.opened) cudaIpcCloseMemHandle(q);
+    if (s->halo.buf) cudaFree(s->halo.buf);
+    if (s->halo.counters) cudaFree(s->halo.counters);
     delete s;
     return B200_OK;
 }
@@ -563,6 +773,75 @@ static int upload_pipe_dir(b200_sys* s, const PipeSchedule& S, const PipeSchedul
     return B200_OK;
 }
 
+// Peer-to-peer halo of a system: every rank publishes the cudaIpc handle of its receive buffer and the table
+// (peer rank, offset, count) of its segments; a rank finds in each neighbour's record where its own data has to go.
+static int setup_halo_link(b200_sys* s)
+{
+    b200_ctx* ctx = s->ctx;
+    PeerLink& L = ctx->peer;
+    const int k = L.sysCount++;
+    if (s->peers.empty()) return B200_OK;
+    b200_sys::HaloLink& H = s->halo;
+    const int nPeers = (int)s->peers.size();
+    H.recvTotal = (size_t)s->recvOff.back();
+    const size_t bytes = 2 * H.recvTotal * sizeof(double) + 2 * (size_t)nPeers * sizeof(unsigned long long);
+    CK(ctx, cudaMalloc((void**)&H.buf, bytes));
+    CK(ctx, cudaMemset(H.buf, 0, bytes));
+    CK(ctx, cudaMalloc((void**)&H.counters, sizeof(unsigned) * nPeers));
+    CK(ctx, cudaMemset(H.counters, 0, sizeof(unsigned) * nPeers));
+    CK(ctx, cudaDeviceSynchronize());
+    struct Seg
+    {
+        int32_t peer, pad;
+        int64_t off, count;
+    };
+    struct Head
+    {
+        cudaIpcMemHandle_t h;
+        int64_t recvTotal;
+        int32_t nPeers, pad;
+    };
+    std::vector<unsigned char> rec(sizeof(Head) + sizeof(Seg) * nPeers);
+    Head* hd = reinterpret_cast<Head*>(rec.data());
+    CK(ctx, cudaIpcGetMemHandle(&hd->h, H.buf));
+    hd->recvTotal = (int64_t)H.recvTotal;
+    hd->nPeers = nPeers;
+    hd->pad = 0;
+    Seg* sg = reinterpret_cast<Seg*>(rec.data() + sizeof(Head));
+    for (int p = 0; p < nPeers; p++) sg[p] = Seg{s->peers[p], 0, s->recvOff[p], s->recvOff[p + 1] - s->recvOff[p]};
+    const std::string tag = "sys" + std::to_string(k);
+    if (!peer_publish(L, "r" + std::to_string(ctx->rank) + "." + tag, rec.data(), rec.size()))
+        return set_err(ctx, B200_ECUDA, "peer-to-peer halo: cannot write the rendezvous record in %s", L.dir.c_str());
+    H.peerData.assign(nPeers, nullptr);
+    H.peerTotal.assign(nPeers, 0);
+    H.peerFlag.assign(nPeers, nullptr);
+    H.peerNPeers.assign(nPeers, 0);
+    for (int p = 0; p < nPeers; p++)
+    {
+        std::vector<unsigned char> theirs;
+        if (!peer_fetch(L, "r" + std::to_string(s->peers[p]) + "." + tag, theirs) || theirs.size() < sizeof(Head))
+            return set_err(ctx, B200_ECUDA, "peer-to-peer halo: rank %d did not publish %s", s->peers[p], tag.c_str());
+        const Head* th = reinterpret_cast<const Head*>(theirs.data());
+        const Seg* ts = reinterpret_cast<const Seg*>(theirs.data() + sizeof(Head));
+        int j = -1;
+        for (int q = 0; q < th->nPeers; q++)
+            if (ts[q].peer == ctx->rank) j = q;
+        const int64_t nSend = s->sendOff[p + 1] - s->sendOff[p];
+        if (j < 0 || ts[j].count != nSend)
+            return set_err(ctx, B200_EINVAL, "peer-to-peer halo: rank %d expects %lld values from rank %d, which sends %lld", s->peers[p],
+                           (long long)(j < 0 ? -1 : ts[j].count), ctx->rank, (long long)nSend);
+        void* q = nullptr;
+        CK(ctx, cudaIpcOpenMemHandle(&q, th->h, cudaIpcMemLazyEnablePeerAccess));
+        H.opened.push_back(q);
+        H.peerData[p] = static_cast<double*>(q) + ts[j].off;
+        H.peerTotal[p] = (size_t)th->recvTotal;
+        H.peerFlag[p] = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(q) + 2 * (size_t)th->recvTotal * sizeof(double)) + j;
+        H.peerNPeers[p] = th->nPeers;
+    }
+    H.enabled = true;
+    return B200_OK;
+}
+
 // Interface / halo plan of the system (schedule.hpp, IfacePlan): built at finalize, and rebuilt (first == false: the
 // coefficient arrays keep their contents) when the GGI interpolation of an interface was replaced.
 static int build_iface_plan(b200_sys* s, bool first)
@@ -603,6 +882,13 @@ static int build_iface_plan(b200_sys* s, bool first)
     }
     CK(ctx, cudaStreamSynchronize(st)); // host vectors go out of scope after return
     s->ifacePlanDirty = false;
+    if (first && ctx->nranks > 1 && ctx->peer.enabled)
+    {
+        const int rc = setup_halo_link(s);
+        if (rc) return rc;
+    }
+    else if (!first && s->halo.enabled && s->halo.recvTotal != (size_t)s->recvOff.back())
+        return set_err(ctx, B200_ESTATE, "the processor patches of a finalized system cannot change");
     return B200_OK;
 }
 
@@ -721,7 +1007,15 @@ extern "C" int b200_sys_finalize(b200_sys* s)
         double* d = s->vec[V_TMP].p;
         double hN = (double)s->N;
         CK(ctx, cudaMemcpyAsync(d, &hN, sizeof(double), cudaMemcpyHostToDevice, st));
-        NK(ctx, g_nccl.AllReduce(d, d, 1, ncclDouble, ncclSum, ctx->comm, st));
+        if (ctx->peer.enabled)
+        {
+            PeerLink& L = ctx->peer;
+            ctx->launches++;
+            k_peer_allreduce<<<1, 32, 0, st>>>(d, 1, PeerAR{L.dPeerMbox, L.mbox, ctx->rank, ctx->nranks, ++L.arSeq}, L.err);
+            CK(ctx, cudaGetLastError());
+        }
+        else
+            NK(ctx, g_nccl.AllReduce(d, d, 1, ncclDouble, ncclSum, ctx->comm, st));
         CK(ctx, cudaMemcpyAsync(&hN, d, sizeof(double), cudaMemcpyDeviceToHost, st));
         CK(ctx, cudaStreamSynchronize(st));
         s->nGlobalCells = hN;
@@ -884,10 +1178,20 @@ static int reduce_finish(b200_sys* s, const PartCounts& cnt, int nd, int op, int
 {
     b200_ctx* ctx = s->ctx;
     const bool multi = ctx->nranks > 1;
+    if (multi && ctx->peer.enabled)
+    { // sums, all-reduce over the peer mailboxes and the scalar recurrences in one launch
+        KScope k(s, B200_K_REDUCE);
+        PeerLink& L = ctx->peer;
+        const PeerAR ar{L.dPeerMbox, L.mbox, ctx->rank, ctx->nranks, ++L.arSeq};
+        k_finalize<<<1, 1024, 0, ctx->stream>>>(s->partials.p, s->pstride, cnt, nd, s->sc.p, op, 1, force, s->history.p, s->devHostFlags, ar,
+                                                 L.err);
+        CK(ctx, cudaGetLastError());
+        return B200_OK;
+    }
     {
         KScope k(s, B200_K_REDUCE);
         k_finalize<<<1, 1024, 0, ctx->stream>>>(s->partials.p, s->pstride, cnt, nd, s->sc.p, op, multi ? 0 : 1, force,
-                                                 s->history.p, s->devHostFlags);
+                                                 s->history.p, s->devHostFlags, PeerAR{nullptr, nullptr, 0, 1, 0}, nullptr);
     }
     if (multi)
     {
@@ -916,7 +1220,29 @@ static int launch_amul(b200_sys* s, const double* x, double* y, int nd, const do
     const double* val = transpose ? s->sellValT.p : s->sellVal.p;
     const double* ifc = transpose ? s->ifCoefInt.p : s->ifCoefBou.p;
     // halo exchange of the shadow-side patchInternalField (processorFvPatchField init/update)
-    if (!s->peers.empty())
+    const unsigned long long* haloFlags = nullptr;
+    int nHaloPeers = 0;
+    unsigned long long haloSeq = 0;
+    const double* recvPtr = s->recvBuf.p;
+    if (!s->peers.empty() && s->halo.enabled)
+    { // peer-to-peer: one push per neighbour, no send / receive buffers, no collective call
+        b200_sys::HaloLink& H = s->halo;
+        haloSeq = ++H.seq;
+        const int par = (int)(haloSeq & 1ull);
+        nHaloPeers = (int)s->peers.size();
+        haloFlags = H.flags(par, nHaloPeers);
+        recvPtr = H.data(par);
+        KScope k(s, B200_K_HALO);
+        for (int p = 0; p < nHaloPeers; p++)
+        {
+            const int ns = s->sendOff[p + 1] - s->sendOff[p];
+            k_halo_push<<<std::max(1, (ns + 255) / 256), 256, 0, st>>>(ns, s->sendCells.p + s->sendOff[p], x,
+                                                                     H.peerData[p] + (size_t)par * H.peerTotal[p],
+                                                                     H.peerFlag[p] + (size_t)par * H.peerNPeers[p], haloSeq, H.counters + p, s->sc.p,
+                                                                     1);
+        }
+    }
+    else if (!s->peers.empty())
     {
         const int nSend = s->sendOff.back();
         if (nSend)
@@ -959,7 +1285,7 @@ static int launch_amul(b200_sys* s, const double* x, double* y, int nd, const do
         KScope k(s, B200_K_IFACE);
 #define IFACE_ARGS                                                                                                           \
     s->nTouched, s->ifRows.p, s->ifRowStart.p, s->ifEntCoef.p, s->ifEntSrc.p, s->ifEntCnt.p, s->ifGSrc.p, s->ifGW.p, ifc, x, \
-        s->recvBuf.p, y, d0, s->partials.p, s->pstride, s->amulBlocks, s->sc.p, force
+        recvPtr, y, d0, s->partials.p, s->pstride, s->amulBlocks, s->sc.p, force, haloFlags, nHaloPeers, haloSeq
         if (op == 1)
             k_iface<0, 1><<<s->ifaceBlocks, 128, 0, st>>>(IFACE_ARGS);
         else if (op == 2)
@@ -1179,6 +1505,15 @@ static int check_device_error(b200_sys* s)
     {
         cudaMemsetAsync(s->devErr.p, 0, sizeof(int), s->ctx->stream);
         return set_err(s->ctx, B200_EDEVICE, "sweep kernel timed out waiting for a dependency (device error %d)", e);
+    }
+    if (s->ctx->peer.enabled)
+    {
+        CK(s->ctx, cudaMemcpy(&e, s->ctx->peer.err, sizeof(int), cudaMemcpyDeviceToHost));
+        if (e)
+        {
+            cudaMemset(s->ctx->peer.err, 0, sizeof(int));
+            return set_err(s->ctx, B200_EDEVICE, "a peer rank did not answer a peer-to-peer all-reduce (device error %d)", e);
+        }
     }
     return B200_OK;
 }
@@ -1755,7 +2090,25 @@ extern "C" int b200_patch_face_to_global(b200_ctx* ctx, int32_t nLocal, const in
         CK(ctx, cudaGetLastError());
     }
     if (ctx->nranks > 1 && nZoneFaces > 0)
-        NK(ctx, g_nccl.AllReduce(dG.p, dG.p, (size_t)nZoneFaces * nComp, ncclDouble, ncclSum, ctx->comm, st)); // reduce(gField, sumOp)
+    {
+        if (ctx->comm)
+            NK(ctx, g_nccl.AllReduce(dG.p, dG.p, (size_t)nZoneFaces * nComp, ncclDouble, ncclSum, ctx->comm, st)); // reduce(gField, sumOp)
+        else
+        { // no NCCL communicator (B200_TRANSPORT=p2p): chunks of the zone array through the peers' exchange areas
+            PeerLink& L = ctx->peer;
+            const size_t total = (size_t)nZoneFaces * nComp;
+            for (size_t o = 0; o < total; o += kXchgCap)
+            {
+                const int n = (int)std::min<size_t>(kXchgCap, total - o);
+                const unsigned long long seq = ++L.xSeq;
+                const int par = (int)(seq & 1ull);
+                ctx->launches += 2;
+                k_xchg_push<<<std::min(64, (n + 255) / 256), 256, 0, st>>>(n, dG.p + o, L.dPeerX, ctx->rank, ctx->nranks, kXchgCap, par, seq, L.counter);
+                k_xchg_sum<<<std::min(64, (n + 255) / 256), 256, 0, st>>>(n, dG.p + o, L.xbuf, ctx->nranks, kXchgCap, par, seq, L.err);
+                CK(ctx, cudaGetLastError());
+            }
+        }
+    }
     if (nZoneFaces) CK(ctx, cudaMemcpyAsync(gField, dG.p, sizeof(double) * nZoneFaces * nComp, cudaMemcpyDeviceToHost, st));
     CK(ctx, cudaStreamSynchronize(st));
     return B200_OK;

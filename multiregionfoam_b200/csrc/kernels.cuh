@@ -253,9 +253,68 @@ struct PartCounts
 {
     int n[kMaxDots];
 };
+// Peer-to-peer all-reduce of the <= kMaxDots sums of a reduction phase, fused into k_finalize (the global sums of
+// gSumProd / gSumMag / gAverage).  Every rank owns a mailbox in its HBM, [2 parities][nranks][8 doubles],
+// mapped into the address space of every other rank (cudaIpc over NVLink, or the same device for ranks that share
+// one).  A rank stores its partial sums into slot [parity][its rank] of EVERY mailbox, fences, stores the sequence
+// number into the slot's last word, then waits until its own mailbox holds the sequence number in all nranks slots
+// and adds the slots up in rank order: every rank gets bit-identical sums, in one kernel, for the latency of one
+// NVLink store instead of a kernel + ncclAllReduce + a kernel.  Two parities: a rank can be one all-reduce ahead of a
+// peer that has not read its slots yet, never two (it needs that peer's contribution to finish the one in between).
+struct PeerAR
+{
+    double* const* peerMbox; // [nranks] device-visible mailbox of every rank (own one included)
+    double* mbox;            // this rank's mailbox
+    int rank, nranks;        // nranks <= 1: no exchange
+    unsigned long long seq;  // sequence number of this all-reduce (>= 1, the same on all ranks)
+};
+constexpr int kMboxSlot = 8; // doubles per mailbox slot: values 0 .. kMaxDots-1, sequence number in the last one
+
+__device__ __forceinline__ void peer_allreduce(const PeerAR& ar, int nd, double* red, int* err)
+{
+    __syncthreads();
+    const int par = (int)(ar.seq & 1ull);
+    if ((int)threadIdx.x < ar.nranks)
+    {
+        const int peer = threadIdx.x;
+        volatile double* dst = ar.peerMbox[peer] + ((size_t)par * ar.nranks + ar.rank) * kMboxSlot;
+        for (int k = 0; k < nd; k++) dst[k] = red[k];
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(dst + kMboxSlot - 1) = ar.seq;
+        const volatile unsigned long long* f =
+            reinterpret_cast<const volatile unsigned long long*>(ar.mbox + ((size_t)par * ar.nranks + peer) * kMboxSlot + kMboxSlot - 1);
+        long long tries = 0;
+        while (*f != ar.seq)
+        {
+            if (++tries > 64) __nanosleep(tries > 100000 ? 1000 : 40);
+            if (tries > (1ll << 27))
+            { // ~2 minutes: a peer is gone
+                atomicExch(err, 2);
+                break;
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        const volatile double* m = ar.mbox + (size_t)par * ar.nranks * kMboxSlot;
+        for (int k = 0; k < nd; k++)
+        {
+            double t = 0.0;
+            for (int r = 0; r < ar.nranks; r++) t += m[(size_t)r * kMboxSlot + k];
+            red[k] = t;
+        }
+    }
+    __syncthreads();
+}
+
+// all-reduce of nd <= kMaxDots doubles that are already on the device (set-up time: the global cell count)
+__global__ void k_peer_allreduce(double* v, int nd, PeerAR ar, int* err) { peer_allreduce(ar, nd, v, err); }
+
 __global__ void __launch_bounds__(1024) k_finalize(const double* __restrict__ partials, int pstride, PartCounts cnt,
                                                     int nd, DevScalars* sc, int op, int applyOp, int force,
-                                                    double* history, volatile int* hostFlags)
+                                                    double* history, volatile int* hostFlags, PeerAR ar, int* err)
 {
     if (sc->done && !force) return;
     __shared__ double sm[32];
@@ -278,6 +337,7 @@ __global__ void __launch_bounds__(1024) k_finalize(const double* __restrict__ pa
         }
         __syncthreads();
     }
+    if (ar.nranks > 1) peer_allreduce(ar, nd, sc->red, err);
     if (applyOp && threadIdx.x == 0) scalar_op(sc, op, history, hostFlags);
 }
 
@@ -379,9 +439,25 @@ __global__ void __launch_bounds__(128) k_iface(int nTouched, const int* __restri
                                                 const double* __restrict__ coef, const double* __restrict__ x,
                                                 const double* __restrict__ recv, double* __restrict__ y,
                                                 const double* __restrict__ d0, double* partials, int pstride,
-                                                int slotBase, const DevScalars* sc, int force)
+                                                int slotBase, const DevScalars* sc, int force,
+                                                const unsigned long long* haloFlags, int nHaloPeers, unsigned long long haloSeq)
 {
     if (sc->done && !force) return;
+    if (nHaloPeers > 0)
+    { // peer-to-peer halo: the neighbours' k_halo_push has published this exchange's sequence number when the data is here
+        if ((int)threadIdx.x < nHaloPeers)
+        {
+            const volatile unsigned long long* f = haloFlags + threadIdx.x;
+            long long tries = 0;
+            while (*f < haloSeq)
+            {
+                if (++tries > 16) __nanosleep(tries > 100000 ? 1000 : 30);
+                if (tries > (1ll << 27)) break; // a peer is gone: the solve's error word is set by the all-reduce that follows
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
     double dots[ND > 0 ? ND : 1];
 #pragma unroll
     for (int k = 0; k < (ND > 0 ? ND : 1); k++) dots[k] = 0.0;
@@ -402,7 +478,7 @@ __global__ void __launch_bounds__(128) k_iface(int nTouched, const int* __restri
             if (cnt == 0)
             {
                 const int s = entSrc[e];
-                pnf = s >= 0 ? x[s] : recv[-1 - s];
+                pnf = s >= 0 ? x[s] : __ldcv(recv + (-1 - s));
             }
             else
             {
@@ -411,7 +487,7 @@ __global__ void __launch_bounds__(128) k_iface(int nTouched, const int* __restri
                 for (int k = 0; k < cnt; k++)
                 {
                     const int s = gSrc[g0 + k];
-                    const double f = s >= 0 ? x[s] : recv[-1 - s];
+                    const double f = s >= 0 ? x[s] : __ldcv(recv + (-1 - s));
                     pnf += f * gW[g0 + k];
                 }
             }
@@ -436,6 +512,82 @@ __global__ void k_halo_pack(int n, const int* __restrict__ cells, const double* 
     if (sc->done && !force) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) sendbuf[i] = x[cells[i]];
+}
+
+// Peer-to-peer halo (processorFvPatchField::initInterfaceMatrixUpdate): the patchInternalField of one
+// processor patch is stored straight into the neighbour rank's receive buffer (mapped peer memory), and the last block
+// of the launch - every block fences and counts itself in - publishes the sequence number of this exchange in the
+// neighbour's flag word.  The neighbour's k_iface waits for that word; the interior rows of its Amul run meanwhile.
+__global__ void k_halo_push(int n, const int* __restrict__ cells, const double* __restrict__ x, double* __restrict__ remote,
+                            unsigned long long* remoteFlag, unsigned long long seq, unsigned* counter, const DevScalars* sc, int force)
+{
+    if (sc->done && !force) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) remote[i] = x[cells[i]];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        const unsigned prev = atomicAdd(counter, 1u);
+        if (prev == gridDim.x - 1)
+        {
+            *counter = 0u;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long*>(remoteFlag) = seq;
+        }
+    }
+}
+
+// zone all-reduce over the peer mailboxes' exchange area (globalPolyPatch::patchFaceToGlobal) for contexts
+// without an NCCL communicator: chunk c of the zone array is pushed into slot [parity][rank] of every rank's exchange
+// buffer, then summed in rank order
+__global__ void k_xchg_push(int n, const double* __restrict__ src, double* const* peerX, int rank, int nranks, int cap, int par,
+                            unsigned long long seq, unsigned* counter)
+{
+    for (int peer = 0; peer < nranks; peer++)
+    {
+        double* dst = peerX[peer] + ((size_t)par * nranks + rank) * (size_t)(cap + 8);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        const unsigned prev = atomicAdd(counter, 1u);
+        if (prev == gridDim.x - 1)
+        {
+            *counter = 0u;
+            __threadfence_system();
+            for (int peer = 0; peer < nranks; peer++)
+                *reinterpret_cast<volatile unsigned long long*>(peerX[peer] + ((size_t)par * nranks + rank) * (size_t)(cap + 8) + cap) = seq;
+        }
+    }
+}
+__global__ void k_xchg_sum(int n, double* __restrict__ dst, const double* xbuf, int nranks, int cap, int par, unsigned long long seq, int* err)
+{
+    if (threadIdx.x < nranks)
+    {
+        const volatile unsigned long long* f =
+            reinterpret_cast<const volatile unsigned long long*>(xbuf + ((size_t)par * nranks + threadIdx.x) * (size_t)(cap + 8) + cap);
+        long long tries = 0;
+        while (*f != seq)
+        {
+            if (++tries > 64) __nanosleep(tries > 100000 ? 1000 : 40);
+            if (tries > (1ll << 27))
+            {
+                atomicExch(err, 2);
+                break;
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        double t = 0.0;
+        for (int r = 0; r < nranks; r++) t += __ldcv(xbuf + ((size_t)par * nranks + r) * (size_t)(cap + 8) + i);
+        dst[i] = t;
+    }
 }
 
 __global__ void k_pack_sell(size_t nSlots, const int* __restrict__ src, const double* __restrict__ coef,
