@@ -116,14 +116,20 @@ def oracle_sample(workload: str, iters: int, nsub: int = 1, threads: int = 1):
     return case.nCells * info["nIterations"] / dt, dt, case.nCells, case.nFaces, info["nIterations"]
 
 
+# decomposition of the CPU arm: a property of the WORKLOAD, not of the box (the iteration count a decomposed
+# block-Jacobi solve needs, and its arithmetic, depend on it); the sub-domains are work items of a thread pool, so the
+# thread count only changes the speed
+REF_SUBDOMAINS = {"C2": 11, "C2-2D": 1, "C3-slab8": 23, "C3": 61, "C3-2D": 1, "C1": 1}
+
+
 def host_decomposition(workload: str):
-    """(sub-domains, threads) of the decomposed CPU arm: the largest divisor of the layer count that the host's
-    cores can take one thread each."""
+    """(sub-domains, threads) of the decomposed CPU arm: a fixed z-slab decomposition per workload (a divisor of its
+    layer count), worked on by min(sub-domains, host cores) threads."""
     from multiregionfoam_b200.assembly import WORKLOADS
     _, L = WORKLOADS[workload]
-    cores = os.cpu_count() or 1
-    nsub = max(d for d in range(1, L + 1) if L % d == 0 and d <= cores)
-    return nsub, nsub
+    nsub = REF_SUBDOMAINS.get(workload, 1)
+    assert L % nsub == 0
+    return nsub, max(1, min(nsub, os.cpu_count() or 1))
 
 
 def run_reference(args):
@@ -131,23 +137,28 @@ def run_reference(args):
     if rank != 0:
         return
     vals, times = [], []
-    it = max(1, min(args.iters, args.ref_iters))
+    # the same step as the GPU arm: args.iters Krylov iterations (--ref-iters only to shorten a manual run); the CPU needs
+    # no five warm-up solves, and the sample is bounded by running at most ref_max_steps of them
+    it = max(1, args.iters if args.ref_iters is None else min(args.iters, args.ref_iters))
     nCells = nFaces = 0
     nsub, threads = host_decomposition(args.workload)
+    args.warmup = min(args.warmup, 1)
+    args.steps = min(args.steps, args.ref_max_steps)
     for s in range(args.warmup + args.steps):
         v, dt, nCells, nFaces, _ = oracle_sample(args.workload, it, nsub, threads)
         if s >= args.warmup:
             vals.append(v)
             times.append(dt)
     total = nCells * it * len(times) / sum(times)
-    sample = (f"{it} BiCGStab+DILU iterations per step on the full {args.workload} system ({nCells} cells) decomposed into {nsub} "
-              f"z-slab sub-domains (block-Jacobi DILU, as foam-extend's MPI run), {threads} threads of the CPU oracle port")
+    sample = (f"{len(times)} steps of {it} BiCGStab+DILU iterations on {'one GPU-share (z-slab) of ' if args.gpus > 1 else 'the full '}"
+              f"{args.workload} ({nCells} cells) decomposed into {nsub} z-slab sub-domains (block-Jacobi DILU, as foam-extend's MPI run), "
+              f"{threads} threads of the CPU oracle port")
     out = {
         "impl": "reference", "metric": METRIC, "value": total, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "cells": nCells, "faces": nFaces, "solver": "BiCGStab", "preconditioner": "DILU",
-                   "iterations_per_step": it, "decomposition": f"simple (1 1 {nsub})"},
+                   "iterations_per_step": it, "decomposition": f"simple (1 1 {nsub})", "cells_per_gpu": nCells},
         "cpu_baseline": {"value": total, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "host_cores_available": os.cpu_count()},
         "e2e": {"value": total, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -163,14 +174,18 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--workload", default=None, help="default: C2 on one GPU (BASELINE configs[1]); C3-slab8 - one eighth of the "
+                    "64 M-cell C3 per GPU, configs[2] - on several")
     ap.add_argument("--iters", type=int, default=50, help="Krylov iterations per step (minIter = maxIter)")
-    ap.add_argument("--ref-iters", type=int, default=8, help="iterations per step of the CPU arm (bounded sample)")
+    ap.add_argument("--ref-iters", type=int, default=None, help="CPU arm: fewer iterations per step than the GPU arm (manual runs only)")
+    ap.add_argument("--ref-max-steps", type=int, default=12, help="CPU arm: at most this many timed steps (bounded sample)")
     ap.add_argument("--cpu-baseline-iters", type=int, default=30)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.workload is None:
+        args.workload = "C2" if args.gpus == 1 else "C3-slab8"
 
     if args.impl == "reference":
         return run_reference(args)
@@ -217,6 +232,45 @@ def main():
         return float(t.item())
 
     ctx = ldu.Context(device=local, rank=rank, nranks=world, unique_id=uid)
+
+    # ---- N > 1: before anything is timed, the halo exchange and the global sums of THIS run's transport are checked
+    # against the CPU oracle on the same decomposition (small case: r = 1, 3 layers per rank): Amul bit-exact, 20
+    # iterations of the residual history within 1e-10, the field within 1e-8.  A run that fails this prints no number.
+    parity = None
+    if world > 1:
+        from multiregionfoam_b200.assembly import cht_rank_slab
+        from multiregionfoam_b200.case import Case
+        prs = cht_rank_slab(1, 3, rank, world)
+        PS = ldu.LduSystem(ctx, prs)
+        px0 = np.concatenate([g.psi for g in prs.regions])
+        pb = np.concatenate([g.source for g in prs.regions])
+        pxr = np.random.default_rng(100 + rank).standard_normal(px0.size)
+        py = PS.amul(pxr)
+        pxs, pinfo = PS.solve(px0, pb, ldu.SOLVER_BICGSTAB, ldu.PRECOND_DILU, tolerance=0.0, minIter=20, maxIter=20)
+        PS.close()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, dict(xr=pxr, y=py, xs=pxs, hist=pinfo["history"]))
+        if rank == 0:
+            from oracle import pyoracle
+            pcase = Case("parity", [cht_rank_slab(1, 3, g, world) for g in range(world)])
+            PO = pyoracle.OracleSystem(pcase)
+            yo = PO.amul(np.concatenate([g["xr"] for g in gathered]))
+            xo, io = PO.solve(pcase.concat("psi"), pcase.concat("source"), "BiCGStab", "DILU", tolerance=0.0, minIter=20, maxIter=20)
+            hg, ho = gathered[0]["hist"][:21], io["history"][:21]
+            parity = {"ranks": world, "cells": int(pcase.nCells),
+                      "amul_bit_exact": bool(np.array_equal(np.concatenate([g["y"] for g in gathered]), yo)),
+                      "history_max_rel_err_20": float(np.max(np.abs(hg - ho) / np.abs(ho))),
+                      "field_rel_l2": float(np.linalg.norm(np.concatenate([g["xs"] for g in gathered]) - xo) / np.linalg.norm(xo)),
+                      "history_identical_on_all_ranks": bool(all(np.array_equal(g["hist"], gathered[0]["hist"]) for g in gathered)),
+                      "transport": os.environ.get("B200_TRANSPORT", "auto (peer-to-peer, NCCL fall-back)")}
+            okp = (parity["amul_bit_exact"] and parity["history_max_rel_err_20"] < 1e-10 and parity["field_rel_l2"] < 1e-8
+                   and parity["history_identical_on_all_ranks"])
+            print(f"[bench] multi-rank parity: {parity}", file=sys.stderr, flush=True)
+        flag = torch.tensor([1 if (rank != 0 or okp) else 0], device="cuda")
+        dist.broadcast(flag, 0)
+        if int(flag.item()) == 0:
+            raise SystemExit("multi-rank parity against the oracle FAILED: no bench line")
+
     rs, (r, L) = build_rank_system(args.workload, rank, world)
     t0 = time.perf_counter()
     S = ldu.LduSystem(ctx, rs)
@@ -412,7 +466,7 @@ def main():
                        "iterations_per_step": args.iters, "l2": "inputs larger than L2 (matrix + vectors >> 126 MB)",
                        "decomposition": f"simple (1 1 {world})"},
             "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "multirank_parity": parity,
             "solve_hbm_gbs_per_gpu": solve_gbs, "solve_roofline_frac": solve_gbs / peak,
             "algorithmic_bytes_per_iteration_per_gpu": bytes_it,
             "kernels": kernels, "wall_ms_per_step": wall_ms / args.steps, "finalize_s": finalize_s,

@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(128) k_iface(int nTouched, const int* __restri
             if (cnt == 0)
             {
                 const int s = entSrc[e];
-                pnf = s >= 0 ? x[s] : __ldcv(recv + (-1 - s));
+                pnf = s >= 0 ? x[s] : __ldcg(recv + (-1 - s));
             }
             else
             {
@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(128) k_iface(int nTouched, const int* __restri
                 for (int k = 0; k < cnt; k++)
                 {
                     const int s = gSrc[g0 + k];
-                    const double f = s >= 0 ? x[s] : __ldcv(recv + (-1 - s));
+                    const double f = s >= 0 ? x[s] : __ldcg(recv + (-1 - s));
                     pnf += f * gW[g0 + k];
                 }
             }
