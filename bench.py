@@ -168,6 +168,316 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+# ------------------------------------------------------------------------------------------ block-coupled workload (C5)
+# BASELINE configs[4]: "block-coupled vector equation" at 16 M cells: the fvBlockMatrix<vector4> p-U system of
+# pUCoupledIcoFluid (src/regions/pUCoupledIcoFluid/pUCoupledIcoFluid.C:584-621) on a structured box, solved by
+# BlockBiCGStab + BlockCholesky through include/b200_blk.h (fvBlockMatrix<vector4>::solve, filesToReplace/fvBlockMatrix.C:1360-1388).
+BLOCK_WORKLOADS = {"C5": (256, 256, 244), "C5-2M": (160, 128, 100)}  # box nx ny nz: 15 990 784 / 2 048 000 cells
+BLOCK_ITERS = 30
+
+
+def block_system(workload: str):
+    from multiregionfoam_b200.assembly import pu_block_matrix
+    from multiregionfoam_b200.mesh import Block, StructuredRegion
+    nx, ny, nz = BLOCK_WORKLOADS[workload]
+    m = StructuredRegion("box", [Block(nx, 0.0, 1.0, 1.0)], ny=ny, nz=nz, y0=0.0, y1=1.0, grady=1.0).build()
+    M = pu_block_matrix(m.nCells, m.lowerAddr, m.upperAddr)
+    return M, (nx, ny, nz)
+
+
+def block_oracle_sample(M, iters: int):
+    from oracle import pyblk
+    O = pyblk.BlockOracle(M.l, M.u, M.nCells, M.diag, M.upper, M.lower)
+    t = time.perf_counter()
+    O.solve(M.psi, M.source, "BiCGStab", "Cholesky", tolerance=0.0, minIter=iters, maxIter=iters)
+    dt = time.perf_counter() - t
+    O.close()
+    return M.nCells * iters / dt, dt
+
+
+def run_block_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    M, box = block_system(args.workload)
+    # bounded sample: the scalar port manages ~1.4 M block cell-iterations/s per core, so a step is `it` iterations with
+    # cells x it / 1.4e6 of the order of 20 s
+    it = max(1, min(BLOCK_ITERS, int(20 * 1.4e6 / M.nCells) or 1))
+    steps = max(1, min(args.steps, 3))
+    times = []
+    for _ in range(steps):
+        _, dt = block_oracle_sample(M, it)
+        times.append(dt)
+    total = M.nCells * it * len(times) / sum(times)
+    sample = (f"{len(times)} steps of {it} BlockBiCGStab+BlockCholesky iterations on the full {args.workload} system ({M.nCells} cells), "
+              f"1 thread of the CPU block oracle port (oracle/blk_oracle.c)")
+    out = {"impl": "reference", "metric": METRIC, "value": total, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": 0,
+           "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic",
+           "config": {"workload": args.workload, "case": f"p-U block system (vector4, SQUARE coefficients), box {box[0]}x{box[1]}x{box[2]}",
+                      "cells": M.nCells, "faces": int(M.l.size), "solver": "BlockBiCGStab", "preconditioner": "BlockCholesky",
+                      "iterations_per_step": it},
+           "cpu_baseline": {"value": total, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample, "host_cores_available": os.cpu_count()},
+           "e2e": {"value": total, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+           "note": "reference = CPU oracle port of foam-extend's BlockBiCGStab / BlockCholesky (foam-extend 4.1 is not in the reference tree)"}
+    print(json.dumps(out))
+
+
+def run_block(args):
+    """bench.py --workload C5: the same contract line for the block-coupled path (one GPU: the block library has no
+    processor patches yet)."""
+    import torch  # noqa: F401  (device bring-up as in the scalar arm)
+    from multiregionfoam_b200 import blockldu, ldu
+    if args.gpus != 1:
+        raise SystemExit("the block-coupled workload runs on one GPU")
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    t0 = time.perf_counter()
+    M, box = block_system(args.workload)
+    n, F = M.nCells, int(M.l.size)
+    assemble_s = time.perf_counter() - t0
+    ctx = ldu.Context(0)
+    t0 = time.perf_counter()
+    S = blockldu.BlockSystem(ctx, M.l, M.u, n)
+    S.set_coeffs(M.diag, M.upper, M.lower)
+    finalize_s = time.perf_counter() - t0
+    S.upload(M.psi, M.source)
+    S.x_save()
+    iters = BLOCK_ITERS
+    opts = dict(solver=blockldu.SOLVER_BICGSTAB, precond=ldu.PRECOND_CHOLESKY, tolerance=0.0, minIter=iters, maxIter=iters)
+
+    def step():
+        S.x_restore()
+        return S.solve_resident(**opts)
+
+    for _ in range(args.warmup):
+        step()
+    clocks = ClockSampler(0)
+    launches0 = ctx.launches
+    dev_ms, its = 0.0, 0
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        p = step()
+        dev_ms += p["deviceMs"]
+        its += p["nIterations"]
+    wall_ms = 1e3 * (time.perf_counter() - wall0)
+    launches = ctx.launches - launches0
+    clk = clocks.stop()
+    value = n * its / (dev_ms * 1e-3)
+    # per kernel class
+    S.set_profiling(True)
+    S.kernel_times(reset=True)
+    for _ in range(min(args.steps, 2)):
+        step()
+    kt = S.kernel_times(reset=True)
+    S.set_profiling(False)
+    peak, peak_src = measured_peak_gbs()
+    dk = 16 if np.asarray(M.diag).ndim == 3 else (4 if np.asarray(M.diag).ndim == 2 else 1)
+    uk = 16 if np.asarray(M.upper).ndim == 3 else (4 if np.asarray(M.upper).ndim == 2 else 1)
+    # algorithmic bytes per launch (SURVEY 8d, block rows): Amul reads diag, x, writes y, reads upper + lower + addressing;
+    # a sweep of BlockCholesky reads the inverted diagonal and one coefficient array, reads and writes the vector
+    alg = {"amul": (8 * dk + 64) * n + (16 * uk + 8) * F, "sweep_fwd": (8 * dk + 64) * n + (8 * uk + 8) * F,
+           "sweep_bwd": (8 * dk + 64) * n + (8 * uk + 8) * F}
+    kernels = {}
+    for k, (ms, cnt) in kt.items():
+        if cnt == 0:
+            continue
+        kernels[k] = {"ms_total": ms, "launches": cnt, "ms_per_launch": ms / cnt}
+        if k in alg and ms > 0:
+            kernels[k]["gbs"] = alg[k] * cnt / (ms * 1e-3) / 1e9
+            kernels[k]["frac"] = kernels[k]["gbs"] / peak
+    tot = sum(v["ms_total"] for v in kernels.values())
+    for v in kernels.values():
+        v["share"] = v["ms_total"] / tot if tot else 0.0
+    dom = max((k for k in kernels if k in alg), key=lambda k: kernels[k]["ms_total"])
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kernels[dom]["frac"],
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom]}
+    # per BlockBiCGStab iteration: 2 Amul + 2 x (fwd + bwd) + 10 vector passes of 32 N
+    bytes_it = 2 * alg["amul"] + 4 * alg["sweep_fwd"] + 320 * n
+    solve_gbs = bytes_it * its / (dev_ms * 1e-3) / 1e9
+    # ---- end to end: coefficients, x and b from (page-locked) host arrays, x back
+    e2e = None
+    if not args.no_e2e:
+        keep = [np.ascontiguousarray(a) for a in (M.diag, M.upper, M.lower, M.source)]
+        xs = [np.ascontiguousarray(M.psi.copy()) for _ in range(4)]
+        for a in keep + xs:
+            ctx.host_register(a)
+        n_e = 2
+
+        def e2e_step(k):
+            S.set_coeffs(keep[0], keep[1], keep[2])
+            x, pp = S.solve(xs[k], keep[3], history=False, **opts)
+            return pp["nIterations"]
+
+        e2e_step(0)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        its_e = sum(e2e_step(1 + k) for k in range(n_e))
+        e_s = time.perf_counter() - t1
+        h2d = sum(a.nbytes for a in keep) + xs[0].nbytes
+        e2e = {"value": n * its_e / e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(xs[0].nbytes),
+               "ms_per_step": 1e3 * e_s / n_e, "steps": n_e}
+        for a in keep + xs:
+            ctx.host_unregister(a)
+    cpu = None
+    if not args.no_cpu_baseline:
+        it = max(1, min(iters, int(20 * 1.4e6 / n) or 1))
+        v, dt = block_oracle_sample(M, it)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{it} BlockBiCGStab+BlockCholesky iterations on the full {args.workload} system ({n} cells), 1 thread of the CPU block "
+                         f"oracle port, {dt:.1f} s", "host_cores_available": os.cpu_count()}
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": args.workload, "case": f"p-U block system (vector4, SQUARE coefficients), box {box[0]}x{box[1]}x{box[2]}",
+                      "cells": n, "faces": F, "cells_per_gpu": n, "solver": "BlockBiCGStab", "preconditioner": "BlockCholesky",
+                      "iterations_per_step": iters, "l2": "inputs larger than L2 (matrix + vectors >> 126 MB)"},
+           "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
+           "solve_hbm_gbs_per_gpu": solve_gbs, "solve_roofline_frac": solve_gbs / peak, "algorithmic_bytes_per_iteration_per_gpu": bytes_it,
+           "kernels": kernels, "wall_ms_per_step": wall_ms / args.steps, "assemble_s": assemble_s, "finalize_s": finalize_s,
+           "final_residual": [float(v) for v in np.atleast_1d(p["finalResidual"])]}
+    real_stdout.write(json.dumps(out) + "\n")
+    real_stdout.flush()
+    S.close()
+    ctx.close()
+
+
+# ------------------------------------------------------------------------------------------ partitioned FSI workload (C4)
+def fsi_oracle_ops(case):
+    """The callbacks of fsi.coupling_iteration on the CPU oracle (cpu_baseline / reference arm only)."""
+    from multiregionfoam_b200.case import Case, RankSystem
+    from oracle import pyoracle
+    O = {k: pyoracle.OracleSystem(Case(k, [RankSystem(0, 1, [reg])])) for k, reg in (("U", case.fluidU), ("p", case.fluidP), ("D", case.solidD))}
+
+    def solve(key, x0, b, solver, precond, iters):
+        return O[key].solve(x0, b, solver, precond, tolerance=0.0, minIter=iters, maxIter=iters)[0]
+
+    def transfer(tab, f):
+        return pyoracle.ggi_interpolate(tab[0], tab[1], tab[2], f, 3)
+
+    return solve, transfer
+
+
+def fsi_config(args, case):
+    from multiregionfoam_b200 import fsi
+    return {"workload": args.workload,
+            "case": f"HronTurekFsi3 topology (fluid 24 blocks + solid (105 6 1)) r={case.r}, {case.layers} z-layers, partitioned coupling over a GGI interface",
+            "cells": case.nFluid + case.nSolid, "cells_fluid": case.nFluid, "cells_solid": case.nSolid,
+            "faces": case.fluidU.nFaces + case.solidD.nFaces, "interface_faces": [int(case.fluidFaceCells.size), int(case.solidFaceCells.size)],
+            "solver": f"per coupling iteration: U 3 x PBiCG+DILU ({fsi.N_U} its), p PCG+DIC ({fsi.N_P}), D 3 x PCG+DIC ({fsi.N_D}), 2 GGI transfers",
+            "cell_iterations_per_step": case.cell_iterations(), "l2": "inputs larger than L2"}
+
+
+def run_fsi_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from multiregionfoam_b200 import fsi
+    from oracle import pyoracle
+    case = fsi.fsi_case(*fsi.FSI_WORKLOADS[args.workload])
+    solve, transfer = fsi_oracle_ops(case)
+    pyoracle.set_threads(min(8, os.cpu_count() or 1))
+    state = fsi.initial_state(case)
+    steps = max(1, min(args.steps, 3))
+    t = time.perf_counter()
+    for _ in range(steps):
+        state = fsi.coupling_iteration(case, solve, transfer, state)
+    dt = time.perf_counter() - t
+    pyoracle.set_threads(1)
+    total = case.cell_iterations() * steps / dt
+    threads = min(8, os.cpu_count() or 1)
+    sample = f"{steps} coupling iterations of the full {args.workload} case on the CPU oracle port ({threads} threads for the vector updates and Amul rows, sweeps serial)"
+    out = {"impl": "reference", "metric": METRIC, "value": total, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": 0,
+           "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": fsi_config(args, case),
+           "cpu_baseline": {"value": total, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "host_cores_available": os.cpu_count()},
+           "e2e": {"value": total, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+           "note": "reference = CPU oracle port (foam-extend 4.1 is not in the reference tree)"}
+    print(json.dumps(out))
+
+
+def run_fsi(args):
+    """bench.py --workload C4: one step = one Dirichlet-Neumann coupling iteration of the partitioned FSI case through the
+    C ABI (every solve: x0 and b host -> device, x back; every interface transfer: b200_ggi_interpolate).  `value` counts the
+    device time of the solves (b200_perf.deviceMs), `e2e` the wall clock of the whole iteration including the transfers."""
+    import torch  # noqa: F401
+    from multiregionfoam_b200 import fsi, ldu
+    if args.gpus != 1:
+        raise SystemExit("the partitioned FSI workload runs on one GPU")
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    case = fsi.fsi_case(*fsi.FSI_WORKLOADS[args.workload])
+    ctx = ldu.Context(0)
+    t0 = time.perf_counter()
+    D = fsi.DeviceFsi(ctx, case)
+    finalize_s = time.perf_counter() - t0
+    state = fsi.initial_state(case)
+    for _ in range(args.warmup):
+        state = fsi.coupling_iteration(case, D.solve, D.transfer, state)
+    D.device_ms, D.iterations = 0.0, 0
+    clocks = ClockSampler(0)
+    launches0 = ctx.launches
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        state = fsi.coupling_iteration(case, D.solve, D.transfer, state)
+    wall_s = time.perf_counter() - t1
+    launches = ctx.launches - launches0
+    clk = clocks.stop()
+    work = case.cell_iterations() * args.steps
+    value = work / (D.device_ms * 1e-3)
+    # per kernel class over the three systems
+    for S in D.sys.values():
+        S.set_profiling(True)
+        S.kernel_times(reset=True)
+    fsi.coupling_iteration(case, D.solve, D.transfer, state)
+    peak, peak_src = measured_peak_gbs()
+    kernels, alg_tot = {}, {}
+    for key, S in D.sys.items():
+        N, F = S.nCells, S.nFaces
+        sym = key != "U"
+        alg = {"amul": 24 * N + (16 if sym else 24) * F, "sweep_fwd": 24 * N + 16 * F, "sweep_bwd": 24 * N + 16 * F}
+        for k, (ms, cnt) in S.kernel_times(reset=True).items():
+            if cnt == 0:
+                continue
+            e = kernels.setdefault(k, {"ms_total": 0.0, "launches": 0})
+            e["ms_total"] += ms
+            e["launches"] += cnt
+            if k in alg:
+                alg_tot[k] = alg_tot.get(k, 0) + alg[k] * cnt
+        S.set_profiling(False)
+    tot = sum(v["ms_total"] for v in kernels.values())
+    for k, v in kernels.items():
+        v["ms_per_launch"] = v["ms_total"] / v["launches"]
+        v["share"] = v["ms_total"] / tot if tot else 0.0
+        if k in alg_tot and v["ms_total"] > 0:
+            v["gbs"] = alg_tot[k] / (v["ms_total"] * 1e-3) / 1e9
+            v["frac"] = v["gbs"] / peak
+    dom = max((k for k in kernels if k in alg_tot), key=lambda k: kernels[k]["ms_total"])
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kernels[dom]["frac"],
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_tot[dom] / kernels[dom]["launches"]}
+    xbytes = 8 * (case.nFluid * 4 + case.nSolid * 3)
+    e2e = {"value": work / wall_s, "unit": UNIT, "h2d_bytes_per_step": int(2 * xbytes), "d2h_bytes_per_step": int(xbytes),
+           "ms_per_step": 1e3 * wall_s / args.steps, "steps": args.steps,
+           "note": "whole coupling iteration through the C ABI: x0 and b of the 7 solves in, x out, interface fields through b200_ggi_interpolate"}
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import pyoracle
+        solve, transfer = fsi_oracle_ops(case)
+        threads = min(8, os.cpu_count() or 1)
+        pyoracle.set_threads(threads)
+        t2 = time.perf_counter()
+        fsi.coupling_iteration(case, solve, transfer, fsi.initial_state(case))
+        dt = time.perf_counter() - t2
+        pyoracle.set_threads(1)
+        cpu = {"value": case.cell_iterations() / dt, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"one coupling iteration of the full {args.workload} case on the CPU oracle port, {dt:.1f} s", "host_cores_available": os.cpu_count()}
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": D.device_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": fsi_config(args, case), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
+           "kernels": kernels, "finalize_s": finalize_s}
+    real_stdout.write(json.dumps(out) + "\n")
+    real_stdout.flush()
+    D.close()
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -187,6 +497,11 @@ def main():
     if args.workload is None:
         args.workload = "C2" if args.gpus == 1 else "C3-slab8"
 
+    from multiregionfoam_b200.fsi import FSI_WORKLOADS
+    if args.workload in FSI_WORKLOADS:
+        return run_fsi_reference(args) if args.impl == "reference" else run_fsi(args)
+    if args.workload in BLOCK_WORKLOADS:
+        return run_block_reference(args) if args.impl == "reference" else run_block(args)
     if args.impl == "reference":
         return run_reference(args)
 
