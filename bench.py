@@ -87,9 +87,18 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# workloads whose TOTAL size is fixed: N ranks share the case (strong scaling); every other workload gives each rank a
+# slab of the listed size (weak scaling)
+STRONG_WORKLOADS = {"C3"}
+
+
 def build_rank_system(workload: str, rank: int, nranks: int):
     from multiregionfoam_b200.assembly import WORKLOADS, cht_rank_slab
     r, L = WORKLOADS[workload]
+    if workload in STRONG_WORKLOADS:
+        if L % nranks:
+            raise SystemExit(f"{workload} has {L} z-layers: not divisible by {nranks} ranks")
+        L //= nranks
     return cht_rank_slab(r, L, rank, nranks), (r, L)
 
 
@@ -119,7 +128,7 @@ def oracle_sample(workload: str, iters: int, nsub: int = 1, threads: int = 1):
 # decomposition of the CPU arm: a property of the WORKLOAD, not of the box (the iteration count a decomposed
 # block-Jacobi solve needs, and its arithmetic, depend on it); the sub-domains are work items of a thread pool, so the
 # thread count only changes the speed
-REF_SUBDOMAINS = {"C2": 11, "C2-2D": 1, "C3-slab8": 23, "C3": 61, "C3-2D": 1, "C1": 1}
+REF_SUBDOMAINS = {"C2": 11, "C2-2D": 1, "C3-slab8": 23, "C3": 23, "C3-2D": 1, "C1": 1}
 
 
 def host_decomposition(workload: str):
@@ -144,18 +153,21 @@ def run_reference(args):
     nsub, threads = host_decomposition(args.workload)
     args.warmup = min(args.warmup, 1)
     args.steps = min(args.steps, args.ref_max_steps)
+    t_begin = time.perf_counter()
     for s in range(args.warmup + args.steps):
         v, dt, nCells, nFaces, _ = oracle_sample(args.workload, it, nsub, threads)
         if s >= args.warmup:
             vals.append(v)
             times.append(dt)
+        if times and time.perf_counter() - t_begin > args.ref_max_seconds:
+            break   # bounded sample: a step of the 64 M-cell case is ~40 s of CPU
     total = nCells * it * len(times) / sum(times)
     sample = (f"{len(times)} steps of {it} BiCGStab+DILU iterations on {'one GPU-share (z-slab) of ' if args.gpus > 1 else 'the full '}"
               f"{args.workload} ({nCells} cells) decomposed into {nsub} z-slab sub-domains (block-Jacobi DILU, as foam-extend's MPI run), "
               f"{threads} threads of the CPU oracle port")
     out = {
         "impl": "reference", "metric": METRIC, "value": total, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "strong" if args.workload in STRONG_WORKLOADS else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "cells": nCells, "faces": nFaces, "solver": "BiCGStab", "preconditioner": "DILU",
                    "iterations_per_step": it, "decomposition": f"simple (1 1 {nsub})", "cells_per_gpu": nCells},
@@ -489,13 +501,17 @@ def main():
     ap.add_argument("--iters", type=int, default=50, help="Krylov iterations per step (minIter = maxIter)")
     ap.add_argument("--ref-iters", type=int, default=None, help="CPU arm: fewer iterations per step than the GPU arm (manual runs only)")
     ap.add_argument("--ref-max-steps", type=int, default=12, help="CPU arm: at most this many timed steps (bounded sample)")
+    ap.add_argument("--ref-max-seconds", type=float, default=150.0, help="CPU arm: no further step is started after this many seconds")
     ap.add_argument("--cpu-baseline-iters", type=int, default=30)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.workload is None:
-        args.workload = "C2" if args.gpus == 1 else "C3-slab8"
+        # the configuration north_star quotes its targets on: the 64 M-cell two-region CHT case (BASELINE configs[2]).  It fits
+        # one B200 (~10 GB), so N = 1 runs the whole case and N = 2 / 4 / 8 split the SAME case into z-slabs (strong scaling);
+        # other rank counts fall back to one C3 slab per rank.  configs[1] (C2, 4.3 M cells) is `--workload C2`.
+        args.workload = "C3" if args.gpus in (1, 2, 4, 8) else "C3-slab8"
 
     from multiregionfoam_b200.fsi import FSI_WORKLOADS
     if args.workload in FSI_WORKLOADS:
@@ -760,10 +776,12 @@ def main():
     # ---- CPU baseline (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        it = max(1, min(args.iters, args.cpu_baseline_iters))
+        # bounded sample (~20 s decomposed + ~15 s serial): iterations scaled to the case with nominal port rates of
+        # 70 M / 18 M cell-iterations/s
+        it = max(2, min(args.iters, args.cpu_baseline_iters, int(20 * 70e6 / nGlobal)))
         nsub, threads = host_decomposition(args.workload)
         v, dt, nc, nf, _ = oracle_sample(args.workload, it, nsub, threads)
-        it1 = max(1, it // 3)
+        it1 = max(1, min(it // 3, int(15 * 18e6 / nGlobal)))
         v1, dt1, _, _, _ = oracle_sample(args.workload, it1)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{it} BiCGStab+DILU iterations on the full {args.workload} system ({nc} cells) decomposed into {nsub} z-slab "
@@ -774,8 +792,8 @@ def main():
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.workload in STRONG_WORKLOADS else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "case": f"two-region CHT (flowOverHeatedPlate topology) r={r}, {L} z-layers per GPU",
                        "cells": nGlobal, "faces": fGlobal, "cells_per_gpu": nLocal, "solver": "BiCGStab", "preconditioner": "DILU",
                        "iterations_per_step": args.iters, "l2": "inputs larger than L2 (matrix + vectors >> 126 MB)",

@@ -180,7 +180,7 @@ WORKLOADS = {
     "C1": (1, 1),        # as-shipped flowOverHeatedPlate mesh, 21 812 cells
     "C2": (3, 22),       # 3-D, 4 318 776 cells   (metric config)
     "C2-2D": (14, 1),    # 2-D-faithful, 4 275 152 cells
-    "C3": (4, 183),      # 3-D, 63 865 536 cells
+    "C3": (4, 184),      # 3-D, 64 214 528 cells (184 = 8 x 23 layers: the case bench.py splits over 1 / 2 / 4 / 8 GPUs)
     "C3-2D": (54, 1),
     "C3-slab8": (4, 23), # one of the 8 z-slabs of C3 (r = 4, 8 x 23 = 184 layers: 64 234 496 cells on 8 ranks), 8 029 312 cells per rank
 }

@@ -757,6 +757,7 @@ static int upload_pipe_dir(b200_sys* s, const PipeSchedule& S, const PipeSchedul
     M.dev.stats = nullptr;
     M.dev.l2Ahead = getenv("B200_SWEEP_L2AHEAD") ? std::max(0, atoi(getenv("B200_SWEEP_L2AHEAD"))) : kL2Ahead;
     M.dev.debugFlags = getenv("B200_SWEEP_DEBUG") ? atoi(getenv("B200_SWEEP_DEBUG")) : 0;
+    M.dev.spinLimit = getenv("B200_SWEEP_SPIN_LIMIT") ? std::max(1, atoi(getenv("B200_SWEEP_SPIN_LIMIT"))) : kSweepSpinLimit;
     if (getenv("B200_SWEEP_INFO"))
     { // developer print: shape of the split streams
         std::map<std::tuple<int, int, int, int>, int> hist;
@@ -971,12 +972,15 @@ extern "C" int b200_sys_finalize(b200_sys* s)
         const int maxSmem = std::max(seen, std::max(s->fwd.smemBytes, s->bwd.smemBytes));
         if (maxSmem > 227 * 1024) return set_err(ctx, B200_EUNSUPPORTED, "sweep stage needs %d bytes of shared memory", maxSmem);
         seen = maxSmem;
-        CK(ctx, cudaFuncSetAttribute(k_sweep<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
-        CK(ctx, cudaFuncSetAttribute(k_sweep<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
-        CK(ctx, cudaFuncSetAttribute(k_sweep<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
-        CK(ctx, cudaFuncSetAttribute(k_sweep<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
-        CK(ctx, cudaFuncSetAttribute(k_sweep<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
-        CK(ctx, cudaFuncSetAttribute(k_sweep<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        CK(ctx, cudaFuncSetAttribute(k_sweep<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        CK(ctx, cudaFuncSetAttribute(k_sweep<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        CK(ctx, cudaFuncSetAttribute(k_sweep<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        CK(ctx, cudaFuncSetAttribute(k_sweep<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        CK(ctx, cudaFuncSetAttribute(k_sweep<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        CK(ctx, cudaFuncSetAttribute(k_sweep<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        CK(ctx, cudaFuncSetAttribute(k_sweep<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        CK(ctx, cudaFuncSetAttribute(k_sweep<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        CK(ctx, cudaFuncSetAttribute(k_sweep<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
     }
     CK(ctx, s->sc.alloc(1));
     CK(ctx, cudaMemsetAsync(s->sc.p, 0, sizeof(DevScalars), st));
@@ -1312,13 +1316,17 @@ static int launch_sweep(b200_sys* s, PipeDirMem& M, PipeDev dev, const double* a
     dev.stats = M.dev.stats;
     // calcReciprocalD (MODE 2) is the once-per-solve preconditioner construction: accounted with the packing kernels
     KScope k(s, MODE == 2 ? B200_K_PACK : (dev.dir > 0 ? B200_K_SWEEP_FWD : B200_K_SWEEP_BWD));
-    if (dev.stats && !(dev.debugFlags & 2)) // debug counters and time stamps: a separately compiled instantiation, the product path carries none
-                                           // (debug flag 2: the product instantiation, recording only each group's start / end time)
-        k_sweep<MODE, true><<<s->nGroups, kSweepThreads, M.smemBytes, ctx->stream>>>(dev, a, b, out, s->ticket.p, s->ticketBase, s->devErr.p,
-                                                                                    s->sc.p, force);
+    // debug counters and time stamps live in separately compiled instantiations, the product path (0) carries none:
+    // 1 = per-block time stamps + counters, 2 (debug flag 2) = cheap per-group counters only
+    if (dev.stats && !(dev.debugFlags & 2))
+        k_sweep<MODE, 1><<<s->nGroups, kSweepThreads, M.smemBytes, ctx->stream>>>(dev, a, b, out, s->ticket.p, s->ticketBase, s->devErr.p, s->sc.p,
+                                                                                 force);
+    else if (dev.stats)
+        k_sweep<MODE, 2><<<s->nGroups, kSweepThreads, M.smemBytes, ctx->stream>>>(dev, a, b, out, s->ticket.p, s->ticketBase, s->devErr.p, s->sc.p,
+                                                                                 force);
     else
-        k_sweep<MODE, false><<<s->nGroups, kSweepThreads, M.smemBytes, ctx->stream>>>(dev, a, b, out, s->ticket.p, s->ticketBase, s->devErr.p,
-                                                                                     s->sc.p, force);
+        k_sweep<MODE, 0><<<s->nGroups, kSweepThreads, M.smemBytes, ctx->stream>>>(dev, a, b, out, s->ticket.p, s->ticketBase, s->devErr.p, s->sc.p,
+                                                                                 force);
     s->ticketBase += (unsigned)s->nGroups;
     CK(ctx, cudaGetLastError());
     return B200_OK;

@@ -638,7 +638,9 @@ struct PipeDev
     const int* pFace;
     const int* cFace;
     int l2Ahead;      // blocks the L2 prefetch runs ahead of the stage fill
-    int debugFlags;   // bit 0: consumer always takes the general (descriptor-driven) path (debug)
+    int debugFlags;   // bit 0: consumer always takes the general (descriptor-driven) path (debug); bit 2: fault injection, the
+                      // first group does nothing, so that every group that depends on it runs into the polling limit (tests)
+    int spinLimit;    // polling rounds before a group gives up and the call returns B200_EDEVICE (B200_SWEEP_SPIN_LIMIT)
     long long* stats; // optional [8 * nGroups]: consumer cycles, wait cycles, start ns, end ns, producer polls, nT, general blocks, blocks (debug)
 };
 
@@ -667,9 +669,9 @@ __device__ __forceinline__ void st_relaxed(double* p, double v)
 #define B200_SWEEP_SPIN_LIMIT (1 << 24)
 #endif
 constexpr int kSweepSpinLimit = B200_SWEEP_SPIN_LIMIT; // polling rounds before a group gives up (B200_EDEVICE)
-__device__ __noinline__ double sweep_spin(const double* p, int* err)
+__device__ __noinline__ double sweep_spin(const double* p, int* err, int spinLimit)
 {
-    for (long long tries = 0; tries < (long long)kSweepSpinLimit; tries++)
+    for (long long tries = 0; tries < (long long)spinLimit; tries++)
     {
         const double v = ld_relaxed(p);
         if (!is_sentinel(v)) return v;
@@ -971,7 +973,7 @@ __device__ __forceinline__ void mbar_wait_u32(unsigned bar, unsigned parity)
 // minimal: the C-block and the hdr part of a stage are plane-major (operands of step q of a plane at q * 256 from
 // the plane's base), which turns the 24 operand loads of a canonical block into loads at immediate offsets from
 // two base registers.
-template <int MODE, int RG, bool STATS>
+template <int MODE, int RG, int STATS>
 __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx& C, const int g, const int lane, double* out)
 {
     constexpr unsigned FULL = 0xffffffffu;
@@ -983,7 +985,7 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
     const int srcLane = (lane - dir) & 31; // the linked neighbour lane of a canonical step
     // cheap accumulators (two clock reads per block, one write at the end) also run in the product instantiation when the
     // caller armed the counters with debug flag 2; the per-block time stamps are in the STATS instantiation only
-    const bool statsOn = STATS || S.stats != nullptr;
+    constexpr bool statsOn = STATS != 0; // STATS: 0 product (no instrumentation at all), 1 per-block time stamps + counters, 2 counters only
     const bool forceGeneral = MODE == 2 || (S.debugFlags & 1);
     const int Kg = C.Kg;
     double h[kSkew]; // h[k]: the value this lane produced k+1 steps ago
@@ -1054,7 +1056,7 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
             sbN = stage0;
             cntN = C.cnt;
         }
-        if (STATS && lane == 0 && blk < kTraceBlocks) S.stats[(long long)kStatsStride * g + 16 + blk * 8 + 0] = clock64();
+        if (STATS == 1 && lane == 0 && blk < kTraceBlocks) S.stats[(long long)kStatsStride * g + 16 + blk * 8 + 0] = clock64();
         const unsigned char* hd = sb + C.offHdr;
         const long long b0 = statsOn ? clock64() : 0;
         const bool canon = c == (unsigned)kNH && !forceGeneral;
@@ -1253,7 +1255,7 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
         { // block done: the stage may be refilled
             st_flag_smem(cntp, 0u);
             st_flag_smem(C.done, (unsigned)(blk + 1));
-            if (STATS && blk < kTraceBlocks) S.stats[(long long)kStatsStride * g + 16 + blk * 8 + 1] = clock64();
+            if (STATS == 1 && blk < kTraceBlocks) S.stats[(long long)kStatsStride * g + 16 + blk * 8 + 1] = clock64();
         }
         sb += C.stageBytes;
         cntp++;
@@ -1275,8 +1277,8 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
         sp[5] = nT;
         sp[6] = nGeneral;
         sp[7] = C.nBlocks;
-        if (!STATS)
-        { // the per-block trace area is unused in the product instantiation: body cycles of canonical / other blocks
+        if (STATS == 2)
+        { // the per-block trace area is unused in this instantiation: body cycles of canonical / other blocks
             sp[16] = tCanon;
             sp[17] = nCanon;
             sp[18] = tOther;
@@ -1292,7 +1294,7 @@ __device__ __forceinline__ void split_consumer(const PipeDev& S, const SplitCtx&
 // operand loads of the current block issued before the wait for the next stage so that their latency overlaps it,
 // no instrumentation in the product instantiation (STATS = false).
 
-template <int MODE, int LG, bool STATS>
+template <int MODE, int LG, int STATS>
 __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx& C, const int g, const int h, const int lane, double* out,
                                                int* err)
 {
@@ -1340,11 +1342,11 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
         }
     };
     unsigned sg = stage0, bar = bar0, cnt = cnt0, par = 0u;
-    const bool timed = (STATS || S.stats != nullptr) && h == 0;
+    const bool timed = (STATS != 0) && h == 0;
     long long tStage = 0, tVal = 0, tSpin = 0, tAll = timed ? clock64() : 0;
     auto step = [&](const int blk, int* codes, double* mv, int* cc, double* mc, int* codesN, double* mvN, int* ccN, double* mcN) {
-        long long* const tr = (STATS && lane == 0 && blk < kTraceBlocks) ? S.stats + (long long)kStatsStride * g + 16 + blk * 8 : nullptr;
-        if (STATS && tr && h == 0) tr[3] = clock64();
+        long long* const tr = (STATS == 1 && lane == 0 && blk < kTraceBlocks) ? S.stats + (long long)kStatsStride * g + 16 + blk * 8 : nullptr;
+        if (STATS == 1 && tr && h == 0) tr[3] = clock64();
         // ---- operands of the current step (its stage landed: waited for one block ago)
         double acc = lds_f64(sg + offA);
         double bb = 0.0;
@@ -1370,7 +1372,7 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
             const long long w0 = timed ? clock64() : 0;
             mbar_wait_u32(barN, parN);
             if (timed) tStage += clock64() - w0;
-            if (STATS && tr && h == 0) tr[4] = clock64();
+            if (STATS == 1 && tr && h == 0) tr[4] = clock64();
             fetch_codes(sgN, codesN, ccN);
         }
         if (MODE == 0) acc *= bb;
@@ -1383,12 +1385,12 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
         for (int k = 0; k < 2; k++) bad |= cc[k] >= 0 && is_sentinel(mc[k]);
         const bool anyBad = __any_sync(FULL, bad);
         const long long v1 = timed ? clock64() : 0;
-        if (STATS && tr && h == 0) tr[5] = v1;
+        if (STATS == 1 && tr && h == 0) tr[5] = v1;
         if (anyBad)
         { // a value had not arrived when it was prefetched: poll for it.  A group that runs right behind the group
           // it depends on gets here in every block; a polling round re-reads, in one batch of independent loads, whatever
           // is still missing of this block.
-            if (STATS && lane == 0) atomicAdd((unsigned long long*)(S.stats + (long long)kStatsStride * g + 4), 1ull);
+            if (STATS == 1 && lane == 0) atomicAdd((unsigned long long*)(S.stats + (long long)kStatsStride * g + 4), 1ull);
             int tries = 0;
             bool still;
             do
@@ -1408,7 +1410,7 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
                 {
                     __nanosleep(tries > 4096 ? 400 : 64);
                     if ((tries & 4095) == 4095 && *(volatile int*)err) break;
-                    if (tries >= kSweepSpinLimit)
+                    if (tries >= S.spinLimit)
                     {
                         atomicExch(err, 1);
                         break;
@@ -1436,8 +1438,8 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
         if (Kg > 1) sts_f64(sg + offHd + 2 * kNH * 256, mc[1]);
         __syncwarp();
         if (lane == 0) asm volatile("red.relaxed.cta.shared.add.u32 [%0], %1;" ::"r"(cnt), "r"(1u + stepKind) : "memory");
-        if (STATS && tr && h == 0) tr[6] = clock64();
-        if (STATS && tr && h == kNH - 1) tr[7] = clock64();
+        if (STATS == 1 && tr && h == 0) tr[6] = clock64();
+        if (STATS == 1 && tr && h == kNH - 1) tr[7] = clock64();
         cnt = (sgN == stage0) ? cnt0 : cnt + 4u;
         sg = sgN;
         bar = barN;
@@ -1463,7 +1465,7 @@ __device__ __forceinline__ void split_producer(const PipeDev& S, const SplitCtx&
 }
 
 // Producer of the set organisation: this warp prepares steps h0 .. h0 + M - 1 of the blocks set, set + nSets, ...
-template <int MODE, int LG, int M, bool STATS>
+template <int MODE, int LG, int M, int STATS>
 __device__ __forceinline__ void split_producer_sets(const PipeDev& S, const SplitCtx& C, const int g, const int set, const int nSets, const int h0,
                                                     const int lane, double* out, int* err, const double* __restrict__ aVec,
                                                     const double* __restrict__ bVec)
@@ -1492,13 +1494,13 @@ __device__ __forceinline__ void split_producer_sets(const PipeDev& S, const Spli
     const unsigned char* const pG0 = C.pStream + (size_t)h0 * C.pRec;
     const double* const aG0 = aVec + ((long long)C.base + (dir > 0 ? h0 : C.nT - 1 - h0)) * 32 + lane;
     const double* const bG0 = bVec ? bVec + ((long long)C.base + (dir > 0 ? h0 : C.nT - 1 - h0)) * 32 + lane : nullptr;
-    const bool timed = (STATS || S.stats != nullptr) && set == 0 && h0 == 0;
+    const bool timed = (STATS != 0) && set == 0 && h0 == 0;
     long long tStage = 0, tVal = 0, tSpin = 0, tAll = timed ? clock64() : 0;
     for (int blk = set; blk < C.nBlocks; blk += nSets)
     {
         const unsigned sg = stage0 + (unsigned)st * stageBytes;
-        long long* const tr = (STATS && lane == 0 && blk < kTraceBlocks) ? S.stats + (long long)kStatsStride * g + 16 + blk * 8 : nullptr;
-        if (STATS && tr && h0 == 0) tr[3] = clock64();
+        long long* const tr = (STATS == 1 && lane == 0 && blk < kTraceBlocks) ? S.stats + (long long)kStatsStride * g + 16 + blk * 8 : nullptr;
+        if (STATS == 1 && tr && h0 == 0) tr[3] = clock64();
         // ---- direct mode: the operands of this block from global memory, issued before anything is waited for
         int cd[M][LGA], kc[M][2];
         double mv[M][LGA], mc[M][2];
@@ -1548,7 +1550,7 @@ __device__ __forceinline__ void split_producer_sets(const PipeDev& S, const Spli
         // answered for an older fill.
         mbar_wait_u32(bar0 + 8u * (unsigned)st, par);
         if (timed) tStage += clock64() - w0;
-        if (STATS && tr && h0 == 0) tr[4] = clock64();
+        if (STATS == 1 && tr && h0 == 0) tr[4] = clock64();
         // ---- ring mode: codes of the cross-group terms, then their loads: the only global accesses of the step
         if (!kProdDirect)
         {
@@ -1604,10 +1606,10 @@ __device__ __forceinline__ void split_producer_sets(const PipeDev& S, const Spli
         }
         const bool anyBad = __any_sync(FULL, bad);
         const long long v1 = timed ? clock64() : 0;
-        if (STATS && tr && h0 == 0) tr[5] = v1;
+        if (STATS == 1 && tr && h0 == 0) tr[5] = v1;
         if (anyBad)
         {
-            if (STATS && lane == 0) atomicAdd((unsigned long long*)(S.stats + (long long)kStatsStride * g + 4), 1ull);
+            if (STATS == 1 && lane == 0) atomicAdd((unsigned long long*)(S.stats + (long long)kStatsStride * g + 4), 1ull);
             int tries = 0;
             bool still;
             do
@@ -1635,7 +1637,7 @@ __device__ __forceinline__ void split_producer_sets(const PipeDev& S, const Spli
                 {
                     __nanosleep(tries > 4096 ? 400 : 64);
                     if ((tries & 4095) == 4095 && *(volatile int*)err) break;
-                    if (tries >= kSweepSpinLimit)
+                    if (tries >= S.spinLimit)
                     {
                         atomicExch(err, 1);
                         break;
@@ -1663,8 +1665,8 @@ __device__ __forceinline__ void split_producer_sets(const PipeDev& S, const Spli
         }
         __syncwarp();
         if (lane == 0) asm volatile("red.relaxed.cta.shared.add.u32 [%0], %1;" ::"r"(cnt0 + 4u * (unsigned)st), "r"((unsigned)M + kind) : "memory");
-        if (STATS && tr && h0 == 0) tr[6] = clock64();
-        if (STATS && tr && h0 + M == kNH) tr[7] = clock64();
+        if (STATS == 1 && tr && h0 == 0) tr[6] = clock64();
+        if (STATS == 1 && tr && h0 + M == kNH) tr[7] = clock64();
         st += nSets;
         while (st >= NS)
         {
@@ -1687,7 +1689,7 @@ __device__ __forceinline__ void split_producer_sets(const PipeDev& S, const Spli
 // only ones that depend on another group's progress - go out as soon as this warp is done with its previous block, as in
 // the single-set producer (split_producer), and the two global round trips of a block do not add up on the path between
 // "the value exists" and "the block is handed to the consumer".
-template <int MODE, int LG, int M, bool STATS>
+template <int MODE, int LG, int M, int STATS>
 __device__ __forceinline__ void split_producer_pipe(const PipeDev& S, const SplitCtx& C, const int g, const int set, const int nSets, const int h0,
                                                     const int lane, double* out, int* err, const double* __restrict__ aVec,
                                                     const double* __restrict__ bVec)
@@ -1706,7 +1708,7 @@ __device__ __forceinline__ void split_producer_pipe(const PipeDev& S, const Spli
     const unsigned char* const pG0 = C.pStream + (size_t)h0 * C.pRec;
     const double* const aG0 = aVec + ((long long)C.base + (dir > 0 ? h0 : C.nT - 1 - h0)) * 32 + lane;
     const double* const bG0 = bVec ? bVec + ((long long)C.base + (dir > 0 ? h0 : C.nT - 1 - h0)) * 32 + lane : nullptr;
-    const bool timed = (STATS || S.stats != nullptr) && set == 0 && h0 == 0;
+    const bool timed = (STATS != 0) && set == 0 && h0 == 0;
     long long tStage = 0, tVal = 0, tSpin = 0, tAll = timed ? clock64() : 0;
     struct Ops
     {
@@ -1779,7 +1781,7 @@ __device__ __forceinline__ void split_producer_pipe(const PipeDev& S, const Spli
         const long long v1 = timed ? clock64() : 0;
         if (anyBad)
         {
-            if (STATS && lane == 0) atomicAdd((unsigned long long*)(S.stats + (long long)kStatsStride * g + 4), 1ull);
+            if (STATS == 1 && lane == 0) atomicAdd((unsigned long long*)(S.stats + (long long)kStatsStride * g + 4), 1ull);
             int tries = 0;
             bool still;
             do
@@ -1807,7 +1809,7 @@ __device__ __forceinline__ void split_producer_pipe(const PipeDev& S, const Spli
                 {
                     __nanosleep(tries > 4096 ? 400 : 64);
                     if ((tries & 4095) == 4095 && *(volatile int*)err) break;
-                    if (tries >= kSweepSpinLimit)
+                    if (tries >= S.spinLimit)
                     {
                         atomicExch(err, 1);
                         break;
@@ -1874,7 +1876,7 @@ __device__ __forceinline__ int sweep_role(int warp)
     return warp - 1;
 }
 
-template <int MODE, bool STATS>
+template <int MODE, int STATS>
 __device__ __forceinline__ void sweep_group_split(const PipeDev& S, const int g, const int warp, const int lane, const double* __restrict__ a,
                                                   const double* __restrict__ b, double* out, int* err, unsigned char* smem)
 {
@@ -1952,7 +1954,7 @@ __device__ __forceinline__ void sweep_group_split(const PipeDev& S, const int g,
                 __syncwarp();
                 if (lane == 0 && blk + C.NS < C.nBlocks)
                 {
-                    if (STATS && blk + C.NS < kTraceBlocks) S.stats[(long long)kStatsStride * g + 16 + (blk + C.NS) * 8 + 2] = clock64();
+                    if (STATS == 1 && blk + C.NS < kTraceBlocks) S.stats[(long long)kStatsStride * g + 16 + (blk + C.NS) * 8 + 2] = clock64();
                     split_issue<MODE>(C, a, b, blk + C.NS, st);
                     split_prefetch<MODE>(C, a, b, blk + C.NS + S.l2Ahead);
                 }
@@ -1961,7 +1963,7 @@ __device__ __forceinline__ void sweep_group_split(const PipeDev& S, const int g,
             return;
         }
         // loader: one thread refills a stage as soon as the consumer has released the block it held
-        const bool probe = S.stats != nullptr; // armed counters: lane 1 measures how long a refill takes to land
+        const bool probe = STATS != 0 && S.stats != nullptr; // armed counters: lane 1 measures how long a refill takes to land
         volatile long long* issueClk = reinterpret_cast<volatile long long*>(smem + 256); // [NS], debug part of the header
         if (lane == 0)
         {
@@ -1970,7 +1972,7 @@ __device__ __forceinline__ void sweep_group_split(const PipeDev& S, const int g,
             {
                 const unsigned need = (unsigned)(blk - C.NS + 1);
                 while (ld_flag_smem(C.done) < need) __nanosleep(20);
-                if (STATS && blk < kTraceBlocks) S.stats[(long long)kStatsStride * g + 16 + blk * 8 + 2] = clock64();
+                if (STATS == 1 && blk < kTraceBlocks) S.stats[(long long)kStatsStride * g + 16 + blk * 8 + 2] = clock64();
                 if (probe) issueClk[st] = clock64();
                 split_issue<MODE>(C, a, b, blk, st);
                 split_prefetch<MODE>(C, a, b, blk + S.l2Ahead);
@@ -2087,7 +2089,7 @@ __device__ __noinline__ void sweep_group_generic(const PipeDev& S, const int g, 
                 if (code >= 0)
                 {
                     v = ld_relaxed(out + code);
-                    if (is_sentinel(v)) v = sweep_spin(out + code, err);
+                    if (is_sentinel(v)) v = sweep_spin(out + code, err, S.spinLimit);
                 }
                 if (code != kCodeNone) acc = sweep_apply<MODE>(acc, cfj, v);
             }
@@ -2111,7 +2113,7 @@ __device__ __noinline__ void sweep_group_generic(const PipeDev& S, const int g, 
 // One CTA (1 consumer + kNH producer warps + 1 loader warp) per group; CTAs take tickets so that groups start in a
 // topological order of the group graph: a group only ever waits for groups that are already running.
 constexpr int kSweepThreads = 32 * kSweepWarps;
-template <int MODE, bool STATS>
+template <int MODE, int STATS>
 __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(PipeDev S, const double* __restrict__ a, const double* __restrict__ b,
                                                           double* out, unsigned* ticket, unsigned ticketBase, int* err,
                                                           const DevScalars* sc, int force)
@@ -2125,7 +2127,8 @@ __global__ void __launch_bounds__(kSweepThreads, 2) k_sweep(PipeDev S, const dou
     if (sc->done && !force) return;
     if ((int)t >= S.nGroups) return;
     const int g = S.order ? S.order[t] : (int)t;
-    const bool stamp = !STATS && S.stats != nullptr && threadIdx.x == 0; // debug flag 2: start / end of the group only
+    if ((S.debugFlags & 4) && t == 0) return; // fault injection (tests): this group's results never appear
+    const bool stamp = STATS != 1 && S.stats != nullptr && threadIdx.x == 0; // start / end of the group
     if (stamp) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(S.stats[(long long)kStatsStride * g + 2]));
     if (S.gFast[g])
         sweep_group_split<MODE, STATS>(S, g, warp, lane, a, b, out, err, smem);
