@@ -57,6 +57,19 @@ int b200_blk_destroy(b200_blk* sys);
 int b200_blk_set_coeffs(b200_blk* sys, int diagKind, const double* diag, int upperKind, const double* upper,
                         int lowerKind, const double* lower);
 
+/* Coupled patches of a decomposed block matrix: BlockLduMatrix<vector4>::interfaces() entries that are
+ * processorFvPatchField<vector4> (foam-extend BlockLduMatrixUpdateMatrixInterfaces.C; reached from the solvers' Amul
+ * exactly like lduMatrix::updateMatrixInterfaces on the scalar path).  Add them after
+ * b200_blk_create and before the first operation, in patch order; peerIface is the index the neighbour gives the
+ * matching patch among ITS interfaces.  peerRank == own rank pairs two patches of this system (a cyclic-like pair; also
+ * what the single-GPU tests use).  Amul then does  Ax[faceCells[f]] -= coupleUpper[f] * xNeighbour[f]  per patch in
+ * patch order after the core product, and gSumProd / gSum / gAverage reduce over all ranks of the context.  Several ranks
+ * need the peer-to-peer transport of the context (b200_ldu.h, B200_TRANSPORT); there is no NCCL leg on this path. */
+int b200_blk_add_interface(b200_blk* sys, int32_t nFaces, const int32_t* faceCells, int32_t peerRank, int32_t peerIface,
+                           int32_t* index);
+/* coupleUpper of the patch, kind SCALAR / LINEAR / SQUARE, [nFaces][kind]; again after every assembly */
+int b200_blk_set_interface_coeffs(b200_blk* sys, int32_t iface, int kind, const double* coupleUpper);
+
 /* BlockLduMatrix<vector4>::Amul */
 int b200_blk_amul(b200_blk* sys, const double* x, double* y);
 /* BlockLduPrecon<vector4>::precondition(w, r) */

@@ -33,6 +33,7 @@ ABI_SYMBOLS = [
     "b200_blk_create", "b200_blk_destroy", "b200_blk_set_coeffs", "b200_blk_amul", "b200_blk_precondition",
     "b200_blk_get_precon_diag", "b200_blk_reduce", "b200_blk_solve", "b200_blk_upload", "b200_blk_solve_resident",
     "b200_blk_download", "b200_blk_x_save", "b200_blk_x_restore", "b200_blk_set_profiling", "b200_blk_get_kernel_times",
+    "b200_blk_add_interface", "b200_blk_set_interface_coeffs",
 ]
 
 # BlockLduSolver / BlockLduPrecon run-time selection names: foam-extend's own and the cuda* names of the drop-in
@@ -62,6 +63,8 @@ def _lib():
         L.b200_blk_create.argtypes = [vp, C.c_int32, C.c_int32, ip, ip, C.POINTER(vp)]
         L.b200_blk_destroy.argtypes = [vp]
         L.b200_blk_set_coeffs.argtypes = [vp, C.c_int, dp, C.c_int, dp, C.c_int, dp]
+        L.b200_blk_add_interface.argtypes = [vp, C.c_int32, ip, C.c_int32, C.c_int32, ip]
+        L.b200_blk_set_interface_coeffs.argtypes = [vp, C.c_int32, C.c_int, dp]
         L.b200_blk_amul.argtypes = [vp, dp, dp]
         L.b200_blk_precondition.argtypes = [vp, C.c_int, dp, dp]
         L.b200_blk_get_precon_diag.argtypes = [vp, C.c_int, dp, C.POINTER(C.c_int)]
@@ -117,6 +120,18 @@ class BlockSystem:
         lo = None if lower is None else ldu._f64(lower)
         self.ctx.check(_lib().b200_blk_set_coeffs(self.h, coeff_kind(d), ldu._dp(d), coeff_kind(u), ldu._dp(u),
                                                   0 if lo is None else coeff_kind(lo), ldu._dp(lo)))
+
+    def add_interface(self, faceCells, peerRank: int, peerIface: int) -> int:
+        """A processor patch of the block matrix (BlockLduMatrix::interfaces()); peerIface: the neighbour's index of
+        the matching patch.  -> the index of this patch."""
+        fc = ldu._i32(faceCells)
+        idx = C.c_int32(-1)
+        self.ctx.check(_lib().b200_blk_add_interface(self.h, int(fc.size), ldu._ip(fc), int(peerRank), int(peerIface), C.byref(idx)))
+        return idx.value
+
+    def set_interface_coeffs(self, iface: int, coupleUpper):
+        cu = ldu._f64(coupleUpper)
+        self.ctx.check(_lib().b200_blk_set_interface_coeffs(self.h, int(iface), coeff_kind(cu), ldu._dp(cu)))
 
     def _field(self, a) -> np.ndarray:
         a = ldu._f64(a)

@@ -15,6 +15,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <algorithm>
 #include <memory>
 #include <string>
 #include <map>
@@ -237,6 +239,37 @@ static int transport_mode()
     return 0;
 }
 
+// Peer-to-peer halo of one system (PeerLink of the context): one allocation [2 parities][recvTotal] doubles | [2][nPeers] flag
+// words, mapped by the neighbours, which store their patch values straight into it (k_halo_push / k_blk_halo_push)
+struct HaloLink
+{
+    bool enabled = false;
+    unsigned char* buf = nullptr;
+    size_t recvTotal = 0;
+    std::vector<double*> peerData;             // per peer: its buffer, at the offset of this rank's segment (parity 0)
+    std::vector<size_t> peerTotal;             // per peer: its recvTotal (parity stride)
+    std::vector<unsigned long long*> peerFlag; // per peer: this rank's flag word in its buffer (parity 0)
+    std::vector<int> peerNPeers;               // per peer: its number of segments (parity stride of the flags)
+    unsigned long long seq = 0;
+    unsigned* counters = nullptr;              // [nPeers] last-block counters of the push kernels
+    std::vector<void*> opened;
+    double* data(int par) const { return reinterpret_cast<double*>(buf) + (size_t)par * recvTotal; }
+    unsigned long long* flags(int par, int nPeers) const
+    {
+        return reinterpret_cast<unsigned long long*>(buf + 2 * recvTotal * sizeof(double)) + (size_t)par * nPeers;
+    }
+    void release()
+    {
+        for (void* q : opened) cudaIpcCloseMemHandle(q);
+        opened.clear();
+        if (buf) cudaFree(buf);
+        if (counters) cudaFree(counters);
+        buf = nullptr;
+        counters = nullptr;
+        enabled = false;
+    }
+};
+
 struct PipeDirMem
 {
     DevBuf<int> gW, gCH, gShflMask, face, order, gLg, gRg, gKg, pFace, cFace;
@@ -309,26 +342,7 @@ struct b200_sys
     int nDetached = 0; // regionCouple interfaces currently detached (regionInterfaceType::detach)
     std::vector<int> peers;
     std::vector<int32_t> sendOff, recvOff;
-    // peer-to-peer halo (PeerLink of the context): one allocation [2 parities][recvTotal] doubles | [2][nPeers] flag words,
-    // mapped by the neighbours, which store their patchInternalField straight into it (k_halo_push)
-    struct HaloLink
-    {
-        bool enabled = false;
-        unsigned char* buf = nullptr;
-        size_t recvTotal = 0;
-        std::vector<double*> peerData;             // per peer: its buffer, at the offset of this rank's segment (parity 0)
-        std::vector<size_t> peerTotal;             // per peer: its recvTotal (parity stride)
-        std::vector<unsigned long long*> peerFlag; // per peer: this rank's flag word in its buffer (parity 0)
-        std::vector<int> peerNPeers;               // per peer: its number of peers (parity stride of the flags)
-        unsigned long long seq = 0;
-        unsigned* counters = nullptr;              // [nPeers] last-block counters of k_halo_push
-        std::vector<void*> opened;
-        double* data(int par) const { return reinterpret_cast<double*>(buf) + (size_t)par * recvTotal; }
-        unsigned long long* flags(int par, int nPeers) const
-        {
-            return reinterpret_cast<unsigned long long*>(buf + 2 * recvTotal * sizeof(double)) + (size_t)par * nPeers;
-        }
-    } halo;
+    HaloLink halo; // peer-to-peer halo of the processor patches
     int64_t nIfCoefs = 0;
     // sweeps
     PipeDirMem fwd, bwd;
@@ -604,9 +618,7 @@ extern "C" int b200_sys_destroy(b200_sys* s)
     if (s->evSolveA) cudaEventDestroy(s->evSolveA);
     if (s->evSolveB) cudaEventDestroy(s->evSolveB);
     if (s->hostFlags) cudaFreeHost(s->hostFlags);
-    for (void* q : s->halo.opened) cudaIpcCloseMemHandle(q);
-    if (s->halo.buf) cudaFree(s->halo.buf);
-    if (s->halo.counters) cudaFree(s->halo.counters);
+    s->halo.release();
     delete s;
     return B200_OK;
 }
@@ -775,16 +787,16 @@ static int upload_pipe_dir(b200_sys* s, const PipeSchedule& S, const PipeSchedul
 }
 
 // Peer-to-peer halo of a system: every rank publishes the cudaIpc handle of its receive buffer and the table
-// (peer rank, offset, count) of its segments; a rank finds in each neighbour's record where its own data has to go.
-static int setup_halo_link(b200_sys* s)
+// (peer rank, offset, count) of its segments; a rank finds in each neighbour's record where its own data has to go:
+// in the segment the neighbour keeps for this rank (matchIndex[p] < 0: one segment per neighbour rank), or in the
+// segment with the given index (block systems: one segment per interface, matchIndex[p] = the peer's interface index).
+// Counts and offsets in doubles.  Collective over the ranks that have segments; `k` names the rendezvous records.
+static int setup_halo_link_generic(b200_ctx* ctx, int k, const std::vector<int>& peers, const std::vector<int64_t>& sendCount,
+                                   const std::vector<int64_t>& recvOff, const std::vector<int>& matchIndex, HaloLink& H)
 {
-    b200_ctx* ctx = s->ctx;
     PeerLink& L = ctx->peer;
-    const int k = L.sysCount++;
-    if (s->peers.empty()) return B200_OK;
-    b200_sys::HaloLink& H = s->halo;
-    const int nPeers = (int)s->peers.size();
-    H.recvTotal = (size_t)s->recvOff.back();
+    const int nPeers = (int)peers.size();
+    H.recvTotal = (size_t)recvOff.back();
     const size_t bytes = 2 * H.recvTotal * sizeof(double) + 2 * (size_t)nPeers * sizeof(unsigned long long);
     CK(ctx, cudaMalloc((void**)&H.buf, bytes));
     CK(ctx, cudaMemset(H.buf, 0, bytes));
@@ -809,7 +821,7 @@ static int setup_halo_link(b200_sys* s)
     hd->nPeers = nPeers;
     hd->pad = 0;
     Seg* sg = reinterpret_cast<Seg*>(rec.data() + sizeof(Head));
-    for (int p = 0; p < nPeers; p++) sg[p] = Seg{s->peers[p], 0, s->recvOff[p], s->recvOff[p + 1] - s->recvOff[p]};
+    for (int p = 0; p < nPeers; p++) sg[p] = Seg{peers[p], 0, recvOff[p], recvOff[p + 1] - recvOff[p]};
     const std::string tag = "sys" + std::to_string(k);
     if (!peer_publish(L, "r" + std::to_string(ctx->rank) + "." + tag, rec.data(), rec.size()))
         return set_err(ctx, B200_ECUDA, "peer-to-peer halo: cannot write the rendezvous record in %s", L.dir.c_str());
@@ -817,23 +829,33 @@ static int setup_halo_link(b200_sys* s)
     H.peerTotal.assign(nPeers, 0);
     H.peerFlag.assign(nPeers, nullptr);
     H.peerNPeers.assign(nPeers, 0);
+    std::map<int, void*> mapped; // one mapping per neighbour rank
     for (int p = 0; p < nPeers; p++)
     {
+        if (peers[p] == ctx->rank) continue; // a pair of patches on this rank: nothing to map (block systems)
         std::vector<unsigned char> theirs;
-        if (!peer_fetch(L, "r" + std::to_string(s->peers[p]) + "." + tag, theirs) || theirs.size() < sizeof(Head))
-            return set_err(ctx, B200_ECUDA, "peer-to-peer halo: rank %d did not publish %s", s->peers[p], tag.c_str());
+        if (!peer_fetch(L, "r" + std::to_string(peers[p]) + "." + tag, theirs) || theirs.size() < sizeof(Head))
+            return set_err(ctx, B200_ECUDA, "peer-to-peer halo: rank %d did not publish %s", peers[p], tag.c_str());
         const Head* th = reinterpret_cast<const Head*>(theirs.data());
         const Seg* ts = reinterpret_cast<const Seg*>(theirs.data() + sizeof(Head));
         int j = -1;
-        for (int q = 0; q < th->nPeers; q++)
-            if (ts[q].peer == ctx->rank) j = q;
-        const int64_t nSend = s->sendOff[p + 1] - s->sendOff[p];
-        if (j < 0 || ts[j].count != nSend)
-            return set_err(ctx, B200_EINVAL, "peer-to-peer halo: rank %d expects %lld values from rank %d, which sends %lld", s->peers[p],
-                           (long long)(j < 0 ? -1 : ts[j].count), ctx->rank, (long long)nSend);
+        if (matchIndex[p] >= 0)
+            j = (matchIndex[p] < th->nPeers && ts[matchIndex[p]].peer == ctx->rank) ? matchIndex[p] : -1;
+        else
+            for (int q = 0; q < th->nPeers; q++)
+                if (ts[q].peer == ctx->rank) j = q;
+        if (j < 0 || ts[j].count != sendCount[p])
+            return set_err(ctx, B200_EINVAL, "peer-to-peer halo: rank %d expects %lld values from rank %d, which sends %lld", peers[p],
+                           (long long)(j < 0 ? -1 : ts[j].count), ctx->rank, (long long)sendCount[p]);
         void* q = nullptr;
-        CK(ctx, cudaIpcOpenMemHandle(&q, th->h, cudaIpcMemLazyEnablePeerAccess));
-        H.opened.push_back(q);
+        if (mapped.count(peers[p]))
+            q = mapped[peers[p]];
+        else
+        {
+            CK(ctx, cudaIpcOpenMemHandle(&q, th->h, cudaIpcMemLazyEnablePeerAccess));
+            H.opened.push_back(q);
+            mapped[peers[p]] = q;
+        }
         H.peerData[p] = static_cast<double*>(q) + ts[j].off;
         H.peerTotal[p] = (size_t)th->recvTotal;
         H.peerFlag[p] = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(q) + 2 * (size_t)th->recvTotal * sizeof(double)) + j;
@@ -841,6 +863,17 @@ static int setup_halo_link(b200_sys* s)
     }
     H.enabled = true;
     return B200_OK;
+}
+
+static int setup_halo_link(b200_sys* s)
+{
+    b200_ctx* ctx = s->ctx;
+    const int k = ctx->peer.sysCount++;
+    if (s->peers.empty()) return B200_OK;
+    const int nPeers = (int)s->peers.size();
+    std::vector<int64_t> sendCount(nPeers), recvOff(s->recvOff.begin(), s->recvOff.end());
+    for (int p = 0; p < nPeers; p++) sendCount[p] = s->sendOff[p + 1] - s->sendOff[p];
+    return setup_halo_link_generic(ctx, k, s->peers, sendCount, recvOff, std::vector<int>(nPeers, -1), s->halo);
 }
 
 // Interface / halo plan of the system (schedule.hpp, IfacePlan): built at finalize, and rebuilt (first == false: the
@@ -1230,7 +1263,7 @@ static int launch_amul(b200_sys* s, const double* x, double* y, int nd, const do
     const double* recvPtr = s->recvBuf.p;
     if (!s->peers.empty() && s->halo.enabled)
     { // peer-to-peer: one push per neighbour, no send / receive buffers, no collective call
-        b200_sys::HaloLink& H = s->halo;
+        HaloLink& H = s->halo;
         haloSeq = ++H.seq;
         const int par = (int)(haloSeq & 1ull);
         nHaloPeers = (int)s->peers.size();

@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(256) k_blk_reduce(long long nCells, const doub
         for (int v = 0; v < NV; v++) partial[(size_t)v * gridDim.x + blockIdx.x] = sh[v][0];
 }
 
-__global__ void __launch_bounds__(256) k_blk_reduce_final(const double* __restrict__ partial, int nBlocks, int nv, double* out)
+__global__ void __launch_bounds__(256) k_blk_reduce_final(const double* __restrict__ partial, int nBlocks, int nv, double* out, PeerAR ar, int* err)
 {
     __shared__ double sh[256];
     for (int v = 0; v < nv; v++)
@@ -594,6 +594,81 @@ __global__ void __launch_bounds__(256) k_blk_reduce_final(const double* __restri
         if (threadIdx.x == 0) out[v] = sh[0];
         __syncthreads();
     }
+    // gSumProd / gSum: the partial sums of the ranks, added in rank order on every rank (kernels.cuh, peer_allreduce)
+    if (ar.nranks > 1) peer_allreduce(ar, nv, out, err);
+}
+
+// ---------------------------------------------------------------------------------------------- coupled patches
+// BlockLduMatrix<Type>::initInterfaces for a processor patch: the patch-internal field x[faceCells] (4 doubles per face)
+// goes straight into the neighbour's receive buffer; the last block publishes the sequence number (cf. k_halo_push).
+__global__ void k_blk_halo_push(int nFaces, const int* __restrict__ cells, const double* __restrict__ x, double* __restrict__ remote,
+                                unsigned long long* remoteFlag, unsigned long long seq, unsigned* counter)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < 4ll * nFaces) remote[t] = x[4ll * cells[t >> 2] + (t & 3)];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        const unsigned prev = atomicAdd(counter, 1u);
+        if (prev == gridDim.x - 1)
+        {
+            *counter = 0u;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long*>(remoteFlag) = seq;
+        }
+    }
+}
+
+// BlockLduMatrix<Type>::updateInterfaces(coupleUpper, Ax, x) for one processor patch (processorFvPatchField<Type>::
+// updateInterfaceMatrix with switchToLhs = false):  Ax[faceCells[f]] -= coupleUpper[f] * xNbr[f], faces in patch order.
+// One thread quad per touched cell (rows = the cells of the patch, each with its faces in patch order).  xNbr comes from
+// the receive buffer (nbr, after the neighbour's flag shows this exchange) or, for a pair of patches on the same rank,
+// from x[nbrCells[f]].
+__global__ void __launch_bounds__(kBlkThreads)
+    k_blk_iface(int nRows, const int* __restrict__ rowCell, const int* __restrict__ rowStart, const int* __restrict__ rowFace, int kind,
+                const double* __restrict__ coef, const double* nbr, const int* __restrict__ nbrCells, const double* __restrict__ x, double* y,
+                const unsigned long long* flag, unsigned long long seq, int* err)
+{
+    if (flag)
+    {
+        if (threadIdx.x == 0)
+        {
+            const volatile unsigned long long* f = flag;
+            long long tries = 0;
+            while (*f < seq)
+            {
+                if (++tries > 64) __nanosleep(tries > 100000 ? 1000 : 40);
+                if (tries > (1ll << 27))
+                {
+                    atomicExch(err, 2);
+                    break;
+                }
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
+    const long long t = (long long)blockIdx.x * kBlkThreads + threadIdx.x;
+    const long long row = t >> 2;
+    const int i = (int)(t & 3);
+    if (row >= nRows) return;
+    const int c = rowCell[row];
+    double acc = y[4ll * c + i];
+    for (int k = rowStart[row]; k < rowStart[row + 1]; k++)
+    {
+        const int f = rowFace[k];
+        double xv[4];
+        if (nbr)
+        {
+            ld_cg2(nbr + 4ll * f, xv[0], xv[1]);
+            ld_cg2(nbr + 4ll * f + 2, xv[2], xv[3]);
+        }
+        else
+            blk_load_x(x, nbrCells[f], xv);
+        acc -= blk_mult_row(kind, coef + (size_t)f * kind, false, xv, i);
+    }
+    y[4ll * c + i] = acc;
 }
 
 } // namespace b200
@@ -618,6 +693,19 @@ struct b200_blk
     unsigned ticketBase = 0;
     DevBuf<int> devErr;
     bool haveCoeffs = false, haveVectors = false;
+    // coupled patches (processor patches of a decomposed block matrix; a pair on the same rank is served locally)
+    struct Iface
+    {
+        int nFaces = 0, peerRank = 0, peerIface = -1, nRows = 0;
+        DevBuf<int> cells, rowCell, rowStart, rowFace;
+        int kind = 0;
+        DevBuf<double> upper; // coupleUpper
+        int64_t recvOff = 0;  // of the patch in the halo buffer, in doubles
+    };
+    std::deque<Iface> ifaces;
+    HaloLink halo;
+    bool ifacesFinal = false;
+    double nGlobal = 0; // cells of all ranks
     bool profiling = false;
     double clsMs[5] = {0};
     int64_t clsLaunches[5] = {0};
@@ -633,6 +721,13 @@ struct b200_blk
 
 namespace
 {
+#define BRC0(call)         \
+    do                     \
+    {                      \
+        int rc0_ = (call); \
+        if (rc0_) return rc0_; \
+    } while (0)
+
 struct BlkScope
 {
     b200_blk* s;
@@ -729,17 +824,104 @@ int blk_check_err(b200_blk* s, const char* what)
     if (e)
     {
         cudaMemsetAsync(s->devErr.p, 0, sizeof(int), ctx->stream);
-        return set_err(ctx, B200_EDEVICE, "%s: a block sweep timed out waiting for a dependency", what);
+        return set_err(ctx, B200_EDEVICE, e == 2 ? "%s: timed out waiting for a neighbour rank (halo or all-reduce)" : "%s: a block sweep timed out waiting for a dependency", what);
     }
     return B200_OK;
 }
 
+// Once per system, at its first operation: pair the coupled patches (same rank) or map the neighbours' receive buffers
+// (other ranks; collective), and count the cells of all ranks for BlockIterativeSolver::normFactor's average.
+int blk_finalize_ifaces(b200_blk* s)
+{
+    if (s->ifacesFinal) return B200_OK;
+    b200_ctx* ctx = s->ctx;
+    const int nI = (int)s->ifaces.size();
+    s->nGlobal = (double)s->n;
+    for (int i = 0; i < nI; i++)
+    {
+        const b200_blk::Iface& I = s->ifaces[i];
+        if (I.peerRank != ctx->rank) continue;
+        if (I.peerIface < 0 || I.peerIface >= nI || I.peerIface == i || s->ifaces[I.peerIface].peerRank != ctx->rank ||
+            s->ifaces[I.peerIface].peerIface != i || s->ifaces[I.peerIface].nFaces != I.nFaces)
+            return set_err(ctx, B200_EINVAL, "b200_blk: interface %d names interface %d of this rank as its neighbour, which does not match it", i,
+                           I.peerIface);
+    }
+    if (ctx->nranks > 1)
+    {
+        if (!ctx->peer.enabled)
+            return set_err(ctx, B200_EUNSUPPORTED,
+                           "b200_blk: block systems on several ranks use the peer-to-peer transport only (B200_TRANSPORT=p2p or auto with peer "
+                           "access between the GPUs)");
+        PeerLink& L = ctx->peer;
+        CK(ctx, cudaMemcpyAsync(s->red.p, &s->nGlobal, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        const PeerAR ar{L.dPeerMbox, L.mbox, ctx->rank, ctx->nranks, ++L.arSeq};
+        k_peer_allreduce<<<1, 64, 0, ctx->stream>>>(s->red.p, 1, ar, s->devErr.p);
+        CK(ctx, cudaGetLastError());
+        CK(ctx, cudaMemcpyAsync(&s->nGlobal, s->red.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        const int k = L.sysCount++;
+        bool remote = false;
+        std::vector<int> peers(nI), match(nI);
+        std::vector<int64_t> sendCount(nI), recvOff((size_t)nI + 1, 0);
+        for (int i = 0; i < nI; i++)
+        {
+            b200_blk::Iface& I = s->ifaces[i];
+            const bool rem = I.peerRank != ctx->rank;
+            remote = remote || rem;
+            peers[i] = I.peerRank;
+            match[i] = I.peerIface;
+            sendCount[i] = rem ? 4ll * I.nFaces : 0;
+            I.recvOff = recvOff[i];
+            recvOff[(size_t)i + 1] = recvOff[i] + sendCount[i];
+        }
+        if (remote) BRC0(setup_halo_link_generic(ctx, k, peers, sendCount, recvOff, match, s->halo));
+    }
+    else
+        for (const auto& I : s->ifaces)
+            if (I.peerRank != ctx->rank) return set_err(ctx, B200_EINVAL, "b200_blk: interface to rank %d in a context of one rank", I.peerRank);
+    s->ifacesFinal = true;
+    return B200_OK;
+}
+
+// BlockLduMatrix<Type>::Amul: initInterfaces, AmulCore, updateInterfaces
 int blk_amul_dev(b200_blk* s, const double* x, double* y)
 {
-    if (s->n == 0) return B200_OK;
-    BlkScope k(s, 0);
-    k_blk_amul<<<(unsigned)((4ll * s->n + kBlkThreads - 1) / kBlkThreads), kBlkThreads, 0, s->ctx->stream>>>(blk_dev(s), x, y);
-    CK(s->ctx, cudaGetLastError());
+    b200_ctx* ctx = s->ctx;
+    BRC0(blk_finalize_ifaces(s));
+    const HaloLink& H = s->halo;
+    unsigned long long seq = 0;
+    int par = 0;
+    if (H.enabled)
+    {
+        seq = ++s->halo.seq;
+        par = (int)(seq & 1ull);
+        for (size_t p = 0; p < s->ifaces.size(); p++)
+        {
+            const b200_blk::Iface& I = s->ifaces[p];
+            if (I.peerRank == ctx->rank) continue;
+            BlkScope k(s, 0);
+            k_blk_halo_push<<<blk_grid(4ll * I.nFaces, 256, 1 << 30), 256, 0, ctx->stream>>>(
+                I.nFaces, I.cells.p, x, H.peerData[p] + (size_t)par * H.peerTotal[p], H.peerFlag[p] + (size_t)par * H.peerNPeers[p], seq,
+                H.counters + p);
+        }
+    }
+    if (s->n)
+    {
+        BlkScope k(s, 0);
+        k_blk_amul<<<(unsigned)((4ll * s->n + kBlkThreads - 1) / kBlkThreads), kBlkThreads, 0, ctx->stream>>>(blk_dev(s), x, y);
+    }
+    for (size_t p = 0; p < s->ifaces.size(); p++)
+    {
+        const b200_blk::Iface& I = s->ifaces[p];
+        const bool rem = I.peerRank != ctx->rank;
+        if (!I.kind) return set_err(ctx, B200_ESTATE, "b200_blk: coupling coefficients of interface %zu not set", p);
+        if (I.nRows == 0 && !rem) continue;
+        BlkScope k(s, 0);
+        k_blk_iface<<<blk_grid(4ll * I.nRows, kBlkThreads, 1 << 30), kBlkThreads, 0, ctx->stream>>>(
+            I.nRows, I.rowCell.p, I.rowStart.p, I.rowFace.p, I.kind, I.upper.p, rem ? H.data(par) + I.recvOff : nullptr,
+            rem ? nullptr : s->ifaces[I.peerIface].cells.p, x, y, rem ? H.flags(par, (int)s->ifaces.size()) + p : nullptr, seq, s->devErr.p);
+    }
+    CK(ctx, cudaGetLastError());
     return B200_OK;
 }
 
@@ -847,6 +1029,7 @@ template <int OP>
 int blk_reduce_dev(b200_blk* s, const double* a, const double* b, const double* c, int nv, double* hostOut)
 {
     b200_ctx* ctx = s->ctx;
+    BRC0(blk_finalize_ifaces(s));
     const int blocks = blk_grid(s->n, 256, kBlkRedBlocks);
     {
         BlkScope k(s, 3);
@@ -854,7 +1037,9 @@ int blk_reduce_dev(b200_blk* s, const double* a, const double* b, const double* 
     }
     {
         BlkScope k(s, 3);
-        k_blk_reduce_final<<<1, 256, 0, ctx->stream>>>(s->partial.p, blocks, nv, s->red.p);
+        PeerAR ar{nullptr, nullptr, ctx->rank, 1, 0};
+        if (ctx->nranks > 1) ar = PeerAR{ctx->peer.dPeerMbox, ctx->peer.mbox, ctx->rank, ctx->nranks, ++ctx->peer.arSeq};
+        k_blk_reduce_final<<<1, 256, 0, ctx->stream>>>(s->partial.p, blocks, nv, s->red.p, ar, s->devErr.p);
     }
     CK(ctx, cudaGetLastError());
     CK(ctx, cudaMemcpyAsync(s->hostRed, s->red.p, sizeof(double) * nv, cudaMemcpyDeviceToHost, ctx->stream));
@@ -923,7 +1108,7 @@ int blk_norm_factor(b200_blk* s, double* nfOut)
 {
     double sum4[4];
     BRC(blk_reduce_dev<BR_SUM4>(s, s->x.p, nullptr, nullptr, 4, sum4));
-    for (int i = 0; i < 4; i++) sum4[i] /= (double)(s->n ? s->n : 1);
+    for (int i = 0; i < 4; i++) sum4[i] /= s->nGlobal > 0 ? s->nGlobal : 1.0; // gAverage
     if (s->n)
     {
         BlkScope k(s, 3);
@@ -1109,6 +1294,7 @@ extern "C" int b200_blk_destroy(b200_blk* s)
     if (s->evB) cudaEventDestroy(s->evB);
     if (s->hostRed) cudaFreeHost(s->hostRed);
     if (s->hostErr) cudaFreeHost(s->hostErr);
+    s->halo.release();
     delete s;
     return B200_OK;
 }
@@ -1140,6 +1326,61 @@ extern "C" int b200_blk_set_coeffs(b200_blk* s, int dK, const double* diag, int 
     s->lK = lower ? lK : 0;
     s->haveCoeffs = true;
     s->precond = -1;
+    return B200_OK;
+}
+
+// BlockLduInterfaceField / processorFvPatchField<vector4>: a coupled patch of the block matrix
+extern "C" int b200_blk_add_interface(b200_blk* s, int32_t nFaces, const int32_t* faceCells, int32_t peerRank, int32_t peerIface, int32_t* index)
+{
+    if (!s) return B200_EINVAL;
+    b200_ctx* ctx = s->ctx;
+    if (s->ifacesFinal) return set_err(ctx, B200_ESTATE, "b200_blk_add_interface: the system has been used already");
+    if (nFaces < 0 || (nFaces && !faceCells) || peerRank < 0 || peerRank >= ctx->nranks || peerIface < 0)
+        return set_err(ctx, B200_EINVAL, "b200_blk_add_interface: bad argument (nFaces %d, peer rank %d, peer interface %d)", nFaces, peerRank, peerIface);
+    for (int f = 0; f < nFaces; f++)
+        if (faceCells[f] < 0 || faceCells[f] >= s->n) return set_err(ctx, B200_EINVAL, "b200_blk_add_interface: faceCells[%d] = %d out of range", f, faceCells[f]);
+    CK(ctx, cudaSetDevice(ctx->device));
+    // rows of the patch: its cells, each with its faces in patch order
+    std::vector<int> order(nFaces), cells(faceCells, faceCells + nFaces), rowCell, rowStart;
+    for (int f = 0; f < nFaces; f++) order[f] = f;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return faceCells[a] < faceCells[b]; });
+    for (int k = 0; k < nFaces; k++)
+        if (k == 0 || faceCells[order[k]] != faceCells[order[k - 1]])
+        {
+            rowCell.push_back(faceCells[order[k]]);
+            rowStart.push_back(k);
+        }
+    rowStart.push_back(nFaces);
+    s->ifaces.emplace_back();
+    b200_blk::Iface& I = s->ifaces.back();
+    I.nFaces = nFaces;
+    I.peerRank = peerRank;
+    I.peerIface = peerIface;
+    I.nRows = (int)rowCell.size();
+    cudaStream_t st = ctx->stream;
+    CK(ctx, I.cells.upload(cells, st));
+    CK(ctx, I.rowCell.upload(rowCell, st));
+    CK(ctx, I.rowStart.upload(rowStart, st));
+    CK(ctx, I.rowFace.upload(order, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    if (index) *index = (int32_t)s->ifaces.size() - 1;
+    return B200_OK;
+}
+
+// BlockLduMatrix<vector4>::coupleUpper()[patch] (coupleLower is used by Tmul only, which the solvers of this path never call)
+extern "C" int b200_blk_set_interface_coeffs(b200_blk* s, int32_t iface, int kind, const double* coupleUpper)
+{
+    if (!s) return B200_EINVAL;
+    b200_ctx* ctx = s->ctx;
+    if (iface < 0 || iface >= (int)s->ifaces.size()) return set_err(ctx, B200_EINVAL, "b200_blk_set_interface_coeffs: no interface %d", iface);
+    b200_blk::Iface& I = s->ifaces[iface];
+    if ((kind != 1 && kind != 4 && kind != 16) || (I.nFaces && !coupleUpper))
+        return set_err(ctx, B200_EINVAL, "b200_blk_set_interface_coeffs: bad kind or null array");
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, I.upper.alloc((size_t)I.nFaces * kind));
+    if (I.nFaces) CK(ctx, cudaMemcpyAsync(I.upper.p, coupleUpper, sizeof(double) * (size_t)I.nFaces * kind, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    I.kind = kind;
     return B200_OK;
 }
 
