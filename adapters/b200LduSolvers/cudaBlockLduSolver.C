@@ -65,16 +65,21 @@ Foam::BlockSolverPerformance<Foam::vector4> Foam::cudaBlockLduSolverBase::solve(
     BlockSolverPerformance<vector4> solverPerf(solverName(), this->fieldName());
     const BlockLduMatrix<vector4>& m = this->matrix_;
 
-    // coupled patches (coupleUpper / coupleLower, fvBlockMatrix.C:315-373): the block library of this version solves
-    // one region on one rank; a matrix with a coupled or processor patch must not silently lose those coefficients
+    // coupled patches (coupleUpper / coupleLower, fvBlockMatrix.C:315-373): processor patches of a decomposed case go to
+    // the library (b200_blk_add_interface); any other coupled patch type must not silently lose its coefficients
+    DynamicList<label> procPatches, procRanks;
     forAll (m.interfaces(), patchI)
     {
-        if (m.interfaces().set(patchI))
+        if (!m.interfaces().set(patchI)) continue;
+        const processorLduInterfaceField* pp = dynamic_cast<const processorLduInterfaceField*>(&m.interfaces()[patchI]);
+        if (!pp)
         {
             FatalErrorIn(where)
-                << "the block-coupled device path has no coupled / processor patches yet (patch " << patchI << ")"
-                << abort(FatalError);
+                << "the block-coupled device path serves processor patches only; patch " << patchI
+                << " is another coupled type" << abort(FatalError);
         }
+        procPatches.append(patchI);
+        procRanks.append(pp->neighbProcNo());
     }
 
     const lduAddressing& addr = m.lduAddr();
@@ -91,7 +96,44 @@ Foam::BlockSolverPerformance<Foam::vector4> Foam::cudaBlockLduSolverBase::solve(
             b200_blk_create(b200Binding::context(), addr.size(), addr.lowerAddr().size(), addr.lowerAddr().begin(), addr.upperAddr().begin(), &sys),
             where
         );
+        // the neighbour's index of the matching patch: the k-th processor patch of rank A towards rank B pairs with the
+        // k-th of B towards A (decomposePar creates the two sides of a cut in the same order), b200Binding::describe pass 3
+        List<labelList> table(Pstream::nProcs());
+        table[Pstream::myProcNo()] = labelList(procRanks);
+        if (Pstream::parRun())
+        {
+            Pstream::gatherList(table);
+            Pstream::scatterList(table);
+        }
+        forAll (procPatches, i)
+        {
+            label kMine = 0;
+            for (label j = 0; j < i; j++) if (procRanks[j] == procRanks[i]) kMine++;
+            const labelList& theirs = table[procRanks[i]];
+            label peerIface = -1, k = 0;
+            forAll (theirs, e)
+            {
+                if (theirs[e] != Pstream::myProcNo()) continue;
+                if (k == kMine) { peerIface = e; break; }
+                k++;
+            }
+            if (peerIface < 0)
+            {
+                FatalErrorIn(where)
+                    << "processor " << procRanks[i] << " has no processor patch that matches patch " << procPatches[i]
+                    << abort(FatalError);
+            }
+            const unallocLabelList& fc = addr.patchAddr(procPatches[i]);
+            int32_t index = -1;
+            b200Binding::check(b200_blk_add_interface(sys, fc.size(), fc.begin(), procRanks[i], peerIface, &index), where);
+        }
         blkCache_.insert(key, sys);
+    }
+    forAll (procPatches, i)
+    {
+        const double* cp = NULL;
+        const int ck = coeffKind(m.coupleUpper()[procPatches[i]], cp);
+        b200Binding::check(b200_blk_set_interface_coeffs(sys, i, ck, cp), where);
     }
 
     const double *dp = NULL, *up = NULL, *lp = NULL;
