@@ -193,17 +193,26 @@ __global__ void __launch_bounds__(kBlkThreads) k_blk_amul(BlkDev M, const double
 // ---------------------------------------------------------------------------------------------- sweeps
 // ILUmultiply of BlockCholeskyPrecon.  BWD = false: out[row] = D b[row] - sum_{lower faces, ascending} D (L x[l]);
 // BWD = true: out[row] = a[row] - sum_{owner faces, DESCENDING} D (U x[u]).  rows: level-ordered row list (-1 = pad).
+#ifndef B200_BLK_MINCTAS
+#define B200_BLK_MINCTAS 2 // resident CTAs per SM the sweep is compiled for (register cap 65536 / (256 * this))
+#endif
+#ifndef B200_BLK_CHUNK
+#define B200_BLK_CHUNK 4 // terms of a row whose coefficients are loaded before the first poll
+#endif
 template <bool BWD>
-__global__ void __launch_bounds__(kBlkThreads)
-    k_blk_sweep(BlkDev M, int pK, int withFaces, const double* __restrict__ pD, const int* __restrict__ rows, int nPos,
-                const double* __restrict__ a, double* out, unsigned* ticket, unsigned ticketBase, int* err)
+__global__ void __launch_bounds__(kBlkThreads, B200_BLK_MINCTAS)
+    k_blk_sweep(BlkDev M, int pK, int withFaces, const double* __restrict__ pD, const int4* __restrict__ meta, const int2* __restrict__ terms,
+                int nPos, const double* __restrict__ a, double* out, unsigned* ticket, unsigned ticketBase, int* err)
 {
     __shared__ unsigned sTicket;
     if (threadIdx.x == 0) sTicket = atomicAdd(ticket, 1u) - ticketBase;
     __syncthreads();
     const long long pos = (long long)sTicket * kBlkRowsPerCta + (threadIdx.x >> 2);
     if (pos >= nPos) return;
-    const int row = rows[pos];
+    // {row, number of terms, first term}: the terms (face, neighbour) of a row lie in sweep order, rows in position order,
+    // so the chain of dependent loads before the first poll is  ticket -> meta -> terms -> coefficients
+    const int4 mt = __ldg(meta + pos);
+    const int row = mt.x;
     if (row < 0) return;
     const int i = threadIdx.x & 3;
     const unsigned lane = threadIdx.x & 31u;
@@ -219,14 +228,14 @@ __global__ void __launch_bounds__(kBlkThreads)
     }
     else
         acc = a[4ll * row + i];
-    const int k0 = BWD ? M.ownerStart[row] : M.losortStart[row], k1 = BWD ? M.ownerStart[row + 1] : M.losortStart[row + 1];
-    const int nTerms = withFaces ? k1 - k0 : 0; // BlockDiagonalPrecon: x = mult(dDiag, b) only
+    const int k0 = mt.z;
+    const int nTerms = withFaces ? mt.y : 0; // BlockDiagonalPrecon: x = mult(dDiag, b) only
     // The rows of one wavefront level wait for the level before: what a row does AFTER its neighbours' values arrive is
     // the critical path of the whole sweep.  Everything that does not depend on those values - face and neighbour
     // indices, this thread's row of each coefficient block (from DRAM) - is therefore loaded for up to kChunk terms at
     // once BEFORE the first poll; after a poll only multiply, quad shuffles and multiply remain (same order of the
     // terms and of the operations as before).
-    constexpr int kChunk = 4;
+    constexpr int kChunk = B200_BLK_CHUNK;
     const bool tr = !(BWD || M.lK);
     const double* const coefBase = (BWD || !M.lK) ? M.upper : M.lower;
     for (int kk0 = 0; kk0 < nTerms; kk0 += kChunk)
@@ -237,8 +246,9 @@ __global__ void __launch_bounds__(kBlkThreads)
         for (int t = 0; t < kChunk; t++)
             if (kk0 + t < nTerms)
             {
-                const int f = BWD ? k1 - 1 - (kk0 + t) : M.losort[k0 + kk0 + t];
-                nbv[t] = BWD ? M.u[f] : M.l[f];
+                const int2 tm = __ldg(terms + k0 + kk0 + t);
+                const int f = tm.x;
+                nbv[t] = tm.y;
                 blk_load_row_tr(M.uK, coefBase + (size_t)f * M.uK, tr, i, cf[t]);
             }
         // the neighbours of a row mostly sit in the level just before it and arrive together: all of them are polled in
@@ -679,6 +689,8 @@ struct b200_blk
     b200_ctx* ctx = nullptr;
     int n = 0, nf = 0;
     DevBuf<int> l, u, losort, losortStart, ownerStart, rowsF, rowsB;
+    DevBuf<int4> metaF, metaB;   // per sweep position {row (-1 pad), number of terms, first term, 0}
+    DevBuf<int2> termsF, termsB; // {face, neighbour row} in the order the sweep subtracts them
     int nPosF = 0, nPosB = 0, nLevelsF = 0, nLevelsB = 0;
     int dK = 0, uK = 0, lK = 0;
     DevBuf<double> diag, upper, lower;
@@ -1006,7 +1018,7 @@ int blk_precondition_dev(b200_blk* s, const double* r, double* w)
     {
         const unsigned ctas = (unsigned)((s->nPosF + kBlkRowsPerCta - 1) / kBlkRowsPerCta);
         BlkScope k(s, 1);
-        k_blk_sweep<false><<<ctas, kBlkThreads, 0, ctx->stream>>>(M, s->pK, chol ? 1 : 0, s->pD.p, s->rowsF.p, s->nPosF, r, fwdOut, s->ticket.p,
+        k_blk_sweep<false><<<ctas, kBlkThreads, 0, ctx->stream>>>(M, s->pK, chol ? 1 : 0, s->pD.p, s->metaF.p, s->termsF.p, s->nPosF, r, fwdOut, s->ticket.p,
                                                                    s->ticketBase, s->devErr.p);
         s->ticketBase += ctas;
         CK(ctx, cudaGetLastError());
@@ -1017,7 +1029,7 @@ int blk_precondition_dev(b200_blk* s, const double* r, double* w)
         if (rc) return rc;
         const unsigned ctas = (unsigned)((s->nPosB + kBlkRowsPerCta - 1) / kBlkRowsPerCta);
         BlkScope k(s, 2);
-        k_blk_sweep<true><<<ctas, kBlkThreads, 0, ctx->stream>>>(M, s->pK, 1, s->pD.p, s->rowsB.p, s->nPosB, fwdOut, w, s->ticket.p, s->ticketBase,
+        k_blk_sweep<true><<<ctas, kBlkThreads, 0, ctx->stream>>>(M, s->pK, 1, s->pD.p, s->metaB.p, s->termsB.p, s->nPosB, fwdOut, w, s->ticket.p, s->ticketBase,
                                                                   s->devErr.p);
         s->ticketBase += ctas;
         CK(ctx, cudaGetLastError());
@@ -1257,6 +1269,34 @@ extern "C" int b200_blk_create(b200_ctx* ctx, int32_t nCells, int32_t nFaces, co
     blk_level_rows(nCells, levB, nLevB, rowsB);
     s->nPosF = (int)rowsF.size();
     s->nPosB = (int)rowsB.size();
+    // sweep-ordered term lists: forward = lower faces of the row ascending (losort order), backward = owner faces DESCENDING
+    std::vector<int4> metaF(rowsF.size()), metaB(rowsB.size());
+    std::vector<int2> termsF((size_t)nFaces), termsB((size_t)nFaces);
+    {
+        int kF = 0, kB = 0;
+        for (size_t pos = 0; pos < rowsF.size(); pos++)
+        {
+            const int row = rowsF[pos];
+            if (row < 0)
+            {
+                metaF[pos] = make_int4(-1, 0, 0, 0);
+                continue;
+            }
+            metaF[pos] = make_int4(row, losortStart[(size_t)row + 1] - losortStart[row], kF, 0);
+            for (int k = losortStart[row]; k < losortStart[(size_t)row + 1]; k++) termsF[(size_t)kF++] = make_int2(losort[k], l[losort[k]]);
+        }
+        for (size_t pos = 0; pos < rowsB.size(); pos++)
+        {
+            const int row = rowsB[pos];
+            if (row < 0)
+            {
+                metaB[pos] = make_int4(-1, 0, 0, 0);
+                continue;
+            }
+            metaB[pos] = make_int4(row, ownerStart[(size_t)row + 1] - ownerStart[row], kB, 0);
+            for (int f = ownerStart[(size_t)row + 1] - 1; f >= ownerStart[row]; f--) termsB[(size_t)kB++] = make_int2(f, u[f]);
+        }
+    }
     s->nLevelsF = nLevF;
     s->nLevelsB = nLevB;
     cudaStream_t st = ctx->stream;
@@ -1267,6 +1307,10 @@ extern "C" int b200_blk_create(b200_ctx* ctx, int32_t nCells, int32_t nFaces, co
     CK(ctx, s->ownerStart.upload(ownerStart, st));
     CK(ctx, s->rowsF.upload(rowsF, st));
     CK(ctx, s->rowsB.upload(rowsB, st));
+    CK(ctx, s->metaF.upload(metaF, st));
+    CK(ctx, s->metaB.upload(metaB, st));
+    CK(ctx, s->termsF.upload(termsF, st));
+    CK(ctx, s->termsB.upload(termsB, st));
     CK(ctx, s->partial.alloc((size_t)kBlkMaxRed * kBlkRedBlocks));
     CK(ctx, s->red.alloc(8));
     CK(ctx, s->ticket.alloc(1));
