@@ -144,6 +144,20 @@ int b200_sys_set_interface_attached(b200_sys* sys, int r, int iface, int attache
  * patch itself (nFaces, faceCells) cannot change: a topology change means destroy and re-create. */
 int b200_sys_set_interface_ggi(b200_sys* sys, int r, int iface, int32_t nPeerFaces, const int32_t* ggiOffsets,
                                const int32_t* ggiAddr, const double* ggiWeights);
+/* A regionCouple patch whose SHADOW patch decomposePar spread over several ranks (each region is decomposed on its own:
+ * tutorials/conjugateHeatTransfer/flowOverHeatedPlate/system/fluid/decomposeParDict:17-27, n (2 1 2)).  foam-extend
+ * interpolates such a pair on the global face zones: the shadow's patch-internal field is expanded to the zone (all ranks
+ * contribute their faces at zoneAddressing()), interpolated with zone-level addressing, and filtered back to the local
+ * faces (the path monolithicCouplingFvPatchField.C:392-405 takes through regionCouplePatch().interpolate() when the
+ * patch is not localParallel()).  Here: add the interface with nPeerFaces = size of the shadow ZONE and GGI tables whose
+ * addresses are zone face labels (rows = the local faces), then name the pieces of the shadow zone: piece k is interface
+ * pieceIface[k] of region pieceRegion[k] on rank pieceRank[k] (own rank allowed) and holds the zone faces
+ * pieceZoneAddr[pieceOffsets[k] .. pieceOffsets[k+1]) in its patch face order.  Every rank that holds a piece of either
+ * zone must list ALL non-empty pieces of the opposite zone (the halo plan sends a patch to the ranks it reads from).
+ * Before b200_sys_finalize.  peerRank / peerRegion / peerIface of b200_sys_add_interface are ignored for such an interface. */
+int b200_sys_set_interface_pieces(b200_sys* sys, int r, int iface, int nPieces, const int32_t* pieceRank,
+                                  const int32_t* pieceRegion, const int32_t* pieceIface, const int32_t* pieceOffsets,
+                                  const int32_t* pieceZoneAddr);
 /* ---- device-side coefficient refresh of the temperature equations --------------------------- */
 /* The two T regions re-assemble their fvScalarMatrix every time step
  *   B200_TEQN_CONDUCT    fvm::ddt(rho*cv, T) == fvm::laplacian(kappa, T)

@@ -33,6 +33,9 @@ class Interface:
     ggiWeights: Optional[np.ndarray] = None
     name: str = ""
     nPeerFaces: Optional[int] = None  # faces of the shadow patch (None: same as this patch)
+    # shadow patch spread over ranks by the decomposition: nPeerFaces = faces of the shadow ZONE, ggiAddr = zone face
+    # labels, pieces = [(rank, region, iface, zoneAddr of that piece's faces)]; peerRank/peerRegion/peerIface unused
+    pieces: Optional[list] = None
 
     @property
     def nFaces(self) -> int:

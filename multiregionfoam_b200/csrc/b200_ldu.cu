@@ -682,6 +682,45 @@ extern "C" int b200_sys_add_interface(b200_sys* s, int r, int kind, int32_t nFac
     return (int)R.ifaces.size() - 1;
 }
 
+// regionCouple patch whose shadow patch decomposePar spread over several ranks (include/b200_ldu.h)
+extern "C" int b200_sys_set_interface_pieces(b200_sys* s, int r, int iface, int nPieces, const int32_t* pieceRank, const int32_t* pieceRegion,
+                                             const int32_t* pieceIface, const int32_t* pieceOffsets, const int32_t* pieceZoneAddr)
+{
+    if (!s) return B200_EINVAL;
+    b200_ctx* ctx = s->ctx;
+    if (s->finalized) return set_err(ctx, B200_ESTATE, "b200_sys_set_interface_pieces: system already finalized");
+    if (r < 0 || r >= (int)s->regs.size() || iface < 0 || iface >= (int)s->regs[r].ifaces.size())
+        return set_err(ctx, B200_EINVAL, "b200_sys_set_interface_pieces: no interface %d of region %d", iface, r);
+    IfaceHost& I = s->regs[r].ifaces[iface];
+    if (I.kind != B200_IFACE_REGION_COUPLE || I.identity)
+        return set_err(ctx, B200_EINVAL, "b200_sys_set_interface_pieces: a regionCouple interface with GGI tables (zone face labels) is needed");
+    if (nPieces < 0 || (nPieces && (!pieceRank || !pieceRegion || !pieceIface || !pieceOffsets)))
+        return set_err(ctx, B200_EINVAL, "b200_sys_set_interface_pieces: bad arguments");
+    std::vector<IfaceHost::Piece> pieces((size_t)nPieces);
+    std::vector<char> seen((size_t)I.nPeerFaces, 0);
+    for (int k = 0; k < nPieces; k++)
+    {
+        IfaceHost::Piece& P = pieces[k];
+        P.rank = pieceRank[k];
+        P.region = pieceRegion[k];
+        P.iface = pieceIface[k];
+        const int32_t a = pieceOffsets[k], b = pieceOffsets[k + 1];
+        if (P.rank < 0 || P.rank >= ctx->nranks || P.region < 0 || P.iface < 0 || a < 0 || b < a || (b > a && !pieceZoneAddr))
+            return set_err(ctx, B200_EINVAL, "b200_sys_set_interface_pieces: piece %d: bad rank / region / interface / offsets", k);
+        P.zoneAddr.assign(pieceZoneAddr + a, pieceZoneAddr + b);
+        for (int32_t z : P.zoneAddr)
+        {
+            if (z < 0 || z >= I.nPeerFaces) return set_err(ctx, B200_EINVAL, "b200_sys_set_interface_pieces: piece %d: zone face %d outside the shadow zone of %d faces", k, z, I.nPeerFaces);
+            if (seen[z]) return set_err(ctx, B200_EINVAL, "b200_sys_set_interface_pieces: zone face %d is held by two pieces", z);
+            seen[z] = 1;
+        }
+    }
+    for (int32_t z : I.ggiAddr)
+        if (nPieces && !seen[z]) return set_err(ctx, B200_EINVAL, "b200_sys_set_interface_pieces: the GGI tables address zone face %d, which no piece holds", z);
+    I.pieces = std::move(pieces);
+    return B200_OK;
+}
+
 static int upload_pipe_dir(b200_sys* s, const PipeSchedule& S, const PipeSchedule::Dir& D, int dir, PipeDirMem& M)
 {
     b200_ctx* ctx = s->ctx;

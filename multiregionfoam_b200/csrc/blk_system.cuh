@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(kBlkThreads) k_blk_amul(BlkDev M, const double
 #define B200_BLK_MINCTAS 2 // resident CTAs per SM the sweep is compiled for (register cap 65536 / (256 * this))
 #endif
 #ifndef B200_BLK_CHUNK
-#define B200_BLK_CHUNK 4 // terms of a row whose coefficients are loaded before the first poll
+#define B200_BLK_CHUNK 3 // terms of a row whose coefficients are loaded before the first poll (a hex cell has 3 per sweep)
 #endif
 template <bool BWD>
 __global__ void __launch_bounds__(kBlkThreads, B200_BLK_MINCTAS)

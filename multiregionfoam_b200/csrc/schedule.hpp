@@ -32,9 +32,12 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <map>
 #include <numeric>
 #include <stdexcept>
 #include <string>
+#include <tuple>
+#include <utility>
 #include <vector>
 
 namespace b200
@@ -52,6 +55,15 @@ struct IfaceHost
     std::vector<double> ggiWeights;
     int64_t coefOffset = 0; // into the concatenated interface-coefficient arrays
     bool attached = true;   // regionInterfaceType::attach()/detach(): a detached regionCouple patch takes no part in a solve
+    // A shadow patch that decomposePar spread over several ranks (regionCouple / ggi with a global zone): the shadow ZONE has
+    // nPeerFaces faces, the GGI addresses are zone face labels, and every piece says which zone faces it holds
+    // (zoneAddressing of that rank's patch).  Empty: one piece {peerRank, peerRegion, peerIface} holding faces 0 .. nPeerFaces-1.
+    struct Piece
+    {
+        int rank = 0, region = 0, iface = 0;
+        std::vector<int32_t> zoneAddr;
+    };
+    std::vector<Piece> pieces;
 };
 
 struct RegionHost
@@ -1020,50 +1032,87 @@ struct IfacePlan
                 I.coefOffset = nCoefs;
                 nCoefs += I.nFaces;
             }
+        // sources of an interface: (rank, region, iface) patches whose patch-internal values it reads, n values each
+        struct Src
+        {
+            int rank, region, iface;
+            int32_t n;
+        };
+        auto sourcesOf = [&](const IfaceHost& I) {
+            std::vector<Src> out;
+            if (I.pieces.empty())
+                out.push_back({I.peerRank, I.peerRegion, I.peerIface, int32_t(I.nPeerFaces)});
+            else
+                for (const auto& P : I.pieces) out.push_back({P.rank, P.region, P.iface, int32_t(P.zoneAddr.size())});
+            return out;
+        };
         for (auto& r : regs)
             for (auto& I : r.ifaces)
-                if (I.peerRank != myRank && std::find(peers.begin(), peers.end(), I.peerRank) == peers.end())
-                    peers.push_back(I.peerRank);
+                for (const Src& q : sourcesOf(I))
+                    if (q.rank != myRank && std::find(peers.begin(), peers.end(), q.rank) == peers.end()) peers.push_back(q.rank);
         std::sort(peers.begin(), peers.end());
         sendOff.assign(peers.size() + 1, 0);
         recvOff.assign(peers.size() + 1, 0);
-        // per remote interface: offset of what the peer sends for it inside the peer's segment
-        struct Rem
-        {
-            int region, iface;
-        };
-        std::vector<std::vector<int32_t>> recvSegOff(regs.size());
-        for (size_t r = 0; r < regs.size(); r++) recvSegOff[r].assign(regs[r].ifaces.size(), -1);
+        // offset of what a remote patch (rank, region, iface) sends, inside the receive buffer
+        std::map<std::tuple<int, int, int>, int32_t> recvSegOff;
         for (size_t p = 0; p < peers.size(); p++)
         {
-            // send layout: my interfaces to this peer in (region, iface) order
+            // send layout: my interfaces that rank peers[p] reads, in (region, iface) order, the whole patch each.  A patch is
+            // read by the ranks it reads from (processor patch: the neighbour; zone piece: the ranks holding pieces of the
+            // shadow zone, which list this piece among THEIR pieces)
             int32_t so = sendOff[p];
             for (size_t r = 0; r < regs.size(); r++)
                 for (auto& I : regs[r].ifaces)
-                    if (I.peerRank == peers[p])
-                    {
-                        for (int i = 0; i < I.nFaces; i++) sendCells.push_back(S.slotOfCell[regs[r].cellOffset + I.faceCells[i]]);
-                        so += I.nFaces;
-                    }
+                {
+                    bool reads = false;
+                    for (const Src& q : sourcesOf(I)) reads = reads || q.rank == peers[p];
+                    if (!reads) continue;
+                    for (int i = 0; i < I.nFaces; i++) sendCells.push_back(S.slotOfCell[regs[r].cellOffset + I.faceCells[i]]);
+                    so += I.nFaces;
+                }
             sendOff[p + 1] = so;
-            // receive layout: the peer's interfaces to me in ITS (region, iface) order = my
-            // interfaces to it sorted by (peerRegion, peerIface)
-            std::vector<Rem> mine;
-            for (size_t r = 0; r < regs.size(); r++)
-                for (size_t i = 0; i < regs[r].ifaces.size(); i++)
-                    if (regs[r].ifaces[i].peerRank == peers[p]) mine.push_back({int(r), int(i)});
-            std::sort(mine.begin(), mine.end(), [&](const Rem& a, const Rem& b) {
-                const IfaceHost& A = regs[a.region].ifaces[a.iface];
-                const IfaceHost& B = regs[b.region].ifaces[b.iface];
-                return A.peerRegion != B.peerRegion ? A.peerRegion < B.peerRegion : A.peerIface < B.peerIface;
-            });
+            // receive layout: the peer's patches I read, in ITS (region, iface) order
+            std::map<std::pair<int, int>, int32_t> theirs;
+            for (auto& r : regs)
+                for (auto& I : r.ifaces)
+                    for (const Src& q : sourcesOf(I))
+                        if (q.rank == peers[p])
+                        {
+                            auto it = theirs.find({q.region, q.iface});
+                            if (it != theirs.end() && it->second != q.n)
+                                throw std::runtime_error("two interfaces disagree about the size of a remote patch");
+                            theirs[{q.region, q.iface}] = q.n;
+                        }
             int32_t ro = recvOff[p];
-            for (auto& m : mine)
+            for (auto& kv : theirs)
             {
-                recvSegOff[m.region][m.iface] = ro;
-                ro += regs[m.region].ifaces[m.iface].nPeerFaces;
+                recvSegOff[std::make_tuple(peers[p], kv.first.first, kv.first.second)] = ro;
+                ro += kv.second;
             }
             recvOff[p + 1] = ro;
+        }
+        // zone face -> (piece, position) of the interfaces whose shadow is spread over pieces
+        std::vector<std::vector<std::vector<int32_t>>> zonePiece(regs.size()), zonePos(regs.size());
+        for (size_t r = 0; r < regs.size(); r++)
+        {
+            zonePiece[r].resize(regs[r].ifaces.size());
+            zonePos[r].resize(regs[r].ifaces.size());
+            for (size_t i = 0; i < regs[r].ifaces.size(); i++)
+            {
+                const IfaceHost& I = regs[r].ifaces[i];
+                if (I.pieces.empty()) continue;
+                zonePiece[r][i].assign((size_t)I.nPeerFaces, -1);
+                zonePos[r][i].assign((size_t)I.nPeerFaces, -1);
+                for (size_t k = 0; k < I.pieces.size(); k++)
+                    for (size_t q = 0; q < I.pieces[k].zoneAddr.size(); q++)
+                    {
+                        const int32_t z = I.pieces[k].zoneAddr[q];
+                        if (z < 0 || z >= I.nPeerFaces) throw std::runtime_error("zone address of a shadow piece out of range");
+                        if (zonePiece[r][i][z] >= 0) throw std::runtime_error("two shadow pieces hold the same zone face");
+                        zonePiece[r][i][z] = int32_t(k);
+                        zonePos[r][i][z] = int32_t(q);
+                    }
+            }
         }
         // entries, keyed (row, phase, iface, face)
         struct Ent
@@ -1101,17 +1150,26 @@ struct IfacePlan
             const IfaceHost& I = regs[E.region].ifaces[E.iface];
             entCoef.push_back(int32_t(I.coefOffset + E.face));
             auto srcCode = [&](int peerFace) -> int32_t {
-                if (I.peerRank == myRank)
-                {
-                    if (I.peerRegion < 0 || I.peerRegion >= int(regs.size()) || I.peerIface < 0 ||
-                        I.peerIface >= int(regs[I.peerRegion].ifaces.size()))
-                        throw std::runtime_error("interface peer (region, iface) does not exist on this rank");
-                    const IfaceHost& Q = regs[I.peerRegion].ifaces[I.peerIface];
-                    if (peerFace < 0 || peerFace >= Q.nFaces) throw std::runtime_error("GGI address out of range of the shadow patch");
-                    return S.slotOfCell[regs[I.peerRegion].cellOffset + Q.faceCells[peerFace]];
-                }
+                int rank = I.peerRank, region = I.peerRegion, iface = I.peerIface, pos = peerFace;
                 if (peerFace < 0 || peerFace >= I.nPeerFaces) throw std::runtime_error("GGI address out of range of the shadow patch");
-                return -1 - (recvSegOff[E.region][E.iface] + peerFace);
+                if (!I.pieces.empty())
+                {
+                    const int32_t k = zonePiece[E.region][E.iface][peerFace];
+                    if (k < 0) throw std::runtime_error("GGI address names a zone face that no shadow piece holds");
+                    rank = I.pieces[k].rank;
+                    region = I.pieces[k].region;
+                    iface = I.pieces[k].iface;
+                    pos = zonePos[E.region][E.iface][peerFace];
+                }
+                if (rank == myRank)
+                {
+                    if (region < 0 || region >= int(regs.size()) || iface < 0 || iface >= int(regs[region].ifaces.size()))
+                        throw std::runtime_error("interface peer (region, iface) does not exist on this rank");
+                    const IfaceHost& Q = regs[region].ifaces[iface];
+                    if (pos < 0 || pos >= Q.nFaces) throw std::runtime_error("GGI address out of range of the shadow patch");
+                    return S.slotOfCell[regs[region].cellOffset + Q.faceCells[pos]];
+                }
+                return -1 - (recvSegOff.at(std::make_tuple(rank, region, iface)) + pos);
             };
             if (I.identity)
             {

@@ -78,7 +78,7 @@ def decompose(case: Case, cellToRank: List[np.ndarray], nRanks: int) -> Case:
             ranks[g].regions.append(sub)
         del lo
 
-    # regionCouple pieces (must pair rank-locally; see DESIGN.md multi-GPU section)
+    # regionCouple pieces
     for ri, reg in enumerate(serial):
         for ii, itf in enumerate(reg.interfaces):
             if itf.kind != REGION_COUPLE:
@@ -86,17 +86,35 @@ def decompose(case: Case, cellToRank: List[np.ndarray], nRanks: int) -> Case:
             peer = serial[itf.peerRegion].interfaces[itf.peerIface]
             myRank = cellToRank[ri][itf.faceCells]
             peerRank = cellToRank[itf.peerRegion][peer.faceCells]
-            if itf.ggiOffsets is not None:
-                raise NotImplementedError("decomposition of non-conformal GGI interfaces")
-            if not np.array_equal(myRank, peerRank):
-                raise NotImplementedError(
-                    "regionCouple face pairs must live on the same rank (choose a decomposition that "
-                    "cuts both regions consistently, e.g. z-slabs)")
+            if itf.ggiOffsets is None and np.array_equal(myRank, peerRank):
+                # conformal pair cut consistently: every face pair stays on one rank (regionCouplePolyPatch::localParallel())
+                for g in range(nRanks):
+                    sel = np.nonzero(myRank == g)[0]
+                    ranks[g].regions[ri].interfaces.append(Interface(
+                        REGION_COUPLE, localIdx[ri][itf.faceCells[sel]], itf.bouCoeffs[sel].copy(),
+                        itf.intCoeffs[sel].copy(), g, itf.peerRegion, itf.peerIface, name=itf.name))
+                continue
+            # general case (non-conformal GGI, or the two regions cut at different places: the shipped n (2 1 2)): the pair
+            # is interpolated on the global zones.  The zone of a patch = its serial face list; rank g holds the faces
+            # sel_g (its zoneAddressing); the GGI rows of those faces address shadow ZONE faces; the shadow zone is held in
+            # pieces by the ranks with shadow faces.
+            nZone = int(peer.faceCells.size)
+            if itf.ggiOffsets is None:
+                go, ga, gw = np.arange(itf.nFaces + 1, dtype=np.int32), np.arange(itf.nFaces, dtype=np.int32), np.ones(itf.nFaces)
+            else:
+                go, ga, gw = itf.ggiOffsets, itf.ggiAddr, itf.ggiWeights
+            pieces = [(h, itf.peerRegion, itf.peerIface, np.nonzero(peerRank == h)[0].astype(np.int32)) for h in range(nRanks)]
+            pieces = [p for p in pieces if p[3].size]
             for g in range(nRanks):
                 sel = np.nonzero(myRank == g)[0]
+                cnt = (go[sel + 1] - go[sel]).astype(np.int64)
+                off = np.zeros(sel.size + 1, np.int32)
+                off[1:] = np.cumsum(cnt)
+                idx = (np.repeat(go[sel].astype(np.int64) - off[:-1], cnt) + np.arange(int(off[-1]))) if sel.size else np.zeros(0, np.int64)
                 ranks[g].regions[ri].interfaces.append(Interface(
-                    REGION_COUPLE, localIdx[ri][itf.faceCells[sel]], itf.bouCoeffs[sel].copy(),
-                    itf.intCoeffs[sel].copy(), g, itf.peerRegion, itf.peerIface, name=itf.name))
+                    REGION_COUPLE, localIdx[ri][itf.faceCells[sel]], itf.bouCoeffs[sel].copy(), itf.intCoeffs[sel].copy(),
+                    g, itf.peerRegion, itf.peerIface, off, np.asarray(ga)[idx].astype(np.int32), np.asarray(gw)[idx].copy(),
+                    name=itf.name, nPeerFaces=nZone, pieces=list(pieces) if sel.size else []))
 
     # processor patches, appended last, ordered by neighbour rank
     for ri, reg in enumerate(serial):
@@ -139,3 +157,33 @@ def decompose_cht_zslabs(case: Case, fluid, solid, nRanks: int) -> Case:
         k = reg.cell_ijk_layer().astype(np.int64)
         maps.append((k * nRanks // reg.nz).astype(np.int32))
     return decompose(case, maps, nRanks)
+
+
+def decompose_cht_simple(case: Case, fluid, solid, n: Sequence[int]) -> Case:
+    """``method simple; n (nx ny nz)`` applied to each region on its own, as decomposePar does it
+    (tutorials/conjugateHeatTransfer/flowOverHeatedPlate/system/{fluid,solid}/decomposeParDict:17-27, n (2 1 2)): the
+    fluid (x in [-0.5, 3]) and the plate (x in [0, 1]) are cut at different x, so pieces of the regionCouple pair face
+    other ranks (Interface.pieces)."""
+    maps = [simple_cell_to_rank(reg.cell_xyz(), n) for reg in (fluid, solid)]
+    return decompose(case, maps, int(np.prod(n)))
+
+
+def flatten_ranks(case: Case) -> Case:
+    """All sub-domains of a decomposed case as the regions of ONE rank (row = rank * nRegions + region, the oracle's row
+    order): the same coupled system, solvable on one device; processor patches become interfaces between regions."""
+    import copy
+    nReg = case.nRegions
+    regions = []
+    for rk in case.ranks:
+        for reg in rk.regions:
+            q = copy.copy(reg)
+            q.interfaces = []
+            for itf in reg.interfaces:
+                j = copy.copy(itf)
+                j.peerRegion = itf.peerRank * nReg + itf.peerRegion
+                j.peerRank = 0
+                if getattr(itf, "pieces", None):
+                    j.pieces = [(0, h * nReg + pr, pi, za) for (h, pr, pi, za) in itf.pieces]
+                q.interfaces.append(j)
+            regions.append(q)
+    return Case(case.name + "_flat", [RankSystem(0, 1, regions)])

@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "b200_amul", "b200_precondition", "b200_get_rD", "b200_reduce", "b200_residual", "b200_sum_a",
     "b200_set_profiling", "b200_get_kernel_times", "b200_launch_count", "b200_debug_sweep_stats",
     "b200_ggi_interpolate", "b200_patch_face_to_global", "b200_global_face_to_patch",
-    "b200_sys_set_interface_attached", "b200_sys_set_interface_ggi",
+    "b200_sys_set_interface_attached", "b200_sys_set_interface_ggi", "b200_sys_set_interface_pieces",
     "b200_sys_set_fv_geometry", "b200_sys_assemble_T",
     "b200_ggi_build", "b200_ggi_fetch", "b200_direct_map_build", "b200_direct_map_transfer",
 ]
@@ -84,6 +84,7 @@ def load():
     L.b200_sys_set_interface_coeffs.argtypes = [vp, C.c_int, C.c_int, dp, dp]
     L.b200_sys_set_interface_attached.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.b200_sys_set_interface_ggi.argtypes = [vp, C.c_int, C.c_int, C.c_int32, ip, ip, dp]
+    L.b200_sys_set_interface_pieces.argtypes = [vp, C.c_int, C.c_int, C.c_int, ip, ip, ip, ip, ip]
     L.b200_sys_set_fv_geometry.argtypes = [vp, C.c_int, dp, dp, dp, C.c_int32, ip, dp, dp]
     L.b200_sys_assemble_T.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, dp, dp]
     L.b200_sys_num_cells.argtypes = [vp]
@@ -263,6 +264,13 @@ class LduSystem:
                 got = ctx.check(L.b200_sys_add_interface(self.h, r, itf.kind, itf.nFaces, _ip(fc), itf.peerRank, itf.peerRegion,
                                                          itf.peerIface, nPeer, _ip(go), _ip(ga), _dp(gw)))
                 assert got == i
+                pieces = getattr(itf, "pieces", None)
+                if pieces:   # shadow patch spread over ranks: (rank, region, iface, zoneAddr) per piece
+                    off = np.zeros(len(pieces) + 1, np.int32)
+                    off[1:] = np.cumsum([len(p[3]) for p in pieces])
+                    za = _i32(np.concatenate([np.asarray(p[3], np.int32) for p in pieces]) if off[-1] else np.zeros(0, np.int32))
+                    pr, pg, pi = (_i32([p[k] for p in pieces]) for k in range(3))
+                    ctx.check(L.b200_sys_set_interface_pieces(self.h, r, i, len(pieces), _ip(pr), _ip(pg), _ip(pi), _ip(off), _ip(za)))
         ctx.check(L.b200_sys_finalize(self.h))
         self.sizes = [reg.nCells for reg in rs.regions]
         if set_coeffs:

@@ -197,6 +197,11 @@ class StructuredRegion:
             xs.append(np.broadcast_to(xc[None, None, :], (self.nz, self.ny, blk.nx)).reshape(-1))
         return np.concatenate(xs)
 
+    def cell_xyz(self):
+        """Cell-centre coordinates as simpleGeomDecomp sorts them (x exact; y and z through the row / layer index, which
+        is monotone in the coordinate)."""
+        return self.cell_centres_x(), self.cell_j().astype(np.float64), self.cell_ijk_layer().astype(np.float64)
+
     def cell_ijk_layer(self) -> np.ndarray:
         """z-layer index k of every cell (used by the z-slab decomposition)."""
         ks = []

@@ -31,6 +31,11 @@ typedef struct orc_iface
     double* ggiWeights;
     double* buf; /* matrixUpdateBuffer_ written by init of THIS patch; size = peer nFaces */
     int bufSize;
+    /* shadow patch spread over several rows (decomposed regionCouple pair, interpolated on the global zones): zone face z
+       of the shadow is face zonePos[z] of interface zoneIface[z] of row zoneRow[z]; pnf = this patch's own neighbour values */
+    int nZone;
+    int *zoneRow, *zoneIface, *zonePos;
+    double* pnf;
 } orc_iface;
 
 typedef struct orc_row
@@ -99,6 +104,10 @@ void orc_destroy(orc_sys* s)
             free(I->ggiAddr);
             free(I->ggiWeights);
             free(I->buf);
+            free(I->zoneRow);
+            free(I->zoneIface);
+            free(I->zonePos);
+            free(I->pnf);
         }
         free(R->ifaces);
     }
@@ -205,6 +214,27 @@ int orc_add_iface(orc_sys* s, int row, int kind, int nFaces, const int* faceCell
     for (int i = 0; i < nFaces; i++)
         if (faceCells[i] < 0 || faceCells[i] >= R->nCells) return -2;
     return R->nIfaces++;
+}
+
+/* Decomposed regionCouple pair (regionCouplePolyPatch not localParallel()): the GGI addresses of interface (row, iface) are
+ * face labels of the shadow's global ZONE; zoneRow/zoneIface/zonePos say where each zone face lives (-1: not held by anybody,
+ * must not be addressed).  foam-extend expands the shadow's patchInternalField to the zone, interpolates with the zone
+ * addressing and filters to the local faces: pnf[i] = sum_k zoneField[addr[k]] * w[k], evaluated here on the receiving side. */
+int orc_set_iface_zone(orc_sys* s, int row, int iface, int nZone, const int* zoneRow, const int* zoneIface, const int* zonePos)
+{
+    if (row < 0 || row >= s->nRows) return -1;
+    orc_row* R = &s->rows[row];
+    if (iface < 0 || iface >= R->nIfaces) return -1;
+    orc_iface* I = &R->ifaces[iface];
+    if (!I->ggiOffsets || nZone < 0) return -2;
+    for (int k = 0; k < I->ggiOffsets[I->nFaces]; k++)
+        if (I->ggiAddr[k] < 0 || I->ggiAddr[k] >= nZone || zoneRow[I->ggiAddr[k]] < 0) return -3;
+    I->nZone = nZone;
+    I->zoneRow = (int*)dupmem(zoneRow, sizeof(int) * (size_t)(nZone ? nZone : 1));
+    I->zoneIface = (int*)dupmem(zoneIface, sizeof(int) * (size_t)(nZone ? nZone : 1));
+    I->zonePos = (int*)dupmem(zonePos, sizeof(int) * (size_t)(nZone ? nZone : 1));
+    I->pnf = (double*)malloc(sizeof(double) * (size_t)(I->nFaces ? I->nFaces : 1));
+    return 0;
 }
 
 int orc_total_cells(const orc_sys* s) { return s->total; }
@@ -459,10 +489,29 @@ void orc_ggi_interpolate(int nTo, const int* offsets, const int* addr, const dou
  * (monolithicCouplingFvPatchField.C:392-405; processorFvPatchField send). */
 static int iface_init(orc_sys* s, orc_row* R, orc_iface* I, const double* x)
 {
+    if (I->zoneRow)
+    { /* shadow spread over rows: gather the zone values this patch's rows address, in addressing order */
+        for (int i = 0; i < I->nFaces; i++)
+        {
+            double acc = 0.0;
+            for (int k = I->ggiOffsets[i]; k < I->ggiOffsets[i + 1]; k++)
+            {
+                const int z = I->ggiAddr[k];
+                const orc_row* SR = &s->rows[I->zoneRow[z]];
+                if (I->zoneIface[z] < 0 || I->zoneIface[z] >= SR->nIfaces) return -3;
+                const orc_iface* Q = &SR->ifaces[I->zoneIface[z]];
+                if (I->zonePos[z] < 0 || I->zonePos[z] >= Q->nFaces) return -3;
+                acc += x[SR->offset + Q->faceCells[I->zonePos[z]]] * I->ggiWeights[k];
+            }
+            I->pnf[i] = acc;
+        }
+        return 0;
+    }
     if (I->peerRow < 0 || I->peerRow >= s->nRows) return -3;
     orc_row* PR = &s->rows[I->peerRow];
     if (I->peerIface < 0 || I->peerIface >= PR->nIfaces) return -3;
     orc_iface* Q = &PR->ifaces[I->peerIface];
+    if (Q->zoneRow) return 0; /* the peer gathers its neighbour values from the zone itself */
     const double* xr = x + R->offset;
     int nOut = Q->nFaces;
     if (I->bufSize < nOut)
@@ -494,8 +543,7 @@ static int iface_init(orc_sys* s, orc_row* R, orc_iface* I, const double* x)
 static void iface_update(orc_sys* s, orc_row* R, orc_iface* I, const double* coeffs, double* y,
                          int switchToLhs)
 {
-    orc_iface* P = &s->rows[I->peerRow].ifaces[I->peerIface];
-    const double* pnf = P->buf;
+    const double* pnf = I->zoneRow ? I->pnf : s->rows[I->peerRow].ifaces[I->peerIface].buf;
     double* yr = y + R->offset;
     if (switchToLhs)
         for (int i = 0; i < I->nFaces; i++) yr[I->faceCells[i]] += coeffs[i] * pnf[i];

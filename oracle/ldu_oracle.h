@@ -110,6 +110,8 @@ int orc_set_coeffs(orc_sys*, int row, const double* diag, const double* upper, c
 int orc_add_iface(orc_sys*, int row, int kind, int nFaces, const int* faceCells,
                   const double* bouCoeffs, const double* intCoeffs, int peerRow, int peerIface,
                   const int* ggiOffsets, const int* ggiAddr, const double* ggiWeights);
+/* regionCouple pair whose shadow patch is spread over rows (decomposed case, interpolation on the global zones) */
+int orc_set_iface_zone(orc_sys*, int row, int iface, int nZone, const int* zoneRow, const int* zoneIface, const int* zonePos);
 int orc_total_cells(const orc_sys*);
 
 /* coupledLduMatrix::Amul / Tmul (Tmul uses intCoeffs on interfaces) */

@@ -58,6 +58,7 @@ def lib():
         L.orc_set_row.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip]
         L.orc_set_coeffs.argtypes = [C.c_void_p, C.c_int, dp, dp, dp]
         L.orc_add_iface.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, ip, dp, dp, C.c_int, C.c_int, ip, ip, dp]
+        L.orc_set_iface_zone.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, ip, ip, ip]
         L.orc_total_cells.argtypes = [C.c_void_p]
         for f in ("orc_amul", "orc_tmul", "orc_precondition", "orc_preconditionT"):
             getattr(L, f).argtypes = [C.c_void_p, dp, dp]
@@ -136,6 +137,19 @@ class OracleSystem:
                                          itf.peerIface, _ip(go), _ip(ga), _dp(gw))
                     if rc < 0:
                         raise RuntimeError(f"orc_add_iface failed rc={rc}")
+        # shadow patches spread over ranks (decompose.py): the zone table, once every row has its interfaces
+        for rk in case.ranks:
+            for ri, reg in enumerate(rk.regions):
+                for ii, itf in enumerate(reg.interfaces):
+                    if not getattr(itf, "pieces", None):
+                        continue
+                    nZone = int(itf.nPeerFaces)
+                    zr, zi, zp = (np.full(nZone, -1, np.int32) for _ in range(3))
+                    for (h, pr, pi, za) in itf.pieces:
+                        zr[za], zi[za], zp[za] = h * nReg + pr, pi, np.arange(len(za), dtype=np.int32)
+                    rc = L.orc_set_iface_zone(self.h, rk.rank * nReg + ri, ii, nZone, _ip(zr), _ip(zi), _ip(zp))
+                    if rc:
+                        raise RuntimeError(f"orc_set_iface_zone failed rc={rc}")
         self.n = L.orc_total_cells(self.h)
 
     def __del__(self):
