@@ -98,52 +98,61 @@ int Foam::b200Binding::precondId(const word& name)
 namespace Foam
 {
 
-// ragged -> CSR
-static void flatten(const labelListList& addr, const scalarListList& w, labelList& offsets, labelList& flatAddr, scalarField& flatW)
+// ragged -> CSR; rows: the rows to take (empty: all)
+static void flatten
+(
+    const labelListList& addr, const scalarListList& w, const labelList& rows, const bool allRows,
+    labelList& offsets, labelList& flatAddr, scalarField& flatW
+)
 {
-    offsets.setSize(addr.size() + 1);
+    const label nRows = allRows ? addr.size() : rows.size();
+    offsets.setSize(nRows + 1);
     label n = 0;
-    forAll (addr, i)
+    for (label i = 0; i < nRows; i++)
     {
         offsets[i] = n;
-        n += addr[i].size();
+        n += addr[allRows ? i : rows[i]].size();
     }
-    offsets[addr.size()] = n;
+    offsets[nRows] = n;
     flatAddr.setSize(n);
     flatW.setSize(n);
     n = 0;
-    forAll (addr, i)
+    for (label i = 0; i < nRows; i++)
     {
-        forAll (addr[i], k)
+        const label row = allRows ? i : rows[i];
+        forAll (addr[row], k)
         {
-            flatAddr[n] = addr[i][k];
-            flatW[n++] = w[i][k];
+            flatAddr[n] = addr[row][k];
+            flatW[n++] = w[row][k];
         }
     }
 }
 
 // The tables regionCoupleFvPatch::interpolate() applies to the shadow's patchInternalField
 // (monolithicCouplingFvPatchField.C:214-217, 401-404): values of the shadow patch seen on the faces of rc.
+// localParallel(): the interpolator lives on the two patches.  Otherwise (the pair is spread over processors, e.g. the
+// shipped  simple; n (2 1 2)  of flowOverHeatedPlate) it lives on the global face zones: rows = zone faces, addresses =
+// shadow zone faces; this rank needs the rows zoneAddressing() of its own faces, and the library is told which rank
+// holds which shadow zone faces (pass 4 of describe, b200_sys_set_interface_pieces).
 static void regionCoupleTables(const regionCoupleFvPatch& rc, b200Binding::ifaceInfo& I)
 {
     const regionCouplePolyPatch& pp = refCast<const regionCouplePolyPatch>(rc.patch());
-    if (Pstream::parRun() && !rc.localParallel())
-    {
-        FatalErrorIn("b200Binding::describe(...)")
-            << "regionCouple patch " << pp.name() << " and its shadow are spread over several processors: "
-            << "this version of libb200ldu needs both sides of a regionCouple pair on one rank "
-            << "(decompose the two regions consistently along the interface)" << abort(FatalError);
-    }
-    I.nPeerFaces = rc.shadow().size();
+    I.zoneMode = Pstream::parRun() && !rc.localParallel();
+    I.nPeerFaces = I.zoneMode ? pp.shadow().zone().size() : rc.shadow().size();
+    if (I.zoneMode) I.zoneAddr = pp.zoneAddressing();
     if (pp.master())
     {
         // interpolate() = patchToPatch().slaveToMaster(): result[mf] = sum_k ff[masterAddr[mf][k]]*masterWeights[mf][k]
-        flatten(pp.patchToPatch().masterAddr(), pp.patchToPatch().masterWeights(), I.ggiOffsets, I.ggiAddr, I.ggiWeights);
+        flatten(pp.patchToPatch().masterAddr(), pp.patchToPatch().masterWeights(), I.zoneAddr, !I.zoneMode, I.ggiOffsets, I.ggiAddr, I.ggiWeights);
     }
     else
     {
         // interpolate() = shadow().patchToPatch().masterToSlave(): the master owns the interpolator
-        flatten(pp.shadow().patchToPatch().slaveAddr(), pp.shadow().patchToPatch().slaveWeights(), I.ggiOffsets, I.ggiAddr, I.ggiWeights);
+        flatten
+        (
+            pp.shadow().patchToPatch().slaveAddr(), pp.shadow().patchToPatch().slaveWeights(), I.zoneAddr, !I.zoneMode,
+            I.ggiOffsets, I.ggiAddr, I.ggiWeights
+        );
     }
 }
 
@@ -271,6 +280,53 @@ void Foam::b200Binding::describe
                     << Pstream::myProcNo() << " that matches patch " << I.patch << abort(FatalError);
             }
         }
+
+        // ---- pass 4: regionCouple pairs on the global zones: who holds which faces of the shadow zone.  Every rank
+        // publishes (row, patch, interface index, nFaces, zoneAddressing...) of its zone-mode regionCouple patches.
+        {
+            List<labelList> zt(Pstream::nProcs());
+            DynamicList<label> mine;
+            forAll (ifaces, r) forAll (ifaces[r], i)
+            {
+                const ifaceInfo& I = ifaces[r][i];
+                if (I.kind != B200_IFACE_REGION_COUPLE || !I.zoneMode) continue;
+                mine.append(r);
+                mine.append(I.patch);
+                mine.append(i);
+                mine.append(I.zoneAddr.size());
+                forAll (I.zoneAddr, f) mine.append(I.zoneAddr[f]);
+            }
+            zt[Pstream::myProcNo()] = labelList(mine);
+            Pstream::gatherList(zt);
+            Pstream::scatterList(zt);
+            forAll (ifaces, r) forAll (ifaces[r], i)
+            {
+                ifaceInfo& I = ifaces[r][i];
+                if (I.kind != B200_IFACE_REGION_COUPLE || !I.zoneMode) continue;
+                const regionCoupleFvPatch& rc = refCast<const regionCoupleFvPatch>(interfaces[r][I.patch].coupledInterface());
+                DynamicList<label> pRank, pIface, pOff, pAddr;
+                pOff.append(0);
+                if (I.zoneAddr.size())   // an empty piece reads nothing
+                {
+                    forAll (zt, h)
+                    {
+                        const labelList& t = zt[h];
+                        for (label e = 0; e + 3 < t.size(); e += 4 + t[e + 3])
+                        {
+                            if (t[e] != I.peerRegion || t[e + 1] != rc.shadowIndex() || t[e + 3] == 0) continue;
+                            pRank.append(h);
+                            pIface.append(t[e + 2]);
+                            for (label f = 0; f < t[e + 3]; f++) pAddr.append(t[e + 4 + f]);
+                            pOff.append(pAddr.size());
+                        }
+                    }
+                }
+                I.pieceRank = labelList(pRank);
+                I.pieceIface = labelList(pIface);
+                I.pieceOffsets = labelList(pOff);
+                I.pieceZoneAddr = labelList(pAddr);
+            }
+        }
     }
 }
 
@@ -347,6 +403,19 @@ Foam::b200Binding::systemEntry& Foam::b200Binding::system
             {
                 const regionCoupleFvPatch& rc = refCast<const regionCoupleFvPatch>(interfaces[r][I.patch].coupledInterface());
                 check(b200_sys_set_interface_attached(E.sys, r, i, rc.coupled() ? 1 : 0), where);
+                if (I.zoneMode && I.pieceRank.size())
+                {
+                    labelList pieceRegion(I.pieceRank.size(), I.peerRegion);
+                    check
+                    (
+                        b200_sys_set_interface_pieces
+                        (
+                            E.sys, r, i, I.pieceRank.size(), I.pieceRank.begin(), pieceRegion.begin(), I.pieceIface.begin(),
+                            I.pieceOffsets.begin(), I.pieceZoneAddr.begin()
+                        ),
+                        where
+                    );
+                }
             }
         }
     }
@@ -462,6 +531,13 @@ void Foam::b200Binding::dump
             const ifaceInfo& I = ifaces[r][i];
             const unallocLabelList& fc = addr.patchAddr(I.patch);
             const bool ggi = I.ggiOffsets.size() > 0;
+            if (I.zoneMode)
+            {
+                FatalErrorIn("b200Binding::dump(...)")
+                    << "patch " << I.patch << " of row " << r << ": regionCouple pairs spread over processors are not covered by the "
+                    << "B200LDU1 format; record golden data with a decomposition that keeps the pair on one processor"
+                    << abort(FatalError);
+            }
             putI(os, I.kind);
             putI(os, fc.size());
             putI(os, I.peerRank);

@@ -102,6 +102,12 @@ bool regionCouplePolyPatch::master() const { return g_rc[g_polyOwner[this]].mast
 bool regionCouplePolyPatch::attached() const { return true; }
 const regionCouplePolyPatch& regionCouplePolyPatch::shadow() const { return *g_rc[g_rc[g_polyOwner[this]].shadow].poly; }
 const ggiZoneInterpolation& regionCouplePolyPatch::patchToPatch() const { return g_interp; }
+// zone members: reached only for pairs spread over processors (localParallel() false), which this harness does not set up
+static faceZone g_zone;
+static labelList g_zoneAddr;
+label faceZone::size() const { return 0; }
+const faceZone& regionCouplePolyPatch::zone() const { return g_zone; }
+const labelList& regionCouplePolyPatch::zoneAddressing() const { return g_zoneAddr; }
 const labelListList& ggiZoneInterpolation::masterAddr() const { return g_mAddr; }
 const scalarListList& ggiZoneInterpolation::masterWeights() const { return g_mW; }
 const labelListList& ggiZoneInterpolation::slaveAddr() const { return g_sAddr; }
@@ -152,6 +158,7 @@ int b200_sys_finalize(b200_sys*) { return -1; }
 int b200_sys_set_coeffs(b200_sys*, int, const double*, const double*, const double*) { return -1; }
 int b200_sys_set_interface_coeffs(b200_sys*, int, int, const double*, const double*) { return -1; }
 int b200_sys_set_interface_attached(b200_sys*, int, int, int) { return -1; }
+int b200_sys_set_interface_pieces(b200_sys*, int, int, int, const int32_t*, const int32_t*, const int32_t*, const int32_t*, const int32_t*) { return -1; }
 int b200_sys_set_interface_ggi(b200_sys*, int, int, int32_t, const int32_t*, const int32_t*, const double*) { return -1; }
 }
 
