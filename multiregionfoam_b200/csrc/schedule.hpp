@@ -30,7 +30,9 @@
 #pragma once
 
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <numeric>
@@ -215,9 +217,37 @@ struct PipeSchedule
         return ch;
     }
 
+    // Warps of linked x-lines are filled across the end of a sequence of linked lines (the j-lines of one k-plane: 164 lines
+    // = 5 full warps + one of 4 lanes) with the head of a later sequence (a plane further on), where the dependencies allow
+    // it: padding lanes cost slots, and slots cost bandwidth in every kernel of the solve.  If the merged warps make the group
+    // graph cyclic (unstructured corner cases) the schedule is rebuilt without merging.
+    bool mergeSequences = true;
+    double mergeGap = 1.5;      // measured on C3 (64 M cells): 0.5 .. 8 scanned, DESIGN.md section 4
+    int mergeMinGroups = 444;   // 1.5 x the 296 resident sweep CTAs: below that the sweep is latency-bound and merging only adds waits
     void build(const GlobalLdu& g, const std::vector<RegionHost>& regs)
     {
+        if (const char* e = getenv("B200_MERGE_SEQ")) mergeSequences = atoi(e) != 0; // developer knobs
+        if (const char* e = getenv("B200_MERGE_GAP")) mergeGap = atof(e);
+        if (const char* e = getenv("B200_MERGE_MIN_GROUPS")) mergeMinGroups = atoi(e);
+        if (mergeSequences)
+        {
+            try
+            {
+                build_impl(g, regs);
+                return;
+            }
+            catch (const std::runtime_error&)
+            {
+                mergeSequences = false;
+            }
+        }
+        build_impl(g, regs);
+    }
+    void build_impl(const GlobalLdu& g, const std::vector<RegionHost>& regs)
+    {
         N = g.N;
+        nLineRegions = nBlockRegions = 0;
+        nPaths = nLinkedGroups = nMemTermsF = nShflTermsF = nOwnTermsF = 0;
         Placement P;
         P.grp.assign(N, -1);
         P.tim.assign(N, -1);
@@ -397,36 +427,74 @@ struct PipeSchedule
             // sequences of linked paths, cut into warps of <= 32 lanes (skew = lane)
             std::vector<std::vector<int32_t>> groups; // lanes -> path
             std::vector<int32_t> singles;
+            std::vector<std::vector<int32_t>> seqs;
             for (int p = 0; p < nP; p++)
             {
                 if (linkPred[p] >= 0) continue;
                 std::vector<int32_t> seq;
                 for (int q = p; q >= 0; q = linkSucc[q]) seq.push_back(q);
-                size_t i = 0;
+                seqs.push_back(std::move(seq));
+            }
+            // admit q as the next lane only if all its dependencies on lanes already in this warp are exactly kSkew
+            // time steps old - the aligned link to the previous lane - and no lane of the warp depends on it
+            auto admit = [&](std::vector<int32_t>& lanes, int q) {
+                for (auto& e : preds[q])
+                {
+                    auto it = std::find(lanes.begin(), lanes.end(), e.first);
+                    if (it == lanes.end()) continue;
+                    if (!(e.second && size_t(it - lanes.begin()) == lanes.size() - 1)) return false;
+                }
+                for (int sq : succs[q])
+                    if (std::find(lanes.begin(), lanes.end(), sq) != lanes.end()) return false;
+                lanes.push_back(q);
+                return true;
+            };
+            // The last warp of a sequence (the j-lines of one k-plane: 164 lines = 5 warps + 4 lanes) is filled with the
+            // first lines of a LATER sequence.  The warp starts when the sequence's chain of warps has reached its end, so
+            // the partner must be a sequence that would not have started earlier anyway: its head lies mergeGap levels per
+            // warp of this sequence further down the path graph (the next plane would wait for this whole plane and
+            // serialise the sweep; measured: 4.6 x slower).
+            const int S = int(seqs.size());
+            std::vector<size_t> headOff(S, 0);
+            // only where the sweep is bound by throughput: many more warps than the device keeps resident (the region's
+            // count scaled to the whole system)
+            int64_t estWarps = 0;
+            for (const auto& seq : seqs) estWarps += int64_t(seq.size() + 31) / 32;
+            const bool merge = mergeSequences && double(estWarps) * double(N) / double(n) >= double(mergeMinGroups);
+            for (int si = 0; si < S; si++)
+            {
+                const auto& seq = seqs[si];
+                size_t i = headOff[si];
+                int nWarps = 0;
                 while (i < seq.size())
                 {
                     std::vector<int32_t> lanes{seq[i]};
                     size_t j = i + 1;
                     for (; j < seq.size() && lanes.size() < 32; j++)
+                        if (!admit(lanes, seq[j])) break;
+                    i = j;
+                    nWarps++;
+                    if (merge && i >= seq.size() && lanes.size() < 32)
                     {
-                        // admit seq[j] as the next lane only if all its dependencies on lanes already in
-                        // this warp are exactly kSkew time steps old: the aligned link to the previous lane
-                        const int q = seq[j];
-                        bool okLane = true;
-                        for (auto& e : preds[q])
+                        const int need = pLevel[seq[0]] + int(std::ceil(mergeGap * nWarps));
+                        int tried = 0;
+                        for (int sj = si + 1; sj < S && tried < 4; sj++)
                         {
-                            auto it = std::find(lanes.begin(), lanes.end(), e.first);
-                            if (it == lanes.end()) continue;
-                            if (!(e.second && size_t(it - lanes.begin()) == lanes.size() - 1)) okLane = false;
+                            if (headOff[sj] != 0 || pLevel[seqs[sj][0]] < need) continue;
+                            tried++;
+                            size_t t = 0;
+                            while (t < seqs[sj].size() && lanes.size() < 32 && admit(lanes, seqs[sj][t])) t++;
+                            if (t > 0)
+                            {
+                                headOff[sj] = t;
+                                break;
+                            }
                         }
-                        if (!okLane) break;
-                        lanes.push_back(q);
                     }
                     if (lanes.size() == 1)
                         singles.push_back(lanes[0]);
                     else
                         groups.push_back(lanes);
-                    i = j;
                 }
             }
             nLinkedGroups += int64_t(groups.size());

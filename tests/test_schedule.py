@@ -57,9 +57,10 @@ def test_tables_reproduce_oracle_bitwise(emu, golden_addr):
         assert np.array_equal(w, O.precondition(r)), reg.name
 
 
-def test_line_structure_on_structured_mesh(emu):
+def test_line_structure_on_structured_mesh(emu, monkeypatch):
     # x-lines continued across the two block seams are the paths: ny*nz of them; lines linked along j are
     # cut into warps of 32 lanes (41 = 32 + 9 per z-layer); every in-warp dependency travels by shuffle
+    monkeypatch.setenv("B200_MERGE_SEQ", "0")   # the warps of one k-plane on their own
     fluid, _ = flow_over_heated_plate(1, 3)
     reg = synthetic_coeffs(fluid.nCells, fluid.lowerAddr, fluid.upperAddr, symmetric=True)
     _, _, _, stats = run_emu(emu, reg, False, random_vec(reg.nCells, 1), random_vec(reg.nCells, 2))
@@ -80,6 +81,42 @@ def test_line_structure_on_structured_mesh(emu):
     assert stats[7] == nz * 32 * (up16(nx + skew * 31) + up16(nx + skew * 8))
     # only the steps in which some lane crosses one of the two block seams leave the canonical (shuffle, own) form
     assert 0 < stats[14] <= 2 * 2 * 41 * nz and 0 < stats[15] <= 2 * 2 * 41 * nz
+    unmerged_slots = int(stats[7])
+
+    # merged: the last warp of a plane is filled with the first lines of a later one (here, gap 0.5: the next one; 41 * 3 = 123
+    # lines = 3 full warps + 27 lanes instead of 3 x (32 + 9)): fewer padding slots, the same terms, every group on the fast path
+    monkeypatch.delenv("B200_MERGE_SEQ")
+    monkeypatch.setenv("B200_MERGE_GAP", "0.5")
+    monkeypatch.setenv("B200_MERGE_MIN_GROUPS", "0")   # merging is reserved for systems with many more warps than resident CTAs
+    _, _, _, stats = run_emu(emu, reg, False, random_vec(reg.nCells, 1), random_vec(reg.nCells, 2))
+    assert stats[8] == 1 and stats[3] == ny * nz
+    assert stats[0] == -(-ny * nz // 32)
+    assert stats[11] == (nx - 1) * ny * nz
+    assert stats[9] + stats[10] == nx * ny * (nz - 1) + nx * (ny - 1) * nz      # k-1 and j-1 neighbours, by memory or by shuffle
+    cuts = sum(1 for b in range(32, ny * nz, 32) if b % ny)                      # warp boundaries inside a plane
+    assert stats[10] == nx * ((ny - 1) * nz - cuts)                              # j-1 links cut there go through memory
+    assert stats[12] == stats[0] and stats[13] == stats[0]
+    assert stats[7] < 0.7 * unmerged_slots
+
+
+def test_default_merge_gap_pairs_planes_further_apart(emu, monkeypatch):
+    """Default gap (1.5 levels per warp of the sequence): with 2 warps per plane the partner is 3 planes on; the tables still
+    reproduce the oracle bit by bit.  Small systems (fewer warps than 1.5 x the resident CTAs) are not merged at all."""
+    fluid, _ = flow_over_heated_plate(1, 12)
+    reg = synthetic_coeffs(fluid.nCells, fluid.lowerAddr, fluid.upperAddr, symmetric=False)
+    O = pyoracle.OracleSystem(single_region_case(reg))
+    x, r = random_vec(reg.nCells, 1), random_vec(reg.nCells, 2)
+    monkeypatch.setenv("B200_MERGE_SEQ", "0")
+    _, _, _, plain = run_emu(emu, reg, True, x, r)
+    monkeypatch.delenv("B200_MERGE_SEQ")
+    _, _, _, small = run_emu(emu, reg, True, x, r)
+    assert small[0] == plain[0] == 24 and small[7] == plain[7]
+    monkeypatch.setenv("B200_MERGE_MIN_GROUPS", "0")
+    y, w, rD, stats = run_emu(emu, reg, True, x, r)
+    assert stats[0] < plain[0]
+    assert stats[7] < plain[7]
+    O.precond_setup("DILU")
+    assert np.array_equal(y, O.amul(x)) and np.array_equal(rD, O.rD()) and np.array_equal(w, O.precondition(r))
 
 
 def test_block_mode_on_unstructured_mesh(emu, golden_addr):
