@@ -191,213 +191,108 @@ __global__ void __launch_bounds__(kBlkThreads) k_blk_amul(BlkDev M, const double
 }
 
 // ---------------------------------------------------------------------------------------------- sweeps
+// ILUmultiply of BlockCholeskyPrecon.  BWD = false: out[row] = D b[row] - sum_{lower faces, ascending} D (L x[l]);
+// BWD = true: out[row] = a[row] - sum_{owner faces, DESCENDING} D (U x[u]).  rows: level-ordered row list (-1 = pad).
 #ifndef B200_BLK_MINCTAS
-#define B200_BLK_MINCTAS 3 // resident CTAs per SM the sweep is compiled for (register cap 65536 / (256 * this))
+#define B200_BLK_MINCTAS 2 // resident CTAs per SM the sweep is compiled for (register cap 65536 / (256 * this))
 #endif
 #ifndef B200_BLK_CHUNK
-#define B200_BLK_CHUNK 3 // terms of a row whose coefficients are staged before the first poll (a hex cell has 3 per sweep)
+#define B200_BLK_CHUNK 3 // terms of a row whose coefficients are loaded before the first poll (a hex cell has 3 per sweep)
 #endif
-constexpr int kBlkChunk = B200_BLK_CHUNK;
-constexpr int kBlkSweepSmem = kBlkThreads * (kBlkChunk + 1) * 32; // per thread: one 32-byte coefficient row per staged term + its pD row
-
-// this thread's row i of a coefficient block (kind 16: 4 doubles; kind 4 / 1: the one entry) from global memory into its
-// private staging slot, asynchronously: the values are needed only after the neighbours' values have arrived, and they
-// must not occupy registers until then (the number of rows a SM keeps in flight is what bounds the sweep)
-__device__ __forceinline__ void blk_stage_row(int kind, const double* blockBase, int i, unsigned slotAddr0, unsigned slotAddr1)
-{
-    if (kind == 16)
-    {
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slotAddr0), "l"(blockBase + 4 * i) : "memory");
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slotAddr1), "l"(blockBase + 4 * i + 2) : "memory");
-    }
-    else
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(slotAddr0), "l"(blockBase + (kind == 4 ? i : 0)) : "memory");
-}
-__device__ __forceinline__ void blk_stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// ILUmultiply of BlockCholeskyPrecon.  BWD = false: out[row] = D b[row] - sum_{lower faces, ascending} D (L x[l]);
-// BWD = true: out[row] = a[row] - sum_{owner faces, DESCENDING} D (U x[u]).
-// Sweep positions are the rows in wavefront-level order (-1 = pad).  Per position: meta = {row, number of terms, first term},
-// metaNb = the neighbour rows of the first three terms; terms (further neighbours), pack (the coefficient of every term, for the
-// forward sweep of a symmetric matrix already transposed) and pDpos (the preconditioner diagonal) lie in POSITION order, so
-// everything but the polled neighbour values and a[row] is a stream, and the chain of dependent loads before the first
-// poll is  ticket -> meta -> {coefficients, neighbour values}.
 template <bool BWD>
 __global__ void __launch_bounds__(kBlkThreads, B200_BLK_MINCTAS)
-    k_blk_sweep(int uK, int pK, int withFaces, const double* __restrict__ pD, const double* __restrict__ pDpos, const double* __restrict__ pack,
-                const int4* __restrict__ meta, const int4* __restrict__ metaNb, const int2* __restrict__ terms, const int* __restrict__ depMax,
-                int gateSlack, int nPos, const double* __restrict__ a, double* out, unsigned* ticket, unsigned ticketBase, unsigned doneBase, int* err)
+    k_blk_sweep(BlkDev M, int pK, int withFaces, const double* __restrict__ pD, const int4* __restrict__ meta, const int2* __restrict__ terms,
+                int nPos, const double* __restrict__ a, double* out, unsigned* ticket, unsigned ticketBase, int* err)
 {
-    extern __shared__ double2 blkStage[]; // [(slot * 2 + half) * kBlkThreads + thread]
     __shared__ unsigned sTicket;
     if (threadIdx.x == 0) sTicket = atomicAdd(ticket, 1u) - ticketBase;
     __syncthreads();
-    const unsigned myTicket = sTicket;
-    const long long pos = (long long)myTicket * kBlkRowsPerCta + (threadIdx.x >> 2);
-    // positions beyond the end and pad rows only take part in the CTA barriers
-    const int4 mt = pos < nPos ? __ldg(meta + pos) : make_int4(-1, 0, 0, 0);
+    const long long pos = (long long)sTicket * kBlkRowsPerCta + (threadIdx.x >> 2);
+    if (pos >= nPos) return;
+    // {row, number of terms, first term}: the terms (face, neighbour) of a row lie in sweep order, rows in position order,
+    // so the chain of dependent loads before the first poll is  ticket -> meta -> terms -> coefficients
+    const int4 mt = __ldg(meta + pos);
     const int row = mt.x;
-    const bool live = row >= 0;
+    if (row < 0) return;
     const int i = threadIdx.x & 3;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned qm = 0xFu << (lane & ~3u);
     const int qb = (int)(lane & ~3u);
-    const unsigned sbase = (unsigned)__cvta_generic_to_shared(blkStage) + threadIdx.x * 16u;
-    auto slotAddr = [&](int slot, int half) { return sbase + (unsigned)((slot * 2 + half) * kBlkThreads) * 16u; };
-    auto readRow = [&](int kind, int slot, double* c) {
-        const double2 p0 = blkStage[(slot * 2) * kBlkThreads + threadIdx.x];
-        c[0] = p0.x;
-        if (kind == 16)
-        {
-            const double2 p1 = blkStage[(slot * 2 + 1) * kBlkThreads + threadIdx.x];
-            c[1] = p0.y;
-            c[2] = p1.x;
-            c[3] = p1.y;
-        }
-    };
-    const int k0 = mt.z;
-    const int nTerms = (withFaces && live) ? mt.y : 0; // BlockDiagonalPrecon: x = mult(dDiag, b) only
-    int nbv[kBlkChunk];
     double d[4], xv[4], tv[4];
-    double acc = 0.0;
-    // ---- phase A: everything that does not depend on other rows is put on its way
-    if (live)
+    blk_load_row(pK, pD + (size_t)row * pK, i, d);
+    double acc;
+    if (!BWD)
     {
-        blk_stage_row(pK, pDpos ? pDpos + (size_t)pos * pK : pD + (size_t)row * pK, i, slotAddr(kBlkChunk, 0), slotAddr(kBlkChunk, 1));
-#pragma unroll
-        for (int t = 0; t < kBlkChunk; t++)
-            if (t < nTerms) blk_stage_row(uK, pack + (size_t)(k0 + t) * uK, i, slotAddr(t, 0), slotAddr(t, 1));
-        if (nTerms > 0)
-        {
-            const int4 nb = __ldg(metaNb + pos);
-#pragma unroll
-            for (int t = 0; t < kBlkChunk; t++)
-                nbv[t] = t == 0 ? nb.x : t == 1 ? nb.y : t == 2 ? nb.z : (t < nTerms ? __ldg(terms + k0 + t).y : 0);
-        }
-        if (!BWD)
-            blk_load_x(a, row, xv);
-        else
-            acc = a[4ll * row + i];
+        blk_load_x(a, row, xv);
+        acc = blk_mult_reg(pK, d, xv, i);
     }
-    // ---- gate: CTAs run ahead of the wavefront by several levels (that is what hides the latency of phase A), but rows that
-    // POLL their neighbours' values from far ahead only load the L2 the rows at the front are waiting on.  One thread waits
-    // until the number of finished CTAs (ticket[1]) is within gateSlack of the last CTA this one depends on (depMax, host
-    // table); the row-level polls below then find their values after a few tries.  The count reaches that number whatever
-    // the order CTAs finish in: all CTAs with smaller tickets are resident or done, and they depend on smaller tickets only.
-    if (depMax)
+    else
+        acc = a[4ll * row + i];
+    const int k0 = mt.z;
+    const int nTerms = withFaces ? mt.y : 0; // BlockDiagonalPrecon: x = mult(dDiag, b) only
+    // The rows of one wavefront level wait for the level before: what a row does AFTER its neighbours' values arrive is
+    // the critical path of the whole sweep.  Everything that does not depend on those values - face and neighbour
+    // indices, this thread's row of each coefficient block (from DRAM) - is therefore loaded for up to kChunk terms at
+    // once BEFORE the first poll; after a poll only multiply, quad shuffles and multiply remain (same order of the
+    // terms and of the operations as before).
+    constexpr int kChunk = B200_BLK_CHUNK;
+    const bool tr = !(BWD || M.lK);
+    const double* const coefBase = (BWD || !M.lK) ? M.upper : M.lower;
+    for (int kk0 = 0; kk0 < nTerms; kk0 += kChunk)
     {
-        if (threadIdx.x == 0)
-        {
-            const int need = __ldg(depMax + myTicket) + 1 - gateSlack;
-            const volatile unsigned* done = ticket + 1;
-            long long tries = 0;
-            while ((int)(*done - doneBase) < need)
+        int nbv[kChunk];
+        double cf[kChunk][4];
+#pragma unroll
+        for (int t = 0; t < kChunk; t++)
+            if (kk0 + t < nTerms)
             {
-                __nanosleep(100);
-                if ((++tries & 255) == 255 && *(volatile int*)err) break;
-                if (tries >= (1ll << 23))
-                {
-                    atomicExch(err, 1);
-                    break;
-                }
+                const int2 tm = __ldg(terms + k0 + kk0 + t);
+                const int f = tm.x;
+                nbv[t] = tm.y;
+                blk_load_row_tr(M.uK, coefBase + (size_t)f * M.uK, tr, i, cf[t]);
             }
-        }
-        __syncthreads();
-    }
-    // ---- phase B: the dependent part
-    if (live)
-    {
-        blk_stage_wait();
-        readRow(pK, kBlkChunk, d);
-        if (!BWD) acc = blk_mult_reg(pK, d, xv, i);
-        for (int kk0 = 0; kk0 < nTerms; kk0 += kBlkChunk)
+        // the neighbours of a row mostly sit in the level just before it and arrive together: all of them are polled in
+        // one batch of independent loads per round instead of one after the other
+        double xn[kChunk][4];
+        bool have[kChunk];
+#pragma unroll
+        for (int t = 0; t < kChunk; t++) have[t] = !(kk0 + t < nTerms);
+        for (long long tries = 0;; tries++)
         {
-            if (kk0 > 0)
-            { // polyhedral rows with more terms than one chunk holds: the next chunk, after the previous one was consumed
 #pragma unroll
-                for (int t = 0; t < kBlkChunk; t++)
-                    if (kk0 + t < nTerms)
-                    {
-                        blk_stage_row(uK, pack + (size_t)(k0 + kk0 + t) * uK, i, slotAddr(t, 0), slotAddr(t, 1));
-                        nbv[t] = __ldg(terms + k0 + kk0 + t).y;
-                    }
-                blk_stage_wait();
-            }
-            // the neighbours of a row mostly sit in the level just before it and arrive together: all of them are polled
-            // in one batch of independent loads per round instead of one after the other
-            double xn[kBlkChunk][4];
-            bool have[kBlkChunk];
+            for (int t = 0; t < kChunk; t++)
+                if (!have[t])
+                {
+                    ld_cg2(out + 4ll * nbv[t], xn[t][0], xn[t][1]);
+                    ld_cg2(out + 4ll * nbv[t] + 2, xn[t][2], xn[t][3]);
+                }
+            bool all = true;
 #pragma unroll
-            for (int t = 0; t < kBlkChunk; t++) have[t] = !(kk0 + t < nTerms);
-            for (long long tries = 0;; tries++)
+            for (int t = 0; t < kChunk; t++)
             {
-#pragma unroll
-                for (int t = 0; t < kBlkChunk; t++)
-                    if (!have[t])
-                    {
-                        ld_cg2(out + 4ll * nbv[t], xn[t][0], xn[t][1]);
-                        ld_cg2(out + 4ll * nbv[t] + 2, xn[t][2], xn[t][3]);
-                    }
-                bool all = true;
-#pragma unroll
-                for (int t = 0; t < kBlkChunk; t++)
-                {
-                    if (!have[t]) have[t] = !is_sentinel(xn[t][0]) && !is_sentinel(xn[t][1]) && !is_sentinel(xn[t][2]) && !is_sentinel(xn[t][3]);
-                    all = all && have[t];
-                }
-                if (all) break;
-                if (tries >= 32) __nanosleep(tries > 4096 ? 1000 : 100);
-                if ((tries & 1023) == 1023 && *(volatile int*)err) break;
-                if (tries >= (1ll << 22))
-                {
-                    atomicExch(err, 1);
-                    break;
-                }
+                if (!have[t]) have[t] = !is_sentinel(xn[t][0]) && !is_sentinel(xn[t][1]) && !is_sentinel(xn[t][2]) && !is_sentinel(xn[t][3]);
+                all = all && have[t];
             }
-#pragma unroll
-            for (int t = 0; t < kBlkChunk; t++)
-                if (kk0 + t < nTerms)
-                {
-                    double cf[4];
-                    readRow(uK, t, cf);
-                    const double ti = blk_mult_reg(uK, cf, xn[t], i);
-#pragma unroll
-                    for (int j = 0; j < 4; j++) tv[j] = __shfl_sync(qm, ti, qb + j);
-                    acc -= blk_mult_reg(pK, d, tv, i);
-                }
+            if (all) break;
+            if (tries >= 32) __nanosleep(tries > 4096 ? 1000 : 100);
+            if ((tries & 1023) == 1023 && *(volatile int*)err) break;
+            if (tries >= (1ll << 22))
+            {
+                atomicExch(err, 1);
+                break;
+            }
         }
-        st_relaxed(out + 4ll * row + i, acc);
+#pragma unroll
+        for (int t = 0; t < kChunk; t++)
+            if (kk0 + t < nTerms)
+            {
+                const double ti = blk_mult_reg(M.uK, cf[t], xn[t], i);
+#pragma unroll
+                for (int j = 0; j < 4; j++) tv[j] = __shfl_sync(qm, ti, qb + j);
+                acc -= blk_mult_reg(pK, d, tv, i);
+            }
     }
-    // this CTA's rows are stored: count it as finished
-    if (depMax)
-    {
-        __syncthreads();
-        if (threadIdx.x == 0)
-        {
-            __threadfence();
-            atomicAdd(ticket + 1, 1u);
-        }
-    }
-}
-
-// coefficients of the sweep terms in term order (k_blk_sweep): out[k] = coef[terms[k].x], transposed when tr (square only)
-__global__ void k_blk_pack_coef(long long nTerms, const int2* __restrict__ terms, const double* __restrict__ coef, int K, int tr, double* __restrict__ out)
-{
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nTerms * K) return;
-    const long long k = t / K;
-    const int j = (int)(t - k * K);
-    const int src = (tr && K == 16) ? (j & 3) * 4 + (j >> 2) : j;
-    out[t] = coef[(size_t)terms[k].x * K + src];
-}
-// the preconditioner diagonal in position order
-__global__ void k_blk_pack_pd(long long nPos, const int4* __restrict__ meta, const double* __restrict__ pD, int pK, double* __restrict__ out)
-{
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nPos * pK) return;
-    const long long pos = t / pK;
-    const int row = meta[pos].x;
-    out[t] = row >= 0 ? pD[(size_t)row * pK + (t - pos * pK)] : 0.0;
+    st_relaxed(out + 4ll * row + i, acc);
 }
 
 // 4x4 inverse: Gauss-Jordan with partial pivoting, operation by operation as oracle/blk_oracle.c blk_inv4
@@ -796,8 +691,6 @@ struct b200_blk
     DevBuf<int> l, u, losort, losortStart, ownerStart, rowsF, rowsB;
     DevBuf<int4> metaF, metaB;   // per sweep position {row (-1 pad), number of terms, first term, 0}
     DevBuf<int2> termsF, termsB; // {face, neighbour row} in the order the sweep subtracts them
-    DevBuf<int4> nbF, nbB;       // per sweep position: the neighbour rows of its first three terms
-    DevBuf<double> packF, packB, pDposF, pDposB; // term-ordered coefficients / position-ordered diagonal (Cholesky)
     int nPosF = 0, nPosB = 0, nLevelsF = 0, nLevelsB = 0;
     int dK = 0, uK = 0, lK = 0;
     DevBuf<double> diag, upper, lower;
@@ -809,9 +702,7 @@ struct b200_blk
     double* hostRed = nullptr; // pinned
     int* hostErr = nullptr;    // pinned copy of devErr, refreshed with every reduction
     DevBuf<unsigned> ticket;
-    unsigned ticketBase = 0, doneBase = 0; // ticket[0] / ticket[1] at the start of the next launch
-    DevBuf<int> depMaxF, depMaxB;           // per sweep CTA: the last CTA (ticket) it waits for, -1: none
-    int gateSlack = 0;                      // < 0: no gate
+    unsigned ticketBase = 0;
     DevBuf<int> devErr;
     bool haveCoeffs = false, haveVectors = false;
     // coupled patches (processor patches of a decomposed block matrix; a pair on the same rank is served locally)
@@ -1098,23 +989,6 @@ int blk_precond_setup(b200_blk* s, int precond)
         CK(ctx, cudaGetLastError());
         int rc = blk_check_err(s, "calcPreconDiag");
         if (rc) return rc;
-        if (chol)
-        { // the sweeps stream their coefficients and the diagonal in sweep order (k_blk_sweep)
-            const long long nT = s->nf, nE = nT * s->uK;
-            CK(ctx, s->packF.alloc((size_t)nE));
-            CK(ctx, s->packB.alloc((size_t)nE));
-            CK(ctx, s->pDposF.alloc((size_t)s->nPosF * pK));
-            CK(ctx, s->pDposB.alloc((size_t)s->nPosB * pK));
-            BlkScope k(s, 4);
-            if (nE)
-            {
-                k_blk_pack_coef<<<blk_grid(nE, 256, 1 << 30), 256, 0, ctx->stream>>>(nT, s->termsF.p, s->lK ? s->lower.p : s->upper.p, s->uK, s->lK ? 0 : 1, s->packF.p);
-                k_blk_pack_coef<<<blk_grid(nE, 256, 1 << 30), 256, 0, ctx->stream>>>(nT, s->termsB.p, s->upper.p, s->uK, 0, s->packB.p);
-            }
-            k_blk_pack_pd<<<blk_grid((long long)s->nPosF * pK, 256, 1 << 30), 256, 0, ctx->stream>>>(s->nPosF, s->metaF.p, s->pD.p, pK, s->pDposF.p);
-            k_blk_pack_pd<<<blk_grid((long long)s->nPosB * pK, 256, 1 << 30), 256, 0, ctx->stream>>>(s->nPosB, s->metaB.p, s->pD.p, pK, s->pDposB.p);
-            CK(ctx, cudaGetLastError());
-        }
     }
     s->precond = precond;
     return B200_OK;
@@ -1132,7 +1006,6 @@ int blk_precondition_dev(b200_blk* s, const double* r, double* w)
         return B200_OK;
     }
     const bool chol = s->precond == B200_PRECOND_CHOLESKY;
-    const bool gate = chol && s->gateSlack >= 0;
     // forward (Cholesky) or plain diagonal scaling: the same kernel, without faces when !chol
     double* fwdOut = chol ? s->tmp2.p : w;
     int rc = B200_OK;
@@ -1141,14 +1014,13 @@ int blk_precondition_dev(b200_blk* s, const double* r, double* w)
         rc = blk_fill_sentinel(s, fwdOut, n4);
         if (rc) return rc;
     }
+    BlkDev M = blk_dev(s);
     {
         const unsigned ctas = (unsigned)((s->nPosF + kBlkRowsPerCta - 1) / kBlkRowsPerCta);
         BlkScope k(s, 1);
-        k_blk_sweep<false><<<ctas, kBlkThreads, kBlkSweepSmem, ctx->stream>>>(s->uK, s->pK, chol ? 1 : 0, s->pD.p, chol ? s->pDposF.p : nullptr, s->packF.p, s->metaF.p,
-                                                                               s->nbF.p, s->termsF.p, gate ? s->depMaxF.p : nullptr, s->gateSlack, s->nPosF, r, fwdOut, s->ticket.p, s->ticketBase,
-                                                                               s->doneBase, s->devErr.p);
+        k_blk_sweep<false><<<ctas, kBlkThreads, 0, ctx->stream>>>(M, s->pK, chol ? 1 : 0, s->pD.p, s->metaF.p, s->termsF.p, s->nPosF, r, fwdOut, s->ticket.p,
+                                                                   s->ticketBase, s->devErr.p);
         s->ticketBase += ctas;
-        if (gate) s->doneBase += ctas;
         CK(ctx, cudaGetLastError());
     }
     if (chol)
@@ -1157,10 +1029,9 @@ int blk_precondition_dev(b200_blk* s, const double* r, double* w)
         if (rc) return rc;
         const unsigned ctas = (unsigned)((s->nPosB + kBlkRowsPerCta - 1) / kBlkRowsPerCta);
         BlkScope k(s, 2);
-        k_blk_sweep<true><<<ctas, kBlkThreads, kBlkSweepSmem, ctx->stream>>>(s->uK, s->pK, 1, s->pD.p, s->pDposB.p, s->packB.p, s->metaB.p, s->nbB.p, s->termsB.p,
-                                                                              gate ? s->depMaxB.p : nullptr, s->gateSlack, s->nPosB, fwdOut, w, s->ticket.p, s->ticketBase, s->doneBase, s->devErr.p);
+        k_blk_sweep<true><<<ctas, kBlkThreads, 0, ctx->stream>>>(M, s->pK, 1, s->pD.p, s->metaB.p, s->termsB.p, s->nPosB, fwdOut, w, s->ticket.p, s->ticketBase,
+                                                                  s->devErr.p);
         s->ticketBase += ctas;
-        if (gate) s->doneBase += ctas;
         CK(ctx, cudaGetLastError());
     }
     return B200_OK;
@@ -1401,10 +1272,6 @@ extern "C" int b200_blk_create(b200_ctx* ctx, int32_t nCells, int32_t nFaces, co
     // sweep-ordered term lists: forward = lower faces of the row ascending (losort order), backward = owner faces DESCENDING
     std::vector<int4> metaF(rowsF.size()), metaB(rowsB.size());
     std::vector<int2> termsF((size_t)nFaces), termsB((size_t)nFaces);
-    std::vector<int4> nbF(rowsF.size(), make_int4(0, 0, 0, 0)), nbB(rowsB.size(), make_int4(0, 0, 0, 0));
-    auto firstThree = [](const std::vector<int2>& terms, int k0, int n) {
-        return make_int4(n > 0 ? terms[(size_t)k0].y : 0, n > 1 ? terms[(size_t)k0 + 1].y : 0, n > 2 ? terms[(size_t)k0 + 2].y : 0, 0);
-    };
     {
         int kF = 0, kB = 0;
         for (size_t pos = 0; pos < rowsF.size(); pos++)
@@ -1417,7 +1284,6 @@ extern "C" int b200_blk_create(b200_ctx* ctx, int32_t nCells, int32_t nFaces, co
             }
             metaF[pos] = make_int4(row, losortStart[(size_t)row + 1] - losortStart[row], kF, 0);
             for (int k = losortStart[row]; k < losortStart[(size_t)row + 1]; k++) termsF[(size_t)kF++] = make_int2(losort[k], l[losort[k]]);
-            nbF[pos] = firstThree(termsF, metaF[pos].z, metaF[pos].y);
         }
         for (size_t pos = 0; pos < rowsB.size(); pos++)
         {
@@ -1429,7 +1295,6 @@ extern "C" int b200_blk_create(b200_ctx* ctx, int32_t nCells, int32_t nFaces, co
             }
             metaB[pos] = make_int4(row, ownerStart[(size_t)row + 1] - ownerStart[row], kB, 0);
             for (int f = ownerStart[(size_t)row + 1] - 1; f >= ownerStart[row]; f--) termsB[(size_t)kB++] = make_int2(f, u[f]);
-            nbB[pos] = firstThree(termsB, metaB[pos].z, metaB[pos].y);
         }
     }
     s->nLevelsF = nLevF;
@@ -1446,33 +1311,11 @@ extern "C" int b200_blk_create(b200_ctx* ctx, int32_t nCells, int32_t nFaces, co
     CK(ctx, s->metaB.upload(metaB, st));
     CK(ctx, s->termsF.upload(termsF, st));
     CK(ctx, s->termsB.upload(termsB, st));
-    CK(ctx, s->nbF.upload(nbF, st));
-    CK(ctx, s->nbB.upload(nbB, st));
-    {
-        // the last CTA (chunk of kBlkRowsPerCta positions) each sweep CTA waits for
-        auto depTable = [&](const std::vector<int>& rows, const std::vector<int4>& meta, const std::vector<int2>& terms) {
-            std::vector<int> posOf((size_t)nCells, 0), dep((rows.size() + kBlkRowsPerCta - 1) / kBlkRowsPerCta, -1);
-            for (size_t pos = 0; pos < rows.size(); pos++)
-                if (rows[pos] >= 0) posOf[(size_t)rows[pos]] = (int)pos;
-            for (size_t pos = 0; pos < rows.size(); pos++)
-                if (rows[pos] >= 0)
-                    for (int k = 0; k < meta[pos].y; k++)
-                    { // rows of the same CTA are left to the row-level poll (a chunk may span two levels)
-                        const int c = posOf[(size_t)terms[(size_t)meta[pos].z + k].y] / kBlkRowsPerCta;
-                        if (c < (int)(pos / kBlkRowsPerCta)) dep[pos / kBlkRowsPerCta] = std::max(dep[pos / kBlkRowsPerCta], c);
-                    }
-            return dep;
-        };
-        CK(ctx, s->depMaxF.upload(depTable(rowsF, metaF, termsF), st));
-        CK(ctx, s->depMaxB.upload(depTable(rowsB, metaB, termsB), st));
-        const char* e = getenv("B200_BLK_GATE_SLACK"); // developer knob: CTAs the gate opens early by; negative: no gate
-        s->gateSlack = e ? atoi(e) : 0;
-    }
     CK(ctx, s->partial.alloc((size_t)kBlkMaxRed * kBlkRedBlocks));
     CK(ctx, s->red.alloc(8));
-    CK(ctx, s->ticket.alloc(2));
+    CK(ctx, s->ticket.alloc(1));
     CK(ctx, s->devErr.alloc(1));
-    CK(ctx, cudaMemsetAsync(s->ticket.p, 0, 2 * sizeof(unsigned), st));
+    CK(ctx, cudaMemsetAsync(s->ticket.p, 0, sizeof(unsigned), st));
     CK(ctx, cudaMemsetAsync(s->devErr.p, 0, sizeof(int), st));
     CK(ctx, cudaMallocHost((void**)&s->hostRed, 8 * sizeof(double)));
     CK(ctx, cudaMallocHost((void**)&s->hostErr, sizeof(int)));
