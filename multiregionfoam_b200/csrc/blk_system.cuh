@@ -199,15 +199,22 @@ __global__ void __launch_bounds__(kBlkThreads) k_blk_amul(BlkDev M, const double
 #ifndef B200_BLK_CHUNK
 #define B200_BLK_CHUNK 3 // terms of a row whose coefficients are loaded before the first poll (a hex cell has 3 per sweep)
 #endif
+#ifndef B200_BLK_SWEEP_THREADS
+#define B200_BLK_SWEEP_THREADS 256 // threads of a sweep CTA (4 per row)
+#endif
+#ifndef B200_BLK_PERSIST
+#define B200_BLK_PERSIST 0 // 1: a CTA works through chunk after chunk and fetches the next ticket while the current chunk runs
+#endif
+constexpr int kBlkSweepThreads = B200_BLK_SWEEP_THREADS;
+constexpr int kBlkSweepRows = kBlkSweepThreads / 4;
+
+// the rows of one chunk (ticket) of a sweep: one thread quad per row
 template <bool BWD>
-__global__ void __launch_bounds__(kBlkThreads, B200_BLK_MINCTAS)
-    k_blk_sweep(BlkDev M, int pK, int withFaces, const double* __restrict__ pD, const int4* __restrict__ meta, const int2* __restrict__ terms,
-                int nPos, const double* __restrict__ a, double* out, unsigned* ticket, unsigned ticketBase, int* err)
+__device__ __forceinline__ void blk_sweep_chunk(const BlkDev& M, int pK, int withFaces, const double* __restrict__ pD, const int4* __restrict__ meta,
+                                                const int2* __restrict__ terms, int nPos, const double* __restrict__ a, double* out, int* err,
+                                                unsigned chunk)
 {
-    __shared__ unsigned sTicket;
-    if (threadIdx.x == 0) sTicket = atomicAdd(ticket, 1u) - ticketBase;
-    __syncthreads();
-    const long long pos = (long long)sTicket * kBlkRowsPerCta + (threadIdx.x >> 2);
+    const long long pos = (long long)chunk * kBlkSweepRows + (threadIdx.x >> 2);
     if (pos >= nPos) return;
     // {row, number of terms, first term}: the terms (face, neighbour) of a row lie in sweep order, rows in position order,
     // so the chain of dependent loads before the first poll is  ticket -> meta -> terms -> coefficients
@@ -293,6 +300,35 @@ __global__ void __launch_bounds__(kBlkThreads, B200_BLK_MINCTAS)
             }
     }
     st_relaxed(out + 4ll * row + i, acc);
+}
+
+// ILUmultiply of BlockCholeskyPrecon.  BWD = false: out[row] = D b[row] - sum_{lower faces, ascending} D (L x[l]);
+// BWD = true: out[row] = a[row] - sum_{owner faces, DESCENDING} D (U x[u]).  Chunks of kBlkSweepRows sweep positions are
+// handed out in order by a ticket counter, so a row only ever waits for rows of CTAs that already run.
+template <bool BWD>
+__global__ void __launch_bounds__(kBlkSweepThreads, B200_BLK_MINCTAS * 256 / kBlkSweepThreads)
+    k_blk_sweep(BlkDev M, int pK, int withFaces, const double* __restrict__ pD, const int4* __restrict__ meta, const int2* __restrict__ terms,
+                int nPos, const double* __restrict__ a, double* out, unsigned* ticket, unsigned ticketBase, int* err)
+{
+    __shared__ unsigned sTicket[2];
+    if (threadIdx.x == 0) sTicket[0] = atomicAdd(ticket, 1u) - ticketBase;
+    __syncthreads();
+#if B200_BLK_PERSIST
+    const unsigned nChunks = (unsigned)((nPos + kBlkSweepRows - 1) / kBlkSweepRows);
+    int par = 0;
+    for (unsigned chunk = sTicket[0]; chunk < nChunks;)
+    {
+        unsigned next = 0;
+        if (threadIdx.x == 0) next = atomicAdd(ticket, 1u) - ticketBase; // on its way while this chunk runs
+        blk_sweep_chunk<BWD>(M, pK, withFaces, pD, meta, terms, nPos, a, out, err, chunk);
+        if (threadIdx.x == 0) sTicket[par ^ 1] = next;
+        __syncthreads();
+        par ^= 1;
+        chunk = sTicket[par];
+    }
+#else
+    blk_sweep_chunk<BWD>(M, pK, withFaces, pD, meta, terms, nPos, a, out, err, sTicket[0]);
+#endif
 }
 
 // 4x4 inverse: Gauss-Jordan with partial pivoting, operation by operation as oracle/blk_oracle.c blk_inv4
@@ -994,6 +1030,26 @@ int blk_precond_setup(b200_blk* s, int precond)
     return B200_OK;
 }
 
+// grid of a sweep over `chunks` tickets, and the tickets it takes (persistent CTAs take one more each: the one past the end)
+inline unsigned blk_sweep_grid(unsigned chunks)
+{
+#if B200_BLK_PERSIST
+    const unsigned resident = 148u * (unsigned)(B200_BLK_MINCTAS * 256 / kBlkSweepThreads);
+    return chunks < resident ? (chunks ? chunks : 1u) : resident;
+#else
+    return chunks;
+#endif
+}
+inline unsigned blk_sweep_tickets(unsigned chunks, unsigned ctas)
+{
+#if B200_BLK_PERSIST
+    return chunks + ctas;
+#else
+    (void)chunks;
+    return ctas;
+#endif
+}
+
 // w = M^-1 r (device pointers; r != w)
 int blk_precondition_dev(b200_blk* s, const double* r, double* w)
 {
@@ -1016,22 +1072,24 @@ int blk_precondition_dev(b200_blk* s, const double* r, double* w)
     }
     BlkDev M = blk_dev(s);
     {
-        const unsigned ctas = (unsigned)((s->nPosF + kBlkRowsPerCta - 1) / kBlkRowsPerCta);
+        const unsigned chunks = (unsigned)((s->nPosF + kBlkSweepRows - 1) / kBlkSweepRows);
+        const unsigned ctas = blk_sweep_grid(chunks);
         BlkScope k(s, 1);
-        k_blk_sweep<false><<<ctas, kBlkThreads, 0, ctx->stream>>>(M, s->pK, chol ? 1 : 0, s->pD.p, s->metaF.p, s->termsF.p, s->nPosF, r, fwdOut, s->ticket.p,
+        k_blk_sweep<false><<<ctas, kBlkSweepThreads, 0, ctx->stream>>>(M, s->pK, chol ? 1 : 0, s->pD.p, s->metaF.p, s->termsF.p, s->nPosF, r, fwdOut, s->ticket.p,
                                                                    s->ticketBase, s->devErr.p);
-        s->ticketBase += ctas;
+        s->ticketBase += blk_sweep_tickets(chunks, ctas);
         CK(ctx, cudaGetLastError());
     }
     if (chol)
     {
         rc = blk_fill_sentinel(s, w, n4);
         if (rc) return rc;
-        const unsigned ctas = (unsigned)((s->nPosB + kBlkRowsPerCta - 1) / kBlkRowsPerCta);
+        const unsigned chunks = (unsigned)((s->nPosB + kBlkSweepRows - 1) / kBlkSweepRows);
+        const unsigned ctas = blk_sweep_grid(chunks);
         BlkScope k(s, 2);
-        k_blk_sweep<true><<<ctas, kBlkThreads, 0, ctx->stream>>>(M, s->pK, 1, s->pD.p, s->metaB.p, s->termsB.p, s->nPosB, fwdOut, w, s->ticket.p, s->ticketBase,
+        k_blk_sweep<true><<<ctas, kBlkSweepThreads, 0, ctx->stream>>>(M, s->pK, 1, s->pD.p, s->metaB.p, s->termsB.p, s->nPosB, fwdOut, w, s->ticket.p, s->ticketBase,
                                                                   s->devErr.p);
-        s->ticketBase += ctas;
+        s->ticketBase += blk_sweep_tickets(chunks, ctas);
         CK(ctx, cudaGetLastError());
     }
     return B200_OK;
