@@ -209,24 +209,49 @@ constexpr int kBlkSweepThreads = B200_BLK_SWEEP_THREADS;
 constexpr int kBlkSweepRows = kBlkSweepThreads / 4;
 
 // the rows of one chunk (ticket) of a sweep: one thread quad per row
+// Position-ordered copies for the Cholesky sweeps (built with the preconditioner): pack = the coefficient blocks of the first
+// kBlkDirect terms of every sweep position ([pos][kBlkDirect][uK], zero where a row has fewer; for the forward sweep of a
+// symmetric matrix already transposed), pDpos = the preconditioner diagonal, nb12 = the neighbour rows of terms 1 and 2 (term
+// 0's sits in meta.w).  Their addresses follow from the position alone, so they are requested together with the position
+// table, not after it: the chain of dependent loads of a row is  ticket -> {meta, coefficients, diagonal} -> neighbour values.
+constexpr int kBlkDirect = 3;
+struct BlkPack
+{
+    const double* pack;  // nullptr: no packed copies (BlockDiagonalPrecon), everything through meta / terms
+    const double* pDpos;
+    const int2* nb12;
+};
+
 template <bool BWD>
 __device__ __forceinline__ void blk_sweep_chunk(const BlkDev& M, int pK, int withFaces, const double* __restrict__ pD, const int4* __restrict__ meta,
-                                                const int2* __restrict__ terms, int nPos, const double* __restrict__ a, double* out, int* err,
-                                                unsigned chunk)
+                                                const int2* __restrict__ terms, const BlkPack& P, int nPos, const double* __restrict__ a,
+                                                double* out, int* err, unsigned chunk)
 {
+    constexpr int kChunk = B200_BLK_CHUNK;
+    static_assert(kChunk == kBlkDirect, "the packed first batch holds kBlkDirect terms");
     const long long pos = (long long)chunk * kBlkSweepRows + (threadIdx.x >> 2);
     if (pos >= nPos) return;
-    // {row, number of terms, first term}: the terms (face, neighbour) of a row lie in sweep order, rows in position order,
-    // so the chain of dependent loads before the first poll is  ticket -> meta -> terms -> coefficients
-    const int4 mt = __ldg(meta + pos);
-    const int row = mt.x;
-    if (row < 0) return;
     const int i = threadIdx.x & 3;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned qm = 0xFu << (lane & ~3u);
     const int qb = (int)(lane & ~3u);
     double d[4], xv[4], tv[4];
-    blk_load_row(pK, pD + (size_t)row * pK, i, d);
+    double cf[kChunk][4];
+    int nbv[kChunk];
+    int2 nb12v = make_int2(0, 0);
+    const bool direct = P.pack != nullptr;
+    if (direct)
+    { // independent of the position table
+#pragma unroll
+        for (int t = 0; t < kChunk; t++) blk_load_row_tr(M.uK, P.pack + ((size_t)pos * kBlkDirect + t) * M.uK, false, i, cf[t]);
+        blk_load_row(pK, P.pDpos + (size_t)pos * pK, i, d);
+        nb12v = __ldg(P.nb12 + pos);
+    }
+    // {row, number of terms, first term, neighbour row of term 0}
+    const int4 mt = __ldg(meta + pos);
+    const int row = mt.x;
+    if (row < 0) return;
+    if (!direct) blk_load_row(pK, pD + (size_t)row * pK, i, d);
     double acc;
     if (!BWD)
     {
@@ -242,22 +267,27 @@ __device__ __forceinline__ void blk_sweep_chunk(const BlkDev& M, int pK, int wit
     // indices, this thread's row of each coefficient block (from DRAM) - is therefore loaded for up to kChunk terms at
     // once BEFORE the first poll; after a poll only multiply, quad shuffles and multiply remain (same order of the
     // terms and of the operations as before).
-    constexpr int kChunk = B200_BLK_CHUNK;
     const bool tr = !(BWD || M.lK);
     const double* const coefBase = (BWD || !M.lK) ? M.upper : M.lower;
     for (int kk0 = 0; kk0 < nTerms; kk0 += kChunk)
     {
-        int nbv[kChunk];
-        double cf[kChunk][4];
+        if (direct && kk0 == 0)
+        {
 #pragma unroll
-        for (int t = 0; t < kChunk; t++)
-            if (kk0 + t < nTerms)
-            {
-                const int2 tm = __ldg(terms + k0 + kk0 + t);
-                const int f = tm.x;
-                nbv[t] = tm.y;
-                blk_load_row_tr(M.uK, coefBase + (size_t)f * M.uK, tr, i, cf[t]);
-            }
+            for (int t = 0; t < kChunk; t++) nbv[t] = t == 0 ? mt.w : t == 1 ? nb12v.x : nb12v.y;
+        }
+        else
+        {
+#pragma unroll
+            for (int t = 0; t < kChunk; t++)
+                if (kk0 + t < nTerms)
+                {
+                    const int2 tm = __ldg(terms + k0 + kk0 + t);
+                    const int f = tm.x;
+                    nbv[t] = tm.y;
+                    blk_load_row_tr(M.uK, coefBase + (size_t)f * M.uK, tr, i, cf[t]);
+                }
+        }
         // the neighbours of a row mostly sit in the level just before it and arrive together: all of them are polled in
         // one batch of independent loads per round instead of one after the other
         double xn[kChunk][4];
@@ -308,7 +338,7 @@ __device__ __forceinline__ void blk_sweep_chunk(const BlkDev& M, int pK, int wit
 template <bool BWD>
 __global__ void __launch_bounds__(kBlkSweepThreads, B200_BLK_MINCTAS * 256 / kBlkSweepThreads)
     k_blk_sweep(BlkDev M, int pK, int withFaces, const double* __restrict__ pD, const int4* __restrict__ meta, const int2* __restrict__ terms,
-                int nPos, const double* __restrict__ a, double* out, unsigned* ticket, unsigned ticketBase, int* err)
+                BlkPack P, int nPos, const double* __restrict__ a, double* out, unsigned* ticket, unsigned ticketBase, int* err)
 {
     __shared__ unsigned sTicket[2];
     if (threadIdx.x == 0) sTicket[0] = atomicAdd(ticket, 1u) - ticketBase;
@@ -320,15 +350,43 @@ __global__ void __launch_bounds__(kBlkSweepThreads, B200_BLK_MINCTAS * 256 / kBl
     {
         unsigned next = 0;
         if (threadIdx.x == 0) next = atomicAdd(ticket, 1u) - ticketBase; // on its way while this chunk runs
-        blk_sweep_chunk<BWD>(M, pK, withFaces, pD, meta, terms, nPos, a, out, err, chunk);
+        blk_sweep_chunk<BWD>(M, pK, withFaces, pD, meta, terms, P, nPos, a, out, err, chunk);
         if (threadIdx.x == 0) sTicket[par ^ 1] = next;
         __syncthreads();
         par ^= 1;
         chunk = sTicket[par];
     }
 #else
-    blk_sweep_chunk<BWD>(M, pK, withFaces, pD, meta, terms, nPos, a, out, err, sTicket[0]);
+    blk_sweep_chunk<BWD>(M, pK, withFaces, pD, meta, terms, P, nPos, a, out, err, sTicket[0]);
 #endif
+}
+
+// the packed copies of BlkPack
+__global__ void k_blk_pack_coef(long long nPos, const int4* __restrict__ meta, const int2* __restrict__ terms, const double* __restrict__ coef, int K,
+                                int tr, double* __restrict__ out)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nPos * kBlkDirect * K) return;
+    const long long slot = t / K;
+    const int j = (int)(t - slot * K);
+    const long long pos = slot / kBlkDirect;
+    const int k = (int)(slot - pos * kBlkDirect);
+    const int4 mt = meta[pos];
+    double v = 0.0;
+    if (mt.x >= 0 && k < mt.y)
+    {
+        const int src = (tr && K == 16) ? (j & 3) * 4 + (j >> 2) : j;
+        v = coef[(size_t)terms[mt.z + k].x * K + src];
+    }
+    out[t] = v;
+}
+__global__ void k_blk_pack_pd(long long nPos, const int4* __restrict__ meta, const double* __restrict__ pD, int pK, double* __restrict__ out)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nPos * pK) return;
+    const long long pos = t / pK;
+    const int row = meta[pos].x;
+    out[t] = row >= 0 ? pD[(size_t)row * pK + (t - pos * pK)] : 0.0;
 }
 
 // 4x4 inverse: Gauss-Jordan with partial pivoting, operation by operation as oracle/blk_oracle.c blk_inv4
@@ -727,6 +785,8 @@ struct b200_blk
     DevBuf<int> l, u, losort, losortStart, ownerStart, rowsF, rowsB;
     DevBuf<int4> metaF, metaB;   // per sweep position {row (-1 pad), number of terms, first term, 0}
     DevBuf<int2> termsF, termsB; // {face, neighbour row} in the order the sweep subtracts them
+    DevBuf<int2> nb12F, nb12B;   // neighbour rows of terms 1 and 2 of every position (term 0: meta.w)
+    DevBuf<double> packF, packB, pDposF, pDposB; // BlkPack copies (Cholesky)
     int nPosF = 0, nPosB = 0, nLevelsF = 0, nLevelsB = 0;
     int dK = 0, uK = 0, lK = 0;
     DevBuf<double> diag, upper, lower;
@@ -1025,6 +1085,21 @@ int blk_precond_setup(b200_blk* s, int precond)
         CK(ctx, cudaGetLastError());
         int rc = blk_check_err(s, "calcPreconDiag");
         if (rc) return rc;
+        if (chol)
+        { // position-ordered copies for the sweeps (BlkPack)
+            const long long nF = (long long)s->nPosF * kBlkDirect * s->uK, nB = (long long)s->nPosB * kBlkDirect * s->uK;
+            CK(ctx, s->packF.alloc((size_t)nF));
+            CK(ctx, s->packB.alloc((size_t)nB));
+            CK(ctx, s->pDposF.alloc((size_t)s->nPosF * pK));
+            CK(ctx, s->pDposB.alloc((size_t)s->nPosB * pK));
+            BlkScope k(s, 4);
+            k_blk_pack_coef<<<blk_grid(nF, 256, 1 << 30), 256, 0, ctx->stream>>>(s->nPosF, s->metaF.p, s->termsF.p, s->lK ? s->lower.p : s->upper.p, s->uK,
+                                                                               s->lK ? 0 : 1, s->packF.p);
+            k_blk_pack_coef<<<blk_grid(nB, 256, 1 << 30), 256, 0, ctx->stream>>>(s->nPosB, s->metaB.p, s->termsB.p, s->upper.p, s->uK, 0, s->packB.p);
+            k_blk_pack_pd<<<blk_grid((long long)s->nPosF * pK, 256, 1 << 30), 256, 0, ctx->stream>>>(s->nPosF, s->metaF.p, s->pD.p, pK, s->pDposF.p);
+            k_blk_pack_pd<<<blk_grid((long long)s->nPosB * pK, 256, 1 << 30), 256, 0, ctx->stream>>>(s->nPosB, s->metaB.p, s->pD.p, pK, s->pDposB.p);
+            CK(ctx, cudaGetLastError());
+        }
     }
     s->precond = precond;
     return B200_OK;
@@ -1062,6 +1137,8 @@ int blk_precondition_dev(b200_blk* s, const double* r, double* w)
         return B200_OK;
     }
     const bool chol = s->precond == B200_PRECOND_CHOLESKY;
+    static const bool packOff = getenv("B200_BLK_NO_PACK") != nullptr; // developer knob: sweep through the term table only
+    const bool usePack = chol && !packOff;
     // forward (Cholesky) or plain diagonal scaling: the same kernel, without faces when !chol
     double* fwdOut = chol ? s->tmp2.p : w;
     int rc = B200_OK;
@@ -1075,7 +1152,8 @@ int blk_precondition_dev(b200_blk* s, const double* r, double* w)
         const unsigned chunks = (unsigned)((s->nPosF + kBlkSweepRows - 1) / kBlkSweepRows);
         const unsigned ctas = blk_sweep_grid(chunks);
         BlkScope k(s, 1);
-        k_blk_sweep<false><<<ctas, kBlkSweepThreads, 0, ctx->stream>>>(M, s->pK, chol ? 1 : 0, s->pD.p, s->metaF.p, s->termsF.p, s->nPosF, r, fwdOut, s->ticket.p,
+        k_blk_sweep<false><<<ctas, kBlkSweepThreads, 0, ctx->stream>>>(M, s->pK, chol ? 1 : 0, s->pD.p, s->metaF.p, s->termsF.p,
+                                                                   usePack ? BlkPack{s->packF.p, s->pDposF.p, s->nb12F.p} : BlkPack{nullptr, nullptr, nullptr}, s->nPosF, r, fwdOut, s->ticket.p,
                                                                    s->ticketBase, s->devErr.p);
         s->ticketBase += blk_sweep_tickets(chunks, ctas);
         CK(ctx, cudaGetLastError());
@@ -1087,7 +1165,8 @@ int blk_precondition_dev(b200_blk* s, const double* r, double* w)
         const unsigned chunks = (unsigned)((s->nPosB + kBlkSweepRows - 1) / kBlkSweepRows);
         const unsigned ctas = blk_sweep_grid(chunks);
         BlkScope k(s, 2);
-        k_blk_sweep<true><<<ctas, kBlkSweepThreads, 0, ctx->stream>>>(M, s->pK, 1, s->pD.p, s->metaB.p, s->termsB.p, s->nPosB, fwdOut, w, s->ticket.p, s->ticketBase,
+        k_blk_sweep<true><<<ctas, kBlkSweepThreads, 0, ctx->stream>>>(M, s->pK, 1, s->pD.p, s->metaB.p, s->termsB.p,
+                                                                  usePack ? BlkPack{s->packB.p, s->pDposB.p, s->nb12B.p} : BlkPack{nullptr, nullptr, nullptr}, s->nPosB, fwdOut, w, s->ticket.p, s->ticketBase,
                                                                   s->devErr.p);
         s->ticketBase += blk_sweep_tickets(chunks, ctas);
         CK(ctx, cudaGetLastError());
@@ -1330,6 +1409,11 @@ extern "C" int b200_blk_create(b200_ctx* ctx, int32_t nCells, int32_t nFaces, co
     // sweep-ordered term lists: forward = lower faces of the row ascending (losort order), backward = owner faces DESCENDING
     std::vector<int4> metaF(rowsF.size()), metaB(rowsB.size());
     std::vector<int2> termsF((size_t)nFaces), termsB((size_t)nFaces);
+    std::vector<int2> nb12F(rowsF.size(), make_int2(0, 0)), nb12B(rowsB.size(), make_int2(0, 0));
+    auto firstThree = [](const std::vector<int2>& terms, int4& mt, int2& nb12) {
+        mt.w = mt.y > 0 ? terms[(size_t)mt.z].y : 0;
+        nb12 = make_int2(mt.y > 1 ? terms[(size_t)mt.z + 1].y : 0, mt.y > 2 ? terms[(size_t)mt.z + 2].y : 0);
+    };
     {
         int kF = 0, kB = 0;
         for (size_t pos = 0; pos < rowsF.size(); pos++)
@@ -1342,6 +1426,7 @@ extern "C" int b200_blk_create(b200_ctx* ctx, int32_t nCells, int32_t nFaces, co
             }
             metaF[pos] = make_int4(row, losortStart[(size_t)row + 1] - losortStart[row], kF, 0);
             for (int k = losortStart[row]; k < losortStart[(size_t)row + 1]; k++) termsF[(size_t)kF++] = make_int2(losort[k], l[losort[k]]);
+            firstThree(termsF, metaF[pos], nb12F[pos]);
         }
         for (size_t pos = 0; pos < rowsB.size(); pos++)
         {
@@ -1353,6 +1438,7 @@ extern "C" int b200_blk_create(b200_ctx* ctx, int32_t nCells, int32_t nFaces, co
             }
             metaB[pos] = make_int4(row, ownerStart[(size_t)row + 1] - ownerStart[row], kB, 0);
             for (int f = ownerStart[(size_t)row + 1] - 1; f >= ownerStart[row]; f--) termsB[(size_t)kB++] = make_int2(f, u[f]);
+            firstThree(termsB, metaB[pos], nb12B[pos]);
         }
     }
     s->nLevelsF = nLevF;
@@ -1369,6 +1455,8 @@ extern "C" int b200_blk_create(b200_ctx* ctx, int32_t nCells, int32_t nFaces, co
     CK(ctx, s->metaB.upload(metaB, st));
     CK(ctx, s->termsF.upload(termsF, st));
     CK(ctx, s->termsB.upload(termsB, st));
+    CK(ctx, s->nb12F.upload(nb12F, st));
+    CK(ctx, s->nb12B.upload(nb12B, st));
     CK(ctx, s->partial.alloc((size_t)kBlkMaxRed * kBlkRedBlocks));
     CK(ctx, s->red.alloc(8));
     CK(ctx, s->ticket.alloc(1));
