@@ -29,10 +29,14 @@ int Pstream::myProcNo() { return g_rank; }
 int Pstream::nProcs() { return g_nprocs; }
 // what the other rank would have published in describe()'s gatherList: (row, neighbour, interface index) triples
 static std::map<int, labelList> g_otherTables;
+// ... and in the second gatherList of describe() (zone pieces of regionCouple pairs spread over processors)
+static std::map<int, labelList> g_otherZoneTables;
+static int g_gatherCalls = 0;
 void Pstream::gatherListHook(void* p)
 {
     List<labelList>& l = *static_cast<List<labelList>*>(p);
-    for (auto& kv : g_otherTables) l[kv.first] = kv.second;
+    for (auto& kv : (g_gatherCalls == 0 ? g_otherTables : g_otherZoneTables)) l[kv.first] = kv.second;
+    g_gatherCalls++;
 }
 
 struct AddrData
@@ -92,7 +96,8 @@ label regionCoupleFvPatch::size() const { return g_rc[this].size; }
 const polyPatch& regionCoupleFvPatch::patch() const { return *g_rc[this].poly; }
 bool regionCoupleFvPatch::coupled() const { return g_rc[this].coupled; }
 bool regionCoupleFvPatch::master() const { return g_rc[this].master; }
-bool regionCoupleFvPatch::localParallel() const { return true; }
+static bool g_zoneMode = false; // the pair is spread over the two processors: interpolation on the global zones
+bool regionCoupleFvPatch::localParallel() const { return !g_zoneMode; }
 label regionCoupleFvPatch::shadowIndex() const { return g_rc[this].shadowIndex; }
 const fvMesh& regionCoupleFvPatch::shadowRegion() const { return *g_rc[this].shadowMesh; }
 const regionCoupleFvPatch& regionCoupleFvPatch::shadow() const { return *g_rc[this].shadow; }
@@ -102,12 +107,13 @@ bool regionCouplePolyPatch::master() const { return g_rc[g_polyOwner[this]].mast
 bool regionCouplePolyPatch::attached() const { return true; }
 const regionCouplePolyPatch& regionCouplePolyPatch::shadow() const { return *g_rc[g_rc[g_polyOwner[this]].shadow].poly; }
 const ggiZoneInterpolation& regionCouplePolyPatch::patchToPatch() const { return g_interp; }
-// zone members: reached only for pairs spread over processors (localParallel() false), which this harness does not set up
-static faceZone g_zone;
-static labelList g_zoneAddr;
-label faceZone::size() const { return 0; }
-const faceZone& regionCouplePolyPatch::zone() const { return g_zone; }
-const labelList& regionCouplePolyPatch::zoneAddressing() const { return g_zoneAddr; }
+// zone members: reached only for pairs spread over processors (harness mode "zone")
+static std::map<const regionCouplePolyPatch*, faceZone> g_zone;
+static std::map<const faceZone*, label> g_zoneSize;
+static std::map<const regionCouplePolyPatch*, labelList> g_zoneAddr;
+label faceZone::size() const { return g_zoneSize[this]; }
+const faceZone& regionCouplePolyPatch::zone() const { return g_zone[this]; }
+const labelList& regionCouplePolyPatch::zoneAddressing() const { return g_zoneAddr[this]; }
 const labelListList& ggiZoneInterpolation::masterAddr() const { return g_mAddr; }
 const scalarListList& ggiZoneInterpolation::masterWeights() const { return g_mW; }
 const labelListList& ggiZoneInterpolation::slaveAddr() const { return g_sAddr; }
@@ -228,6 +234,32 @@ int main(int argc, char** argv)
     // the other rank's table: the same patch layout, so its interface indices are fluid: 1, solid: 1
     g_otherTables[1 - g_rank] = L({0, g_rank, 1, 1, g_rank, 1});
 
+    if (argc > 3 && std::string(argv[3]) == "zone")
+    {
+        // The pair on its global zones: master zone 5 faces, slave zone 4; this rank (1) holds master zone faces 2, 3, 4 and
+        // slave zone faces 2, 3, rank 0 the others.  patchToPatch() is the ZONE-level interpolator.
+        g_zoneMode = true;
+        g_zoneSize[&g_zone[&ppF]] = 5;
+        g_zoneSize[&g_zone[&ppS]] = 4;
+        g_zoneAddr[&ppF] = L({2, 3, 4});
+        g_zoneAddr[&ppS] = L({2, 3});
+        g_mAddr.setSize(5);
+        g_mW.setSize(5);
+        g_mAddr[0] = L({0});        g_mW[0] = F({1.0});
+        g_mAddr[1] = L({0, 1});     g_mW[1] = F({0.5, 0.5});
+        g_mAddr[2] = L({1, 2});     g_mW[2] = F({0.25, 0.75});
+        g_mAddr[3] = L({2, 3});     g_mW[3] = F({0.5, 0.5});
+        g_mAddr[4] = L({3});        g_mW[4] = F({1.0});
+        g_sAddr.setSize(4);
+        g_sW.setSize(4);
+        g_sAddr[0] = L({0, 1});     g_sW[0] = F({0.5, 0.5});
+        g_sAddr[1] = L({1, 2});     g_sW[1] = F({0.5, 0.5});
+        g_sAddr[2] = L({2, 3});     g_sW[2] = F({0.375, 0.625});
+        g_sAddr[3] = L({3, 4});     g_sW[3] = F({0.5, 0.5});
+        // rank 0's zone table: (row, patch, interface index, nFaces, zone faces...) per zone-mode patch
+        g_otherZoneTables[1 - g_rank] = L({0, 1, 0, 2, 0, 1, 1, 0, 0, 2, 0, 1});
+    }
+
     UPtrList<const lduMatrix> matrices(2);
     matrices.set(0, &mF);
     matrices.set(1, &mS);
@@ -254,6 +286,31 @@ int main(int argc, char** argv)
     UPtrList<const scalarField> xs(2), bs(2);
     xs.set(0, &xF); xs.set(1, &xS);
     bs.set(0, &sF); bs.set(1, &sS);
+    if (g_zoneMode)
+    { // the dump format does not carry zone pieces: print what describe() found instead
+        List<List<b200Binding::ifaceInfo> > info;
+        b200Binding::describe(matrices, ifaces, info);
+        forAll (info, r) forAll (info[r], i)
+        {
+            const b200Binding::ifaceInfo& I = info[r][i];
+            std::cout << "iface " << r << " " << i << " kind " << I.kind << " zoneMode " << int(I.zoneMode) << " nPeerFaces " << I.nPeerFaces
+                      << " peer " << I.peerRegion << " " << I.peerIface << " offsets";
+            forAll (I.ggiOffsets, k) std::cout << " " << I.ggiOffsets[k];
+            std::cout << " addr";
+            forAll (I.ggiAddr, k) std::cout << " " << I.ggiAddr[k];
+            std::cout << " w";
+            forAll (I.ggiWeights, k) std::cout << " " << I.ggiWeights[k];
+            std::cout << " pieces";
+            forAll (I.pieceRank, k)
+            {
+                std::cout << " [" << I.pieceRank[k] << " " << I.pieceIface[k] << ":";
+                for (label q = I.pieceOffsets[k]; q < I.pieceOffsets[k + 1]; q++) std::cout << " " << I.pieceZoneAddr[q];
+                std::cout << "]";
+            }
+            std::cout << "\n";
+        }
+        return 0;
+    }
     b200Binding::dump(fileName(std::string(argv[1])), matrices, ifaces, bou, inte, xs, bs, word("BiCGStab"), word("Cholesky"), 1e-15, 0.0, 0, 200,
                       F({0.5, 0.25, 0.125}));
     return 0;

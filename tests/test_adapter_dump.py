@@ -85,3 +85,19 @@ def test_dumped_region_couple_tables_drive_the_oracle(harness, tmp_path):
     pnf = np.array([own[0], 0.5 * own[0] + 0.5 * own[1], own[1]])              # onto the 3 fluid faces
     yf[fluid.interfaces[0].faceCells] -= fluid.interfaces[0].bouCoeffs * pnf
     assert np.allclose(y[:6], yf, rtol=1e-14, atol=0)
+
+
+def test_adapter_describes_a_pair_spread_over_processors(harness, tmp_path):
+    """!localParallel(): the adapter takes the rows zoneAddressing() of the ZONE-level interpolator, the size of the shadow zone,
+    and - through the second Pstream::gatherList - who holds which shadow zone faces (b200_sys_set_interface_pieces)."""
+    r = subprocess.run([harness, str(tmp_path / "unused"), "1", "zone"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stderr == "", r.stderr
+    lines = {tuple(l.split()[1:3]): l for l in r.stdout.splitlines() if l.startswith("iface ")}
+    fluid, solid = lines[("0", "0")], lines[("1", "0")]
+    # master side, local faces = master zone faces 2, 3, 4 -> rows 2, 3, 4 of masterAddr; shadow zone (slave) has 4 faces,
+    # of which rank 0 holds 0, 1 (its interface 0 of row 1) and this rank 2, 3
+    assert "kind 0 zoneMode 1 nPeerFaces 4 peer 1 0 offsets 0 2 4 5 addr 1 2 2 3 3 w 0.25 0.75 0.5 0.5 1 pieces [0 0: 0 1] [1 0: 2 3]" in fluid
+    # slave side, local faces = slave zone faces 2, 3 -> rows 2, 3 of the master's slaveAddr; shadow zone (master) has 5 faces
+    assert "kind 0 zoneMode 1 nPeerFaces 5 peer 0 0 offsets 0 2 4 addr 2 3 3 4 w 0.375 0.625 0.5 0.5 pieces [0 0: 0 1] [1 0: 2 3 4]" in solid
+    # the processor patches are described as before
+    assert "kind 1 zoneMode 0" in lines[("0", "1")] and "kind 1 zoneMode 0" in lines[("1", "1")]
