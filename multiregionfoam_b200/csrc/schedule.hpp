@@ -39,6 +39,7 @@
 #include <stdexcept>
 #include <string>
 #include <tuple>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -221,12 +222,14 @@ struct PipeSchedule
     // = 5 full warps + one of 4 lanes) with the head of a later sequence (a plane further on), where the dependencies allow
     // it: padding lanes cost slots, and slots cost bandwidth in every kernel of the solve.  If the merged warps make the group
     // graph cyclic (unstructured corner cases) the schedule is rebuilt without merging.
+    bool slotOrderChain = false; // slot layout of the groups: ticket order, or chain order (see order_and_number; B200_SLOT_ORDER=chain)
     bool mergeSequences = true;
     double mergeGap = 1.5;      // measured on C3 (64 M cells): 0.5 .. 8 scanned, DESIGN.md section 4
     int mergeMinGroups = 444;   // 1.5 x the 296 resident sweep CTAs: below that the sweep is latency-bound and merging only adds waits
     void build(const GlobalLdu& g, const std::vector<RegionHost>& regs)
     {
-        if (const char* e = getenv("B200_MERGE_SEQ")) mergeSequences = atoi(e) != 0; // developer knobs
+        if (const char* e = getenv("B200_SLOT_ORDER")) slotOrderChain = std::string(e) == "chain"; // developer knobs
+        if (const char* e = getenv("B200_MERGE_SEQ")) mergeSequences = atoi(e) != 0;
         if (const char* e = getenv("B200_MERGE_GAP")) mergeGap = atof(e);
         if (const char* e = getenv("B200_MERGE_MIN_GROUPS")) mergeMinGroups = atoi(e);
         if (mergeSequences)
@@ -590,13 +593,27 @@ struct PipeSchedule
         // group graph: edge H -> G if a row of G has a lower neighbour in H
         std::vector<std::vector<int32_t>> succ(nG);
         std::vector<int32_t> indeg(nG, 0);
+        std::unordered_map<uint64_t, int64_t> pairFaces; // faces between two groups (unordered pair)
         {
+            uint64_t lastKey = ~uint64_t(0);
+            int64_t lastCount = 0;
             std::vector<int64_t> edges;
             for (int64_t f = 0; f < g.F; f++)
             {
                 const int32_t a = P.grp[g.L[f]], b = P.grp[g.U[f]];
                 if (a != b)
+                {
                     edges.push_back((int64_t(a) << 32) | uint32_t(b));
+                    const uint64_t key = (uint64_t(uint32_t(std::min(a, b))) << 32) | uint32_t(std::max(a, b));
+                    if (key == lastKey)
+                        lastCount++;
+                    else
+                    {
+                        if (lastCount) pairFaces[lastKey] += lastCount;
+                        lastKey = key;
+                        lastCount = 1;
+                    }
+                }
                 else if (P.tim[g.L[f]] >= P.tim[g.U[f]])
                     throw std::runtime_error("internal: in-warp dependency does not point back in time");
                 if (edges.size() > (size_t(1) << 22))
@@ -605,6 +622,7 @@ struct PipeSchedule
                     edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
                 }
             }
+            if (lastCount) pairFaces[lastKey] += lastCount;
             std::sort(edges.begin(), edges.end());
             edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
             for (int64_t e : edges)
@@ -643,14 +661,54 @@ struct PipeSchedule
         gNT.resize(nG);
         gBase.resize(nG);
         std::vector<int32_t> lb(nG);
-        int64_t base = 0;
         for (int i = 0; i < nG; i++)
         {
             const int old = ordF[i];
             gNT[i] = (grpNT[old] + CH - 1) / CH * CH;
+            lb[i] = levB[old];
+        }
+        // Where the groups lie in slot space does not have to follow the ticket order.  Chain order (optional): the next
+        // group in memory is the unplaced group that shares the most faces with the one just placed (the k-column of a
+        // j-block), starting a new chain at the lowest ticket left - the groups Amul gathers x from then lie next to each
+        // other.  Measured on the B200: no difference (C3 Amul 1 254 -> 1 247 us; Amul already moves its bytes at 0.94 of the
+        // copy bandwidth, its traffic is the 104 B per slot it needs plus ~10 %), so ticket order stays the default.
+        std::vector<int32_t> layout;
+        layout.reserve(nG);
+        if (slotOrderChain)
+        {
+            std::vector<std::vector<std::pair<int32_t, int64_t>>> nbrs(nG); // in ticket ids
+            for (auto& kv : pairFaces)
+            {
+                const int a = newId[int32_t(kv.first >> 32)], b = newId[int32_t(kv.first & 0xffffffffu)];
+                nbrs[a].push_back({b, kv.second});
+                nbrs[b].push_back({a, kv.second});
+            }
+            std::vector<uint8_t> placed(nG, 0);
+            for (int start = 0; start < nG; start++)
+            {
+                for (int cur = placed[start] ? -1 : start; cur >= 0;)
+                {
+                    placed[cur] = 1;
+                    layout.push_back(cur);
+                    int best = -1;
+                    int64_t bestW = 0;
+                    for (auto& e : nbrs[cur])
+                        if (!placed[e.first] && (e.second > bestW || (e.second == bestW && best >= 0 && e.first < best)))
+                        {
+                            best = e.first;
+                            bestW = e.second;
+                        }
+                    cur = best;
+                }
+            }
+        }
+        else
+            for (int i = 0; i < nG; i++) layout.push_back(i);
+        int64_t base = 0;
+        for (int i : layout)
+        {
             gBase[i] = int32_t(base);
             base += gNT[i];
-            lb[i] = levB[old];
         }
         if (base * 32 >= (int64_t(1) << 31)) throw std::runtime_error("slot space exceeds int32");
         nSlots = base * 32;
