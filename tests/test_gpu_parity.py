@@ -337,10 +337,11 @@ def test_full_size_properties(gpu_ctx):
         S.close()
 
 
-@pytest.mark.parametrize("workload", ["C2", "C3-slab8"])
+@pytest.mark.parametrize("workload", ["C2", "C3-slab8", "C3"])
 def test_bench_config_history_against_oracle(gpu_ctx, workload):
     """The bench configurations themselves against the oracle (not only through properties): BASELINE config C2
-    (4.3 M cells) and one z-slab of C3 as `bench.py --gpus 8` gives it to a GPU (8 M cells), monolithic BiCGStab + DILU,
+    (4.3 M cells), one z-slab of C3 as `bench.py --gpus 8` gives it to a GPU (8 M cells) and the whole 64 M-cell C3 of the
+    default bench (the only size at which the sweep schedule fills warps across plane ends), monolithic BiCGStab + DILU,
     20 iterations from the bench's initial guess: Amul and the preconditioner bit-exact, the residual history within
     1e-10 relative, the field within 1e-8 relative L2 (north_star's bars)."""
     from multiregionfoam_b200.assembly import WORKLOADS, cht_rank_slab
@@ -362,8 +363,34 @@ def test_bench_config_history_against_oracle(gpu_ctx, workload):
         xg, ig = S.solve(x0, b, ldu.SOLVER_BICGSTAB, ldu.PRECOND_DILU, tolerance=0.0, minIter=20, maxIter=20)
         assert ig["nIterations"] == io["nIterations"] == 20
         ho, hg = io["history"][:21], ig["history"][:21]
-        assert np.max(np.abs(hg - ho) / np.abs(ho)) < HIST_RTOL
-        assert rel_l2(xg, xo) < FIELD_RTOL
+        err = np.max(np.abs(hg - ho) / np.abs(ho))
+        if workload == "C3":
+            # 64 M terms per global sum, and a system on which BiCGStab has a nearly singular step (iteration 10 multiplies any
+            # rounding difference by ~1e6: measured on the B200, the oracle with SEQUENTIAL sums - the reference's - and the same
+            # oracle with pairwise sums are 1e-11 apart for nine iterations and 1e-8 from the tenth on).  No two correct
+            # implementations with different summation orders meet 1e-10 there.  What is held instead: the device follows the
+            # order-insensitive (pairwise) oracle to 1e-12 for the ten iterations before that step (measured: 2e-16 .. 3e-13),
+            # stays within the oracle's own sensitivity to the summation order afterwards, and the fields agree to 1e-8.
+            O.set_reduction_mode(1)
+            xp, ip = O.solve(x0, b, "BiCGStab", "DILU", tolerance=0.0, minIter=20, maxIter=20)
+            O.set_reduction_mode(0)
+            hp = ip["history"][:21]
+            dev_pair = np.abs(hg - hp) / np.abs(hp)
+            seq_pair = np.abs(ho - hp) / np.abs(hp)
+            own = seq_pair.max()
+            print(f"C3 history: device vs sequential oracle {err:.2e}, device vs pairwise oracle {dev_pair.max():.2e}, sequential vs pairwise oracle {own:.2e}")
+            print("  per iteration, device vs pairwise:", " ".join(f"{v:.1e}" for v in dev_pair))
+            print("  per iteration, sequential vs pairwise:", " ".join(f"{v:.1e}" for v in seq_pair))
+            print("  normFactor device / sequential / pairwise:", repr(ig["normFactor"]), repr(io["normFactor"]), repr(ip["normFactor"]))
+            assert abs(ig["normFactor"] - ip["normFactor"]) <= 1e-14 * ip["normFactor"]
+            assert seq_pair[:10].max() < HIST_RTOL and dev_pair[:10].max() < 1e-12   # before the sensitive step
+            assert dev_pair.max() < max(HIST_RTOL, own)  # never further from the pairwise oracle than the sequential one is
+            assert err < max(HIST_RTOL, 3.0 * own)
+            assert rel_l2(xg, xp) < FIELD_RTOL
+            assert rel_l2(xg, xo) < max(FIELD_RTOL, 10.0 * rel_l2(xo, xp))
+        else:
+            assert err < HIST_RTOL
+            assert rel_l2(xg, xo) < FIELD_RTOL
     finally:
         pyoracle.set_threads(1)
         S.close()
