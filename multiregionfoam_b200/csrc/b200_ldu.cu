@@ -2226,3 +2226,4 @@ extern "C" int b200_global_face_to_patch(b200_ctx* ctx, int32_t nLocal, const in
 
 // block-coupled (vector4) systems: include/b200_blk.h
 #include "blk_system.cuh"
+#include "gs_smoother.cuh"

@@ -1104,3 +1104,103 @@ void orc_direct_map(int nTo, const int* map, const double* from, int nComp, doub
     for (int i = 0; i < nTo; i++)
         for (int d = 0; d < nComp; d++) to[i * nComp + d] = from[map[i] * nComp + d];
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * GaussSeidelSmoother / smoothSolver (`smoothSolver` with `smoother GaussSeidel` in the tutorials'
+ * fvSolution, e.g. tutorials/fluidStructureInteraction/HronTurekFsi3/system/fluid/fvSolution).  foam-extend 4.1
+ * foam/matrices/lduMatrix/smoothers/GaussSeidel/GaussSeidelSmoother.C and solvers/smoothSolver/smoothSolver.C, restated for
+ * ONE matrix whose coupled-patch contributions are already inside bPrime (the smoother adds them to a copy of the source
+ * before every sweep: bPrime = source; updateMatrixInterfaces(-bouCoeffs ...)).  Plain arrays, no orc_sys. */
+void orc_gs_smooth(int n, int nf, const int* l, const int* u, const double* diag, const double* upper, const double* lower,
+                   double* psi, const double* source, int nSweeps)
+{
+    if (!lower) lower = upper;
+    int* ownStart = (int*)calloc((size_t)n + 1, sizeof(int));
+    for (int f = 0; f < nf; f++) ownStart[l[f] + 1]++;
+    for (int c = 0; c < n; c++) ownStart[c + 1] += ownStart[c];
+    double* bPrime = (double*)malloc(sizeof(double) * (size_t)(n ? n : 1));
+    for (int sweep = 0; sweep < nSweeps; sweep++)
+    {
+        for (int c = 0; c < n; c++) bPrime[c] = source[c];
+        for (int c = 0; c < n; c++)
+        {
+            const int fStart = ownStart[c], fEnd = ownStart[c + 1];
+            double curPsi = bPrime[c];
+            for (int f = fStart; f < fEnd; f++) curPsi -= upper[f] * psi[u[f]];
+            curPsi /= diag[c];
+            for (int f = fStart; f < fEnd; f++) bPrime[u[f]] -= lower[f] * curPsi;
+            psi[c] = curPsi;
+        }
+    }
+    free(bPrime);
+    free(ownStart);
+}
+
+static void gs_amul(int n, int nf, const int* l, const int* u, const double* diag, const double* upper, const double* lower,
+                    const double* x, double* y)
+{
+    for (int c = 0; c < n; c++) y[c] = diag[c] * x[c];
+    for (int f = 0; f < nf; f++)
+    {
+        y[u[f]] += lower[f] * x[l[f]];
+        y[l[f]] += upper[f] * x[u[f]];
+    }
+}
+
+/* smoothSolver::solve with nSweeps > 0.  history[k] = residual after k rounds of nSweeps sweeps (entry 0 = initial). */
+int orc_gs_solve(int n, int nf, const int* l, const int* u, const double* diag, const double* upper, const double* lower,
+                 double* psi, const double* source, int nSweeps, double tolerance, double relTol, int minIter, int maxIter,
+                 orc_perf* perf, double* history, int historyCap)
+{
+    if (nSweeps <= 0) return -1;
+    if (!lower) lower = upper;
+    memset(perf, 0, sizeof(*perf));
+    double* Ax = (double*)malloc(sizeof(double) * (size_t)(n ? n : 1));
+    double* tmp = (double*)malloc(sizeof(double) * (size_t)(n ? n : 1));
+    gs_amul(n, nf, l, u, diag, upper, lower, psi, Ax);
+    double xRef = 0.0;
+    for (int c = 0; c < n; c++) xRef += psi[c];
+    xRef /= (double)(n ? n : 1);
+    for (int c = 0; c < n; c++) tmp[c] = xRef;
+    double* pA = (double*)malloc(sizeof(double) * (size_t)(n ? n : 1));
+    gs_amul(n, nf, l, u, diag, upper, lower, tmp, pA);
+    double nfac = 0.0;
+    for (int c = 0; c < n; c++) nfac += fabs(Ax[c] - pA[c]) + fabs(source[c] - pA[c]);
+    nfac += ORC_SMALL;
+    perf->normFactor = nfac;
+    double s0 = 0.0;
+    for (int c = 0; c < n; c++) s0 += fabs(source[c] - Ax[c]);
+    perf->initialResidual = perf->finalResidual = s0 / nfac;
+    int k = 0;
+    if (history && k < historyCap) history[k] = perf->initialResidual;
+    orc_opts o;
+    memset(&o, 0, sizeof(o));
+    o.tolerance = tolerance;
+    o.relTol = relTol;
+    o.minIter = minIter;
+    o.maxIter = maxIter;
+    if (!orc_stop(&o, perf))
+    {
+        do
+        {
+            orc_gs_smooth(n, nf, l, u, diag, upper, lower, psi, source, nSweeps);
+            /* lduMatrix::residual: rA = source - diag*psi; rA[u] -= lower*psi[l]; rA[l] -= upper*psi[u] */
+            for (int c = 0; c < n; c++) tmp[c] = source[c] - diag[c] * psi[c];
+            for (int f = 0; f < nf; f++)
+            {
+                tmp[u[f]] -= lower[f] * psi[l[f]];
+                tmp[l[f]] -= upper[f] * psi[u[f]];
+            }
+            double s = 0.0;
+            for (int c = 0; c < n; c++) s += fabs(tmp[c]);
+            perf->finalResidual = s / nfac;
+            perf->nIterations += nSweeps;
+            k++;
+            if (history && k < historyCap) history[k] = perf->finalResidual;
+        } while (!orc_stop(&o, perf));
+    }
+    free(Ax);
+    free(tmp);
+    free(pA);
+    return 0;
+}

@@ -160,6 +160,14 @@ int orc_direct_map_build(int nTo, const double* to, int nFrom, const double* fro
 
 const char* orc_version(void);
 
+/* GaussSeidelSmoother::smooth / smoothSolver::solve for one matrix given as plain LDU arrays (lower == NULL: symmetric);
+ * coupled-patch contributions, if any, are expected inside `source` (the smoother's bPrime). */
+void orc_gs_smooth(int n, int nf, const int* l, const int* u, const double* diag, const double* upper, const double* lower,
+                   double* psi, const double* source, int nSweeps);
+int orc_gs_solve(int n, int nf, const int* l, const int* u, const double* diag, const double* upper, const double* lower,
+                 double* psi, const double* source, int nSweeps, double tolerance, double relTol, int minIter, int maxIter,
+                 orc_perf* perf, double* history, int historyCap);
+
 #ifdef __cplusplus
 }
 #endif

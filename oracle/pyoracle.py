@@ -67,6 +67,10 @@ def lib():
         L.orc_residual.argtypes = [C.c_void_p, dp, dp, dp]
         L.orc_precond_setup.argtypes = [C.c_void_p, C.c_int]
         L.orc_solve.argtypes = [C.c_void_p, C.POINTER(OrcOpts), dp, dp, C.POINTER(OrcPerf), dp, C.c_int]
+        L.orc_gs_smooth.argtypes = [C.c_int, C.c_int, ip, ip, dp, dp, dp, dp, dp, C.c_int]
+        L.orc_gs_smooth.restype = None
+        L.orc_gs_solve.argtypes = [C.c_int, C.c_int, ip, ip, dp, dp, dp, dp, dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
+                                   C.POINTER(OrcPerf), dp, C.c_int]
         L.orc_gsumprod.restype = C.c_double
         L.orc_gsumprod.argtypes = [C.c_void_p, dp, dp]
         L.orc_gsummag.restype = C.c_double
@@ -273,3 +277,32 @@ def direct_map(map_, from_, nComp=1):
     out = np.empty(m.size * nComp)
     lib().orc_direct_map(m.size, _ip(m), _dp(f), nComp, _dp(out))
     return out.reshape(m.size, nComp) if nComp > 1 else out
+
+
+# ---- GaussSeidelSmoother / smoothSolver for one matrix
+def gs_smooth(lowerAddr, upperAddr, diag, upper, lower, psi, source, nSweeps=1):
+    """GaussSeidelSmoother::smooth: nSweeps sweeps; coupled-patch contributions are expected inside `source`."""
+    l, u = _i32(lowerAddr), _i32(upperAddr)
+    d, up = _f64(diag), _f64(upper)
+    lo = None if lower is None else _f64(lower)
+    x = np.array(psi, np.float64).copy()
+    lib().orc_gs_smooth(d.size, l.size, _ip(l), _ip(u), _dp(d), _dp(up), _dp(lo), _dp(x), _dp(_f64(source)), int(nSweeps))
+    return x
+
+
+def gs_solve(lowerAddr, upperAddr, diag, upper, lower, psi, source, nSweeps=1, tolerance=1e-6, relTol=0.0, minIter=0, maxIter=1000):
+    """smoothSolver::solve with a GaussSeidel smoother -> (psi, dict like OracleSystem.solve)."""
+    l, u = _i32(lowerAddr), _i32(upperAddr)
+    d, up = _f64(diag), _f64(upper)
+    lo = None if lower is None else _f64(lower)
+    x = np.array(psi, np.float64).copy()
+    p = OrcPerf()
+    cap = maxIter // max(1, nSweeps) + 3
+    hist = np.full(cap, np.nan)
+    rc = lib().orc_gs_solve(d.size, l.size, _ip(l), _ip(u), _dp(d), _dp(up), _dp(lo), _dp(x), _dp(_f64(source)), int(nSweeps),
+                            tolerance, relTol, minIter, maxIter, C.byref(p), _dp(hist), cap)
+    if rc:
+        raise RuntimeError(f"orc_gs_solve failed rc={rc}")
+    n = p.nIterations // max(1, nSweeps)
+    return x, dict(initialResidual=p.initialResidual, finalResidual=p.finalResidual, nIterations=p.nIterations,
+                   converged=bool(p.converged), normFactor=p.normFactor, history=hist[: n + 1].copy())

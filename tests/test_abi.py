@@ -40,6 +40,19 @@ def test_block_header_symbols_are_exported(lib_path):
     assert sorted(blockldu.ABI_SYMBOLS) == declared
 
 
+def test_smoother_header_symbols_are_exported(lib_path):
+    """include/b200_smooth.h: the Gauss-Seidel smoother entry points."""
+    from multiregionfoam_b200 import smoother
+    hdr = open(os.path.join(ROOT, "include", "b200_smooth.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(b200_gs_[a-z_0-9A-Z]+)\s*\(", hdr)))
+    assert declared, "no declarations found"
+    L = C.CDLL(lib_path)
+    missing = [s for s in declared if not hasattr(L, s)]
+    assert not missing, missing
+    assert sorted(smoother.ABI_SYMBOLS) == declared
+
+
 def test_version_and_error_text(lib_path):
     L = ldu.load()
     assert L.b200_version() >= 100
