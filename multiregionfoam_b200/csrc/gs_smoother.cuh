@@ -37,11 +37,29 @@ __global__ void __launch_bounds__(kGsThreads)
     double acc = bPrime[row];
     const double rd = M.diag[row];
     const int o0 = M.ownerStart[row], o1 = M.ownerStart[row + 1];
-    for (int k = M.losortStart[row]; k < M.losortStart[row + 1]; k++)
+    const int k0 = M.losortStart[row], k1 = M.losortStart[row + 1];
+    // Everything that does not depend on other rows of this sweep is fetched BEFORE the first poll - the rows of a level wait
+    // for the level before, so what a row does after its neighbours' values arrive is the critical path: the lower
+    // coefficients and neighbour indices, and the products upper[f]*psiOld[u[f]] (subtracted AFTER the lower terms, in face
+    // order, as the reference does; forming the products early does not change them).  Up to kPre faces per side in
+    // registers, the rest (polyhedral cells) in the loops below.
+    constexpr int kPre = 4;
+    double lc[kPre], up[kPre];
+    int ln[kPre];
+#pragma unroll
+    for (int t = 0; t < kPre; t++)
     {
-        const int f = M.losort[k];
-        const double c = M.lower[f];
-        const double* p = psiNew + M.l[f];
+        lc[t] = up[t] = 0.0;
+        ln[t] = 0;
+        if (k0 + t < k1)
+        {
+            const int f = M.losort[k0 + t];
+            lc[t] = M.lower[f];
+            ln[t] = M.l[f];
+        }
+        if (o0 + t < o1) up[t] = M.upper[o0 + t] * psiOld[M.u[o0 + t]];
+    }
+    auto wait_for = [&](const double* p) {
         double v = ld_relaxed(p);
         for (long long tries = 0; is_sentinel(v); tries++)
         {
@@ -54,9 +72,20 @@ __global__ void __launch_bounds__(kGsThreads)
             }
             v = ld_relaxed(p);
         }
-        acc -= c * v;
+        return v;
+    };
+#pragma unroll
+    for (int t = 0; t < kPre; t++)
+        if (k0 + t < k1) acc -= lc[t] * wait_for(psiNew + ln[t]);
+    for (int k = k0 + kPre; k < k1; k++)
+    {
+        const int f = M.losort[k];
+        acc -= M.lower[f] * wait_for(psiNew + M.l[f]);
     }
-    for (int f = o0; f < o1; f++) acc -= M.upper[f] * psiOld[M.u[f]];
+#pragma unroll
+    for (int t = 0; t < kPre; t++)
+        if (o0 + t < o1) acc -= up[t];
+    for (int f = o0 + kPre; f < o1; f++) acc -= M.upper[f] * psiOld[M.u[f]];
     st_relaxed(psiNew + row, acc / rd);
 }
 
