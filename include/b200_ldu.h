@@ -218,6 +218,11 @@ int b200_residual(b200_sys* sys, const double* const* x, const double* const* b,
 /* lduMatrix::sumA: sumA[c] = diag[c] + the row's lower / upper coefficients, minus the boundaryCoeffs of the coupled
  * patches at their faceCells (same file).  Uses the coefficients of the last b200_sys_set_coeffs. */
 int b200_sum_a(b200_sys* sys, double* const* sumA);
+/* lduMatrix::smoother of the DIC / DILU family (foam-extend DICSmoother.C / DILUSmoother.C; with B200_PRECOND_CHOLESKY the "ILU"
+ * smoother some tutorials select): nSweeps times  rA = residual(psi, source); rA = M^-1 rA; psi += rA  - the preconditioner's
+ * own sweeps applied to the residual, so it runs at the speed of the DIC / DILU sweeps, on all regions, interfaces and ranks
+ * of the system.  x in/out.  (The Gauss-Seidel smoother is include/b200_smooth.h.) */
+int b200_smooth(b200_sys* sys, int precond, int nSweeps, double* const* x, const double* const* b);
 /* w = M^-1 r with the given preconditioner (transpose != 0: preconditionT) */
 int b200_precondition(b200_sys* sys, int precond, const double* const* r, double* const* w, int transpose);
 /* reciprocal preconditioned diagonal of the last preconditioner setup */

@@ -2027,6 +2027,38 @@ extern "C" int b200_precondition(b200_sys* s, int precond, const double* const* 
     return check_device_error(s);
 }
 
+// DICSmoother / DILUSmoother::smooth (and foam-extend's ILU smoother with the Cholesky-type preconditioner): nSweeps times
+//   rA = residual(psi, source);  rA = M^-1 rA;  psi += rA        (include/b200_ldu.h)
+extern "C" int b200_smooth(b200_sys* s, int precond, int nSweeps, double* const* x, const double* const* b)
+{
+    if (!s || !x || !b || nSweeps < 0) return B200_EINVAL;
+    if (!s->finalized) return set_err(s->ctx, B200_ESTATE, "smooth before finalize");
+    if (precond < B200_PRECOND_DIAGONAL || precond > B200_PRECOND_CHOLESKY) return set_err(s->ctx, B200_EINVAL, "b200_smooth: no such smoother (preconditioner %d)", precond);
+    b200_ctx* ctx = s->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    for (size_t q = 0; q < s->regs.size(); q++)
+        if (!s->regionHasCoeffs[q]) return set_err(ctx, B200_ESTATE, "region %zu has no coefficients", q);
+    int rc;
+    if ((rc = upload_vec(s, V_P, x))) return rc;
+    if ((rc = upload_vec(s, V_S, b))) return rc;
+    if ((rc = ensure_precond(s, precond, false))) return rc;
+    for (int sweep = 0; sweep < nSweeps; sweep++)
+    {
+        if ((rc = launch_amul(s, s->vec[V_P].p, s->vec[V_V].p, 0, s->vec[V_S].p, false, 1, nullptr, 1))) return rc; // lduMatrix::residual
+        if ((rc = launch_precondition(s, precond, s->vec[V_V].p, s->vec[V_SH].p, s->vec[V_TMP2].p, false, 1, false))) return rc;
+        if (s->nSlots)
+        {
+            KScope k(s, B200_K_VECTOR);
+            k_add_inplace<<<s->vecBlocks, 256, 0, ctx->stream>>>((size_t)s->nSlots, s->vec[V_P].p, s->vec[V_SH].p);
+            CK(ctx, cudaGetLastError());
+        }
+    }
+    if ((rc = download_vec(s, s->vec[V_P].p, x))) return rc;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (s->profiling) harvest_events(s);
+    return check_device_error(s);
+}
+
 extern "C" int b200_get_rD(b200_sys* s, int precond, double* const* rD)
 {
     if (!s || !rD) return B200_EINVAL;

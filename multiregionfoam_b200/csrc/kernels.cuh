@@ -2365,6 +2365,12 @@ __global__ void __launch_bounds__(256) k_bicg_xr(size_t n, double* __restrict__ 
     block_reduce_store<2>(d, partials, pstride, blockIdx.x);
 }
 
+// DIC / DILU smoother: psi += M^-1 (source - A psi)
+__global__ void __launch_bounds__(256) k_add_inplace(size_t n, double* __restrict__ x, const double* __restrict__ w)
+{
+    B200_GRID_STRIDE(i, n) x[i] = x[i] + w[i];
+}
+
 // (a,b) with sentinel fill of two arrays
 __global__ void __launch_bounds__(256) k_dot(size_t n, const double* __restrict__ a, const double* __restrict__ b,
                                               double* partials, int pstride, const DevScalars* sc)

@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "b200_sys_set_coeffs", "b200_sys_set_interface_coeffs", "b200_sys_num_cells", "b200_sys_num_faces",
     "b200_solve", "b200_upload", "b200_solve_resident", "b200_download",
     "b200_x_save", "b200_x_restore", "b200_host_register", "b200_host_unregister",
-    "b200_amul", "b200_precondition", "b200_get_rD", "b200_reduce", "b200_residual", "b200_sum_a",
+    "b200_amul", "b200_precondition", "b200_get_rD", "b200_reduce", "b200_residual", "b200_sum_a", "b200_smooth",
     "b200_set_profiling", "b200_get_kernel_times", "b200_launch_count", "b200_debug_sweep_stats",
     "b200_ggi_interpolate", "b200_patch_face_to_global", "b200_global_face_to_patch",
     "b200_sys_set_interface_attached", "b200_sys_set_interface_ggi", "b200_sys_set_interface_pieces",
@@ -102,6 +102,7 @@ def load():
     L.b200_amul.argtypes = [vp, dpp, dpp, C.c_int]
     L.b200_precondition.argtypes = [vp, C.c_int, dpp, dpp, C.c_int]
     L.b200_residual.argtypes = [vp, dpp, dpp, dpp]
+    L.b200_smooth.argtypes = [vp, C.c_int, C.c_int, dpp, dpp]
     L.b200_sum_a.argtypes = [vp, dpp]
     L.b200_get_rD.argtypes = [vp, C.c_int, dpp]
     L.b200_reduce.argtypes = [vp, dpp, dpp, dp]
@@ -367,6 +368,12 @@ class LduSystem:
         rs_, ws = self.split(r), self._empty()
         self.ctx.check(load().b200_precondition(self.h, precond, _dpp(rs_), _dpp(ws), int(transpose)))
         return np.concatenate(ws) if ws else np.empty(0)
+
+    def smooth(self, precond: int, x: np.ndarray, b: np.ndarray, nSweeps: int = 1) -> np.ndarray:
+        """DICSmoother / DILUSmoother::smooth: nSweeps times  psi += M^-1 (source - A psi)  with the preconditioner's sweeps."""
+        xs, bs = [np.array(v, copy=True) for v in self.split(x)], self.split(b)
+        self.ctx.check(load().b200_smooth(self.h, precond, int(nSweeps), _dpp(xs), _dpp(bs)))
+        return np.concatenate(xs) if xs else np.empty(0)
 
     def rD(self, precond: int) -> np.ndarray:
         out = self._empty()

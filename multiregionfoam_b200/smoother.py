@@ -13,7 +13,13 @@ from . import ldu
 # every symbol include/b200_smooth.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = ["b200_gs_create", "b200_gs_destroy", "b200_gs_set_coeffs", "b200_gs_sweep", "b200_gs_smooth", "b200_gs_solve"]
 
-SMOOTHER_TABLE = {"GaussSeidel": "gs", "cudaGaussSeidel": "gs"}   # lduMatrix::smoother names served here
+# lduMatrix::smoother names served by the library: Gauss-Seidel (this module, b200_gs_*), the DIC / DILU family
+# (ldu.LduSystem.smooth = b200_smooth: the preconditioner's sweeps applied to the residual) and their combination
+SMOOTHER_TABLE = {
+    "GaussSeidel": "gs", "cudaGaussSeidel": "gs",
+    "DIC": "dic", "cudaDIC": "dic", "DILU": "dilu", "cudaDILU": "dilu",
+    "DICGaussSeidel": "dic+gs", "cudaDICGaussSeidel": "dic+gs",
+}
 
 _bound = False
 

@@ -41,10 +41,14 @@ def test_registered_names_match_the_python_mirror():
     words = set()
     for src in glob.glob(os.path.join(ADAPT, "*.H")):
         text = open(src).read()
-        words |= set(re.findall(r'declareCuda\w+\((cuda\w+),', text))
+        words |= set(re.findall(r'declareCuda(?!LduSmoother)\w+\((cuda\w+),', text))
         words |= set(re.findall(r'declareCudaCoupledLduSolver\(\w+, "(cuda\w+)"', text))
+        words |= set(re.findall(r'declareCudaLduSmoother\(\w+, "(cuda\w+)"', text))      # smoother table words
+        words |= set(re.findall(r'TypeName\("(cuda\w*GaussSeidel)"\)', text))
     words = {w for w in words if not w.startswith("cudaCoupled")}
-    known = set(solvers.SOLVER_TABLE) | set(solvers.PRECOND_TABLE)
+    from multiregionfoam_b200 import smoother
+    known = set(solvers.SOLVER_TABLE) | set(solvers.PRECOND_TABLE) | set(smoother.SMOOTHER_TABLE)
+    assert {"cudaGaussSeidel", "cudaDICGaussSeidel"} <= words
     from multiregionfoam_b200 import blockldu
     known |= set(getattr(blockldu, "BLOCK_SOLVER_TABLE", {}))
     assert {"cudaPCG", "cudaPBiCGStab", "cudaPBiCG", "cudaDIC", "cudaDILU", "cudaBlockCG", "cudaBlockBiCGStab"} <= words
