@@ -206,3 +206,90 @@ def solve_coupled(ctx: ldu.Context, rs: RankSystem, fieldName: str, fvSolution: 
     finally:
         if own:
             system.close()
+
+
+# --------------------------------------------------------------------------- smoothSolver
+
+class smoothSolver:
+    """``solver smoothSolver; smoother <name>; nSweeps n;`` on the coupled device system of one rank
+    (foam-extend smoothSolver.C: smooth nSweeps times, check ``gSumMag(residual) / normFactor``, repeat).
+
+    DIC / DILU smoothers run through ``LduSystem.smooth`` (b200_smooth: the preconditioner's sweeps applied to the residual),
+    GaussSeidel through :class:`multiregionfoam_b200.smoother.GaussSeidel` (one region without coupled patches), DICGaussSeidel
+    = both in turn.  Residuals use ``LduSystem.residual`` (lduMatrix::residual) and ``LduSystem.amul``; the norms are summed on
+    the host in this mirror (the foam-extend adapters leave them to smoothSolver itself)."""
+
+    def __init__(self, fieldName: str, system: ldu.LduSystem, solverDict: dict):
+        from . import smoother as sm
+        name = solverDict.get("smoother")
+        if name not in sm.SMOOTHER_TABLE:
+            raise FatalError(f"Unknown smoother {name}; valid smoothers are {sorted(sm.SMOOTHER_TABLE)}")
+        self.kind = sm.SMOOTHER_TABLE[name]
+        self.fieldName, self.system = fieldName, system
+        self.nSweeps = int(solverDict.get("nSweeps", 1))
+        c = read_controls(dict(solverDict, solver="smoothSolver"))
+        self.controls = c
+        regs = system.rs.regions
+        sym = all(r.symmetric for r in regs)
+        if self.kind in ("dic", "dic+gs") and not sym:
+            raise FatalError(f"Unknown asymmetric matrix smoother {name}")
+        if self.kind == "dilu" and sym:
+            raise FatalError(f"Unknown symmetric matrix smoother {name}")
+        self.gs = None
+        if "gs" in self.kind:
+            if len(regs) != 1 or regs[0].interfaces:
+                raise FatalError("the GaussSeidel smoother of this mirror serves one region without coupled patches "
+                                 "(with coupled patches: adapters/b200LduSolvers/cudaGaussSeidelSmoother.C builds bPrime on the host)")
+            r = regs[0]
+            self.gs = sm.GaussSeidel(system.ctx, r.lowerAddr, r.upperAddr, r.nCells)
+            self.gs.set_coeffs(r.diag, r.upper, r.lower)
+
+    @classmethod
+    def New(cls, fieldName: str, system: ldu.LduSystem, solverDict: dict) -> "smoothSolver":
+        return cls(fieldName, system, solverDict)
+
+    def close(self):
+        if self.gs is not None:
+            self.gs.close()
+            self.gs = None
+
+    def _smooth(self, x: np.ndarray, b: np.ndarray, n: int) -> np.ndarray:
+        if self.kind in ("dic", "dic+gs"):
+            x = self.system.smooth(ldu.PRECOND_DIC, x, b, n)
+        elif self.kind == "dilu":
+            x = self.system.smooth(ldu.PRECOND_DILU, x, b, n)
+        if "gs" in self.kind:
+            x = self.gs.smooth(x, b, n)
+        return x
+
+    def solve(self, x: np.ndarray, b: np.ndarray) -> lduSolverPerformance:
+        """x is updated in place."""
+        c, S = self.controls, self.system
+        perf = lduSolverPerformance("smoothSolver", self.fieldName)
+        if self.nSweeps < 0:
+            x[...] = self._smooth(x, b, -self.nSweeps)
+            perf.nIterations = -self.nSweeps
+            return perf
+        Ax = S.amul(x)
+        pA = S.amul(np.full_like(x, x.sum() / max(1, x.size)))
+        perf.normFactor = float(np.abs(Ax - pA).sum() + np.abs(b - pA).sum() + 1e-20)
+        perf.initialResidual = perf.finalResidual = float(np.abs(b - Ax).sum() / perf.normFactor)
+        hist = [perf.initialResidual]
+
+        def stop() -> bool:
+            if perf.nIterations < c["minIter"]:
+                return False
+            perf.converged = bool(perf.finalResidual < c["tolerance"]
+                                  or (c["relTol"] > 1e-15 and perf.finalResidual <= c["relTol"] * perf.initialResidual))
+            return perf.nIterations >= c["maxIter"] or perf.converged
+
+        if not stop():
+            while True:
+                x[...] = self._smooth(x, b, self.nSweeps)
+                perf.finalResidual = float(np.abs(S.residual(x, b)).sum() / perf.normFactor)
+                perf.nIterations += self.nSweeps
+                hist.append(perf.finalResidual)
+                if stop():
+                    break
+        perf.history = np.array(hist)
+        return perf

@@ -83,3 +83,56 @@ def test_dic_dilu_smoother_is_residual_precondition_add(gpu_ctx, pre, name):
         assert r3 < 0.5 * r0
     finally:
         S.close()
+
+
+def test_smooth_solver_mirror_selects_by_dictionary(gpu_ctx):
+    """`solver smoothSolver; smoother ...; nSweeps n;` as the tutorials' fvSolution write it, through the Python mirror of the
+    selection (solvers.smoothSolver): GaussSeidel and DICGaussSeidel on one symmetric region, DILU on the coupled asymmetric
+    CHT system; every variant against the oracle composition of the same steps."""
+    from multiregionfoam_b200 import solvers
+    from multiregionfoam_b200.assembly import cht_case
+    from multiregionfoam_b200.case import Case, RankSystem
+    case, _, _ = cht_case(1, 2)
+    d = solvers.parse_dictionary("T { solver smoothSolver; smoother DILU; nSweeps 2; tolerance 1e-7; relTol 0; maxIter 60; }")["T"]
+    S = ldu.LduSystem(gpu_ctx, case.ranks[0])
+    O = pyoracle.OracleSystem(case)
+    try:
+        x, b = case.concat("psi").copy(), case.concat("source")
+        perf = solvers.smoothSolver.New("T", S, d).solve(x, b)
+        O.precond_setup("DILU")
+        ref = case.concat("psi").copy()
+        for _ in range(perf.nIterations):
+            ref = ref + O.precondition(O.residual(ref, b))
+        assert perf.nIterations % 2 == 0 and perf.nIterations > 0
+        assert np.array_equal(x, ref)
+        assert perf.finalResidual < perf.initialResidual
+        assert "smoothSolver:  Solving for T" in perf.line()
+        with pytest.raises(solvers.FatalError):
+            solvers.smoothSolver.New("T", S, dict(d, smoother="DIC"))       # asymmetric rows
+        with pytest.raises(solvers.FatalError):
+            solvers.smoothSolver.New("T", S, dict(d, smoother="symGaussSeidel"))
+    finally:
+        S.close()
+    # one symmetric region without coupled patches: GaussSeidel and DICGaussSeidel
+    solid = case.ranks[0].regions[1]
+    import copy
+    reg = copy.copy(solid)
+    reg.interfaces = []
+    one = Case("solid", [RankSystem(0, 1, [reg])])
+    S1, O1 = ldu.LduSystem(gpu_ctx, one.ranks[0]), pyoracle.OracleSystem(one)
+    try:
+        for name in ("GaussSeidel", "DICGaussSeidel"):
+            sol = solvers.smoothSolver.New("T", S1, dict(solver="smoothSolver", smoother=name, nSweeps=1, tolerance=0.0, maxIter=4))
+            x, b = reg.psi.copy(), reg.source
+            perf = sol.solve(x, b)
+            sol.close()
+            assert perf.nIterations == 4
+            ref = reg.psi.copy()
+            O1.precond_setup("DIC")
+            for _ in range(4):
+                if name == "DICGaussSeidel":
+                    ref = ref + O1.precondition(O1.residual(ref, b))
+                ref = pyoracle.gs_smooth(reg.lowerAddr, reg.upperAddr, reg.diag, reg.upper, reg.lower, ref, b, 1)
+            assert np.array_equal(x, ref), name
+    finally:
+        S1.close()
