@@ -347,6 +347,10 @@ def test_bench_config_history_against_oracle(gpu_ctx, workload):
     from multiregionfoam_b200.assembly import WORKLOADS, cht_rank_slab
     from multiregionfoam_b200.case import Case
     r, L = WORKLOADS[workload]
+    if workload == "C3":   # 64 M cells: the case, the oracle's copy and the library's host staging need ~25 GB of host memory
+        import psutil
+        if psutil.virtual_memory().available < 48 * 2**30:
+            pytest.skip("not enough host memory for the 64 M-cell oracle run")
     case = Case(workload, [cht_rank_slab(r, L, 0, 1)])
     O = pyoracle.OracleSystem(case)
     pyoracle.set_threads(min(8, __import__("os").cpu_count() or 1))  # vector updates / Amul rows only: same bits for any count
